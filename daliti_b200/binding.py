@@ -1,0 +1,265 @@
+"""ctypes binding of include/daliti_b200.h (the device-path C ABI).
+
+Mirrors the reference-side variables that cross the cut in
+eskf_lio/src/laserMapping.cpp:820-979.  Plumbing only: every
+computation happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def default_library_path() -> str:
+    return os.path.join(_HERE, "lib", "libdaliti_b200.so")
+
+
+class DltError(RuntimeError):
+    pass
+
+
+class DltConfig(C.Structure):
+    _fields_ = [
+        ("ds_scan", C.c_float),
+        ("ds_map", C.c_float),
+        ("max_sq_dist", C.c_float),
+        ("plane_thr", C.c_float),
+        ("extrinsic_est_en", C.c_int),
+        ("device", C.c_int),
+        ("max_scan_points", C.c_int),
+        ("max_map_points", C.c_int),
+        ("voxel_bitmap_bits", C.c_longlong),
+        ("shard_rank", C.c_int),
+        ("shard_count", C.c_int),
+        ("shard_tile_shift", C.c_int),
+    ]
+
+
+class _MeasureOut(C.Structure):
+    _fields_ = [
+        ("HtH", C.c_double * 144),
+        ("Htr", C.c_double * 12),
+        ("total_residual", C.c_double),
+        ("eigvals", C.c_double * 6),
+        ("eigvecs", C.c_double * 36),
+        ("effct_feat_num", C.c_int),
+        ("n_down", C.c_int),
+        ("n_unresolved", C.c_int),
+        ("reserved", C.c_int),
+    ]
+
+
+@dataclass
+class Measurement:
+    HtH: np.ndarray
+    Htr: np.ndarray
+    total_residual: float
+    eigvals: np.ndarray
+    eigvecs: np.ndarray
+    effct_feat_num: int
+    n_down: int
+    n_unresolved: int
+
+
+_ERR = {1: "invalid argument", 2: "no usable CUDA device (there is no CPU path)", 3: "CUDA error", 4: "capacity exceeded", 5: "call-sequence error"}
+
+_SYMBOLS = [
+    "dlt_default_config", "dlt_create", "dlt_destroy", "dlt_last_error", "dlt_set_stream", "dlt_sync",
+    "dlt_map_build", "dlt_map_add", "dlt_map_delete_boxes", "dlt_map_valid_count", "dlt_map_export", "dlt_map_knn",
+    "dlt_scan_deskew", "dlt_scan_downsample", "dlt_scan_get_undistorted", "dlt_scan_get_down", "dlt_scan_set_down",
+    "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
+    "dlt_degeneracy", "dlt_map_incremental",
+]
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load the CUDA library.  Raises DltError when it has not been built."""
+    path = path or default_library_path()
+    if not os.path.exists(path):
+        raise DltError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  daliti_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(path)
+    for s in _SYMBOLS:
+        if not hasattr(lib, s):
+            raise DltError(f"{path} does not export {s}")
+    lib.dlt_last_error.restype = C.c_char_p
+    lib.dlt_last_error.argtypes = [C.c_void_p]
+    return lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ScanToMap:
+    """One handle of the device path: map + current scan + measurement model."""
+
+    def __init__(self, lib: C.CDLL | None = None, **cfg):
+        self.lib = lib or load_library()
+        c = DltConfig()
+        self.lib.dlt_default_config(C.byref(c))
+        for k, v in cfg.items():
+            if not hasattr(c, k):
+                raise TypeError(f"unknown config field {k}")
+            setattr(c, k, v)
+        self.cfg = c
+        self.h = C.c_void_p()
+        rc = self.lib.dlt_create(C.byref(c), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise DltError(f"dlt_create failed: {_ERR.get(rc, rc)}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dlt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.dlt_last_error(self.h)
+            raise DltError(f"{_ERR.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    # ---- map
+    def map_build(self, xyzi):
+        a = _f32(xyzi).reshape(-1, 4)
+        self._ck(self.lib.dlt_map_build(self.h, _p(a), C.c_int(a.shape[0])))
+
+    def map_add(self, xyzi, downsample: bool):
+        a = _f32(xyzi).reshape(-1, 4)
+        self._ck(self.lib.dlt_map_add(self.h, _p(a), C.c_int(a.shape[0]), C.c_int(1 if downsample else 0)))
+
+    def map_delete_boxes(self, boxes) -> int:
+        b = _f32(boxes).reshape(-1, 6)
+        d = C.c_int(0)
+        self._ck(self.lib.dlt_map_delete_boxes(self.h, _p(b), C.c_int(b.shape[0]), C.byref(d)))
+        return d.value
+
+    def map_valid_count(self) -> int:
+        n = C.c_int(0)
+        self._ck(self.lib.dlt_map_valid_count(self.h, C.byref(n)))
+        return n.value
+
+    def map_export(self) -> np.ndarray:
+        n = self.map_valid_count()
+        out = np.zeros((max(n, 1), 4), np.float32)
+        m = C.c_int(0)
+        self._ck(self.lib.dlt_map_export(self.h, _p(out), C.c_int(out.shape[0]), C.byref(m)))
+        return out[: min(m.value, n)]
+
+    def map_knn(self, q_xyz):
+        q = _f32(q_xyz).reshape(-1, 3)
+        nq = q.shape[0]
+        pts = np.zeros((nq, 5, 4), np.float32)
+        d2 = np.zeros((nq, 5), np.float32)
+        cnt = np.zeros(nq, np.int32)
+        self._ck(self.lib.dlt_map_knn(self.h, _p(q), C.c_int(nq), _p(pts), _p(d2), _p(cnt)))
+        return pts, d2, cnt
+
+    # ---- scan
+    def scan_deskew(self, pts48, imu_pose22=None, pose24=None):
+        a = np.ascontiguousarray(pts48, dtype=np.float32).reshape(-1, 12)
+        if imu_pose22 is None:
+            self._ck(self.lib.dlt_scan_deskew(self.h, _p(a), C.c_int(a.shape[0]), None, C.c_int(0), None))
+        else:
+            ip = _f64(imu_pose22).reshape(-1, 22)
+            ps = _f64(pose24).reshape(24)
+            self._ck(self.lib.dlt_scan_deskew(self.h, _p(a), C.c_int(a.shape[0]), _p(ip), C.c_int(ip.shape[0]), _p(ps)))
+
+    def scan_downsample(self) -> int:
+        n = C.c_int(0)
+        self._ck(self.lib.dlt_scan_downsample(self.h, C.byref(n)))
+        return n.value
+
+    def scan_get_undistorted(self, n_raw) -> np.ndarray:
+        out = np.zeros((max(n_raw, 1), 4), np.float32)
+        n = C.c_int(0)
+        self._ck(self.lib.dlt_scan_get_undistorted(self.h, _p(out), C.c_int(out.shape[0]), C.byref(n)))
+        return out[: n.value]
+
+    def scan_get_down(self, cap) -> np.ndarray:
+        out = np.zeros((max(cap, 1), 4), np.float32)
+        n = C.c_int(0)
+        self._ck(self.lib.dlt_scan_get_down(self.h, _p(out), C.c_int(out.shape[0]), C.byref(n)))
+        return out[: n.value]
+
+    def scan_set_down(self, xyzi):
+        a = _f32(xyzi).reshape(-1, 4)
+        self._ck(self.lib.dlt_scan_set_down(self.h, _p(a), C.c_int(a.shape[0])))
+
+    def scan_get_voxel_of_point(self, n_raw) -> np.ndarray:
+        out = np.zeros(max(n_raw, 1), np.int32)
+        self._ck(self.lib.dlt_scan_get_voxel_of_point(self.h, _p(out), C.c_int(n_raw)))
+        return out[:n_raw]
+
+    # ---- measurement model
+    def measure(self, pose24, do_match: bool) -> Measurement:
+        ps = _f64(pose24).reshape(24)
+        o = _MeasureOut()
+        self._ck(self.lib.dlt_measure(self.h, _p(ps), C.c_int(1 if do_match else 0), C.byref(o)))
+        return Measurement(
+            HtH=np.array(o.HtH, dtype=np.float64).reshape(12, 12),
+            Htr=np.array(o.Htr, dtype=np.float64),
+            total_residual=o.total_residual,
+            eigvals=np.array(o.eigvals, dtype=np.float64),
+            eigvecs=np.array(o.eigvecs, dtype=np.float64).reshape(6, 6),
+            effct_feat_num=o.effct_feat_num,
+            n_down=o.n_down,
+            n_unresolved=o.n_unresolved,
+        )
+
+    def measure_dev(self, pose24, do_match: bool, result_dev_ptr: int):
+        ps = _f64(pose24).reshape(24)
+        self._ck(self.lib.dlt_measure_dev(self.h, _p(ps), C.c_int(1 if do_match else 0), C.c_void_p(result_dev_ptr)))
+
+    def effective_points(self, cap):
+        xyzi = np.zeros((max(cap, 1), 4), np.float32)
+        coeff = np.zeros((max(cap, 1), 4), np.float32)
+        n = C.c_int(0)
+        self._ck(self.lib.dlt_effective_points(self.h, _p(xyzi), _p(coeff), C.c_int(cap), C.byref(n)))
+        return xyzi[: n.value], coeff[: n.value]
+
+    def get_nearest(self, n_down):
+        nbr = np.zeros((max(n_down, 1), 5, 4), np.float32)
+        cnt = np.zeros(max(n_down, 1), np.int32)
+        sel = np.zeros(max(n_down, 1), np.uint8)
+        self._ck(self.lib.dlt_get_nearest(self.h, _p(nbr), _p(cnt), _p(sel), C.c_int(n_down)))
+        return nbr[:n_down], cnt[:n_down], sel[:n_down]
+
+    def degeneracy(self):
+        ev = np.zeros(6, np.float64)
+        vec = np.zeros(36, np.float64)
+        self._ck(self.lib.dlt_degeneracy(self.h, _p(ev), _p(vec)))
+        return ev, vec.reshape(6, 6)
+
+    def map_incremental(self, pose24, flg_EKF_inited: bool = True):
+        ps = _f64(pose24).reshape(24)
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.dlt_map_incremental(self.h, _p(ps), C.c_int(1 if flg_EKF_inited else 0), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._ck(self.lib.dlt_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def sync(self):
+        self._ck(self.lib.dlt_sync(self.h))

@@ -1,0 +1,646 @@
+// daliti_b200/csrc/dlt_api.cu -- the C ABI declared in include/daliti_b200.h.
+//
+// One handle = one CUDA stream + the device-resident state of one LiDAR sequence: the
+// voxel-hash map, the current scan (raw / undistorted / downsampled), the neighbour sets
+// and cached planes of the current IEKF update.  Host buffers in, host buffers out; every
+// kernel is in the three *_kernels.cuh headers.  There is no CPU code path here.
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/daliti_b200.h"
+#include "dlt_map_kernels.cuh"
+#include "dlt_measure_kernels.cuh"
+#include "dlt_rt.h"
+#include "dlt_scan_kernels.cuh"
+
+using namespace dlt;
+
+namespace {
+constexpr int kMaxImuPoses = 512;
+constexpr int kFarChunk = 4096;
+constexpr int kFarSlices = 64;
+constexpr int kFarGroupsX = 4;
+}  // namespace
+
+struct dlt_handle_s {
+    dlt_config cfg;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int cap = 0;  // per-point array capacity (max_scan_points)
+
+    // map
+    MapView map;
+    size_t table_cap = 0;
+    int *d_counters = nullptr;  // [0] n_buckets [1] n_live [2] error [3] deleted [4] export counter [5] far_count
+    // scan
+    int n_raw = 0, n_down = 0;
+    bool have_raw = false, have_down = false, have_match = false;
+    float4 *d_raw = nullptr, *d_undist = nullptr, *d_down = nullptr;
+    ImuPoseDev *d_poses = nullptr;
+    ScanScalars *d_sc = nullptr;
+    unsigned *d_bitmap = nullptr, *d_wprefix = nullptr, *d_blksum = nullptr, *d_blkoff = nullptr, *d_vidx = nullptr;
+    long long bitmap_bits = 0;
+    int n_scan_blocks = 0;
+    VoxAcc acc;
+    int *d_vop = nullptr;
+    // measure
+    KnnOut knn;
+    float4 *d_plane = nullptr, *d_coeff = nullptr;
+    unsigned char *d_sel = nullptr, *d_eff = nullptr;
+    double *d_partials = nullptr, *d_result = nullptr;
+    unsigned *d_ticket = nullptr;
+    Cand *d_far_partial = nullptr;
+    // insert
+    float4 *d_pw = nullptr;
+    unsigned char *d_dsflag = nullptr, *d_addflag = nullptr;
+    int *d_cellslot = nullptr, *d_vslot = nullptr;
+    DsScratch scratch;
+    // pinned host staging
+    double *h_result = nullptr;
+    int *h_ints = nullptr;
+    ScanScalars *h_sc = nullptr;
+    std::vector<void *> allocs;
+};
+
+#define DLT_FAIL(h, code, msg)  \
+    do {                        \
+        (h)->err = (msg);       \
+        return (code);          \
+    } while (0)
+#define DLT_RT(h, expr)                                                                    \
+    do {                                                                                   \
+        if ((expr) != 0) {                                                                 \
+            (h)->err = std::string(#expr) + ": " + rt::last_error();                       \
+            return DLT_E_CUDA;                                                             \
+        }                                                                                  \
+    } while (0)
+
+template <typename T>
+static int dalloc(dlt_handle h, T **p, size_t count) {
+    void *v = nullptr;
+    if (rt::alloc(&v, count * sizeof(T)) != 0) return 1;
+    h->allocs.push_back(v);
+    *p = static_cast<T *>(v);
+    return 0;
+}
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static Pose pose_from(const double *p) {
+    Pose P;
+    for (int i = 0; i < 9; i++) P.rot_end[i] = p[i];
+    for (int i = 0; i < 3; i++) P.pos_end[i] = p[9 + i];
+    for (int i = 0; i < 9; i++) P.R_L_I[i] = p[12 + i];
+    for (int i = 0; i < 3; i++) P.T_L_I[i] = p[21 + i];
+    return P;
+}
+
+static int map_reset(dlt_handle h) {
+    DLT_RT(h, rt::fill(h->map.table, 0xFF, h->table_cap * sizeof(Slot), h->stream));
+    DLT_RT(h, rt::fill(h->d_counters, 0, 8 * sizeof(int), h->stream));
+    return DLT_OK;
+}
+
+static int map_check_error(dlt_handle h) {
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
+    if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
+    return DLT_OK;
+}
+
+// claim | (bid, resolve) | append over n device points with per-point flags
+static int insert_points(dlt_handle h, const float4 *d_pts, int n, bool any_ds) {
+    if (n <= 0) return DLT_OK;
+    const int B = 256, G = div_up(n, B);
+    DLT_LAUNCH(k_map_claim, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
+               h->d_cellslot, h->map.shard_count > 1 ? 1 : 0);
+    if (any_ds) {
+        DLT_RT(h, rt::fill(h->scratch.vkeys, 0xFF, ((size_t)h->scratch.mask + 1) * sizeof(unsigned long long), h->stream));
+        DLT_RT(h, rt::fill(h->scratch.vwin, 0xFF, ((size_t)h->scratch.mask + 1) * sizeof(unsigned long long), h->stream));
+        DLT_LAUNCH(k_ds_bid, G, B, h->stream, h->map, h->scratch, d_pts, n, (const unsigned char *)h->d_dsflag, h->d_vslot);
+        DLT_LAUNCH(k_ds_resolve, G, B, h->stream, h->map, h->scratch, d_pts, n, (const unsigned char *)h->d_dsflag, (const int *)h->d_vslot,
+                   (const int *)h->d_cellslot, h->d_addflag);
+    }
+    DLT_LAUNCH(k_map_append, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_addflag, (const int *)h->d_cellslot);
+    DLT_RT(h, rt::check_launch());
+    return DLT_OK;
+}
+
+static int add_host_points(dlt_handle h, const float *xyzi, int n, int downsample_on) {
+    for (int off = 0; off < n; off += h->cap) {
+        int c = n - off < h->cap ? n - off : h->cap;
+        DLT_RT(h, rt::h2d(h->d_pw, xyzi + (size_t)off * 4, (size_t)c * sizeof(float4), h->stream));
+        DLT_RT(h, rt::fill(h->d_dsflag, downsample_on ? 1 : 0, (size_t)c, h->stream));
+        DLT_RT(h, rt::fill(h->d_addflag, downsample_on ? 0 : 1, (size_t)c, h->stream));
+        int rc = insert_points(h, h->d_pw, c, downsample_on != 0);
+        if (rc) return rc;
+        // the staging buffers are reused by the next chunk
+        DLT_RT(h, rt::sync(h->stream));
+    }
+    return map_check_error(h);
+}
+
+// exact neighbours for the queries the ring search could not resolve
+static int run_far(dlt_handle h, int *n_far_out) {
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    int nfar = h->h_ints[5], n_buckets = h->h_ints[0];
+    if (n_far_out) *n_far_out = nfar;
+    if (nfar <= 0) return DLT_OK;
+    for (int off = 0; off < nfar; off += kFarChunk) {
+        int c = nfar - off < kFarChunk ? nfar - off : kFarChunk;
+        DLT_LAUNCH(k_far_scan, dim3(kFarGroupsX, kFarSlices), kFarWarps * 32, h->stream, h->map, n_buckets, (const float4 *)h->knn.qw,
+                   (const int *)h->knn.far_list, off, c, kFarSlices, h->d_far_partial);
+        DLT_LAUNCH(k_far_merge, div_up(c, 128), 128, h->stream, (const int *)h->knn.far_list, off, c, kFarSlices,
+                   (const Cand *)h->d_far_partial, h->cfg.max_sq_dist, h->knn);
+    }
+    DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
+    DLT_RT(h, rt::check_launch());
+    return DLT_OK;
+}
+
+extern "C" {
+
+void dlt_default_config(dlt_config *c) {
+    c->ds_scan = 0.5f;
+    c->ds_map = 0.5f;
+    c->max_sq_dist = 5.0f;
+    c->plane_thr = 0.1f;
+    c->extrinsic_est_en = 0;
+    c->device = 0;
+    c->max_scan_points = 262144;
+    c->max_map_points = 4 * 1024 * 1024;
+    c->voxel_bitmap_bits = 0;
+    c->shard_rank = 0;
+    c->shard_count = 1;
+    c->shard_tile_shift = 0;
+}
+
+int dlt_destroy(dlt_handle h) {
+    if (!h) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    if (h->own_stream) rt::sync(h->own_stream);
+    for (void *p : h->allocs) rt::release(p);
+    rt::pinned_release(h->h_result);
+    rt::pinned_release(h->h_ints);
+    rt::pinned_release(h->h_sc);
+    rt::stream_destroy(h->own_stream);
+    delete h;
+    return DLT_OK;
+}
+
+int dlt_create(const dlt_config *cfg, dlt_handle *out) {
+    if (!cfg || !out) return DLT_E_INVALID;
+    *out = nullptr;
+    if (cfg->ds_scan <= 0.f || cfg->ds_map <= 0.f || cfg->max_scan_points <= 0 || cfg->max_map_points <= 0 || cfg->shard_count < 1 ||
+        cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count)
+        return DLT_E_INVALID;
+    if (rt::device_count() <= cfg->device) return DLT_E_NO_DEVICE;  // no CPU path: fail loudly
+    if (rt::set_device(cfg->device) != 0) return DLT_E_NO_DEVICE;
+    dlt_handle h = new dlt_handle_s();
+    h->cfg = *cfg;
+    h->cap = cfg->max_scan_points;
+    bool ok = rt::stream_create(&h->own_stream) == 0;
+    h->stream = h->own_stream;
+
+    // search cell edge = ds_map * 2^shift with 3 edges covering sqrt(max_sq_dist)
+    int shift = 1;
+    while (3.0 * cfg->ds_map * (double)(1 << shift) < 1.05 * std::sqrt((double)cfg->max_sq_dist) && shift < 12) shift++;
+    size_t bucket_cap = (size_t)cfg->max_map_points;
+    if (bucket_cap < 4096) bucket_cap = 4096;
+    size_t tcap = 1;
+    while (tcap < 2 * bucket_cap) tcap <<= 1;
+    h->table_cap = tcap;
+    h->map.table_mask = (unsigned)(tcap - 1);
+    h->map.bucket_cap = (int)bucket_cap;
+    h->map.ds = cfg->ds_map;
+    h->map.cell_shift = shift;
+    h->map.shard_rank = cfg->shard_rank;
+    h->map.shard_count = cfg->shard_count;
+    h->map.tile_shift = cfg->shard_tile_shift > 0 ? cfg->shard_tile_shift : 5;
+    h->bitmap_bits = cfg->voxel_bitmap_bits > 0 ? cfg->voxel_bitmap_bits : (1ll << 27);
+    const size_t words = (size_t)((h->bitmap_bits + 31) / 32);
+    h->n_scan_blocks = div_up((long long)words, kScanWordsPerBlock);
+    const size_t cap = (size_t)h->cap;
+    const int blocks_max = div_up((long long)cap, kResidBlock);
+    size_t sc_cap = 1;
+    while (sc_cap < 4 * cap) sc_cap <<= 1;
+    h->scratch.mask = (unsigned)(sc_cap - 1);
+
+    ok = ok && !dalloc(h, &h->map.table, tcap) && !dalloc(h, &h->map.buckets, bucket_cap) && !dalloc(h, &h->d_counters, 8) &&
+         !dalloc(h, &h->d_raw, cap * kRawStride4) && !dalloc(h, &h->d_undist, cap) && !dalloc(h, &h->d_down, cap) &&
+         !dalloc(h, &h->d_poses, kMaxImuPoses) && !dalloc(h, &h->d_sc, 1) && !dalloc(h, &h->d_bitmap, words) &&
+         !dalloc(h, &h->d_wprefix, words) && !dalloc(h, &h->d_blksum, (size_t)h->n_scan_blocks) &&
+         !dalloc(h, &h->d_blkoff, (size_t)h->n_scan_blocks) && !dalloc(h, &h->d_vidx, cap) && !dalloc(h, &h->acc.sx, cap) &&
+         !dalloc(h, &h->acc.sy, cap) && !dalloc(h, &h->acc.sz, cap) && !dalloc(h, &h->acc.si, cap) && !dalloc(h, &h->acc.cnt, cap) &&
+         !dalloc(h, &h->acc.idx, cap) && !dalloc(h, &h->d_vop, cap) && !dalloc(h, &h->knn.qw, cap) && !dalloc(h, &h->knn.nbr, cap * kK) &&
+         !dalloc(h, &h->knn.nbr_id, cap * kK) && !dalloc(h, &h->knn.nbr_cnt, cap) && !dalloc(h, &h->knn.flags, cap) &&
+         !dalloc(h, &h->knn.far_list, cap) && !dalloc(h, &h->d_plane, cap) && !dalloc(h, &h->d_coeff, cap) && !dalloc(h, &h->d_sel, cap) &&
+         !dalloc(h, &h->d_eff, cap) && !dalloc(h, &h->d_partials, (size_t)blocks_max * NormalEq<true>::NR) &&
+         !dalloc(h, &h->d_result, (size_t)kResultDoubles) && !dalloc(h, &h->d_ticket, 4) &&
+         !dalloc(h, &h->d_far_partial, (size_t)kFarChunk * kFarSlices * kK) && !dalloc(h, &h->d_pw, cap) && !dalloc(h, &h->d_dsflag, cap) &&
+         !dalloc(h, &h->d_addflag, cap) && !dalloc(h, &h->d_cellslot, cap) && !dalloc(h, &h->d_vslot, cap) &&
+         !dalloc(h, &h->scratch.vkeys, sc_cap) && !dalloc(h, &h->scratch.vwin, sc_cap);
+    void *p = nullptr;
+    ok = ok && rt::pinned_alloc(&p, kResultDoubles * sizeof(double)) == 0;
+    h->h_result = (double *)p;
+    ok = ok && rt::pinned_alloc(&p, 64 * sizeof(int)) == 0;
+    h->h_ints = (int *)p;
+    ok = ok && rt::pinned_alloc(&p, sizeof(ScanScalars)) == 0;
+    h->h_sc = (ScanScalars *)p;
+    if (!ok) {
+        dlt_destroy(h);
+        return DLT_E_CUDA;
+    }
+    h->map.n_buckets = h->d_counters + 0;
+    h->map.n_live = h->d_counters + 1;
+    h->map.error = h->d_counters + 2;
+    h->knn.far_count = h->d_counters + 5;
+    // accumulators and bitmap are kept zero between scans by k_vox_final
+    bool z = rt::fill(h->d_bitmap, 0, words * 4, h->stream) == 0 && rt::fill(h->acc.sx, 0, cap * 8, h->stream) == 0 &&
+             rt::fill(h->acc.sy, 0, cap * 8, h->stream) == 0 && rt::fill(h->acc.sz, 0, cap * 8, h->stream) == 0 &&
+             rt::fill(h->acc.si, 0, cap * 8, h->stream) == 0 && rt::fill(h->acc.cnt, 0, cap * 4, h->stream) == 0 &&
+             rt::fill(h->d_ticket, 0, 16, h->stream) == 0 && rt::fill(h->d_sel, 0, cap, h->stream) == 0 &&
+             rt::fill(h->d_result, 0, kResultDoubles * sizeof(double), h->stream) == 0;
+    if (!z || map_reset(h) != DLT_OK || rt::sync(h->stream) != 0) {
+        dlt_destroy(h);
+        return DLT_E_CUDA;
+    }
+    *out = h;
+    return DLT_OK;
+}
+
+const char *dlt_last_error(dlt_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int dlt_set_stream(dlt_handle h, void *s) {
+    if (!h) return DLT_E_INVALID;
+    rt::sync(h->stream);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return DLT_OK;
+}
+int dlt_sync(dlt_handle h) {
+    if (!h) return DLT_E_INVALID;
+    DLT_RT(h, rt::sync(h->stream));
+    return DLT_OK;
+}
+
+// ------------------------------------------------------------------ map
+int dlt_map_build(dlt_handle h, const float *xyzi, int n) {
+    if (!h || (n > 0 && !xyzi) || n < 0) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    int rc = map_reset(h);
+    if (rc) return rc;
+    h->have_match = false;
+    return add_host_points(h, xyzi, n, 0);
+}
+
+int dlt_map_add(dlt_handle h, const float *xyzi, int n, int downsample_on) {
+    if (!h || (n > 0 && !xyzi) || n < 0) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    h->have_match = false;
+    return add_host_points(h, xyzi, n, downsample_on);
+}
+
+int dlt_map_delete_boxes(dlt_handle h, const float *boxes6, int nb, int *deleted) {
+    if (!h || nb < 0 || (nb > 0 && !boxes6)) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    DLT_RT(h, rt::fill(h->d_counters + 3, 0, sizeof(int), h->stream));
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    int n_buckets = h->h_ints[0];
+    for (int off = 0; off < nb && n_buckets > 0; off += 8) {
+        BoxSet bs;
+        bs.n = nb - off < 8 ? nb - off : 8;
+        for (int k = 0; k < bs.n; k++)
+            for (int a = 0; a < 3; a++) {
+                bs.mn[k][a] = boxes6[(size_t)(off + k) * 6 + a];
+                bs.mx[k][a] = boxes6[(size_t)(off + k) * 6 + 3 + a];
+            }
+        DLT_LAUNCH(k_map_delete_boxes, div_up((long long)n_buckets * 8, 256), 256, h->stream, h->map, bs, n_buckets, h->d_counters + 3);
+    }
+    DLT_RT(h, rt::check_launch());
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    if (deleted) *deleted = h->h_ints[3];
+    h->have_match = false;
+    return DLT_OK;
+}
+
+int dlt_map_valid_count(dlt_handle h, int *n) {
+    if (!h || !n) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    *n = h->h_ints[1];
+    return DLT_OK;
+}
+
+int dlt_map_export(dlt_handle h, float *xyzi, int cap, int *n) {
+    if (!h || !n || cap < 0 || (cap > 0 && !xyzi)) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    DLT_RT(h, rt::fill(h->d_counters + 4, 0, sizeof(int), h->stream));
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    int n_buckets = h->h_ints[0], live = h->h_ints[1];
+    *n = live;
+    if (cap == 0 || live == 0 || n_buckets == 0) return DLT_OK;
+    float4 *d_out = nullptr;
+    void *v = nullptr;
+    if (rt::alloc(&v, (size_t)cap * sizeof(float4)) != 0) DLT_FAIL(h, DLT_E_CUDA, "export buffer allocation failed");
+    d_out = (float4 *)v;
+    DLT_LAUNCH(k_map_export, div_up((long long)n_buckets * 8, 256), 256, h->stream, h->map, n_buckets, d_out, cap, h->d_counters + 4);
+    int rc = rt::check_launch();
+    int m = live < cap ? live : cap;
+    if (!rc) rc = rt::d2h(xyzi, d_out, (size_t)m * sizeof(float4), h->stream);
+    if (!rc) rc = rt::sync(h->stream);
+    rt::release(v);
+    if (rc) DLT_FAIL(h, DLT_E_CUDA, std::string("map export: ") + rt::last_error());
+    return DLT_OK;
+}
+
+int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *out_d2, int *out_cnt) {
+    if (!h || nq < 0 || (nq > 0 && (!q || !out_xyzi || !out_d2 || !out_cnt))) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    h->have_match = false;  // the neighbour buffers of the current scan are reused
+    Pose P = {};
+    std::vector<float> stage;
+    std::vector<float4> nb;
+    for (int off = 0; off < nq; off += h->cap) {
+        int c = nq - off < h->cap ? nq - off : h->cap;
+        stage.assign((size_t)c * 4, 0.f);
+        for (int i = 0; i < c; i++) {
+            stage[4 * (size_t)i] = q[3 * (size_t)(off + i)];
+            stage[4 * (size_t)i + 1] = q[3 * (size_t)(off + i) + 1];
+            stage[4 * (size_t)i + 2] = q[3 * (size_t)(off + i) + 2];
+        }
+        DLT_RT(h, rt::h2d(h->d_pw, stage.data(), (size_t)c * sizeof(float4), h->stream));
+        DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
+        DLT_LAUNCH(k_knn, div_up(c, kKnnWarps), kKnnWarps * 32, h->stream, h->map, (const float4 *)h->d_pw, c, 0, P, h->cfg.max_sq_dist, h->knn);
+        DLT_RT(h, rt::check_launch());
+        int rc = run_far(h, nullptr);
+        if (rc) return rc;
+        nb.resize((size_t)c * kK);
+        DLT_RT(h, rt::d2h(nb.data(), h->knn.nbr, (size_t)c * kK * sizeof(float4), h->stream));
+        DLT_RT(h, rt::d2h(out_cnt + off, h->knn.nbr_cnt, (size_t)c * sizeof(int), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+        for (size_t i = 0; i < (size_t)c * kK; i++) {
+            float *o = out_xyzi + ((size_t)off * kK + i) * 4;
+            bool ok = nb[i].w >= 0.f;
+            o[0] = nb[i].x;
+            o[1] = nb[i].y;
+            o[2] = nb[i].z;
+            o[3] = 0.f;
+            out_d2[(size_t)off * kK + i] = ok ? nb[i].w : -1.f;
+        }
+    }
+    return DLT_OK;
+}
+
+// ------------------------------------------------------------------ scan
+int dlt_scan_deskew(dlt_handle h, const void *pts48, int n_raw, const double *imu_pose22, int n_pose, const double *pose24) {
+    if (!h || n_raw < 0 || (n_raw > 0 && !pts48) || n_pose < 0 || (n_pose > 0 && !imu_pose22) || (n_pose >= 2 && !pose24)) return DLT_E_INVALID;
+    if (n_raw > h->cap) DLT_FAIL(h, DLT_E_CAPACITY, "scan larger than max_scan_points");
+    if (n_pose > kMaxImuPoses) DLT_FAIL(h, DLT_E_CAPACITY, "too many IMU poses");
+    rt::set_device(h->cfg.device);
+    h->n_raw = n_raw;
+    h->have_raw = true;
+    h->have_down = false;
+    h->have_match = false;
+    DLT_LAUNCH(k_scan_reset, 1, 32, h->stream, h->d_sc);
+    if (n_raw == 0) return DLT_OK;
+    DLT_RT(h, rt::h2d(h->d_raw, pts48, (size_t)n_raw * 48, h->stream));
+    Pose P = {};
+    if (n_pose >= 2) {
+        static_assert(sizeof(ImuPoseDev) == 22 * sizeof(double), "Pose6D layout");
+        DLT_RT(h, rt::h2d(h->d_poses, imu_pose22, (size_t)n_pose * sizeof(ImuPoseDev), h->stream));
+        P = pose_from(pose24);
+        DLT_LAUNCH(k_scan_first, div_up(n_raw, 256), 256, h->stream, (const float4 *)h->d_raw, n_raw, h->d_sc);
+    }
+    DLT_LAUNCH(k_scan_deskew, div_up(n_raw, kDeskewBlock), kDeskewBlock, h->stream, (const float4 *)h->d_raw, n_raw,
+               (const ImuPoseDev *)h->d_poses, n_pose, P, n_pose >= 2 ? 1 : 0, h->d_undist, h->d_sc);
+    DLT_RT(h, rt::check_launch());
+    return DLT_OK;
+}
+
+int dlt_scan_downsample(dlt_handle h, int *n_down) {
+    if (!h || !n_down) return DLT_E_INVALID;
+    if (!h->have_raw) DLT_FAIL(h, DLT_E_STATE, "dlt_scan_downsample before dlt_scan_deskew");
+    rt::set_device(h->cfg.device);
+    const int n = h->n_raw;
+    h->n_down = 0;
+    *n_down = 0;
+    h->have_match = false;
+    if (n == 0) {
+        h->have_down = true;
+        return DLT_OK;
+    }
+    const int B = 256, G = div_up(n, B);
+    DLT_LAUNCH(k_vox_mark, G, B, h->stream, (const float4 *)h->d_undist, n, h->cfg.ds_scan, h->d_sc, h->d_bitmap, h->bitmap_bits, h->d_vidx);
+    DLT_LAUNCH(k_vox_scan1, h->n_scan_blocks, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, (const ScanScalars *)h->d_sc, h->d_wprefix,
+               h->d_blksum);
+    DLT_LAUNCH(k_vox_scan2, 1, 1024, h->stream, h->d_sc, (const unsigned *)h->d_blksum, h->d_blkoff);
+    DLT_LAUNCH(k_vox_accum, G, B, h->stream, (const float4 *)h->d_undist, n, (const ScanScalars *)h->d_sc, (const unsigned *)h->d_bitmap,
+               (const unsigned *)h->d_wprefix, (const unsigned *)h->d_blkoff, (const unsigned *)h->d_vidx, h->acc, h->d_vop);
+    DLT_LAUNCH(k_vox_final, G, B, h->stream, (const ScanScalars *)h->d_sc, h->acc, h->d_bitmap, h->d_down, n);
+    DLT_LAUNCH(k_vox_passthrough, G, B, h->stream, (const float4 *)h->d_undist, n, h->d_sc, h->d_down);
+    DLT_RT(h, rt::check_launch());
+    DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    if (h->h_sc->vox_status == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    h->n_down = h->h_sc->n_down;
+    *n_down = h->n_down;
+    h->have_down = true;
+    return DLT_OK;
+}
+
+int dlt_scan_get_undistorted(dlt_handle h, float *xyzi, int cap, int *n) {
+    if (!h || !n) return DLT_E_INVALID;
+    if (!h->have_raw) DLT_FAIL(h, DLT_E_STATE, "no scan");
+    *n = h->n_raw;
+    int m = h->n_raw < cap ? h->n_raw : cap;
+    if (m > 0 && xyzi) {
+        DLT_RT(h, rt::d2h(xyzi, h->d_undist, (size_t)m * sizeof(float4), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+    }
+    return DLT_OK;
+}
+int dlt_scan_get_down(dlt_handle h, float *xyzi, int cap, int *n) {
+    if (!h || !n) return DLT_E_INVALID;
+    if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "no downsampled scan");
+    *n = h->n_down;
+    int m = h->n_down < cap ? h->n_down : cap;
+    if (m > 0 && xyzi) {
+        DLT_RT(h, rt::d2h(xyzi, h->d_down, (size_t)m * sizeof(float4), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+    }
+    return DLT_OK;
+}
+int dlt_scan_set_down(dlt_handle h, const float *xyzi, int n) {
+    if (!h || n < 0 || (n > 0 && !xyzi)) return DLT_E_INVALID;
+    if (n > h->cap) DLT_FAIL(h, DLT_E_CAPACITY, "scan larger than max_scan_points");
+    rt::set_device(h->cfg.device);
+    if (n > 0) DLT_RT(h, rt::h2d(h->d_down, xyzi, (size_t)n * sizeof(float4), h->stream));
+    h->n_down = n;
+    h->have_down = true;
+    h->have_match = false;
+    return DLT_OK;
+}
+int dlt_scan_get_voxel_of_point(dlt_handle h, int *slot, int cap) {
+    if (!h || !slot) return DLT_E_INVALID;
+    if (!h->have_down || !h->have_raw) DLT_FAIL(h, DLT_E_STATE, "no downsampled scan");
+    int m = h->n_raw < cap ? h->n_raw : cap;
+    if (m > 0) {
+        DLT_RT(h, rt::d2h(slot, h->d_vop, (size_t)m * sizeof(int), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+    }
+    return DLT_OK;
+}
+
+// ------------------------------------------------------------------ measurement model
+int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev) {
+    if (!h || !pose24 || !result_dev) return DLT_E_INVALID;
+    if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_measure before a downsampled scan is set");
+    if (!do_match && !h->have_match) DLT_FAIL(h, DLT_E_STATE, "dlt_measure(do_match=0) before any match pass");
+    rt::set_device(h->cfg.device);
+    const int n = h->n_down;
+    Pose P = pose_from(pose24);
+    if (n == 0) {
+        DLT_RT(h, rt::fill(result_dev, 0, kResultDoubles * sizeof(double), h->stream));
+        h->have_match = true;
+        return DLT_OK;
+    }
+    if (do_match) {
+        DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
+        DLT_LAUNCH(k_knn, div_up(n, kKnnWarps), kKnnWarps * 32, h->stream, h->map, (const float4 *)h->d_down, n, 1, P, h->cfg.max_sq_dist, h->knn);
+        h->have_match = true;
+    }
+    MeasureBufs mb;
+    mb.down = h->d_down;
+    mb.nbr = h->knn.nbr;
+    mb.flags = h->knn.flags;
+    mb.plane = h->d_plane;
+    mb.coeff = h->d_coeff;
+    mb.sel = h->d_sel;
+    mb.eff = h->d_eff;
+    mb.partials = h->d_partials;
+    mb.ticket = h->d_ticket;
+    mb.result = result_dev;
+    const int G = div_up(n, kResidBlock);
+    if (h->cfg.extrinsic_est_en)
+        DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr);
+    else
+        DLT_LAUNCH(k_residual<false>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr);
+    DLT_RT(h, rt::check_launch());
+    return DLT_OK;
+}
+
+int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_out *out) {
+    if (!h || !out) return DLT_E_INVALID;
+    int rc = dlt_measure_dev(h, pose24, do_match, h->d_result);
+    if (rc) return rc;
+    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kResultDoubles * sizeof(double), h->stream));
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    const double *R = h->h_result;
+    for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
+    for (int i = 0; i < 12; i++) out->Htr[i] = R[144 + i];
+    out->effct_feat_num = (int)(R[156] + 0.5);
+    out->total_residual = R[157];
+    for (int i = 0; i < 6; i++) out->eigvals[i] = R[158 + i];
+    for (int i = 0; i < 36; i++) out->eigvecs[i] = R[164 + i];
+    out->n_down = h->n_down;
+    out->n_unresolved = h->h_ints[5];
+    out->reserved = 0;
+    return DLT_OK;
+}
+
+int dlt_effective_points(dlt_handle h, float *xyzi, float *coeff, int cap, int *n) {
+    if (!h || !n) return DLT_E_INVALID;
+    if (!h->have_match) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");
+    const int nd = h->n_down;
+    std::vector<unsigned char> eff(nd);
+    std::vector<float4> pts(nd), cf(nd);
+    if (nd > 0) {
+        DLT_RT(h, rt::d2h(eff.data(), h->d_eff, (size_t)nd, h->stream));
+        DLT_RT(h, rt::d2h(pts.data(), h->d_down, (size_t)nd * sizeof(float4), h->stream));
+        DLT_RT(h, rt::d2h(cf.data(), h->d_coeff, (size_t)nd * sizeof(float4), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+    }
+    int m = 0;
+    for (int i = 0; i < nd; i++) {
+        if (!eff[i]) continue;
+        if (m < cap) {
+            if (xyzi) std::memcpy(xyzi + 4 * (size_t)m, &pts[i], 16);
+            if (coeff) std::memcpy(coeff + 4 * (size_t)m, &cf[i], 16);
+        }
+        m++;
+    }
+    *n = m;
+    return DLT_OK;
+}
+
+int dlt_get_nearest(dlt_handle h, float *nbr, int *cnt, unsigned char *selected, int cap) {
+    if (!h) return DLT_E_INVALID;
+    if (!h->have_match) DLT_FAIL(h, DLT_E_STATE, "no match pass yet");
+    int rc = run_far(h, nullptr);  // make every neighbour set exact before handing it out
+    if (rc) return rc;
+    int m = h->n_down < cap ? h->n_down : cap;
+    if (m > 0) {
+        if (nbr) DLT_RT(h, rt::d2h(nbr, h->knn.nbr, (size_t)m * kK * sizeof(float4), h->stream));
+        if (cnt) DLT_RT(h, rt::d2h(cnt, h->knn.nbr_cnt, (size_t)m * sizeof(int), h->stream));
+        if (selected) DLT_RT(h, rt::d2h(selected, h->d_sel, (size_t)m, h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+    }
+    return DLT_OK;
+}
+
+int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
+    if (!h || !eigvals6 || !eigvecs36) return DLT_E_INVALID;
+    if (!h->have_match) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");
+    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kResultDoubles * sizeof(double), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    for (int i = 0; i < 6; i++) eigvals6[i] = h->h_result[158 + i];
+    for (int i = 0; i < 36; i++) eigvecs36[i] = h->h_result[164 + i];
+    return DLT_OK;
+}
+
+// ------------------------------------------------------------------ map_incremental
+int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_ds, int *n_raw) {
+    if (!h || !pose24) return DLT_E_INVALID;
+    if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental before a scan");
+    if (h->map.shard_count > 1) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental is not supported on a sharded map yet");
+    rt::set_device(h->cfg.device);
+    const int n = h->n_down;
+    if (n_ds) *n_ds = 0;
+    if (n_raw) *n_raw = 0;
+    if (n == 0) return DLT_OK;
+    if (h->have_match) {
+        int rc = run_far(h, nullptr);
+        if (rc) return rc;
+    } else {
+        DLT_RT(h, rt::fill(h->knn.nbr_cnt, 0, (size_t)n * sizeof(int), h->stream));  // Nearest_Points empty
+    }
+    Pose P = pose_from(pose24);
+    DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
+               (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag);
+    if (n_ds || n_raw) {
+        std::vector<unsigned char> a(n), b(n);
+        DLT_RT(h, rt::d2h(a.data(), h->d_dsflag, (size_t)n, h->stream));
+        DLT_RT(h, rt::d2h(b.data(), h->d_addflag, (size_t)n, h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+        int cd = 0, cr = 0;
+        for (int i = 0; i < n; i++) {
+            cd += a[i] ? 1 : 0;
+            cr += b[i] ? 1 : 0;
+        }
+        if (n_ds) *n_ds = cd;
+        if (n_raw) *n_raw = cr;
+    }
+    int rc = insert_points(h, h->d_pw, n, true);
+    if (rc) return rc;
+    h->have_match = false;  // the map changed: neighbour sets are stale
+    return map_check_error(h);
+}
+
+}  // extern "C"

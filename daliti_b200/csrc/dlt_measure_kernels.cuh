@@ -1,0 +1,642 @@
+// daliti_b200/csrc/dlt_measure_kernels.cuh
+//
+// The IEKF measurement model of eskf_lio (eskf_lio/src/laserMapping.cpp:820-979) on the
+// device, for one iteration at a given pose:
+//   k_knn      body->world transform (:835-840) + exact k=5 nearest neighbours in the
+//              voxel-hash map (replaces KD_TREE::Nearest_Search, ikd_Tree.cpp:425-461,
+//              1061-1244) + the match gate (:852-854).  One warp per query point; the
+//              buckets of the 3x3x3 / 5x5x5 / 7x7x7 cell rings are staged through shared
+//              memory and the 5 best are selected with warp shuffles.
+//   k_residual plane fit (esti_plane, common_lib.h:267-299; cached between matches, F7),
+//              point-to-plane residual and gates (:866-880, :889), the 1x12 Jacobian row
+//              (:948-979) and its contribution to H^T H, H^T r, the effective count and
+//              the residual sum, reduced with warp shuffles + shared memory per block and
+//              deterministically across blocks; the last block also runs the 6x6 Jacobi
+//              eigen-decomposition of the pose block (the new degeneracy output).
+#pragma once
+#include "dlt_common.cuh"
+#include "dlt_map_kernels.cuh"
+
+namespace dlt {
+
+// per-point flag bits
+constexpr unsigned char kFlagMatched = 1;     // 5 neighbours found and d2[4] <= max_sq_dist
+constexpr unsigned char kFlagUnresolved = 2;  // ring-3 search could not prove exactness (far / crowded)
+constexpr unsigned char kFlagForeign = 4;     // query owned by another shard
+
+constexpr int kKnnWarps = 4;
+constexpr int kCandMax = 128;
+constexpr int kWlMax = 96;
+
+DLT_D Cand cand_inf() {
+    Cand c;
+    c.d2 = INFINITY;
+    c.x = c.y = c.z = 0.f;
+    c.id = 0x7FFFFFFF;
+    return c;
+}
+DLT_D Cand warp_min_cand(Cand c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand t;
+        t.d2 = __shfl_xor_sync(0xffffffffu, c.d2, o);
+        t.x = __shfl_xor_sync(0xffffffffu, c.x, o);
+        t.y = __shfl_xor_sync(0xffffffffu, c.y, o);
+        t.z = __shfl_xor_sync(0xffffffffu, c.z, o);
+        t.id = __shfl_xor_sync(0xffffffffu, c.id, o);
+        if (cand_less(t, c)) c = t;
+    }
+    return c;
+}
+
+struct KnnOut {
+    float4 *qw;            // [n] world-frame query (x y z intensity) of this match pass
+    float4 *nbr;           // [n][5] neighbour x y z d2, ascending
+    int *nbr_id;           // [n][5] bucket*8+slot
+    int *nbr_cnt;          // [n]
+    unsigned char *flags;  // [n]
+    int *far_list;         // indices of unresolved queries
+    int *far_count;
+};
+
+// distance from q to the slab of cell c along one axis (conservative: shrunk by a rounding slack)
+DLT_D float axis_gap(float q, int c, float cell_edge, float slack) {
+    float lo = (float)c * cell_edge, hi = (float)(c + 1) * cell_edge;
+    float g = fmaxf(fmaxf(lo - q, q - hi), 0.f) - slack;
+    return g > 0.f ? g : 0.f;
+}
+
+// Merge the staged candidates into the running 5 best (stated order: d2, x, y, z, id).
+// Five rounds of "smallest key greater than the previous pick", each a warp-wide argmin.
+DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane) {
+    Cand mine_old = cand_inf();
+#pragma unroll
+    for (int t = 0; t < kK; t++)
+        if (lane == t && t < nbest) mine_old = best[t];
+    Cand prev;
+    prev.d2 = -1.f;
+    prev.x = prev.y = prev.z = 0.f;
+    prev.id = -1;
+    int nb = 0;
+#pragma unroll
+    for (int t = 0; t < kK; t++) {
+        Cand loc = cand_inf();
+        if (cand_less(prev, mine_old)) loc = mine_old;
+        for (int c = lane; c < ncand; c += 32) {
+            float4 e = cand[c];
+            Cand k;
+            k.d2 = e.w;
+            k.x = e.x;
+            k.y = e.y;
+            k.z = e.z;
+            k.id = cid[c];
+            if (cand_less(prev, k) && cand_less(k, loc)) loc = k;
+        }
+        loc = warp_min_cand(loc);
+        best[t] = loc;
+        if (loc.d2 < INFINITY) nb++;
+        prev = loc;
+    }
+    nbest = nb;
+    d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
+}
+
+__global__ void __launch_bounds__(kKnnWarps * 32)
+    k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out) {
+    __shared__ float4 s_cand[kKnnWarps][kCandMax];
+    __shared__ int s_cid[kKnnWarps][kCandMax];
+    __shared__ int s_wl[kKnnWarps][kWlMax];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * kKnnWarps + warp;
+    if (qi >= n) return;  // warp-uniform; the kernel has no block-level barrier
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float4 qb = q_pts[qi];
+    float qx = qb.x, qy = qb.y, qz = qb.z;
+    if (body_frame) body_to_world(P, qb.x, qb.y, qb.z, qx, qy, qz);
+    const float cell_edge = m.ds * (float)(1 << m.cell_shift);
+    int cx, cy, cz;
+    cell_of_point(m, qx, qy, qz, cx, cy, cz);
+    if (lane == 0) out.qw[qi] = make_float4(qx, qy, qz, qb.w);
+
+    if (m.shard_count > 1 && tile_owner(cx, cy, cz, m.tile_shift, m.shard_count) != m.shard_rank) {
+        if (lane == 0) {
+            out.nbr_cnt[qi] = 0;
+            out.flags[qi] = kFlagForeign;
+        }
+        return;
+    }
+
+    float4 *cand = s_cand[warp];
+    int *cid = s_cid[warp];
+    int *wl = s_wl[warp];
+    Cand best[kK];
+#pragma unroll
+    for (int t = 0; t < kK; t++) best[t] = cand_inf();
+    int nbest = 0, ncand = 0;
+    float d5 = INFINITY;
+    bool overflow = false, resolved = false;
+    const float slack = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
+    const int grp = lane >> 3, sub = lane & 7;
+
+    for (int R = 1; R <= 3 && !resolved; R++) {
+        const int side = 2 * R + 1, total = side * side * side;
+        for (int base = 0; base < total; base += 32) {
+            // ---- probe up to 32 cells of this ring
+            int idx = base + lane;
+            int b = -1;
+            if (idx < total) {
+                int dz = idx % side - R, dy = (idx / side) % side - R, dx = idx / (side * side) - R;
+                int cheb = max(max(abs(dx), abs(dy)), abs(dz));
+                if (cheb == R || (R == 1 && cheb == 0)) {
+                    bool prune = false;
+                    if (nbest == kK) {
+                        float gx = axis_gap(qx, cx + dx, cell_edge, slack), gy = axis_gap(qy, cy + dy, cell_edge, slack),
+                              gz = axis_gap(qz, cz + dz, cell_edge, slack);
+                        float bd = gx * gx + gy * gy + gz * gz;
+                        prune = bd * 0.99999f > d5;
+                    }
+                    if (!prune) b = map_find(m, pack_key(cx + dx, cy + dy, cz + dz));
+                }
+            }
+            unsigned found = __ballot_sync(FULL, b >= 0);
+            int nwl = __popc(found);
+            if (b >= 0) wl[__popc(found & lt_mask)] = b;
+            __syncwarp();
+            // ---- stage the buckets: 4 per step, 8 lanes x 16 B = one 128-byte line each
+            for (int j0 = 0; j0 < nwl;) {
+                const int step = min(4, nwl - j0);  // chain buckets pushed below are picked up by a later step
+                const int j = j0 + grp;
+                const bool act = grp < step;
+                int bidx = act ? wl[j] : 0;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act) v = reinterpret_cast<const float4 *>(&m.buckets[bidx])[sub];
+                int hdr_next = __shfl_sync(FULL, __float_as_int(v.z), lane & ~7);
+                unsigned hdr_mask = __shfl_sync(FULL, __float_as_uint(v.w), lane & ~7);
+                bool pushn = act && sub == 0 && hdr_next >= 0;
+                unsigned pm = __ballot_sync(FULL, pushn);
+                if (pushn) {
+                    int pos = nwl + __popc(pm & lt_mask);
+                    if (pos < kWlMax) wl[pos] = hdr_next;
+                }
+                bool has = act && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u);
+                float d2 = has ? calc_dist(qx, qy, qz, v.x, v.y, v.z) : INFINITY;
+                bool keep = has && (nbest < kK || d2 <= d5);
+                unsigned km = __ballot_sync(FULL, keep);
+                if (keep) {
+                    int pos = ncand + __popc(km & lt_mask);
+                    cand[pos] = make_float4(v.x, v.y, v.z, d2);
+                    cid[pos] = bidx * 8 + sub;
+                }
+                ncand += __popc(km);
+                nwl += __popc(pm);
+                j0 += step;
+                if (nwl > kWlMax) {
+                    overflow = true;  // pathological chain length; exact result comes from k_far_*
+                    nwl = kWlMax;
+                }
+                __syncwarp();
+                if (ncand > kCandMax - 32) {  // staging area nearly full: fold it into the running best
+                    knn_select(best, nbest, d5, cand, cid, ncand, lane);
+                    ncand = 0;
+                    __syncwarp();
+                }
+            }
+        }
+        if (ncand > 0) {
+            knn_select(best, nbest, d5, cand, cid, ncand, lane);
+            ncand = 0;
+            __syncwarp();
+        }
+        // ---- exactness: every unseen point lies outside the (2R+1)^3 block of cells
+        if (nbest == kK && !overflow) {
+            float cov = INFINITY;
+            cov = fminf(cov, qx - (float)(cx - R) * cell_edge);
+            cov = fminf(cov, (float)(cx + R + 1) * cell_edge - qx);
+            cov = fminf(cov, qy - (float)(cy - R) * cell_edge);
+            cov = fminf(cov, (float)(cy + R + 1) * cell_edge - qy);
+            cov = fminf(cov, qz - (float)(cz - R) * cell_edge);
+            cov = fminf(cov, (float)(cz + R + 1) * cell_edge - qz);
+            cov -= slack;
+            if (cov > 0.f && d5 < cov * cov * 0.99999f) resolved = true;
+        }
+    }
+
+    // The match gate (laserMapping.cpp:852-854) is decided here even for unresolved queries:
+    // the 7^3 block covers >= 3 cell edges > sqrt(max_sq_dist) (dlt_create picks cell_shift so),
+    // hence "5 found with d2[4] <= max_sq_dist" implies resolved.  Unresolved queries (nothing
+    // close, or a pathological chain) get their exact neighbours lazily from k_far_* before
+    // map_incremental consumes them.
+    unsigned char fl = 0;
+    if (resolved && best[kK - 1].d2 <= max_sq_dist) fl |= kFlagMatched;
+    if (!resolved) fl |= kFlagUnresolved;
+#pragma unroll
+    for (int t = 0; t < kK; t++) {
+        if (lane == t) {
+            bool ok = t < nbest;
+            out.nbr[(size_t)qi * kK + t] = ok ? make_float4(best[t].x, best[t].y, best[t].z, best[t].d2) : make_float4(0.f, 0.f, 0.f, -1.f);
+            out.nbr_id[(size_t)qi * kK + t] = ok ? best[t].id : -1;
+        }
+    }
+    if (lane == 0) {
+        out.nbr_cnt[qi] = nbest;
+        out.flags[qi] = fl;
+        if (!resolved) {
+            int pos = atomicAdd(out.far_count, 1);
+            out.far_list[pos] = qi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ exact fallback for unresolved queries
+// Streams the whole bucket pool once; lane = query, so a warp serves 32 queries and keeps
+// their running 5 best in registers.  grid = (query groups, map slices); partial results
+// are merged by k_far_merge.  Only needed for points with no 5 neighbours within ~3 cells
+// (or > kCandMax candidates): their exact neighbours feed map_incremental
+// (laserMapping.cpp:593-617), never the residuals.
+constexpr int kFarWarps = 4;
+constexpr int kFarTile = 128;  // buckets per shared-memory tile
+
+DLT_D void topk_insert(Cand (&b)[kK], const Cand &c) {
+    if (!cand_less(c, b[kK - 1])) return;
+    b[kK - 1] = c;
+#pragma unroll
+    for (int t = kK - 1; t > 0; t--) {
+        if (cand_less(b[t], b[t - 1])) {
+            Cand tmp = b[t];
+            b[t] = b[t - 1];
+            b[t - 1] = tmp;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFarWarps * 32)
+    k_far_scan(MapView m, int n_buckets, const float4 *__restrict__ qw, const int *__restrict__ far_list, int far_off, int nfar,
+               int n_slices, Cand *__restrict__ partial /* [far][slice][5] */) {
+    __shared__ float4 tile[kFarTile * 8];
+    const int groups = (nfar + kFarWarps * 32 - 1) / (kFarWarps * 32);
+    const int slice = blockIdx.y;
+    const int per = (n_buckets + n_slices - 1) / n_slices;
+    const int b0 = slice * per, b1 = min(n_buckets, b0 + per);
+    for (int g = blockIdx.x; g < groups; g += gridDim.x) {  // block-uniform loop
+        const int f = g * kFarWarps * 32 + threadIdx.x;
+        const bool live = f < nfar;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (live) {
+            float4 q = qw[far_list[far_off + f]];
+            qx = q.x;
+            qy = q.y;
+            qz = q.z;
+        }
+        Cand best[kK];
+#pragma unroll
+        for (int t = 0; t < kK; t++) best[t] = cand_inf();
+        for (int tb = b0; tb < b1; tb += kFarTile) {
+            const int nb = min(kFarTile, b1 - tb);
+            __syncthreads();
+            for (int k = threadIdx.x; k < nb * 8; k += kFarWarps * 32) tile[k] = reinterpret_cast<const float4 *>(&m.buckets[tb])[k];
+            __syncthreads();
+            if (live) {
+                for (int k = 0; k < nb; k++) {
+                    unsigned msk = __float_as_uint(tile[k * 8].w) & 0x7Fu;
+                    while (msk) {
+                        int s = __ffs((int)msk) - 1;
+                        msk &= msk - 1u;
+                        float4 e = tile[k * 8 + 1 + s];
+                        Cand c;
+                        c.d2 = calc_dist(qx, qy, qz, e.x, e.y, e.z);
+                        c.x = e.x;
+                        c.y = e.y;
+                        c.z = e.z;
+                        c.id = (tb + k) * 8 + 1 + s;
+                        topk_insert(best, c);
+                    }
+                }
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int t = 0; t < kK; t++) partial[((size_t)f * n_slices + slice) * kK + t] = best[t];
+        }
+    }
+}
+
+__global__ void k_far_merge(const int *__restrict__ far_list, int far_off, int nfar, int n_slices, const Cand *__restrict__ partial,
+                            float max_sq_dist, KnnOut out) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfar; f += gridDim.x * blockDim.x) {
+        Cand best[kK];
+#pragma unroll
+        for (int t = 0; t < kK; t++) best[t] = cand_inf();
+        for (int s = 0; s < n_slices; s++)
+            for (int t = 0; t < kK; t++) {
+                Cand c = partial[((size_t)f * n_slices + s) * kK + t];
+                if (c.d2 < INFINITY) topk_insert(best, c);
+            }
+        const int qi = far_list[far_off + f];
+        int nb = 0;
+#pragma unroll
+        for (int t = 0; t < kK; t++) {
+            bool ok = best[t].d2 < INFINITY;
+            nb += ok ? 1 : 0;
+            out.nbr[(size_t)qi * kK + t] = ok ? make_float4(best[t].x, best[t].y, best[t].z, best[t].d2) : make_float4(0.f, 0.f, 0.f, -1.f);
+            out.nbr_id[(size_t)qi * kK + t] = ok ? best[t].id : -1;
+        }
+        out.nbr_cnt[qi] = nb;
+        unsigned char fl = 0;
+        if (nb == kK && best[kK - 1].d2 <= max_sq_dist) fl |= kFlagMatched;
+        out.flags[qi] = fl;  // now exact
+    }
+}
+
+// ------------------------------------------------------------------ residual / Jacobian / reduction
+template <bool EXT>
+struct NormalEq {
+    static constexpr int D = EXT ? 12 : 6;
+    static constexpr int TRI = D * (D + 1) / 2;
+    static constexpr int NR = TRI + D + 2;  // upper triangle of H^T H, H^T r, effective count, sum |r|
+};
+constexpr int kResidBlock = 128;
+constexpr int kResultDoubles = 144 + 12 + 2 + 6 + 36;  // HtH, Htr, count, res_sum, eigvals, eigvecs
+
+struct MeasureBufs {
+    const float4 *down;       // [n] body-frame downsampled scan (x y z intensity)
+    const float4 *nbr;        // [n][5]
+    const unsigned char *flags;
+    float4 *plane;            // [n] cached plane (a b c d)
+    float4 *coeff;            // [n] (a b c pd2) of the current iteration (coeffSel_tmpt)
+    unsigned char *sel;       // [n] point_selected_surf, persistent across iterations
+    unsigned char *eff;       // [n] effective this iteration
+    double *partials;         // [blocks][NR]
+    unsigned *ticket;
+    double *result;           // kResultDoubles
+};
+
+DLT_D void jacobi6(const double *Ain, double *evals, double *V) {
+    // cyclic Jacobi, ascending eigenvalues, eigenvectors in the columns of V (row-major)
+    double A[36];
+    for (int i = 0; i < 36; i++) {
+        A[i] = Ain[i];
+        V[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+                double v = A[i * 6 + j] * A[i * 6 + j];
+                if (i == j)
+                    diag += v;
+                else
+                    off += v;
+            }
+        if (off <= 1e-30 * diag || off == 0.0) break;
+        for (int p = 0; p < 5; p++)
+            for (int q = p + 1; q < 6; q++) {
+                double apq = A[p * 6 + q];
+                if (apq == 0.0) continue;
+                double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 6; k++) {
+                    double akp = A[k * 6 + p], akq = A[k * 6 + q];
+                    A[k * 6 + p] = c * akp - s * akq;
+                    A[k * 6 + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 6; k++) {
+                    double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+                    A[p * 6 + k] = c * apk - s * aqk;
+                    A[q * 6 + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 6; k++) {
+                    double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
+                    V[k * 6 + p] = c * vkp - s * vkq;
+                    V[k * 6 + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 6; i++) evals[i] = A[i * 6 + i];
+    for (int i = 0; i < 5; i++) {
+        int mn = i;
+        for (int j = i + 1; j < 6; j++)
+            if (evals[j] < evals[mn]) mn = j;
+        if (mn != i) {
+            double t = evals[i];
+            evals[i] = evals[mn];
+            evals[mn] = t;
+            for (int k = 0; k < 6; k++) {
+                double u = V[k * 6 + i];
+                V[k * 6 + i] = V[k * 6 + mn];
+                V[k * 6 + mn] = u;
+            }
+        }
+    }
+}
+
+template <bool EXT>
+__global__ void __launch_bounds__(kResidBlock)
+    k_residual(MeasureBufs mb, int n, int do_match, Pose P, float plane_thr) {
+    using NE = NormalEq<EXT>;
+    constexpr int D = NE::D, NR = NE::NR;
+    __shared__ double s_part[kResidBlock / 32][NR];
+    __shared__ int s_last;
+    const int i = blockIdx.x * kResidBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    double row[D];
+    double meas = 0.0, absr = 0.0;
+    bool effective = false;
+#pragma unroll
+    for (int d = 0; d < D; d++) row[d] = 0.0;
+
+    if (i < n) {
+        float4 pb = mb.down[i];
+        float wx, wy, wz;
+        body_to_world(P, pb.x, pb.y, pb.z, wx, wy, wz);
+        bool sel;
+        float4 pl;
+        if (do_match) {  // :847-863
+            sel = (mb.flags[i] & kFlagMatched) != 0;
+            pl = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sel) {
+                float px[5], py[5], pz[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    float4 e = mb.nbr[(size_t)i * kK + j];
+                    px[j] = e.x;
+                    py[j] = e.y;
+                    pz[j] = e.z;
+                }
+                float pabcd[4];
+                sel = esti_plane(pabcd, px, py, pz, plane_thr);
+                pl = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
+            }
+            mb.plane[i] = pl;
+        } else {
+            sel = mb.sel[i] != 0;
+            pl = mb.plane[i];
+        }
+        bool sel_out = false;
+        if (sel) {
+            float pd2 = pl.x * wx + pl.y * wy;  // :866
+            pd2 = pd2 + pl.z * wz;
+            pd2 = pd2 + pl.w;
+            double bn = sqrt(((double)pb.x * (double)pb.x + (double)pb.y * (double)pb.y) + (double)pb.z * (double)pb.z);
+            float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(bn));  // :868
+            if ((double)s > 0.9) {                                         // :870
+                sel_out = true;
+                mb.coeff[i] = make_float4(pl.x, pl.y, pl.z, pd2);
+                absr = (double)fabsf(pd2);  // res_last, :879
+                if (absr <= 2.0) {           // :889
+                    effective = true;
+                    // Jacobian row, :948-977
+                    double tx, ty, tz, Cx, Cy, Cz;
+                    mat3_vec(P.R_L_I, (double)pb.x, (double)pb.y, (double)pb.z, tx, ty, tz);
+                    tx += P.T_L_I[0];
+                    ty += P.T_L_I[1];
+                    tz += P.T_L_I[2];
+                    mat3T_vec(P.rot_end, (double)pl.x, (double)pl.y, (double)pl.z, Cx, Cy, Cz);
+                    row[0] = ty * Cz - tz * Cy;  // [point_this]x * C
+                    row[1] = tz * Cx - tx * Cz;
+                    row[2] = tx * Cy - ty * Cx;
+                    row[3] = (double)pl.x;
+                    row[4] = (double)pl.y;
+                    row[5] = (double)pl.z;
+                    if (EXT) {
+                        double ux, uy, uz;  // R_L_I^T * C
+                        mat3T_vec(P.R_L_I, Cx, Cy, Cz, ux, uy, uz);
+                        double bx = (double)pb.x, by = (double)pb.y, bz = (double)pb.z;
+                        row[D - 6] = by * uz - bz * uy;  // [point_this_be]x * R_L_I^T * C
+                        row[D - 5] = bz * ux - bx * uz;
+                        row[D - 4] = bx * uy - by * ux;
+                        row[D - 3] = Cx;
+                        row[D - 2] = Cy;
+                        row[D - 1] = Cz;
+                    }
+                    meas = -(double)pd2;  // :977
+                }
+            }
+        }
+        mb.sel[i] = sel_out ? 1 : 0;
+        mb.eff[i] = effective ? 1 : 0;
+    }
+
+    // ---- warp shuffle reduction of the NR accumulators, then shared memory across warps
+    {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+#pragma unroll
+            for (int b = a; b < D; b++) {
+                double v = effective ? row[a] * row[b] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) s_part[warp][k] = v;
+                k++;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+            double v = effective ? row[a] * meas : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_part[warp][k] = v;
+            k++;
+        }
+        double c = effective ? 1.0 : 0.0, r = effective ? absr : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            r += __shfl_xor_sync(0xffffffffu, r, o);
+        }
+        if (lane == 0) {
+            s_part[warp][k] = c;
+            s_part[warp][k + 1] = r;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kResidBlock / 32; w++) v += s_part[w][threadIdx.x];
+        mb.partials[(size_t)blockIdx.x * NR + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(mb.ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // ---- last block: fixed-order sum over blocks (deterministic), unpack, eigen-decompose
+    __threadfence();
+    __shared__ double s_sum[NR];
+    if (threadIdx.x < NR) {
+        const volatile double *vp = mb.partials;
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) v += vp[(size_t)b * NR + threadIdx.x];
+        s_sum[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *R = mb.result;
+        for (int k = 0; k < 144 + 12; k++) R[k] = 0.0;
+        int k = 0;
+        for (int a = 0; a < D; a++)
+            for (int b = a; b < D; b++) {
+                double v = s_sum[k++];
+                R[a * 12 + b] = v;
+                R[b * 12 + a] = v;
+            }
+        for (int a = 0; a < D; a++) R[144 + a] = s_sum[k++];
+        R[156] = s_sum[k];
+        R[157] = s_sum[k + 1];
+        double A6[36];
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b < 6; b++) A6[a * 6 + b] = R[a * 12 + b];
+        jacobi6(A6, R + 158, R + 164);
+        *mb.ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------ map_incremental classification
+// laserMapping.cpp:582-630: decide per downsampled point whether it is added raw
+// (PointNoNeedDownsample), through downsample-on-insert (PointToAdd) or dropped.
+__global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P, const float4 *__restrict__ nbr, const int *__restrict__ nbr_cnt,
+                                double fs, int ekf_inited, float4 *__restrict__ pw, unsigned char *__restrict__ ds_flag,
+                                unsigned char *__restrict__ add_flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 pb = down[i];
+    float wx, wy, wz;
+    body_to_world(P, pb.x, pb.y, pb.z, wx, wy, wz);  // :591
+    pw[i] = make_float4(wx, wy, wz, pb.w);
+    int cnt = nbr_cnt[i];
+    unsigned char ds = 1, add = 0;  // default: PointToAdd (:621-624)
+    if (cnt > 0 && ekf_inited) {    // :593
+        float mx = (float)(floor((double)wx / fs) * fs + 0.5 * fs);  // :599-601
+        float my = (float)(floor((double)wy / fs) * fs + 0.5 * fs);
+        float mz = (float)(floor((double)wz / fs) * fs + 0.5 * fs);
+        float dist = calc_dist(wx, wy, wz, mx, my, mz);  // :602
+        float4 n0 = nbr[(size_t)i * kK];
+        if ((double)fabsf(n0.x - mx) > 0.5 * fs && (double)fabsf(n0.y - my) > 0.5 * fs && (double)fabsf(n0.z - mz) > 0.5 * fs) {  // :603
+            ds = 0;
+            add = 1;  // PointNoNeedDownsample
+        } else {
+            bool need_add = true;
+            if (cnt >= kK) {  // :610
+                for (int j = 0; j < kK; j++) {
+                    float4 e = nbr[(size_t)i * kK + j];
+                    if (calc_dist(e.x, e.y, e.z, mx, my, mz) < dist) {  // :612
+                        need_add = false;
+                        break;
+                    }
+                }
+            }
+            ds = need_add ? 1 : 0;
+        }
+    }
+    ds_flag[i] = ds;
+    add_flag[i] = add;
+}
+
+}  // namespace dlt

@@ -1,0 +1,133 @@
+/* include/daliti_b200.h -- C ABI of the B200 scan-to-map measurement path.
+ *
+ * Drop-in boundary for DaLiTI's eskf_lio LiDAR measurement update.  The reference has no
+ * function at this boundary: the update is inlined in main(),
+ * eskf_lio/src/laserMapping.cpp:731-1177.  Each entry point below names the reference
+ * statements it replaces (paths relative to the DaLiTI tree).  Plain pointers and sizes
+ * only; all buffers are caller-owned HOST memory unless a name ends in `_dev`.
+ *
+ * Conventions: every function returns 0 on success or a DLT_E_* code; a handle owns one
+ * CUDA stream and is not thread-safe; there is no CPU fallback -- dlt_create fails with
+ * DLT_E_NO_DEVICE when no CUDA device is usable.
+ *
+ * Layouts
+ *   xyzi   : float[4] per point  = x, y, z, intensity
+ *   pts48  : pcl::PointXYZINormal, 48 bytes = x y z 1 | normal_x (time ratio) normal_y (ring)
+ *            normal_z (sweep span, s) 0 | intensity curvature pad pad
+ *            (eskf_lio/include/my_utility.h:57, eskf_lio/src/feature_extract.cpp:337-346)
+ *   pose24 : double[24] = rot_end[9] (row-major), pos_end[3], R_L_I[9], T_L_I[3]
+ *            (StatesGroup, eskf_lio/include/common_lib.h:219-222)
+ *   imu pose: double[22] = offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9]
+ *            (eskf_lio/msg/Pose6D.msg)
+ */
+#ifndef DALITI_B200_H
+#define DALITI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLT_OK 0
+#define DLT_E_INVALID 1      /* bad argument */
+#define DLT_E_NO_DEVICE 2    /* no usable CUDA device (there is no CPU path) */
+#define DLT_E_CUDA 3         /* CUDA runtime error, see dlt_last_error */
+#define DLT_E_CAPACITY 4     /* a configured capacity was exceeded */
+#define DLT_E_STATE 5        /* call sequence error (e.g. measure before a scan is set) */
+
+typedef struct dlt_handle_s *dlt_handle;
+
+typedef struct dlt_config {
+    float ds_scan;        /* mapping/filter_size_surf, VoxelGrid leaf (feat.yaml:47)              */
+    float ds_map;         /* mapping/filter_size_map, ikd-Tree downsample size (feat.yaml:48)      */
+    float max_sq_dist;    /* match gate on the 5th neighbour, 5 (laserMapping.cpp:853)             */
+    float plane_thr;      /* esti_plane threshold, 0.1 (laserMapping.cpp:863)                      */
+    int extrinsic_est_en; /* mapping/extrinsic_est_en (laserMapping.cpp:968)                       */
+    int device;           /* CUDA device ordinal                                                   */
+    int max_scan_points;  /* capacity: raw points per scan                                         */
+    int max_map_points;   /* capacity: live map points                                             */
+    long long voxel_bitmap_bits; /* capacity of the VoxelGrid occupancy bitmap (0 = 2^27)          */
+    int shard_rank;       /* spatial map sharding across GPUs: this rank ...                       */
+    int shard_count;      /* ... of shard_count (1 = unsharded)                                    */
+    int shard_tile_shift; /* tile edge = search-cell edge * 2^shift (0 = default 5)                */
+} dlt_config;
+
+/* Outputs of one evaluation of the measurement model.  What the reference later does with
+ * Hsub / meas_vec / K factors through these (laserMapping.cpp:1015-1032, 1084):
+ *   K z = K_1[:, :12] H^T r,  K H = K_1[:, :12] H^T H.                                          */
+typedef struct dlt_measure_out {
+    double HtH[144];        /* 12x12 row-major  H^T H   (laserMapping.cpp:1015)                    */
+    double Htr[12];         /* H^T meas_vec     (meas_vec = -pd2, laserMapping.cpp:977)            */
+    double total_residual;  /* sum of res_last over effective points (laserMapping.cpp:893)        */
+    double eigvals[6];      /* ascending eigenvalues of HtH[0:6,0:6] (new output)    */
+    double eigvecs[36];     /* eigenvectors in columns, row-major 6x6                              */
+    int effct_feat_num;     /* laserMapping.cpp:885-896                                            */
+    int n_down;             /* feats_down_size                                                     */
+    int n_unresolved;       /* queries whose exact neighbours are deferred to map_incremental      */
+    int reserved;
+} dlt_measure_out;
+
+void dlt_default_config(dlt_config *cfg);
+int dlt_create(const dlt_config *cfg, dlt_handle *out);
+int dlt_destroy(dlt_handle h);
+const char *dlt_last_error(dlt_handle h);
+/* Adopt an external CUDA stream (cudaStream_t) for all work of this handle, or NULL to go
+ * back to the handle's own stream.  Used to order work with torch / NCCL.                       */
+int dlt_set_stream(dlt_handle h, void *cuda_stream);
+int dlt_sync(dlt_handle h);
+
+/* ---- map: replaces the global `KD_TREE<PointType> ikdtree` (laserMapping.cpp:164) ---------- */
+/* ikdtree.Build(feats_down_world->points)                       laserMapping.cpp:790            */
+int dlt_map_build(dlt_handle h, const float *xyzi, int n);
+/* ikdtree.Add_Points(points, downsample_on)                     laserMapping.cpp:627-628        */
+int dlt_map_add(dlt_handle h, const float *xyzi, int n, int downsample_on);
+/* ikdtree.Delete_Point_Boxes(cub_needrm), boxes = min xyz, max xyz   laserMapping.cpp:368       */
+int dlt_map_delete_boxes(dlt_handle h, const float *boxes6, int n_boxes, int *deleted);
+/* ikdtree.validnum()                                            laserMapping.cpp:794            */
+int dlt_map_valid_count(dlt_handle h, int *n);
+/* ikdtree.flatten(Root_Node, PCL_Storage, NOT_RECORD)           laserMapping.cpp:1171-1174      */
+int dlt_map_export(dlt_handle h, float *xyzi, int cap, int *n);
+/* ikdtree.Nearest_Search(point, 5, points_near, sq_dis) for nq world-frame points:
+ * out_xyzi nq*5*4 floats (ascending), out_d2 nq*5, out_cnt nq    laserMapping.cpp:850           */
+int dlt_map_knn(dlt_handle h, const float *q_xyz, int nq, float *out_xyzi, float *out_d2, int *out_cnt);
+
+/* ---- scan preparation ---------------------------------------------------------------------- */
+/* ImuProcess::UndistortPcl backward pass (IMU_Processing.hpp:332-370) over n_raw points with
+ * the IMUpose list of the forward pass and the propagated end state; n_imu_pose < 2 copies
+ * the points through.  Also the input of dlt_scan_downsample.                                   */
+int dlt_scan_deskew(dlt_handle h, const void *pts48, int n_raw, const double *imu_pose22, int n_imu_pose, const double *pose24);
+/* downSizeFilterSurf.filter(*feats_down)                        laserMapping.cpp:775-776        */
+int dlt_scan_downsample(dlt_handle h, int *n_down);
+/* feats_undistort / feats_down read-back (publishing, laserMapping.cpp:1185,1208)               */
+int dlt_scan_get_undistorted(dlt_handle h, float *xyzi, int cap, int *n);
+int dlt_scan_get_down(dlt_handle h, float *xyzi, int cap, int *n);
+/* set feats_down directly (body frame), bypassing deskew + VoxelGrid                            */
+int dlt_scan_set_down(dlt_handle h, const float *xyzi, int n);
+/* output slot of every raw point of the last dlt_scan_downsample (voxel assignment)             */
+int dlt_scan_get_voxel_of_point(dlt_handle h, int *slot, int cap);
+
+/* ---- the measurement model, one IEKF iteration ---------------------------------------------- */
+/* laserMapping.cpp:829-979 at the given state: transform, (re)match when do_match
+ * (iterCount == 0 || rematch_en, :847), plane fit, residual + gates, Jacobian, and the
+ * reduction to H^T H / H^T r.  Nearest_Points, point_selected_surf and the cached planes
+ * persist in the handle between calls of one scan.                                              */
+int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_out *out);
+/* Same, but leaves the 200-double result block (HtH[144] Htr[12] count res_sum eigvals[6]
+ * eigvecs[36]) in DEVICE memory at result_dev without synchronising -- the partial sums of
+ * one map shard, ready for an NCCL all-reduce of the first 158 doubles.                         */
+int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev);
+/* laserCloudOri / coeffSel of the last dlt_measure (published as /cloud_effected,
+ * laserMapping.cpp:891-892, 1213-1227): body-frame xyzi and (normal, pd2) per effective point   */
+int dlt_effective_points(dlt_handle h, float *xyzi, float *coeff, int cap, int *n);
+/* Nearest_Points of the last match pass: nbr n_down*5*4 floats (x y z d2), cnt n_down,
+ * selected n_down (point_selected_surf after the last dlt_measure)                              */
+int dlt_get_nearest(dlt_handle h, float *nbr, int *cnt, unsigned char *selected, int cap);
+/* degradation output of the last dlt_measure: eigen-decomposition of HtH[0:6,0:6]              */
+int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36);
+
+/* ---- map_incremental()                                       laserMapping.cpp:582-630, 1167 - */
+int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_add_downsample, int *n_add_raw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DALITI_B200_H */
