@@ -38,7 +38,11 @@ void Lio::process_scan(const MeasureGroup &meas, const ThermalInputs &th, ScanRe
     t_deskew = now_sec() - t0;
     State state_propagat = state;                                     // :752
     V3 pos_lid = state_propagat.pos_end + state_propagat.rot_end * state_propagat.T_L_I;  // :753
-    state_to_flat(state_propagat, res.state_prop);
+    {
+        double f[36 + DIM * DIM];
+        state_to_flat(state_propagat, f);
+        std::memcpy(res.state_prop, f, sizeof(res.state_prop));
+    }
     res.n_raw = (int)feats_undistort.size();
     if (feats_undistort.empty()) return;  // :755-759
     res.had_points = true;
