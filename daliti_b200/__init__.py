@@ -13,3 +13,4 @@ from .binding import (  # noqa: F401
     default_library_path,
     load_library,
 )
+from .lio import LaserMapping, LioConfig, LioScanOut, LioThermal  # noqa: F401

@@ -70,7 +70,7 @@ _ERR = {1: "invalid argument", 2: "no usable CUDA device (there is no CPU path)"
 
 _SYMBOLS = [
     "dlt_default_config", "dlt_create", "dlt_destroy", "dlt_last_error", "dlt_set_stream", "dlt_sync",
-    "dlt_map_build", "dlt_map_add", "dlt_map_delete_boxes", "dlt_map_valid_count", "dlt_map_export", "dlt_map_knn",
+    "dlt_map_build", "dlt_map_build_from_scan", "dlt_map_add", "dlt_map_delete_boxes", "dlt_map_valid_count", "dlt_map_export", "dlt_map_knn",
     "dlt_scan_deskew", "dlt_scan_downsample", "dlt_scan_get_undistorted", "dlt_scan_get_down", "dlt_scan_set_down",
     "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
     "dlt_degeneracy", "dlt_map_incremental",
@@ -144,6 +144,10 @@ class ScanToMap:
     def map_build(self, xyzi):
         a = _f32(xyzi).reshape(-1, 4)
         self._ck(self.lib.dlt_map_build(self.h, _p(a), C.c_int(a.shape[0])))
+
+    def map_build_from_scan(self, pose24):
+        ps = _f64(pose24).reshape(24)
+        self._ck(self.lib.dlt_map_build_from_scan(self.h, _p(ps)))
 
     def map_add(self, xyzi, downsample: bool):
         a = _f32(xyzi).reshape(-1, 4)

@@ -295,6 +295,22 @@ int dlt_map_build(dlt_handle h, const float *xyzi, int n) {
     return add_host_points(h, xyzi, n, 0);
 }
 
+int dlt_map_build_from_scan(dlt_handle h, const double *pose24) {
+    if (!h || !pose24) return DLT_E_INVALID;
+    if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_build_from_scan before a downsampled scan is set");
+    rt::set_device(h->cfg.device);
+    int rc = map_reset(h);
+    if (rc) return rc;
+    h->have_match = false;
+    const int n = h->n_down;
+    if (n == 0) return DLT_OK;
+    Pose P = pose_from(pose24);
+    DLT_LAUNCH(k_scan_to_world, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, h->d_pw, h->d_dsflag, h->d_addflag);
+    rc = insert_points(h, h->d_pw, n, false);
+    if (rc) return rc;
+    return map_check_error(h);
+}
+
 int dlt_map_add(dlt_handle h, const float *xyzi, int n, int downsample_on) {
     if (!h || (n > 0 && !xyzi) || n < 0) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);

@@ -639,4 +639,17 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P, 
     add_flag[i] = add;
 }
 
+// pointBodyToWorld over the downsampled scan (laserMapping.cpp:786-789), every point flagged for a raw add
+__global__ void k_scan_to_world(const float4 *__restrict__ down, int n, Pose P, float4 *__restrict__ pw, unsigned char *__restrict__ ds_flag,
+                                unsigned char *__restrict__ add_flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 pb = down[i];
+    float wx, wy, wz;
+    body_to_world(P, pb.x, pb.y, pb.z, wx, wy, wz);
+    pw[i] = make_float4(wx, wy, wz, pb.w);
+    ds_flag[i] = 0;
+    add_flag[i] = 1;
+}
+
 }  // namespace dlt

@@ -1,0 +1,789 @@
+// daliti_b200/csrc/host/eskf_lio_host.cpp -- see eskf_lio_host.hpp.
+// Reference lines are cited as path:line relative to the DaLiTI tree.
+#include "eskf_lio_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+
+namespace dlt_host {
+
+static double wall() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ------------------------------------------------------------------ SO(3)
+static Mat3 rodrigues(const Vec3 &axis, double ang) {
+    // Eye3 + sin(ang) K + (1 - cos(ang)) K K
+    Mat3 K = Mat3::hat(axis);
+    return Mat3::identity() + K * std::sin(ang) + (K * (1.0 - std::cos(ang))) * K;
+}
+Mat3 so3_exp_rate(const Vec3 &w, double dt) {
+    double n = w.norm();
+    if (n > 0.0000001) return rodrigues(w / n, n * dt);
+    return Mat3::identity();
+}
+Mat3 so3_exp(double v1, double v2, double v3) {
+    double n = std::sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+    if (n > 0.00001) return rodrigues(Vec3(v1 / n, v2 / n, v3 / n), n);
+    return Mat3::identity();
+}
+Vec3 so3_log(const Mat3 &R) {
+    double tr = R.trace();
+    double theta = (tr > 3.0 - 1e-6) ? 0.0 : std::acos(0.5 * (tr - 1));
+    Vec3 K(R.a[7] - R.a[5], R.a[2] - R.a[6], R.a[3] - R.a[1]);
+    return (std::abs(theta) < 0.001) ? (K * 0.5) : (K * (0.5 * theta / std::sin(theta)));
+}
+Mat3 quat_to_rot(double w, double x, double y, double z) {  // Eigen::Quaterniond::toRotationMatrix
+    Mat3 r;
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    r.a[0] = 1 - (tyy + tzz);
+    r.a[1] = txy - twz;
+    r.a[2] = txz + twy;
+    r.a[3] = txy + twz;
+    r.a[4] = 1 - (txx + tzz);
+    r.a[5] = tyz - twx;
+    r.a[6] = txz - twy;
+    r.a[7] = tyz + twx;
+    r.a[8] = 1 - (txx + tyy);
+    return r;
+}
+
+// ------------------------------------------------------------------ StatesGroup
+StatesGroup::StatesGroup() {
+    std::memset(cov, 0, sizeof(cov));
+    for (int i = 0; i < kDim; i++) cov[i * kDim + i] = 1.0;  // INIT_COV, common_lib.h:28,85
+}
+StatesGroup StatesGroup::boxplus(const double *d) const {
+    StatesGroup a;
+    a.rot_end = rot_end * so3_exp(d[0], d[1], d[2]);
+    a.pos_end = pos_end + Vec3(d + 3);
+    a.R_L_I = R_L_I * so3_exp(d[6], d[7], d[8]);
+    a.T_L_I = T_L_I + Vec3(d + 9);
+    a.vel_end = vel_end + Vec3(d + 12);
+    a.bias_g = bias_g + Vec3(d + 15);
+    a.bias_a = bias_a + Vec3(d + 18);
+    a.gravity = gravity + Vec3(d + 21);
+    std::memcpy(a.cov, cov, sizeof(cov));
+    return a;
+}
+StatesGroup StatesGroup::compose(const StatesGroup &b) const {
+    StatesGroup r;
+    r.rot_end = rot_end * b.rot_end;
+    r.pos_end = pos_end + b.pos_end;
+    r.R_L_I = R_L_I * b.R_L_I;
+    r.T_L_I = T_L_I + b.T_L_I;
+    r.vel_end = vel_end + b.vel_end;
+    r.bias_g = bias_g;
+    r.bias_a = bias_a;
+    r.gravity = gravity;
+    std::memcpy(r.cov, cov, sizeof(cov));
+    return r;
+}
+void StatesGroup::boxplus_inplace(const double *d) {
+    rot_end = rot_end * so3_exp(d[0], d[1], d[2]);
+    pos_end = pos_end + Vec3(d + 3);
+    R_L_I = R_L_I * so3_exp(d[6], d[7], d[8]);
+    T_L_I = T_L_I + Vec3(d + 9);
+    vel_end = vel_end + Vec3(d + 12);
+    bias_g = bias_g + Vec3(d + 15);
+    bias_a = bias_a + Vec3(d + 18);
+    gravity = gravity + Vec3(d + 21);
+}
+void StatesGroup::boxminus(const StatesGroup &b, double *o) const {
+    so3_log(b.rot_end.t() * rot_end).store(o);
+    (pos_end - b.pos_end).store(o + 3);
+    so3_log(b.R_L_I.t() * R_L_I).store(o + 6);
+    (T_L_I - b.T_L_I).store(o + 9);
+    (vel_end - b.vel_end).store(o + 12);
+    (bias_g - b.bias_g).store(o + 15);
+    (bias_a - b.bias_a).store(o + 18);
+    (gravity - b.gravity).store(o + 21);
+}
+StatesGroup StatesGroup::scaled(double s) const {
+    StatesGroup a;
+    Vec3 so3 = so3_log(rot_end);
+    a.rot_end = so3_exp(so3.x * s, so3.y * s, so3.z * s);
+    a.pos_end = pos_end * s;
+    a.R_L_I = R_L_I;
+    a.T_L_I = T_L_I * s;
+    a.vel_end = vel_end * s;
+    a.bias_g = bias_g * s;
+    a.bias_a = bias_a * s;
+    a.gravity = gravity * s;
+    std::memcpy(a.cov, cov, sizeof(cov));
+    return a;
+}
+void StatesGroup::pose24(double *p) const {
+    std::memcpy(p, rot_end.a, 72);
+    pos_end.store(p + 9);
+    std::memcpy(p + 12, R_L_I.a, 72);
+    T_L_I.store(p + 21);
+}
+void StatesGroup::to_flat(double *f) const {
+    pose24(f);
+    vel_end.store(f + 24);
+    bias_g.store(f + 27);
+    bias_a.store(f + 30);
+    gravity.store(f + 33);
+    std::memcpy(f + 36, cov, sizeof(cov));
+}
+void StatesGroup::from_flat(const double *f) {
+    rot_end = Mat3::from(f);
+    pos_end = Vec3(f + 9);
+    R_L_I = Mat3::from(f + 12);
+    T_L_I = Vec3(f + 21);
+    vel_end = Vec3(f + 24);
+    bias_g = Vec3(f + 27);
+    bias_a = Vec3(f + 30);
+    gravity = Vec3(f + 33);
+    std::memcpy(cov, f + 36, sizeof(cov));
+}
+
+// ------------------------------------------------------------------ dense helpers
+bool invert(const double *A, int n, double *out) {
+    // Gauss-Jordan on [A | I] with partial pivoting
+    std::vector<double> w((size_t)n * 2 * n);
+    const int W = 2 * n;
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) {
+            w[(size_t)i * W + j] = A[(size_t)i * n + j];
+            w[(size_t)i * W + n + j] = (i == j) ? 1.0 : 0.0;
+        }
+    }
+    for (int c = 0; c < n; c++) {
+        int p = c;
+        for (int r = c + 1; r < n; r++)
+            if (std::fabs(w[(size_t)r * W + c]) > std::fabs(w[(size_t)p * W + c])) p = r;
+        if (w[(size_t)p * W + c] == 0.0) return false;
+        if (p != c)
+            for (int j = 0; j < W; j++) std::swap(w[(size_t)p * W + j], w[(size_t)c * W + j]);
+        const double inv = 1.0 / w[(size_t)c * W + c];
+        for (int j = 0; j < W; j++) w[(size_t)c * W + j] *= inv;
+        for (int r = 0; r < n; r++) {
+            if (r == c) continue;
+            const double f = w[(size_t)r * W + c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < W; j++) w[(size_t)r * W + j] -= f * w[(size_t)c * W + j];
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) out[(size_t)i * n + j] = w[(size_t)i * W + n + j];
+    return true;
+}
+
+static void set_block3(double *M, int r0, int c0, const Mat3 &B) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) M[(r0 + i) * kDim + c0 + j] = B.a[3 * i + j];
+}
+
+// ------------------------------------------------------------------ ImuProcess
+static const double G_m_s2 = 9.8099;  // common_lib.h:23
+static const int MAX_INI_COUNT = 100;  // IMU_Processing.hpp:29
+
+ImuProcess::ImuProcess() { std::memset(&last_imu_, 0, sizeof(last_imu_)); }
+
+void ImuProcess::Reset() {
+    angvel_last = Vec3();
+    cov_acc = Vec3(0.1, 0.1, 0.1);
+    cov_gyr = Vec3(0.1, 0.1, 0.1);
+    mean_acc = Vec3(0, 0, -1.0);
+    mean_gyr = Vec3();
+    imu_need_init_ = true;
+    b_first_frame_ = true;
+    init_iter_num = 1;
+    std::memset(&last_imu_, 0, sizeof(last_imu_));
+    IMUpose.clear();
+}
+void ImuProcess::set_extrinsic(const Vec3 &t, const Mat3 &r) {
+    Lidar_T_wrt_IMU = t;
+    Lidar_R_wrt_IMU = r;
+}
+void ImuProcess::force_ready(const Vec3 &m, const ImuSample &last) {
+    imu_need_init_ = false;
+    b_first_frame_ = false;
+    init_iter_num = MAX_INI_COUNT + 1;
+    mean_acc = m;
+    last_imu_ = last;
+}
+
+void ImuProcess::IMU_Initial(const std::vector<ImuSample> &imu, StatesGroup &st, int &N) {
+    if (b_first_frame_) {
+        Reset();
+        N = 1;
+        b_first_frame_ = false;
+        mean_acc = Vec3(imu.front().acc);
+        mean_gyr = Vec3(imu.front().gyr);
+    }
+    for (const ImuSample &s : imu) {
+        Vec3 ca(s.acc), cg(s.gyr);
+        mean_acc = mean_acc + (ca - mean_acc) / N;
+        mean_gyr = mean_gyr + (cg - mean_gyr) / N;
+        Vec3 da = ca - mean_acc, dg = cg - mean_gyr;
+        cov_acc = Vec3(cov_acc.x * (N - 1.0) / N + da.x * da.x * (N - 1.0) / (N * N), cov_acc.y * (N - 1.0) / N + da.y * da.y * (N - 1.0) / (N * N),
+                       cov_acc.z * (N - 1.0) / N + da.z * da.z * (N - 1.0) / (N * N));
+        cov_gyr = Vec3(cov_gyr.x * (N - 1.0) / N + dg.x * dg.x * (N - 1.0) / (N * N), cov_gyr.y * (N - 1.0) / N + dg.y * dg.y * (N - 1.0) / (N * N),
+                       cov_gyr.z * (N - 1.0) / N + dg.z * dg.z * (N - 1.0) / (N * N));
+        N++;
+    }
+    st.gravity = (mean_acc * -1.0) / mean_acc.norm() * G_m_s2;
+    st.bias_g = mean_gyr;
+    st.R_L_I = Lidar_R_wrt_IMU;
+    st.T_L_I = Lidar_T_wrt_IMU;
+    last_imu_ = imu.back();
+}
+
+void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_time, double pcl_end_time, StatesGroup &st, bool EKF_stop_flg) {
+    std::vector<ImuSample> v;
+    v.reserve(imu.size() + 1);
+    v.push_back(last_imu_);  // IMU_Processing.hpp:207-208
+    v.insert(v.end(), imu.begin(), imu.end());
+    const double imu_end_time = v.back().t;
+
+    IMUpose.clear();
+    Pose6D p0;
+    p0.offset_time = 0.0;
+    acc_s_last.store(p0.acc);
+    angvel_last.store(p0.gyr);
+    st.vel_end.store(p0.vel);
+    st.pos_end.store(p0.pos);
+    std::memcpy(p0.rot, st.rot_end.a, sizeof(p0.rot));
+    IMUpose.push_back(p0);  // :224
+
+    Vec3 acc_imu, angvel_avr, acc_avr, vel_imu = st.vel_end, pos_imu = st.pos_end;
+    Mat3 R_imu = st.rot_end;
+    double dt = 0;
+    std::vector<double> F(kDim * kDim), Q(kDim * kDim), FP(kDim * kDim);
+    for (size_t k = 0; k + 1 < v.size(); k++) {
+        const ImuSample &head = v[k], &tail = v[k + 1];
+        if (tail.t < last_observation_end_time_) continue;  // :237
+        angvel_avr = (Vec3(head.gyr) + Vec3(tail.gyr)) * 0.5 - st.bias_g;
+        acc_avr = (Vec3(head.acc) + Vec3(tail.acc)) * 0.5 * G_m_s2 / mean_acc.norm() - st.bias_a;  // :248
+        dt = (head.t < last_observation_end_time_) ? tail.t - last_observation_end_time_ : tail.t - head.t;
+
+        // covariance propagation, :262-288
+        const Mat3 Exp_f = so3_exp_rate(angvel_avr, dt);
+        std::fill(F.begin(), F.end(), 0.0);
+        std::fill(Q.begin(), Q.end(), 0.0);
+        for (int i = 0; i < kDim; i++) F[i * kDim + i] = 1.0;
+        set_block3(F.data(), 0, 0, so3_exp_rate(angvel_avr, -dt));
+        set_block3(F.data(), 0, 15, Mat3::identity() * (-dt));
+        set_block3(F.data(), 3, 12, Mat3::identity() * dt);
+        set_block3(F.data(), 12, 0, (R_imu * -1.0) * Mat3::hat(acc_avr) * dt);
+        set_block3(F.data(), 12, 18, R_imu * (-dt));
+        set_block3(F.data(), 12, 21, Mat3::identity() * dt);
+        Mat3 Ca, Cg;
+        Ca.a[0] = cov_acc.x;
+        Ca.a[4] = cov_acc.y;
+        Ca.a[8] = cov_acc.z;
+        Cg.a[0] = cov_gyr.x;
+        Cg.a[4] = cov_gyr.y;
+        Cg.a[8] = cov_gyr.z;
+        Q[0 * kDim + 0] = cov_gyr.x * dt * dt * 10000;
+        Q[1 * kDim + 1] = cov_gyr.y * dt * dt * 10000;
+        Q[2 * kDim + 2] = cov_gyr.z * dt * dt * 10000;
+        set_block3(Q.data(), 3, 3, R_imu * Cg * R_imu.t() * dt * dt * 10000);
+        set_block3(Q.data(), 12, 12, R_imu * Ca * R_imu.t() * dt * dt * 10000);
+        for (int a = 0; a < 3; a++) {
+            Q[(15 + a) * kDim + 15 + a] = 0.0001 * dt * dt;
+            Q[(18 + a) * kDim + 18 + a] = 0.0001 * dt * dt;
+        }
+        // cov = F cov F^T + Q
+        for (int i = 0; i < kDim; i++)
+            for (int j = 0; j < kDim; j++) {
+                double s = 0;
+                for (int l = 0; l < kDim; l++) s += F[i * kDim + l] * st.cov[l * kDim + j];
+                FP[i * kDim + j] = s;
+            }
+        for (int i = 0; i < kDim; i++)
+            for (int j = 0; j < kDim; j++) {
+                double s = 0;
+                for (int l = 0; l < kDim; l++) s += FP[i * kDim + l] * F[j * kDim + l];
+                st.cov[i * kDim + j] = s + Q[i * kDim + j];
+            }
+
+        R_imu = R_imu * Exp_f;                                      // :291
+        acc_imu = R_imu * acc_avr + st.gravity;                     // :294
+        pos_imu = pos_imu + vel_imu * dt + acc_imu * 0.5 * dt * dt;  // :297
+        vel_imu = vel_imu + acc_imu * dt;                           // :300
+        angvel_last = angvel_avr;
+        acc_s_last = acc_imu;
+        Pose6D p;
+        p.offset_time = tail.t - pcl_beg_time;
+        acc_imu.store(p.acc);
+        angvel_avr.store(p.gyr);
+        vel_imu.store(p.vel);
+        pos_imu.store(p.pos);
+        std::memcpy(p.rot, R_imu.a, sizeof(p.rot));
+        IMUpose.push_back(p);  // :307
+    }
+    dt = pcl_end_time - imu_end_time;  // :313
+    if (!EKF_stop_flg) {
+        st.vel_end = vel_imu + acc_imu * dt;
+        st.rot_end = R_imu * so3_exp_rate(angvel_avr, dt);
+        st.pos_end = pos_imu + vel_imu * dt + acc_imu * 0.5 * dt * dt;
+    }
+    last_observation_end_time_ = pcl_end_time;  // :325
+}
+
+bool ImuProcess::Process(const std::vector<ImuSample> &imu, double lidar_beg_time, double observation_end_time, StatesGroup &st,
+                         bool EKF_stop_flg) {
+    if (imu.empty()) return false;  // :378-382
+    if (imu_need_init_) {
+        IMU_Initial(imu, st, init_iter_num);
+        imu_need_init_ = true;
+        last_imu_ = imu.back();
+        if (init_iter_num > MAX_INI_COUNT) {
+            imu_need_init_ = false;
+            cov_acc = Vec3(0.1, 0.1, 0.1);
+            cov_gyr = Vec3(0.1, 0.1, 0.1);
+        }
+        return false;
+    }
+    st.gravity = Vec3(0, 0, -9.801);  // :408-412: overwritten by constants every scan (reference quirk)
+    st.bias_a = Vec3(1.44e-04, 1.44e-04, 1.44e-04);
+    st.bias_g = Vec3(5.3e-05, 5.3e-05, 5.3e-05);
+    st.R_L_I = Lidar_R_wrt_IMU;
+    st.T_L_I = Lidar_T_wrt_IMU;
+    Propagate(imu, lidar_beg_time, observation_end_time, st, EKF_stop_flg);
+    last_imu_ = imu.back();  // :422
+    return true;
+}
+
+// ------------------------------------------------------------------ LaserMapping
+static StatesGroup odom_to_state(const double *pos, const double *q, const double *vel, const double *cs) {
+    StatesGroup r;  // odomToStateGruop, laserMapping.cpp:218-239
+    r.pos_end = Vec3(pos);
+    r.rot_end = quat_to_rot(q[0], q[1], q[2], q[3]);
+    r.vel_end = Vec3(vel);
+    r.bias_g = Vec3(cs[4], cs[5], cs[6]);
+    r.bias_a = Vec3(cs[1], cs[2], cs[3]);
+    r.gravity = Vec3(0, 0, cs[7]);
+    return r;
+}
+
+LaserMapping::LaserMapping(const dlt_lio_config &c) : cfg(c) {
+    imu_.set_extrinsic(Vec3(cfg.extrinT), Mat3::from(cfg.extrinR));  // laserMapping.cpp:666-667, 706
+    create_rc_ = dlt_create(&cfg.dev, &dev_);
+    if (create_rc_ != 0) dev_ = nullptr;
+}
+LaserMapping::~LaserMapping() {
+    if (dev_) dlt_destroy(dev_);
+}
+void LaserMapping::on_lidar_msg() {
+    lidar_frame_counter_num++;
+    if (lidar_frame_counter_num > 100) dynamic_effect_featurepoints_threshold = cfg.featptsThreshold;
+    lidar_cnt++;
+}
+void LaserMapping::on_edge_count(int recv_n) {
+    double alpha_t = recv_n / 307200.0;  // Mta, laserMapping.cpp:107
+    zeta_t = 2.0 / (1.0 + std::exp(-alpha_t)) - 1;
+}
+
+int LaserMapping::fov_segment(const Vec3 &pos, int *deleted) {
+    *deleted = 0;
+    const float MOV_THRESHOLD = 1.5f, DET_RANGE = cfg.det_range;
+    const double p[3] = {pos.x, pos.y, pos.z};
+    if (!Localmap_Initialized) {
+        for (int i = 0; i < 3; i++) {
+            LocalMap_min[i] = (float)(p[i] - cfg.cube_len / 2.0);
+            LocalMap_max[i] = (float)(p[i] + cfg.cube_len / 2.0);
+        }
+        Localmap_Initialized = true;
+        return 0;
+    }
+    float edge[3][2];
+    bool need_move = false;
+    for (int i = 0; i < 3; i++) {
+        edge[i][0] = (float)std::fabs(p[i] - (double)LocalMap_min[i]);
+        edge[i][1] = (float)std::fabs(p[i] - (double)LocalMap_max[i]);
+        if (edge[i][0] <= MOV_THRESHOLD * DET_RANGE || edge[i][1] <= MOV_THRESHOLD * DET_RANGE) need_move = true;
+    }
+    if (!need_move) return 0;
+    float nmin[3], nmax[3];
+    std::memcpy(nmin, LocalMap_min, sizeof(nmin));
+    std::memcpy(nmax, LocalMap_max, sizeof(nmax));
+    const float mov_dist = (float)std::max((cfg.cube_len - 2.0 * MOV_THRESHOLD * DET_RANGE) * 0.5 * 0.9, double(DET_RANGE * (MOV_THRESHOLD - 1)));
+    std::vector<float> boxes;
+    for (int i = 0; i < 3; i++) {
+        float bmin[3], bmax[3];
+        std::memcpy(bmin, LocalMap_min, sizeof(bmin));
+        std::memcpy(bmax, LocalMap_max, sizeof(bmax));
+        if (edge[i][0] <= MOV_THRESHOLD * DET_RANGE) {
+            nmax[i] -= mov_dist;
+            nmin[i] -= mov_dist;
+            bmin[i] = LocalMap_max[i] - mov_dist;
+        } else if (edge[i][1] <= MOV_THRESHOLD * DET_RANGE) {
+            nmax[i] += mov_dist;
+            nmin[i] += mov_dist;
+            bmax[i] = LocalMap_min[i] + mov_dist;
+        } else {
+            continue;
+        }
+        boxes.insert(boxes.end(), bmin, bmin + 3);
+        boxes.insert(boxes.end(), bmax, bmax + 3);
+    }
+    std::memcpy(LocalMap_min, nmin, sizeof(nmin));
+    std::memcpy(LocalMap_max, nmax, sizeof(nmax));
+    if (!boxes.empty() && map_built) return dlt_map_delete_boxes(dev_, boxes.data(), (int)(boxes.size() / 6), deleted);
+    return 0;
+}
+
+#define LM_CK(expr)                               \
+    do {                                          \
+        int rc__ = (expr);                        \
+        if (rc__ != 0) {                          \
+            err = dlt_last_error(dev_);           \
+            return rc__;                          \
+        }                                         \
+    } while (0)
+
+int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, const ImuSample *imu, int n_imu, const dlt_lio_thermal *th,
+                               dlt_lio_scan_out *out) {
+    const double LASER_POINT_COV = 0.0015;  // laserMapping.cpp:76
+    const int QUEUE_SIZE = 10;              // :192
+    const int NUM_MAX_ITERATIONS = cfg.max_iteration;
+    static const dlt_lio_thermal no_thermal = {0, 0, {0, 0, 0}, {1, 0, 0, 0}, {0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0},
+                                               {0, 0, 0}, {1, 0, 0, 0}, {0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
+    if (!th) th = &no_thermal;
+    std::memset(out, 0, sizeof(*out));
+    iters.clear();
+    const double t_begin = wall();
+    if (flg_first_scan) {  // :736-740
+        first_lidar_time = lidar_beg_time;
+        flg_first_scan = false;
+    }
+    // observation_end_time = lidar_beg_time + points.back().normal_z      :546
+    double observation_end_time = lidar_beg_time;
+    if (n > 0) observation_end_time += (double)reinterpret_cast<const float *>(pts48)[(size_t)(n - 1) * 12 + 6];
+
+    // ---- p_imu->Process(Measures, state, feats_undistort, EKF_stop_flg)   :750
+    double t0 = wall();
+    std::vector<ImuSample> imu_v(imu, imu + n_imu);
+    bool undistorted = imu_.Process(imu_v, lidar_beg_time, observation_end_time, state, EKF_stop_flg);
+    int n_raw = 0;
+    if (undistorted && n > 0) {
+        double pose[24];
+        state.pose24(pose);
+        LM_CK(dlt_scan_deskew(dev_, pts48, n, reinterpret_cast<const double *>(imu_.IMUpose.data()), (int)imu_.IMUpose.size(), pose));
+        n_raw = n;
+    }
+    out->t_deskew = wall() - t0;
+    StatesGroup state_propagat = state;                                 // :752
+    Vec3 pos_lid = state_propagat.pos_end + state_propagat.rot_end * state_propagat.T_L_I;  // :753
+    {
+        double f[36 + kDim * kDim];
+        state_propagat.to_flat(f);
+        std::memcpy(out->state_prop, f, sizeof(out->state_prop));
+    }
+    out->n_raw = n_raw;
+    if (n_raw == 0) {  // :755-759  "No point, not ready for odometry, skip this scan"
+        out->t_total = wall() - t_begin;
+        return 0;
+    }
+    out->had_points = 1;
+    flg_EKF_inited = true;  // :762 with INIT_TIME == 0 (:75)
+
+    t0 = wall();
+    LM_CK(fov_segment(pos_lid, &out->deleted));  // :772
+    out->t_delete = wall() - t0;
+
+    t0 = wall();
+    int feats_down_size = 0;
+    LM_CK(dlt_scan_downsample(dev_, &feats_down_size));  // :775-778
+    out->t_voxel = wall() - t0;
+    out->n_down = feats_down_size;
+
+    if (!map_built) {  // ikdtree.Root_Node == nullptr, :780-793
+        if (feats_down_size > 5) {
+            double pose[24];
+            state.pose24(pose);
+            LM_CK(dlt_map_build_from_scan(dev_, pose));
+            map_built = true;
+            out->built_map = 1;
+        }
+        out->t_total = wall() - t_begin;
+        return 0;
+    }
+    int featsFromMapNum = 0;
+    LM_CK(dlt_map_valid_count(dev_, &featsFromMapNum));  // :794
+    out->map_points_before = featsFromMapNum;
+
+    int effct_feat_num = 0;
+    if (featsFromMapNum >= 5) {  // :804
+        out->did_update = 1;
+        t0 = wall();
+        int rematch_num = 0;
+        bool rematch_en = false, flg_EKF_converged = false;
+        double K1c[kDim * 12];  // K_1[:, :12] of the last Kalman update
+        double HtH12[144];
+        bool have_gain = false;
+        dlt_measure_out m;
+        for (int iterCount = 0; iterCount < NUM_MAX_ITERATIONS; iterCount++) {  // :820
+            dlt_lio_iter rec;
+            std::memset(&rec, 0, sizeof(rec));
+            rec.iter = iterCount;
+            rec.did_match = (iterCount == 0 || rematch_en) ? 1 : 0;  // :847
+            state.pose24(rec.pose_in);
+            LM_CK(dlt_measure(dev_, rec.pose_in, rec.did_match, &m));  // :829-979 on the device
+            effct_feat_num = m.effct_feat_num;
+            const double total_residual = m.total_residual;
+            rec.n_down = m.n_down;
+            rec.effct_feat_num = effct_feat_num;
+            rec.total_residual = total_residual;
+            rec.res_mean_last = total_residual / effct_feat_num;  // :932 (nan when 0, as in the reference)
+            std::memcpy(rec.HtH, m.HtH, sizeof(rec.HtH));
+            std::memcpy(rec.Htr, m.Htr, sizeof(rec.Htr));
+
+            effct_q.push_back(effct_feat_num);  // :899-918
+            if ((int)effct_q.size() > QUEUE_SIZE) effct_q.pop_front();
+            EKF_stop_flg = false;
+            for (int v : effct_q)
+                if (v <= dynamic_effect_featurepoints_threshold) {
+                    EKF_stop_flg = true;
+                    break;
+                }
+            rec.ekf_stop = EKF_stop_flg ? 1 : 0;
+
+            // (the `!flg_EKF_inited && !EKF_stop_flg` branch at :986-1011 cannot be reached: INIT_TIME is 0
+            //  and flg_EKF_inited is only cleared at :1062, right before the loop breaks at :1095-1100)
+            if (!EKF_stop_flg) {  // :1012-1053
+                double A[kDim * kDim], Pn[kDim * kDim], K1[kDim * kDim];
+                for (int i = 0; i < kDim * kDim; i++) Pn[i] = state.cov[i] / LASER_POINT_COV;
+                if (!invert(Pn, kDim, A)) {
+                    err = "covariance is singular";
+                    return DLT_E_STATE;
+                }
+                for (int a = 0; a < 12; a++)
+                    for (int b = 0; b < 12; b++) A[a * kDim + b] += m.HtH[a * 12 + b];
+                if (!invert(A, kDim, K1)) {
+                    err = "H^T H + (P/R)^-1 is singular";
+                    return DLT_E_STATE;
+                }
+                for (int i = 0; i < kDim; i++)
+                    for (int j = 0; j < 12; j++) K1c[i * 12 + j] = K1[i * kDim + j];
+                std::memcpy(HtH12, m.HtH, sizeof(HtH12));
+                have_gain = true;
+                double vec[kDim];
+                state_propagat.boxminus(state, vec);  // :1028
+                // solution = K z + vec - K H vec_12 = K_1[:, :12] (H^T r - H^T H vec_12) + vec      :1032
+                double rhs[12];
+                for (int a = 0; a < 12; a++) {
+                    double s = 0;
+                    for (int b = 0; b < 12; b++) s += m.HtH[a * 12 + b] * vec[b];
+                    rhs[a] = m.Htr[a] - s;
+                }
+                double solution[kDim];
+                for (int i = 0; i < kDim; i++) {
+                    double s = 0;
+                    for (int a = 0; a < 12; a++) s += K1c[i * 12 + a] * rhs[a];
+                    solution[i] = s + vec[i];
+                }
+                state.boxplus_inplace(solution);  // :1033
+                std::memcpy(rec.solution, solution, sizeof(solution));
+                const double rn = std::sqrt(solution[0] * solution[0] + solution[1] * solution[1] + solution[2] * solution[2]);
+                const double tn = std::sqrt(solution[3] * solution[3] + solution[4] * solution[4] + solution[5] * solution[5]);
+                flg_EKF_converged = (rn * 57.3 < 0.01) && (tn * 100 < 0.015);  // :1040
+                last_nodegared_state = state;                                  // :1050
+            } else {  // :1054-1063
+                StatesGroup d = odom_to_state(th->delta_pos, th->delta_quat, th->delta_vel, th->cov_slots);
+                state = last_nodegared_state.compose(d);
+                flg_EKF_inited = false;
+            }
+            rec.converged = flg_EKF_converged ? 1 : 0;
+            {
+                double f[36 + kDim * kDim];
+                state.to_flat(f);
+                std::memcpy(rec.state_out, f, sizeof(rec.state_out));
+            }
+            iters.push_back(rec);
+
+            rematch_en = false;  // :1069-1076
+            if (flg_EKF_converged || ((rematch_num == 0) && (iterCount == (NUM_MAX_ITERATIONS - 2)))) {
+                rematch_en = true;
+                rematch_num++;
+            }
+            if (rematch_num >= 2 || (iterCount == NUM_MAX_ITERATIONS - 1)) {  // :1078-1094
+                if (flg_EKF_inited && have_gain) {
+                    // G[:, :12] = K H = K_1[:, :12] H^T H;  cov = (I - G) cov      :1084-1085
+                    double G[kDim * 12], ncov[kDim * kDim];
+                    for (int i = 0; i < kDim; i++)
+                        for (int j = 0; j < 12; j++) {
+                            double s = 0;
+                            for (int a = 0; a < 12; a++) s += K1c[i * 12 + a] * HtH12[a * 12 + j];
+                            G[i * 12 + j] = s;
+                        }
+                    for (int i = 0; i < kDim; i++)
+                        for (int j = 0; j < kDim; j++) {
+                            double s = state.cov[i * kDim + j];
+                            for (int a = 0; a < 12; a++) s -= G[i * 12 + a] * state.cov[a * kDim + j];
+                            ncov[i * kDim + j] = s;
+                        }
+                    std::memcpy(state.cov, ncov, sizeof(ncov));
+                }
+                break;
+            } else if (EKF_stop_flg) {  // :1095-1101
+                break;
+            }
+        }
+        out->t_iterate = wall() - t0;
+        if (!iters.empty()) {
+            std::memcpy(out->eigvals, m.eigvals, sizeof(out->eigvals));
+            std::memcpy(out->eigvecs, m.eigvecs, sizeof(out->eigvecs));
+            out->degenerate = (m.eigvals[0] < cfg.degeneracy_eig_threshold) ? 1 : 0;
+        }
+
+        // ---- zeta blend, :1105-1129
+        if ((lidar_cnt < 100) || (!th->tis_online) || (th->tis_online && lidar_cnt % 2 == 1)) {
+            const double alpha_l = effct_feat_num / (cfg.beta * 65536.0);  // Nla, :106
+            zeta_l = 2.0 / (1.0 + std::exp(-alpha_l)) - 1;
+            double zeta_l_norm = zeta_l / (zeta_l + zeta_t);
+            if (lidar_cnt < 100) zeta_l_norm = 1;
+            double v1[kDim], v2[kDim];
+            state_propagat.boxminus(last_state, v1);
+            state.boxminus(last_state, v2);
+            for (int i = 0; i < kDim; i++) {
+                v1[i] *= (1 - zeta_l_norm);
+                v2[i] *= zeta_l_norm;
+            }
+            state = last_state.boxplus(v1).boxplus(v2);  // :1119 -- the result carries last_state.cov (reference quirk)
+        } else {
+            const double zeta_t_norm = zeta_t / (zeta_l + zeta_t);
+            double v1[kDim];
+            state.boxminus(last_state, v1);
+            for (int i = 0; i < kDim; i++) v1[i] *= (1 - zeta_t_norm);
+            StatesGroup o = odom_to_state(th->l2l_pos, th->l2l_quat, th->l2l_vel, th->l2l_cov_slots);
+            state = last_state.boxplus(v1).compose(o.scaled(zeta_t_norm));  // :1127
+        }
+        last_state = state;  // :1131
+
+        // ---- map_incremental(), :1164-1168
+        t0 = wall();
+        if (!EKF_stop_flg) {
+            double pose[24];
+            state.pose24(pose);
+            LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
+            out->added = out->n_added_ds + out->n_added_raw;
+        }
+        out->t_insert = wall() - t0;
+    }
+    out->ekf_stop = EKF_stop_flg ? 1 : 0;
+    out->n_iters = (int)iters.size();
+    out->t_total = wall() - t_begin;
+    return 0;
+}
+
+}  // namespace dlt_host
+
+// ------------------------------------------------------------------ C ABI
+using dlt_host::ImuSample;
+using dlt_host::LaserMapping;
+
+extern "C" {
+
+void dlt_lio_default_config(dlt_lio_config *c) {
+    dlt_default_config(&c->dev);
+    c->max_iteration = 4;     // BASELINE configs (feat.yaml:46 ships 10)
+    c->cube_len = 1000.0;     // feat.yaml:49
+    c->featptsThreshold = 30; // feat.yaml:7
+    c->beta = 0.1;            // feat.yaml:8
+    c->det_range = 300.0f;    // laserMapping.cpp:304
+    for (int i = 0; i < 3; i++) c->extrinT[i] = 0.0;
+    for (int i = 0; i < 9; i++) c->extrinR[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    c->degeneracy_eig_threshold = 100.0;
+}
+
+int dlt_lio_create(const dlt_lio_config *cfg, dlt_lio *out) {
+    if (!cfg || !out) return DLT_E_INVALID;
+    *out = nullptr;
+    LaserMapping *lm = new LaserMapping(*cfg);
+    if (!lm->ok()) {
+        int rc = lm->create_rc();
+        delete lm;
+        return rc ? rc : DLT_E_CUDA;
+    }
+    dlt_lio h = new dlt_lio_s;
+    h->lm = lm;
+    *out = h;
+    return DLT_OK;
+}
+int dlt_lio_destroy(dlt_lio h) {
+    if (!h) return DLT_E_INVALID;
+    delete h->lm;
+    delete h;
+    return DLT_OK;
+}
+const char *dlt_lio_last_error(dlt_lio h) { return h ? h->lm->err.c_str() : "null handle"; }
+dlt_handle dlt_lio_device(dlt_lio h) { return h ? h->lm->dev_ : nullptr; }
+int dlt_lio_on_lidar_msg(dlt_lio h) {
+    if (!h) return DLT_E_INVALID;
+    h->lm->on_lidar_msg();
+    return DLT_OK;
+}
+int dlt_lio_on_edge_count(dlt_lio h, int n) {
+    if (!h) return DLT_E_INVALID;
+    h->lm->on_edge_count(n);
+    return DLT_OK;
+}
+int dlt_lio_force_imu_ready(dlt_lio h, const double *mean_acc3, const double *last_imu7) {
+    if (!h || !mean_acc3 || !last_imu7) return DLT_E_INVALID;
+    ImuSample s;
+    s.t = last_imu7[0];
+    std::memcpy(s.acc, last_imu7 + 1, 24);
+    std::memcpy(s.gyr, last_imu7 + 4, 24);
+    h->lm->imu_.force_ready(dlt_host::Vec3(mean_acc3), s);
+    return DLT_OK;
+}
+int dlt_lio_get_state(dlt_lio h, double *s) {
+    if (!h || !s) return DLT_E_INVALID;
+    h->lm->state.to_flat(s);
+    return DLT_OK;
+}
+int dlt_lio_set_state(dlt_lio h, const double *s, int also_last) {
+    if (!h || !s) return DLT_E_INVALID;
+    h->lm->state.from_flat(s);
+    if (also_last) {
+        h->lm->last_state.from_flat(s);
+        h->lm->last_nodegared_state.from_flat(s);
+    }
+    return DLT_OK;
+}
+int dlt_lio_get_flags(dlt_lio h, int *f) {
+    if (!h || !f) return DLT_E_INVALID;
+    LaserMapping *l = h->lm;
+    f[0] = l->EKF_stop_flg;
+    f[1] = l->flg_EKF_inited;
+    f[2] = l->dynamic_effect_featurepoints_threshold;
+    f[3] = (int)l->lidar_cnt;
+    f[4] = l->Localmap_Initialized;
+    f[5] = (int)l->effct_q.size();
+    f[6] = l->map_built;
+    f[7] = l->imu_.need_init() ? 0 : 1;
+    return DLT_OK;
+}
+int dlt_lio_get_localmap(dlt_lio h, float *b) {
+    if (!h || !b) return DLT_E_INVALID;
+    std::memcpy(b, h->lm->LocalMap_min, 12);
+    std::memcpy(b + 3, h->lm->LocalMap_max, 12);
+    return DLT_OK;
+}
+int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_time, const double *imu7, int n_imu,
+                         const dlt_lio_thermal *thermal, dlt_lio_scan_out *out) {
+    if (!h || !out || n < 0 || n_imu < 0 || (n > 0 && !pts48) || (n_imu > 0 && !imu7)) return DLT_E_INVALID;
+    static_assert(sizeof(ImuSample) == 7 * sizeof(double), "imu7 layout");
+    return h->lm->process_scan(pts48, n, lidar_beg_time, reinterpret_cast<const ImuSample *>(imu7), n_imu, thermal, out);
+}
+int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap) {
+    if (!h) return DLT_E_INVALID;
+    int n = (int)h->lm->iters.size();
+    for (int i = 0; i < n && i < cap; i++) iters[i] = h->lm->iters[i];
+    return n;
+}
+int dlt_lio_get_imu_poses(dlt_lio h, double *pose22, int cap) {
+    if (!h) return DLT_E_INVALID;
+    int n = (int)h->lm->imu_.IMUpose.size();
+    for (int i = 0; i < n && i < cap; i++) std::memcpy(pose22 + 22 * (size_t)i, &h->lm->imu_.IMUpose[i], sizeof(dlt_host::Pose6D));
+    return n;
+}
+
+}  // extern "C"

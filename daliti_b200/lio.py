@@ -1,0 +1,174 @@
+"""ctypes binding of include/daliti_b200_lio.h: the host-side per-scan update
+(eskf_lio/src/laserMapping.cpp:731-1177 mirrored in C++ over the device C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .binding import DltConfig, DltError, ScanToMap, _ERR, _f64, _p, load_library
+
+
+class LioConfig(C.Structure):
+    _fields_ = [
+        ("dev", DltConfig),
+        ("max_iteration", C.c_int),
+        ("cube_len", C.c_double),
+        ("featptsThreshold", C.c_int),
+        ("beta", C.c_double),
+        ("det_range", C.c_float),
+        ("extrinT", C.c_double * 3),
+        ("extrinR", C.c_double * 9),
+        ("degeneracy_eig_threshold", C.c_double),
+    ]
+
+
+class LioThermal(C.Structure):
+    _fields_ = [
+        ("tis_online", C.c_int), ("recv_n", C.c_int),
+        ("delta_pos", C.c_double * 3), ("delta_quat", C.c_double * 4), ("delta_vel", C.c_double * 3), ("cov_slots", C.c_double * 8),
+        ("l2l_pos", C.c_double * 3), ("l2l_quat", C.c_double * 4), ("l2l_vel", C.c_double * 3), ("l2l_cov_slots", C.c_double * 8),
+    ]
+
+
+class LioIter(C.Structure):
+    _fields_ = [
+        ("iter", C.c_int), ("effct_feat_num", C.c_int), ("converged", C.c_int), ("ekf_stop", C.c_int),
+        ("did_match", C.c_int), ("n_down", C.c_int),
+        ("total_residual", C.c_double), ("res_mean_last", C.c_double),
+        ("HtH", C.c_double * 144), ("Htr", C.c_double * 12), ("pose_in", C.c_double * 24),
+        ("state_out", C.c_double * 36), ("solution", C.c_double * 24),
+    ]
+
+
+class LioScanOut(C.Structure):
+    _fields_ = [
+        ("had_points", C.c_int), ("built_map", C.c_int), ("did_update", C.c_int), ("ekf_stop", C.c_int),
+        ("n_raw", C.c_int), ("n_down", C.c_int), ("map_points_before", C.c_int), ("deleted", C.c_int),
+        ("added", C.c_int), ("n_iters", C.c_int), ("n_added_ds", C.c_int), ("n_added_raw", C.c_int),
+        ("eigvals", C.c_double * 6), ("eigvecs", C.c_double * 36), ("state_prop", C.c_double * 36),
+        ("degenerate", C.c_int), ("reserved", C.c_int),
+        ("t_deskew", C.c_double), ("t_voxel", C.c_double), ("t_iterate", C.c_double), ("t_insert", C.c_double),
+        ("t_delete", C.c_double), ("t_total", C.c_double),
+    ]
+
+
+_LIO_SYMBOLS = [
+    "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
+    "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
+    "dlt_lio_get_localmap", "dlt_lio_process_scan", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
+]
+
+
+class LaserMapping:
+    """The reference-facing call: one `process_scan` per LiDAR scan."""
+
+    def __init__(self, lib: C.CDLL | None = None, dev: dict | None = None, **cfg):
+        self.lib = lib or load_library()
+        for s in _LIO_SYMBOLS:
+            if not hasattr(self.lib, s):
+                raise DltError(f"library does not export {s}")
+        self.lib.dlt_lio_last_error.restype = C.c_char_p
+        self.lib.dlt_lio_last_error.argtypes = [C.c_void_p]
+        self.lib.dlt_lio_device.restype = C.c_void_p
+        self.lib.dlt_lio_device.argtypes = [C.c_void_p]
+        c = LioConfig()
+        self.lib.dlt_lio_default_config(C.byref(c))
+        for k, v in (dev or {}).items():
+            if not hasattr(c.dev, k):
+                raise TypeError(f"unknown device config field {k}")
+            setattr(c.dev, k, v)
+        for k, v in cfg.items():
+            if k in ("extrinT", "extrinR"):
+                for i, x in enumerate(v):
+                    getattr(c, k)[i] = float(x)
+            elif hasattr(c, k):
+                setattr(c, k, v)
+            else:
+                raise TypeError(f"unknown config field {k}")
+        self.cfg = c
+        self.h = C.c_void_p()
+        rc = self.lib.dlt_lio_create(C.byref(c), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise DltError(f"dlt_lio_create failed: {_ERR.get(rc, rc)}")
+        self.out = LioScanOut()
+        # a non-owning view of the device handle (map export, neighbour read-back, ...)
+        self.device = ScanToMap.__new__(ScanToMap)
+        self.device.lib = self.lib
+        self.device.h = C.c_void_p(self.lib.dlt_lio_device(self.h))
+        self.device.close = lambda: None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dlt_lio_destroy(self.h)
+            self.h = None
+            self.device.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.dlt_lio_last_error(self.h)
+            raise DltError(f"{_ERR.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def on_lidar_msg(self):
+        self._ck(self.lib.dlt_lio_on_lidar_msg(self.h))
+
+    def on_edge_count(self, n):
+        self._ck(self.lib.dlt_lio_on_edge_count(self.h, C.c_int(n)))
+
+    def force_imu_ready(self, mean_acc, last_imu7):
+        a, b = _f64(mean_acc), _f64(last_imu7)
+        self._ck(self.lib.dlt_lio_force_imu_ready(self.h, _p(a), _p(b)))
+
+    def get_state(self) -> np.ndarray:
+        s = np.zeros(612, np.float64)
+        self._ck(self.lib.dlt_lio_get_state(self.h, _p(s)))
+        return s
+
+    def set_state(self, s, also_last=True):
+        s = _f64(s)
+        assert s.size == 612
+        self._ck(self.lib.dlt_lio_set_state(self.h, _p(s), C.c_int(1 if also_last else 0)))
+
+    def flags(self):
+        f = np.zeros(8, np.int32)
+        self._ck(self.lib.dlt_lio_get_flags(self.h, _p(f)))
+        return dict(ekf_stop=int(f[0]), ekf_inited=int(f[1]), threshold=int(f[2]), lidar_cnt=int(f[3]), localmap_init=int(f[4]),
+                    queue=int(f[5]), map_built=int(f[6]), imu_ready=int(f[7]))
+
+    def localmap(self):
+        b = np.zeros(6, np.float32)
+        self._ck(self.lib.dlt_lio_get_localmap(self.h, _p(b)))
+        return b
+
+    def process_scan(self, pts48, lidar_beg_time, imu7, thermal: LioThermal | None = None) -> LioScanOut:
+        """pts48 / imu7 may be numpy arrays or torch CPU tensors (pinned or not): only their data pointer is used."""
+        if hasattr(pts48, "data_ptr"):
+            n = int(pts48.shape[0])
+            pp = C.c_void_p(pts48.data_ptr())
+        else:
+            a = np.ascontiguousarray(pts48, dtype=np.float32).reshape(-1, 12)
+            n = a.shape[0]
+            pp = _p(a)
+        im = _f64(imu7).reshape(-1, 7)
+        th = C.byref(thermal) if thermal is not None else None
+        self._ck(self.lib.dlt_lio_process_scan(self.h, pp, C.c_int(n), C.c_double(lidar_beg_time), _p(im), C.c_int(im.shape[0]), th,
+                                               C.byref(self.out)))
+        return self.out
+
+    def iters(self):
+        n = self.out.n_iters
+        arr = (LioIter * max(n, 1))()
+        self.lib.dlt_lio_get_iters(self.h, arr, C.c_int(n))
+        return [arr[i] for i in range(n)]
+
+    def imu_poses(self) -> np.ndarray:
+        out = np.zeros((512, 22), np.float64)
+        n = self.lib.dlt_lio_get_imu_poses(self.h, _p(out), C.c_int(512))
+        return out[:n]

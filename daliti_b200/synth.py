@@ -194,7 +194,11 @@ def _raycast(scene: Scene, o: np.ndarray, d: np.ndarray, max_range: float) -> np
             ok = (d[:, 2] > 0) & (t > 0)
             best = np.where(ok & (t < best), t, best)
         inv = 1.0 / d
+        c = o.mean(0)
+        reach = max_range + float(np.abs(o - c).max()) + 1.0
         for b in scene.boxes:
+            if (b[0] - c[0] > reach or c[0] - b[3] > reach or b[1] - c[1] > reach or c[1] - b[4] > reach):
+                continue
             t1 = (b[0:3] - o) * inv
             t2 = (b[3:6] - o) * inv
             tmin = np.minimum(t1, t2).max(1)
@@ -226,7 +230,7 @@ def simulate_scan(scene: Scene, traj: Trajectory, t_beg: float, beams: int, azim
     d_world = np.einsum("nij,nj->ni", R, d_body)
     rngs = _raycast(scene, o, d_world, max_range)
     ok = np.isfinite(rngs) & (rngs >= min_range)
-    rngs = rngs + rng.normal(0, range_sigma, len(rngs))
+    rngs = np.where(ok, rngs, 0.0) + rng.normal(0, range_sigma, len(rngs))
     p = d_body * rngs[:, None]
     out = np.zeros((int(ok.sum()), 12), np.float32)
     out[:, 0:3] = p[ok]

@@ -78,6 +78,9 @@ int dlt_sync(dlt_handle h);
 /* ---- map: replaces the global `KD_TREE<PointType> ikdtree` (laserMapping.cpp:164) ---------- */
 /* ikdtree.Build(feats_down_world->points)                       laserMapping.cpp:790            */
 int dlt_map_build(dlt_handle h, const float *xyzi, int n);
+/* first-scan map initialisation: pointBodyToWorld over feats_down, then ikdtree.Build
+ *                                                               laserMapping.cpp:780-791        */
+int dlt_map_build_from_scan(dlt_handle h, const double *pose24);
 /* ikdtree.Add_Points(points, downsample_on)                     laserMapping.cpp:627-628        */
 int dlt_map_add(dlt_handle h, const float *xyzi, int n, int downsample_on);
 /* ikdtree.Delete_Point_Boxes(cub_needrm), boxes = min xyz, max xyz   laserMapping.cpp:368       */

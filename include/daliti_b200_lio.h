@@ -1,0 +1,94 @@
+/* include/daliti_b200_lio.h -- C ABI of the host-side per-scan update.
+ *
+ * Mirrors the body of eskf_lio's main loop, `while (sync_packages(Measures)) { ... }`
+ * (eskf_lio/src/laserMapping.cpp:731-1177), with the device path of daliti_b200.h
+ * underneath: IMU forward propagation and the 24-state Kalman algebra stay on the host
+ * (they are sequential and tiny), everything per-point runs on the B200.
+ *
+ * What the ROS node keeps: callbacks, sync_packages, publishing (laserMapping.cpp:424-574,
+ * 1183-1290).  What it hands over, per scan: the PointXYZINormal cloud of
+ * /laser_cloud_surf, its header stamp, the IMU samples sync_packages selected, and the
+ * scalars the thermal callbacks leave behind.  What it gets back: the updated StatesGroup,
+ * EKF_stop_flg, effct_feat_num and the degeneracy eigen-values.
+ */
+#ifndef DALITI_B200_LIO_H
+#define DALITI_B200_LIO_H
+
+#include "daliti_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dlt_lio_s *dlt_lio;
+
+typedef struct dlt_lio_config {
+    dlt_config dev;          /* device path configuration                                         */
+    int max_iteration;       /* mapping/max_iteration            laserMapping.cpp:656              */
+    double cube_len;         /* mapping/cube_side_length         laserMapping.cpp:659              */
+    int featptsThreshold;    /* common/featptsThreshold          laserMapping.cpp:654              */
+    double beta;             /* common/beta                      laserMapping.cpp:664              */
+    float det_range;         /* DET_RANGE                        laserMapping.cpp:304              */
+    double extrinT[3];       /* mapping/extrinsic_T              laserMapping.cpp:661              */
+    double extrinR[9];       /* mapping/extrinsic_R (row-major)  laserMapping.cpp:662              */
+    double degeneracy_eig_threshold; /* new: flag when min eigenvalue of HtH[0:6,0:6] is below     */
+} dlt_lio_config;
+
+/* State left behind by tis_cbk / tn_cbk (laserMapping.cpp:471-498): g_tis_odom_delta and
+ * g_tis_odom_delta_lframe2lframe as position, quaternion (w x y z), linear velocity and
+ * the pose.covariance[0..7] slots odomToStateGruop reads (laserMapping.cpp:218-239).           */
+typedef struct dlt_lio_thermal {
+    int tis_online, recv_n;
+    double delta_pos[3], delta_quat[4], delta_vel[3], cov_slots[8];
+    double l2l_pos[3], l2l_quat[4], l2l_vel[3], l2l_cov_slots[8];
+} dlt_lio_thermal;
+
+/* One row of Log/mat_out.txt (laserMapping.cpp:936-937) plus the algebra of the iteration.    */
+typedef struct dlt_lio_iter {
+    int iter, effct_feat_num, converged, ekf_stop, did_match, n_down;
+    double total_residual, res_mean_last;
+    double HtH[144], Htr[12], pose_in[24], state_out[36], solution[24];
+} dlt_lio_iter;
+
+typedef struct dlt_lio_scan_out {
+    int had_points, built_map, did_update, ekf_stop;
+    int n_raw, n_down, map_points_before, deleted, added, n_iters;
+    int n_added_ds, n_added_raw;
+    double eigvals[6], eigvecs[36];  /* of the last iteration's HtH[0:6,0:6]                      */
+    double state_prop[36];           /* state_propagat                     laserMapping.cpp:752    */
+    int degenerate;                  /* eigvals[0] < degeneracy_eig_threshold; slot odom.pose.covariance[0]
+                                        read at daliti/src/lidar_odometry/imuPreintegration.cpp:290 */
+    int reserved;
+    double t_deskew, t_voxel, t_iterate, t_insert, t_delete, t_total; /* host wall clock, seconds  */
+} dlt_lio_scan_out;
+
+void dlt_lio_default_config(dlt_lio_config *cfg);
+int dlt_lio_create(const dlt_lio_config *cfg, dlt_lio *out);
+int dlt_lio_destroy(dlt_lio h);
+const char *dlt_lio_last_error(dlt_lio h);
+dlt_handle dlt_lio_device(dlt_lio h);            /* the device handle (map access, exports)        */
+
+/* feat_points_cbk / tn_cbk bookkeeping               laserMapping.cpp:424-446, 491-498            */
+int dlt_lio_on_lidar_msg(dlt_lio h);
+int dlt_lio_on_edge_count(dlt_lio h, int recv_n);
+/* skip ImuProcess::IMU_Initial's ~100 samples (IMU_Processing.hpp:385-405) with a known mean_acc
+ * and last IMU sample (t, acc[3], gyr[3])                                                        */
+int dlt_lio_force_imu_ready(dlt_lio h, const double *mean_acc3, const double *last_imu7);
+/* StatesGroup as 36 + 576 doubles: rot_end[9] pos_end[3] R_L_I[9] T_L_I[3] vel_end[3] bias_g[3]
+ * bias_a[3] gravity[3] cov[576]                       common_lib.h:73-228                         */
+int dlt_lio_get_state(dlt_lio h, double *state612);
+int dlt_lio_set_state(dlt_lio h, const double *state612, int also_last_states);
+int dlt_lio_get_flags(dlt_lio h, int *flags8);   /* EKF_stop_flg, flg_EKF_inited, threshold, lidar_cnt, localmap_init, queue size, map_built, imu_ready */
+int dlt_lio_get_localmap(dlt_lio h, float *box6);
+
+/* The per-scan update.  pts48: n PointXYZINormal records; imu7: n_imu rows of t, acc[3], gyr[3]. */
+int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_time, const double *imu7, int n_imu,
+                         const dlt_lio_thermal *thermal, dlt_lio_scan_out *out);
+int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap);
+/* IMUpose list of the last scan's forward propagation (22 doubles each)                          */
+int dlt_lio_get_imu_poses(dlt_lio h, double *pose22, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DALITI_B200_LIO_H */

@@ -18,9 +18,9 @@ def state612(traj: synth.Trajectory, t: float, R_L_I=None, T_L_I=None) -> np.nda
 
 def small_sequence(seed=0, half=30.0, beams=16, azimuths=360, speed=1.0, yaw_rate=0.1, n_boxes=10, tunnel=False):
     if tunnel:
-        scene = synth.make_tunnel(length=60.0)
+        scene = synth.make_tunnel(length=200.0)
         traj = synth.Trajectory(speed=speed, yaw_rate=0.0, x0=-20.0, z0=1.2)
-        spec = synth.ScanSpec(beams, azimuths, (-22.5, 22.5), max_range=60.0)
+        spec = synth.ScanSpec(beams, azimuths, (-22.5, 22.5), max_range=40.0)  # end caps out of range
     else:
         scene = synth.make_box_world(half=half, n_boxes=n_boxes, seed=seed, keep_clear=4.0)
         traj = synth.Trajectory(speed=speed, yaw_rate=yaw_rate, z0=1.5)

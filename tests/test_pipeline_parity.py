@@ -1,0 +1,142 @@
+"""The full per-scan update through the reference-facing call (dlt_lio_process_scan: host
+mirror of laserMapping.cpp:731-1177 over the device path) vs the restated reference loop on
+the same raw scans + IMU: deskew -> VoxelGrid -> IEKF iterations -> zeta blend -> map_incremental.
+
+Chained end to end the two paths are not bit-identical (CUDA vs glibc sin/cos in the deskew, and
+the order-independent fixed-point VoxelGrid centroids differ from PCL's float sums in the last
+bit), so poses are compared at the north-star tolerance (1e-5 relative), counts within 1%."""
+import numpy as np
+import pytest
+
+import helpers
+from daliti_b200 import synth
+from daliti_b200.lio import LaserMapping, LioThermal
+from oracle_binding import MAP_PORT, MAP_REF, OrcThermal
+
+
+def start_pair(lib, oracle, seq, map_pts, max_pts, max_map, **kw):
+    kind = MAP_REF if oracle.ref_ok else MAP_PORT
+    lio = helpers.start_oracle_lio(oracle, seq, map_pts, kind, **kw)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=max_pts, max_map_points=max_map), **kw)
+    lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
+    lm.set_state(helpers.state612(seq.traj, seq.t_start))
+    if map_pts is not None:
+        lm.device.map_build(map_pts)
+        # ikdtree.Root_Node != nullptr: tell the host mirror the map exists
+        import ctypes as C
+        # (a prebuilt map is a test convenience; the first-scan Build path is covered separately)
+        lm._prebuilt = True
+    return lio, lm
+
+
+def pose_close(a, b, tol=1e-5):
+    a, b = np.asarray(a), np.asarray(b)
+    rot_err = np.abs(a[0:9] - b[0:9]).max()
+    pos_err = np.abs(a[9:12] - b[9:12]).max() / max(1.0, np.abs(b[9:12]).max())
+    return rot_err < tol and pos_err < tol, (rot_err, pos_err)
+
+
+def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal=None, pre_msgs=0, **kw):
+    kind = MAP_REF if oracle.ref_ok else MAP_PORT
+    lio = helpers.start_oracle_lio(oracle, seq, None, kind, **kw)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=max_pts, max_map_points=1 << 18), **kw)
+    lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
+    lm.set_state(helpers.state612(seq.traj, seq.t_start))
+    stops = 0
+    for _ in range(pre_msgs):  # lidar messages received before (feat_points_cbk counters, laserMapping.cpp:426-430)
+        lio.on_lidar_msg()
+        lm.on_lidar_msg()
+    for k in range(n_scans):
+        pts, t_beg, imu = seq.scan(k)
+        lio.on_lidar_msg()
+        lm.on_lidar_msg()
+        th_o = th_d = None
+        if thermal is not None:
+            th_o, th_d = thermal(k)
+        so = lio.process_scan(pts, t_beg, imu, th_o)
+        sd = lm.process_scan(pts, t_beg, imu, th_d)
+        assert (sd.had_points, sd.built_map, sd.did_update) == (so.had_points, so.built_map, so.did_update), k
+        assert sd.n_raw == so.n_raw
+        assert abs(sd.n_down - so.n_down) <= max(2, so.n_down // 200), (sd.n_down, so.n_down)
+        ok, e = pose_close(np.array(sd.state_prop), np.array(so.state_prop), 1e-9 if k == 0 else 1e-5)
+        assert ok, ("state_propagat", k, e)
+        if so.did_update:
+            assert sd.n_iters == so.n_iters, (k, sd.n_iters, so.n_iters)
+            for a, b in zip(lm.iters(), lio.iters()):
+                assert (a.did_match, a.ekf_stop, a.converged) == (b.did_match, b.ekf_stop, b.converged), (k, a.iter)
+                assert abs(a.effct_feat_num - b.effct_feat_num) <= max(3, b.effct_feat_num // 100), (k, a.iter, a.effct_feat_num, b.effct_feat_num)
+                ok, e = pose_close(np.array(a.state_out), np.array(b.state_out))
+                assert ok, ("iteration state", k, a.iter, e)
+            assert sd.ekf_stop == so.ekf_stop
+            stops += so.ekf_stop
+        s_d, s_o = lm.get_state(), lio.get_state()
+        ok, e = pose_close(s_d, s_o)
+        assert ok, ("state after scan", k, e)
+        np.testing.assert_allclose(s_d[24:36], s_o[24:36], rtol=1e-5, atol=1e-6)     # vel, biases, gravity
+        np.testing.assert_allclose(s_d[36:], s_o[36:], rtol=1e-6, atol=1e-9)         # covariance
+        n_d, n_o = lm.device.map_valid_count(), lio.map().validnum()
+        assert abs(n_d - n_o) <= max(4, n_o // 100), (k, n_d, n_o)
+        assert lm.flags()["ekf_stop"] == lio.flags()["ekf_stop"]
+    lm.close()
+    return stops
+
+
+def test_pipeline_first_scan_builds_map(dev, oracle):
+    lib, is_gpu = dev
+    if is_gpu:
+        seq = helpers.small_sequence(seed=11, half=50.0, beams=32, azimuths=1024, n_boxes=20, speed=2.0, yaw_rate=0.2)
+        n, cap = 8, 65536
+    else:
+        seq = helpers.small_sequence(seed=11, half=25.0, beams=16, azimuths=240, n_boxes=8, speed=2.0, yaw_rate=0.2)
+        n, cap = 4, 8192
+    stops = run_pair(lib, oracle, seq, n, cap, featptsThreshold=5)
+    assert stops == 0
+
+
+def test_pipeline_degradation_stop_and_thermal(dev, oracle):
+    """a threshold no scan can meet: the count window raises EKF_stop_flg, the update falls back to
+    last_nodegared_state (+) thermal-odometry delta, map insertion is skipped (laserMapping.cpp:899-918,
+    1054-1063, 1165)"""
+    lib, is_gpu = dev
+    seq = helpers.small_sequence(seed=12, half=25.0, beams=16, azimuths=240 if not is_gpu else 900, n_boxes=8)
+
+    def thermal(k):
+        o, d = OrcThermal(), LioThermal()
+        for t in (o, d):
+            t.tis_online = 1
+            t.recv_n = 20000
+            t.delta_pos[0], t.delta_pos[1], t.delta_pos[2] = 0.01 * k, -0.02, 0.0
+            t.delta_quat[0], t.delta_quat[3] = np.cos(0.005), np.sin(0.005)
+            t.l2l_pos[0] = 0.02
+            t.l2l_quat[0] = 1.0
+            t.cov_slots[7] = -9.8
+            t.l2l_cov_slots[7] = -9.8
+        return o, d
+
+    kind = MAP_REF if oracle.ref_ok else MAP_PORT
+    # after 100 lidar messages the window threshold becomes featptsThreshold; scans alternate between a
+    # reachable and an unreachable threshold by alternating... here: unreachable, so every update stops
+    stops = run_pair(lib, oracle, seq, 5, 32768 if is_gpu else 8192, thermal=thermal, pre_msgs=101, featptsThreshold=1000000)
+    assert stops >= 3
+
+
+def test_pipeline_tunnel_degenerate_axis(dev, oracle):
+    """C3-like corridor: the weakest eigenvector of the 6x6 pose block is the tunnel axis (x translation)"""
+    lib, is_gpu = dev
+    seq = helpers.small_sequence(seed=13, beams=32 if is_gpu else 16, azimuths=900 if is_gpu else 240, tunnel=True)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=65536 if is_gpu else 8192, max_map_points=1 << 18), featptsThreshold=5)
+    lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, 0.0]]))
+    lm.set_state(helpers.state612(seq.traj, seq.t_start))
+    for k in range(3):
+        pts, t_beg, imu = seq.scan(k)
+        lm.on_lidar_msg()
+        out = lm.process_scan(pts, t_beg, imu)
+    assert out.did_update and out.n_iters >= 1
+    ev = np.array(out.eigvals)
+    vec = np.array(out.eigvecs).reshape(6, 6)
+    assert (np.diff(ev) >= 0).all()
+    weakest = np.abs(vec[:, 0])
+    assert weakest.argmax() == 3, weakest  # state order: rotation(3), translation(3) -> index 3 = x translation
+    assert ev[0] < 0.5 * ev[1]  # plane-normal noise leaves a floor of ~N*sigma^2 on the corridor axis
+    assert out.degenerate == 1  # min eigenvalue below degeneracy_eig_threshold: the flag for odom.pose.covariance[0]
+    lm.close()
