@@ -71,9 +71,9 @@ _ERR = {1: "invalid argument", 2: "no usable CUDA device (there is no CPU path)"
 _SYMBOLS = [
     "dlt_default_config", "dlt_create", "dlt_destroy", "dlt_last_error", "dlt_set_stream", "dlt_sync",
     "dlt_map_build", "dlt_map_build_from_scan", "dlt_map_add", "dlt_map_delete_boxes", "dlt_map_valid_count", "dlt_map_export", "dlt_map_knn",
-    "dlt_scan_deskew", "dlt_scan_downsample", "dlt_scan_get_undistorted", "dlt_scan_get_down", "dlt_scan_set_down",
+    "dlt_scan_deskew", "dlt_scan_deskew_dev", "dlt_scan_downsample", "dlt_scan_get_undistorted", "dlt_scan_get_down", "dlt_scan_set_down",
     "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
-    "dlt_degeneracy", "dlt_map_incremental",
+    "dlt_degeneracy", "dlt_map_incremental", "dlt_set_profiling", "dlt_get_profile", "dlt_launch_count",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library(path: str | None = None) -> C.CDLL:
             raise DltError(f"{path} does not export {s}")
     lib.dlt_last_error.restype = C.c_char_p
     lib.dlt_last_error.argtypes = [C.c_void_p]
+    lib.dlt_launch_count.restype = C.c_ulonglong
     return lib
 
 
@@ -261,6 +262,20 @@ class ScanToMap:
         a, b = C.c_int(0), C.c_int(0)
         self._ck(self.lib.dlt_map_incremental(self.h, _p(ps), C.c_int(1 if flg_EKF_inited else 0), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    PROFILE_GROUPS = ("knn", "residual", "deskew", "voxelgrid", "insert", "far_fallback", "spare6", "spare7")
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.dlt_set_profiling(self.h, C.c_int(1 if on else 0)))
+
+    def get_profile(self, reset=True) -> dict:
+        ms = np.zeros(8, np.float64)
+        cnt = np.zeros(8, np.int64)
+        self._ck(self.lib.dlt_get_profile(self.h, _p(ms), _p(cnt), C.c_int(1 if reset else 0)))
+        return {g: (float(ms[i]), int(cnt[i])) for i, g in enumerate(self.PROFILE_GROUPS)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.dlt_launch_count())
 
     def set_stream(self, cuda_stream_ptr: int | None):
         self._ck(self.lib.dlt_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))

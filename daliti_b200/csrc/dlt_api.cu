@@ -16,8 +16,15 @@
 
 using namespace dlt;
 
+unsigned long long dlt::rt::g_launches = 0;
+
 namespace {
 constexpr int kMaxImuPoses = 512;
+constexpr int kProfKinds = 8;  // 0 knn, 1 residual, 2 deskew, 3 voxelgrid, 4 insert, 5 far fallback, 6 delete/export, 7 spare
+struct ProfSpan {
+    int kind;
+    rt::Event a, b;
+};
 constexpr int kFarChunk = 4096;
 constexpr int kFarSlices = 64;
 constexpr int kFarGroupsX = 4;
@@ -32,7 +39,7 @@ struct dlt_handle_s {
     // map
     MapView map;
     size_t table_cap = 0;
-    int *d_counters = nullptr;  // [0] n_buckets [1] n_live [2] error [3] deleted [4] export counter [5] far_count
+    int *d_counters = nullptr;  // [0] n_buckets [1] n_live [2] error [3] deleted [4] export counter [5] far_count [6] ds adds [7] raw adds
     // scan
     int n_raw = 0, n_down = 0;
     bool have_raw = false, have_down = false, have_match = false;
@@ -61,7 +68,34 @@ struct dlt_handle_s {
     int *h_ints = nullptr;
     ScanScalars *h_sc = nullptr;
     std::vector<void *> allocs;
+    // optional per-kernel timing with CUDA events on the launching stream
+    bool prof_on = false;
+    std::vector<ProfSpan> spans;
+    double prof_ms[kProfKinds] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_n[kProfKinds] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+namespace {
+struct ProfScope {  // records an event pair around the launches issued inside the scope
+    dlt_handle h;
+    ProfSpan sp;
+    bool on;
+    ProfScope(dlt_handle h_, int kind) : h(h_), on(h_->prof_on) {
+        if (!on) return;
+        sp.kind = kind;
+        if (rt::event_create(&sp.a) || rt::event_create(&sp.b)) {
+            on = false;
+            return;
+        }
+        rt::event_record(sp.a, h->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        rt::event_record(sp.b, h->stream);
+        h->spans.push_back(sp);
+    }
+};
+}  // namespace
 
 #define DLT_FAIL(h, code, msg)  \
     do {                        \
@@ -112,6 +146,7 @@ static int map_check_error(dlt_handle h) {
 // claim | (bid, resolve) | append over n device points with per-point flags
 static int insert_points(dlt_handle h, const float4 *d_pts, int n, bool any_ds) {
     if (n <= 0) return DLT_OK;
+    ProfScope prof(h, 4);
     const int B = 256, G = div_up(n, B);
     DLT_LAUNCH(k_map_claim, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
                h->d_cellslot, h->map.shard_count > 1 ? 1 : 0);
@@ -148,6 +183,7 @@ static int run_far(dlt_handle h, int *n_far_out) {
     int nfar = h->h_ints[5], n_buckets = h->h_ints[0];
     if (n_far_out) *n_far_out = nfar;
     if (nfar <= 0) return DLT_OK;
+    ProfScope prof(h, 5);
     for (int off = 0; off < nfar; off += kFarChunk) {
         int c = nfar - off < kFarChunk ? nfar - off : kFarChunk;
         DLT_LAUNCH(k_far_scan, dim3(kFarGroupsX, kFarSlices), kFarWarps * 32, h->stream, h->map, n_buckets, (const float4 *)h->knn.qw,
@@ -414,7 +450,8 @@ int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *ou
 }
 
 // ------------------------------------------------------------------ scan
-int dlt_scan_deskew(dlt_handle h, const void *pts48, int n_raw, const double *imu_pose22, int n_pose, const double *pose24) {
+static int scan_deskew_impl(dlt_handle h, const void *pts48, bool on_device, int n_raw, const double *imu_pose22, int n_pose,
+                            const double *pose24) {
     if (!h || n_raw < 0 || (n_raw > 0 && !pts48) || n_pose < 0 || (n_pose > 0 && !imu_pose22) || (n_pose >= 2 && !pose24)) return DLT_E_INVALID;
     if (n_raw > h->cap) DLT_FAIL(h, DLT_E_CAPACITY, "scan larger than max_scan_points");
     if (n_pose > kMaxImuPoses) DLT_FAIL(h, DLT_E_CAPACITY, "too many IMU poses");
@@ -425,18 +462,30 @@ int dlt_scan_deskew(dlt_handle h, const void *pts48, int n_raw, const double *im
     h->have_match = false;
     DLT_LAUNCH(k_scan_reset, 1, 32, h->stream, h->d_sc);
     if (n_raw == 0) return DLT_OK;
-    DLT_RT(h, rt::h2d(h->d_raw, pts48, (size_t)n_raw * 48, h->stream));
+    const float4 *d_in = h->d_raw;
+    if (on_device)
+        d_in = static_cast<const float4 *>(pts48);
+    else
+        DLT_RT(h, rt::h2d(h->d_raw, pts48, (size_t)n_raw * 48, h->stream));
     Pose P = {};
+    ProfScope prof(h, 2);
     if (n_pose >= 2) {
         static_assert(sizeof(ImuPoseDev) == 22 * sizeof(double), "Pose6D layout");
         DLT_RT(h, rt::h2d(h->d_poses, imu_pose22, (size_t)n_pose * sizeof(ImuPoseDev), h->stream));
         P = pose_from(pose24);
-        DLT_LAUNCH(k_scan_first, div_up(n_raw, 256), 256, h->stream, (const float4 *)h->d_raw, n_raw, h->d_sc);
+        DLT_LAUNCH(k_scan_first, div_up(n_raw, 256), 256, h->stream, d_in, n_raw, h->d_sc);
     }
-    DLT_LAUNCH(k_scan_deskew, div_up(n_raw, kDeskewBlock), kDeskewBlock, h->stream, (const float4 *)h->d_raw, n_raw,
-               (const ImuPoseDev *)h->d_poses, n_pose, P, n_pose >= 2 ? 1 : 0, h->d_undist, h->d_sc);
+    DLT_LAUNCH(k_scan_deskew, div_up(n_raw, kDeskewBlock), kDeskewBlock, h->stream, d_in, n_raw, (const ImuPoseDev *)h->d_poses, n_pose, P,
+               n_pose >= 2 ? 1 : 0, h->d_undist, h->d_sc);
     DLT_RT(h, rt::check_launch());
     return DLT_OK;
+}
+
+int dlt_scan_deskew(dlt_handle h, const void *pts48, int n_raw, const double *imu_pose22, int n_pose, const double *pose24) {
+    return scan_deskew_impl(h, pts48, false, n_raw, imu_pose22, n_pose, pose24);
+}
+int dlt_scan_deskew_dev(dlt_handle h, const void *pts48_dev, int n_raw, const double *imu_pose22, int n_pose, const double *pose24) {
+    return scan_deskew_impl(h, pts48_dev, true, n_raw, imu_pose22, n_pose, pose24);
 }
 
 int dlt_scan_downsample(dlt_handle h, int *n_down) {
@@ -452,6 +501,7 @@ int dlt_scan_downsample(dlt_handle h, int *n_down) {
         return DLT_OK;
     }
     const int B = 256, G = div_up(n, B);
+    ProfScope *prof = new ProfScope(h, 3);
     DLT_LAUNCH(k_vox_mark, G, B, h->stream, (const float4 *)h->d_undist, n, h->cfg.ds_scan, h->d_sc, h->d_bitmap, h->bitmap_bits, h->d_vidx);
     DLT_LAUNCH(k_vox_scan1, h->n_scan_blocks, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, (const ScanScalars *)h->d_sc, h->d_wprefix,
                h->d_blksum);
@@ -460,6 +510,7 @@ int dlt_scan_downsample(dlt_handle h, int *n_down) {
                (const unsigned *)h->d_wprefix, (const unsigned *)h->d_blkoff, (const unsigned *)h->d_vidx, h->acc, h->d_vop);
     DLT_LAUNCH(k_vox_final, G, B, h->stream, (const ScanScalars *)h->d_sc, h->acc, h->d_bitmap, h->d_down, n);
     DLT_LAUNCH(k_vox_passthrough, G, B, h->stream, (const float4 *)h->d_undist, n, h->d_sc, h->d_down);
+    delete prof;
     DLT_RT(h, rt::check_launch());
     DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
     DLT_RT(h, rt::sync(h->stream));
@@ -528,6 +579,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     }
     if (do_match) {
         DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
+        ProfScope prof(h, 0);
         DLT_LAUNCH(k_knn, div_up(n, kKnnWarps), kKnnWarps * 32, h->stream, h->map, (const float4 *)h->d_down, n, 1, P, h->cfg.max_sq_dist, h->knn);
         h->have_match = true;
     }
@@ -543,6 +595,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     mb.ticket = h->d_ticket;
     mb.result = result_dev;
     const int G = div_up(n, kResidBlock);
+    ProfScope prof(h, 1);
     if (h->cfg.extrinsic_est_en)
         DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr);
     else
@@ -638,25 +691,44 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
         DLT_RT(h, rt::fill(h->knn.nbr_cnt, 0, (size_t)n * sizeof(int), h->stream));  // Nearest_Points empty
     }
     Pose P = pose_from(pose24);
+    DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
-               (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag);
-    if (n_ds || n_raw) {
-        std::vector<unsigned char> a(n), b(n);
-        DLT_RT(h, rt::d2h(a.data(), h->d_dsflag, (size_t)n, h->stream));
-        DLT_RT(h, rt::d2h(b.data(), h->d_addflag, (size_t)n, h->stream));
-        DLT_RT(h, rt::sync(h->stream));
-        int cd = 0, cr = 0;
-        for (int i = 0; i < n; i++) {
-            cd += a[i] ? 1 : 0;
-            cr += b[i] ? 1 : 0;
-        }
-        if (n_ds) *n_ds = cd;
-        if (n_raw) *n_raw = cr;
-    }
+               (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6);
     int rc = insert_points(h, h->d_pw, n, true);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
-    return map_check_error(h);
+    rc = map_check_error(h);  // reads the 8 counters back
+    if (n_ds) *n_ds = h->h_ints[6];
+    if (n_raw) *n_raw = h->h_ints[7];
+    return rc;
 }
+
+// ------------------------------------------------------------------ instrumentation
+int dlt_set_profiling(dlt_handle h, int on) {
+    if (!h) return DLT_E_INVALID;
+    h->prof_on = on != 0;
+    return DLT_OK;
+}
+int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset) {
+    if (!h || !ms8 || !count8) return DLT_E_INVALID;
+    DLT_RT(h, rt::sync(h->stream));
+    for (ProfSpan &sp : h->spans) {
+        h->prof_ms[sp.kind] += (double)rt::event_elapsed_ms(sp.a, sp.b);
+        h->prof_n[sp.kind] += 1;
+        rt::event_destroy(sp.a);
+        rt::event_destroy(sp.b);
+    }
+    h->spans.clear();
+    for (int k = 0; k < kProfKinds; k++) {
+        ms8[k] = h->prof_ms[k];
+        count8[k] = h->prof_n[k];
+        if (reset) {
+            h->prof_ms[k] = 0;
+            h->prof_n[k] = 0;
+        }
+    }
+    return DLT_OK;
+}
+unsigned long long dlt_launch_count(void) { return rt::g_launches; }
 
 }  // extern "C"

@@ -603,15 +603,16 @@ __global__ void __launch_bounds__(kResidBlock)
 // (PointNoNeedDownsample), through downsample-on-insert (PointToAdd) or dropped.
 __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P, const float4 *__restrict__ nbr, const int *__restrict__ nbr_cnt,
                                 double fs, int ekf_inited, float4 *__restrict__ pw, unsigned char *__restrict__ ds_flag,
-                                unsigned char *__restrict__ add_flag) {
+                                unsigned char *__restrict__ add_flag, int *__restrict__ class_counts /* [0] downsample adds, [1] raw adds */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    unsigned char ds = 0, add = 0;
+    if (i < n) {
     float4 pb = down[i];
     float wx, wy, wz;
     body_to_world(P, pb.x, pb.y, pb.z, wx, wy, wz);  // :591
     pw[i] = make_float4(wx, wy, wz, pb.w);
     int cnt = nbr_cnt[i];
-    unsigned char ds = 1, add = 0;  // default: PointToAdd (:621-624)
+    ds = 1;  // default: PointToAdd (:621-624)
     if (cnt > 0 && ekf_inited) {    // :593
         float mx = (float)(floor((double)wx / fs) * fs + 0.5 * fs);  // :599-601
         float my = (float)(floor((double)wy / fs) * fs + 0.5 * fs);
@@ -637,6 +638,12 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P, 
     }
     ds_flag[i] = ds;
     add_flag[i] = add;
+    }
+    unsigned bd = __ballot_sync(0xffffffffu, ds != 0), ba = __ballot_sync(0xffffffffu, add != 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (bd) atomicAdd(&class_counts[0], __popc(bd));
+        if (ba) atomicAdd(&class_counts[1], __popc(ba));
+    }
 }
 
 // pointBodyToWorld over the downsampled scan (laserMapping.cpp:786-789), every point flagged for a raw add

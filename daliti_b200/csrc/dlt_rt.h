@@ -13,6 +13,12 @@
 
 namespace dlt {
 namespace rt {
+extern unsigned long long g_launches;
+struct Event {};
+inline int event_create(Event *) { return 0; }
+inline void event_destroy(Event) {}
+inline int event_record(Event, cudaStream_t) { return 0; }
+inline float event_elapsed_ms(Event, Event) { return 0.f; }
 inline int alloc(void **p, size_t bytes) {
     size_t n = (bytes + 255) & ~(size_t)255;
     if (n == 0) n = 256;
@@ -54,10 +60,24 @@ inline int check_launch() { return 0; }
 
 #else  // ------------------------------------------------------------------ CUDA
 
-#define DLT_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+namespace dlt { namespace rt { extern unsigned long long g_launches; } }
+#define DLT_LAUNCH(kernel, grid, block, stream, ...)                      \
+    do {                                                                  \
+        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);            \
+        ++dlt::rt::g_launches;                                            \
+    } while (0)
 
 namespace dlt {
 namespace rt {
+typedef cudaEvent_t Event;
+inline int event_create(Event *e) { return cudaEventCreate(e) == cudaSuccess ? 0 : 1; }
+inline void event_destroy(Event e) { cudaEventDestroy(e); }
+inline int event_record(Event e, cudaStream_t s) { return cudaEventRecord(e, s) == cudaSuccess ? 0 : 1; }
+inline float event_elapsed_ms(Event a, Event b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
 inline int alloc(void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 256) == cudaSuccess ? 0 : 1; }
 inline void release(void *p) {
     if (p) cudaFree(p);

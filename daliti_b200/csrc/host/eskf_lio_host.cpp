@@ -439,7 +439,7 @@ int LaserMapping::fov_segment(const Vec3 &pos, int *deleted) {
     } while (0)
 
 int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, const ImuSample *imu, int n_imu, const dlt_lio_thermal *th,
-                               dlt_lio_scan_out *out) {
+                               dlt_lio_scan_out *out, bool pts_on_device, double observation_end_time_in) {
     const double LASER_POINT_COV = 0.0015;  // laserMapping.cpp:76
     const int QUEUE_SIZE = 10;              // :192
     const int NUM_MAX_ITERATIONS = cfg.max_iteration;
@@ -455,7 +455,10 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     }
     // observation_end_time = lidar_beg_time + points.back().normal_z      :546
     double observation_end_time = lidar_beg_time;
-    if (n > 0) observation_end_time += (double)reinterpret_cast<const float *>(pts48)[(size_t)(n - 1) * 12 + 6];
+    if (pts_on_device)
+        observation_end_time = observation_end_time_in;
+    else if (n > 0)
+        observation_end_time += (double)reinterpret_cast<const float *>(pts48)[(size_t)(n - 1) * 12 + 6];
 
     // ---- p_imu->Process(Measures, state, feats_undistort, EKF_stop_flg)   :750
     double t0 = wall();
@@ -465,7 +468,10 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     if (undistorted && n > 0) {
         double pose[24];
         state.pose24(pose);
-        LM_CK(dlt_scan_deskew(dev_, pts48, n, reinterpret_cast<const double *>(imu_.IMUpose.data()), (int)imu_.IMUpose.size(), pose));
+        if (pts_on_device)
+            LM_CK(dlt_scan_deskew_dev(dev_, pts48, n, reinterpret_cast<const double *>(imu_.IMUpose.data()), (int)imu_.IMUpose.size(), pose));
+        else
+            LM_CK(dlt_scan_deskew(dev_, pts48, n, reinterpret_cast<const double *>(imu_.IMUpose.data()), (int)imu_.IMUpose.size(), pose));
         n_raw = n;
     }
     out->t_deskew = wall() - t0;
@@ -494,6 +500,11 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     out->t_voxel = wall() - t0;
     out->n_down = feats_down_size;
 
+    if (!map_built) {  // a map built directly through the device handle (dlt_map_build) also counts as a root
+        int c = 0;
+        LM_CK(dlt_map_valid_count(dev_, &c));
+        if (c > 0) map_built = true;
+    }
     if (!map_built) {  // ikdtree.Root_Node == nullptr, :780-793
         if (feats_down_size > 5) {
             double pose[24];
@@ -772,6 +783,12 @@ int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_t
     if (!h || !out || n < 0 || n_imu < 0 || (n > 0 && !pts48) || (n_imu > 0 && !imu7)) return DLT_E_INVALID;
     static_assert(sizeof(ImuSample) == 7 * sizeof(double), "imu7 layout");
     return h->lm->process_scan(pts48, n, lidar_beg_time, reinterpret_cast<const ImuSample *>(imu7), n_imu, thermal, out);
+}
+int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lidar_beg_time, double observation_end_time, const double *imu7,
+                             int n_imu, const dlt_lio_thermal *thermal, dlt_lio_scan_out *out) {
+    if (!h || !out || n < 0 || n_imu < 0 || (n > 0 && !pts48_dev) || (n_imu > 0 && !imu7)) return DLT_E_INVALID;
+    return h->lm->process_scan(pts48_dev, n, lidar_beg_time, reinterpret_cast<const ImuSample *>(imu7), n_imu, thermal, out, true,
+                               observation_end_time);
 }
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap) {
     if (!h) return DLT_E_INVALID;

@@ -160,8 +160,9 @@ class LaserMapping {
     ~LaserMapping();
     bool ok() const { return dev_ != nullptr; }
     int create_rc() const { return create_rc_; }
+    // pts_on_device: pts48 is a device pointer and observation_end_time is given by the caller
     int process_scan(const void *pts48, int n, double lidar_beg_time, const ImuSample *imu, int n_imu, const dlt_lio_thermal *th,
-                     dlt_lio_scan_out *out);
+                     dlt_lio_scan_out *out, bool pts_on_device = false, double observation_end_time_in = 0.0);
     void on_lidar_msg();       // feat_points_cbk, laserMapping.cpp:424-446
     void on_edge_count(int n); // tn_cbk, :491-498
 

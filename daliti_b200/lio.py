@@ -56,7 +56,7 @@ class LioScanOut(C.Structure):
 _LIO_SYMBOLS = [
     "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
     "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
-    "dlt_lio_get_localmap", "dlt_lio_process_scan", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
+    "dlt_lio_get_localmap", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
 ]
 
 
@@ -160,6 +160,14 @@ class LaserMapping:
         th = C.byref(thermal) if thermal is not None else None
         self._ck(self.lib.dlt_lio_process_scan(self.h, pp, C.c_int(n), C.c_double(lidar_beg_time), _p(im), C.c_int(im.shape[0]), th,
                                                C.byref(self.out)))
+        return self.out
+
+    def process_scan_dev(self, pts48_dev_ptr: int, n: int, lidar_beg_time, observation_end_time, imu7, thermal: LioThermal | None = None) -> LioScanOut:
+        """the scan is already resident in device memory (pointer to n 48-byte records)"""
+        im = _f64(imu7).reshape(-1, 7)
+        th = C.byref(thermal) if thermal is not None else None
+        self._ck(self.lib.dlt_lio_process_scan_dev(self.h, C.c_void_p(pts48_dev_ptr), C.c_int(n), C.c_double(lidar_beg_time),
+                                                   C.c_double(observation_end_time), _p(im), C.c_int(im.shape[0]), th, C.byref(self.out)))
         return self.out
 
     def iters(self):

@@ -27,7 +27,8 @@ class Scene:
     name: str = "box-world"
 
 
-def make_box_world(half: float = 100.0, n_boxes: int = 48, seed: int = 1, keep_clear: float = 6.0) -> Scene:
+def make_box_world(half: float = 100.0, n_boxes: int = 48, seed: int = 1, keep_clear: float = 6.0, height: tuple = (2.0, 15.0),
+                   max_size: float | None = None) -> Scene:
     """Ground + outer walls + n_boxes pillars/buildings; a corridor around the x axis stays free."""
     rng = np.random.default_rng(SEED_BASE + seed)
     boxes = []
@@ -41,8 +42,8 @@ def make_box_world(half: float = 100.0, n_boxes: int = 48, seed: int = 1, keep_c
     while len(boxes) < 4 + n_boxes and tries < 100000:
         tries += 1
         cx, cy = rng.uniform(-half * 0.95, half * 0.95, 2)
-        sx, sy = rng.uniform(1.0, 0.12 * half + 2.0, 2)
-        hh = rng.uniform(2.0, 15.0)
+        sx, sy = rng.uniform(1.0, (0.12 * half + 2.0) if max_size is None else max_size, 2)
+        hh = rng.uniform(height[0], height[1])
         if abs(cy) - sy / 2 < keep_clear:
             continue
         boxes.append([cx - sx / 2, cy - sy / 2, 0, cx + sx / 2, cy + sy / 2, hh])
@@ -108,7 +109,7 @@ def sample_map(scene: Scene, spacing: float = 0.5, jitter: float = 0.2, seed: in
             else:
                 p = np.column_stack([g[:, 0], nrm, g[:, 1]])
             pts.append(p)
-        if scene.name != "tunnel" and zmax < 20:
+        if scene.name != "tunnel" and zmax < 8:
             g = grid(xmin, xmax, ymin, ymax)
             if len(g):
                 pts.append(np.column_stack([g, zmax + rng.normal(0, 0.01, len(g))]))

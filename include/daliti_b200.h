@@ -98,6 +98,8 @@ int dlt_map_knn(dlt_handle h, const float *q_xyz, int nq, float *out_xyzi, float
  * the IMUpose list of the forward pass and the propagated end state; n_imu_pose < 2 copies
  * the points through.  Also the input of dlt_scan_downsample.                                   */
 int dlt_scan_deskew(dlt_handle h, const void *pts48, int n_raw, const double *imu_pose22, int n_imu_pose, const double *pose24);
+/* same with the PointXYZINormal records already resident in DEVICE memory (no host->device copy) */
+int dlt_scan_deskew_dev(dlt_handle h, const void *pts48_dev, int n_raw, const double *imu_pose22, int n_imu_pose, const double *pose24);
 /* downSizeFilterSurf.filter(*feats_down)                        laserMapping.cpp:775-776        */
 int dlt_scan_downsample(dlt_handle h, int *n_down);
 /* feats_undistort / feats_down read-back (publishing, laserMapping.cpp:1185,1208)               */
@@ -129,6 +131,14 @@ int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36);
 
 /* ---- map_incremental()                                       laserMapping.cpp:582-630, 1167 - */
 int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_add_downsample, int *n_add_raw);
+
+/* ---- instrumentation (no reference counterpart) ---------------------------------------------- */
+/* Per-kernel-group device time from CUDA events on the launching stream.  Groups: 0 k_knn,
+ * 1 k_residual, 2 deskew, 3 VoxelGrid, 4 map insert, 5 exact-neighbour fallback, 6-7 spare.      */
+int dlt_set_profiling(dlt_handle h, int on);
+int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset);
+/* kernels launched by this library in this process so far                                         */
+unsigned long long dlt_launch_count(void);
 
 #ifdef __cplusplus
 }

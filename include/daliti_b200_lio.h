@@ -84,6 +84,10 @@ int dlt_lio_get_localmap(dlt_lio h, float *box6);
 /* The per-scan update.  pts48: n PointXYZINormal records; imu7: n_imu rows of t, acc[3], gyr[3]. */
 int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_time, const double *imu7, int n_imu,
                          const dlt_lio_thermal *thermal, dlt_lio_scan_out *out);
+/* Same with the scan already resident in DEVICE memory (pts48_dev); observation_end_time is then
+ * passed explicitly (the host cannot read points.back().normal_z, laserMapping.cpp:546).            */
+int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lidar_beg_time, double observation_end_time,
+                             const double *imu7, int n_imu, const dlt_lio_thermal *thermal, dlt_lio_scan_out *out);
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap);
 /* IMUpose list of the last scan's forward propagation (22 doubles each)                          */
 int dlt_lio_get_imu_poses(dlt_lio h, double *pose22, int cap);

@@ -190,5 +190,9 @@ static inline T atomicAnd(T *a, T v) {
 using std::max;
 using std::min;
 
-#define DLT_LAUNCH(kernel, grid, block, stream, ...) \
-    emu::launch(dim3(grid), dim3(block), [=]() { kernel(__VA_ARGS__); })
+namespace dlt { namespace rt { extern unsigned long long g_launches; } }
+#define DLT_LAUNCH(kernel, grid, block, stream, ...)                              \
+    do {                                                                          \
+        emu::launch(dim3(grid), dim3(block), [=]() { kernel(__VA_ARGS__); });     \
+        ++dlt::rt::g_launches;                                                    \
+    } while (0)
