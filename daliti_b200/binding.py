@@ -45,8 +45,6 @@ class _MeasureOut(C.Structure):
         ("HtH", C.c_double * 144),
         ("Htr", C.c_double * 12),
         ("total_residual", C.c_double),
-        ("eigvals", C.c_double * 6),
-        ("eigvecs", C.c_double * 36),
         ("effct_feat_num", C.c_int),
         ("n_down", C.c_int),
         ("n_unresolved", C.c_int),
@@ -59,8 +57,6 @@ class Measurement:
     HtH: np.ndarray
     Htr: np.ndarray
     total_residual: float
-    eigvals: np.ndarray
-    eigvecs: np.ndarray
     effct_feat_num: int
     n_down: int
     n_unresolved: int
@@ -226,8 +222,6 @@ class ScanToMap:
             HtH=np.array(o.HtH, dtype=np.float64).reshape(12, 12),
             Htr=np.array(o.Htr, dtype=np.float64),
             total_residual=o.total_residual,
-            eigvals=np.array(o.eigvals, dtype=np.float64),
-            eigvecs=np.array(o.eigvecs, dtype=np.float64).reshape(6, 6),
             effct_feat_num=o.effct_feat_num,
             n_down=o.n_down,
             n_unresolved=o.n_unresolved,

@@ -43,6 +43,10 @@ struct dlt_handle_s {
     // scan
     int n_raw = 0, n_down = 0;
     bool have_raw = false, have_down = false, have_match = false;
+    bool counters_fresh = false;  // h_ints mirrors d_counters (no map mutation since the last read-back)
+    bool nfar_known = false;      // h_last_nfar is the far_count of the last match pass
+    int h_last_nfar = 0;
+    bool eig_valid = false;       // d_result[158..199] belongs to d_result[0..157]
     float4 *d_raw = nullptr, *d_undist = nullptr, *d_down = nullptr;
     ImuPoseDev *d_poses = nullptr;
     ScanScalars *d_sc = nullptr;
@@ -130,6 +134,7 @@ static Pose pose_from(const double *p) {
 }
 
 static int map_reset(dlt_handle h) {
+    h->counters_fresh = false;
     DLT_RT(h, rt::fill(h->map.table, 0xFF, h->table_cap * sizeof(Slot), h->stream));
     DLT_RT(h, rt::fill(h->d_counters, 0, 8 * sizeof(int), h->stream));
     return DLT_OK;
@@ -138,6 +143,7 @@ static int map_reset(dlt_handle h) {
 static int map_check_error(dlt_handle h) {
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
+    h->counters_fresh = true;
     if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
     if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
     return DLT_OK;
@@ -146,6 +152,7 @@ static int map_check_error(dlt_handle h) {
 // claim | (bid, resolve) | append over n device points with per-point flags
 static int insert_points(dlt_handle h, const float4 *d_pts, int n, bool any_ds) {
     if (n <= 0) return DLT_OK;
+    h->counters_fresh = false;
     ProfScope prof(h, 4);
     const int B = 256, G = div_up(n, B);
     DLT_LAUNCH(k_map_claim, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
@@ -178,6 +185,10 @@ static int add_host_points(dlt_handle h, const float *xyzi, int n, int downsampl
 
 // exact neighbours for the queries the ring search could not resolve
 static int run_far(dlt_handle h, int *n_far_out) {
+    if (h->nfar_known && h->h_last_nfar == 0) {
+        if (n_far_out) *n_far_out = 0;
+        return DLT_OK;
+    }
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     int nfar = h->h_ints[5], n_buckets = h->h_ints[0];
@@ -193,6 +204,8 @@ static int run_far(dlt_handle h, int *n_far_out) {
     }
     DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::check_launch());
+    h->nfar_known = true;
+    h->h_last_nfar = 0;
     return DLT_OK;
 }
 
@@ -357,6 +370,7 @@ int dlt_map_add(dlt_handle h, const float *xyzi, int n, int downsample_on) {
 int dlt_map_delete_boxes(dlt_handle h, const float *boxes6, int nb, int *deleted) {
     if (!h || nb < 0 || (nb > 0 && !boxes6)) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
+    h->counters_fresh = false;
     DLT_RT(h, rt::fill(h->d_counters + 3, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
@@ -376,14 +390,18 @@ int dlt_map_delete_boxes(dlt_handle h, const float *boxes6, int nb, int *deleted
     DLT_RT(h, rt::sync(h->stream));
     if (deleted) *deleted = h->h_ints[3];
     h->have_match = false;
+    h->counters_fresh = true;
     return DLT_OK;
 }
 
 int dlt_map_valid_count(dlt_handle h, int *n) {
     if (!h || !n) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
-    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
-    DLT_RT(h, rt::sync(h->stream));
+    if (!h->counters_fresh) {
+        DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+        h->counters_fresh = true;
+    }
     *n = h->h_ints[1];
     return DLT_OK;
 }
@@ -577,7 +595,9 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
         h->have_match = true;
         return DLT_OK;
     }
+    if (result_dev == h->d_result) h->eig_valid = false;
     if (do_match) {
+        h->nfar_known = false;
         DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
         ProfScope prof(h, 0);
         DLT_LAUNCH(k_knn, div_up(n, kKnnWarps), kKnnWarps * 32, h->stream, h->map, (const float4 *)h->d_down, n, 1, P, h->cfg.max_sq_dist, h->knn);
@@ -608,18 +628,20 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
     if (!h || !out) return DLT_E_INVALID;
     int rc = dlt_measure_dev(h, pose24, do_match, h->d_result);
     if (rc) return rc;
-    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kResultDoubles * sizeof(double), h->stream));
-    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kNormalEqDoubles * sizeof(double), h->stream));
+    DLT_RT(h, rt::d2h(h->h_ints + 8, h->d_counters + 5, sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     const double *R = h->h_result;
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
     for (int i = 0; i < 12; i++) out->Htr[i] = R[144 + i];
     out->effct_feat_num = (int)(R[156] + 0.5);
     out->total_residual = R[157];
-    for (int i = 0; i < 6; i++) out->eigvals[i] = R[158 + i];
-    for (int i = 0; i < 36; i++) out->eigvecs[i] = R[164 + i];
     out->n_down = h->n_down;
-    out->n_unresolved = h->h_ints[5];
+    if (do_match) {
+        h->h_last_nfar = h->h_ints[8];
+        h->nfar_known = true;
+    }
+    out->n_unresolved = h->nfar_known ? h->h_last_nfar : 0;
     out->reserved = 0;
     return DLT_OK;
 }
@@ -667,7 +689,13 @@ int dlt_get_nearest(dlt_handle h, float *nbr, int *cnt, unsigned char *selected,
 int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
     if (!h || !eigvals6 || !eigvecs36) return DLT_E_INVALID;
     if (!h->have_match) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");
-    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kResultDoubles * sizeof(double), h->stream));
+    rt::set_device(h->cfg.device);
+    if (!h->eig_valid) {
+        DLT_LAUNCH(k_eigen6, 1, 32, h->stream, h->d_result);
+        DLT_RT(h, rt::check_launch());
+        h->eig_valid = true;
+    }
+    DLT_RT(h, rt::d2h(h->h_result + kNormalEqDoubles, h->d_result + kNormalEqDoubles, 42 * sizeof(double), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     for (int i = 0; i < 6; i++) eigvals6[i] = h->h_result[158 + i];
     for (int i = 0; i < 36; i++) eigvecs36[i] = h->h_result[164 + i];

@@ -66,9 +66,9 @@ DLT_D float axis_gap(float q, int c, float cell_edge, float slack) {
     return g > 0.f ? g : 0.f;
 }
 
-// Merge the staged candidates into the running 5 best (stated order: d2, x, y, z, id).
-// Five rounds of "smallest key greater than the previous pick", each a warp-wide argmin.
-DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane) {
+// Merge the staged candidates into the running 5 best, exact version: stated order
+// (d2, x, y, z, id), five rounds of "smallest key greater than the previous pick".
+DLT_D void knn_select_exact(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane) {
     Cand mine_old = cand_inf();
 #pragma unroll
     for (int t = 0; t < kK; t++)
@@ -96,6 +96,76 @@ DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *can
         best[t] = loc;
         if (loc.d2 < INFINITY) nb++;
         prev = loc;
+    }
+    nbest = nb;
+    d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
+}
+
+DLT_D unsigned long long warp_min_u64(unsigned long long k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
+        k = t < k ? t : k;
+    }
+    return k;
+}
+
+// Same result, fast path: order by the 64-bit key (d2 bits << 32 | staging slot).  d2 >= 0, so
+// its bit pattern orders like the float.  The six smallest keys are extracted; only when two
+// neighbours among them share the same d2 (an exact distance tie, where the stated order looks
+// at x, y, z) does the exact version run instead.
+DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane) {
+    const unsigned long long NONE = 0xFFFFFFFFFFFFFFFFull;
+    unsigned long long mine_old = NONE;
+#pragma unroll
+    for (int t = 0; t < kK; t++)
+        if (lane == t && t < nbest) mine_old = ((unsigned long long)__float_as_uint(best[t].d2) << 32) | (unsigned)(kCandMax + t);
+    unsigned long long sel[kK + 1];
+    unsigned long long lo = 0ull;
+#pragma unroll
+    for (int t = 0; t < kK + 1; t++) {
+        unsigned long long loc = NONE;
+        if (mine_old >= lo) loc = mine_old;
+        for (int c = lane; c < ncand; c += 32) {
+            unsigned long long k = ((unsigned long long)__float_as_uint(cand[c].w) << 32) | (unsigned)c;
+            if (k >= lo && k < loc) loc = k;
+        }
+        loc = warp_min_u64(loc);
+        sel[t] = loc;
+        lo = (loc == NONE) ? NONE : loc + 1ull;
+    }
+    bool tie = false;
+#pragma unroll
+    for (int t = 0; t < kK; t++)
+        if (sel[t + 1] != NONE && (sel[t] >> 32) == (sel[t + 1] >> 32)) tie = true;
+    if (tie) {  // warp-uniform: sel[] is identical in every lane
+        knn_select_exact(best, nbest, d5, cand, cid, ncand, lane);
+        return;
+    }
+    Cand old[kK];
+#pragma unroll
+    for (int t = 0; t < kK; t++) old[t] = best[t];
+    int nb = 0;
+#pragma unroll
+    for (int t = 0; t < kK; t++) {
+        Cand r = cand_inf();
+        if (sel[t] != NONE) {
+            const int slot = (int)(unsigned)(sel[t] & 0xFFFFFFFFull);
+            if (slot >= kCandMax) {
+#pragma unroll
+                for (int u = 0; u < kK; u++)
+                    if (slot - kCandMax == u) r = old[u];
+            } else {
+                float4 e = cand[slot];
+                r.d2 = e.w;
+                r.x = e.x;
+                r.y = e.y;
+                r.z = e.z;
+                r.id = cid[slot];
+            }
+            nb++;
+        }
+        best[t] = r;
     }
     nbest = nb;
     d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
@@ -144,6 +214,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32)
         for (int base = 0; base < total; base += 32) {
             // ---- probe up to 32 cells of this ring
             int idx = base + lane;
+            if (R == 1) idx = (idx == 0) ? 13 : (idx == 13) ? 0 : idx;  // the query's own cell first: d5 tightens early
             int b = -1;
             if (idx < total) {
                 int dz = idx % side - R, dy = (idx / side) % side - R, dx = idx / (side * side) - R;
@@ -356,7 +427,9 @@ struct NormalEq {
     static constexpr int NR = TRI + D + 2;  // upper triangle of H^T H, H^T r, effective count, sum |r|
 };
 constexpr int kResidBlock = 128;
-constexpr int kResultDoubles = 144 + 12 + 2 + 6 + 36;  // HtH, Htr, count, res_sum, eigvals, eigvecs
+constexpr int kResultDoubles = 144 + 12 + 2 + 6 + 36;  // HtH, Htr, count, res_sum | eigvals, eigvecs (k_eigen6)
+constexpr int kNormalEqDoubles = 158;
+static_assert(kResidBlock == 128, "the final reduce combines exactly 4 warp slices");
 
 struct MeasureBufs {
     const float4 *down;       // [n] body-frame downsampled scan (x y z intensity)
@@ -370,66 +443,6 @@ struct MeasureBufs {
     unsigned *ticket;
     double *result;           // kResultDoubles
 };
-
-DLT_D void jacobi6(const double *Ain, double *evals, double *V) {
-    // cyclic Jacobi, ascending eigenvalues, eigenvectors in the columns of V (row-major)
-    double A[36];
-    for (int i = 0; i < 36; i++) {
-        A[i] = Ain[i];
-        V[i] = (i % 7 == 0) ? 1.0 : 0.0;
-    }
-    for (int sweep = 0; sweep < 60; sweep++) {
-        double off = 0.0, diag = 0.0;
-        for (int i = 0; i < 6; i++)
-            for (int j = 0; j < 6; j++) {
-                double v = A[i * 6 + j] * A[i * 6 + j];
-                if (i == j)
-                    diag += v;
-                else
-                    off += v;
-            }
-        if (off <= 1e-30 * diag || off == 0.0) break;
-        for (int p = 0; p < 5; p++)
-            for (int q = p + 1; q < 6; q++) {
-                double apq = A[p * 6 + q];
-                if (apq == 0.0) continue;
-                double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
-                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 6; k++) {
-                    double akp = A[k * 6 + p], akq = A[k * 6 + q];
-                    A[k * 6 + p] = c * akp - s * akq;
-                    A[k * 6 + q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < 6; k++) {
-                    double apk = A[p * 6 + k], aqk = A[q * 6 + k];
-                    A[p * 6 + k] = c * apk - s * aqk;
-                    A[q * 6 + k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < 6; k++) {
-                    double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
-                    V[k * 6 + p] = c * vkp - s * vkq;
-                    V[k * 6 + q] = s * vkp + c * vkq;
-                }
-            }
-    }
-    for (int i = 0; i < 6; i++) evals[i] = A[i * 6 + i];
-    for (int i = 0; i < 5; i++) {
-        int mn = i;
-        for (int j = i + 1; j < 6; j++)
-            if (evals[j] < evals[mn]) mn = j;
-        if (mn != i) {
-            double t = evals[i];
-            evals[i] = evals[mn];
-            evals[mn] = t;
-            for (int k = 0; k < 6; k++) {
-                double u = V[k * 6 + i];
-                V[k * 6 + i] = V[k * 6 + mn];
-                V[k * 6 + mn] = u;
-            }
-        }
-    }
-}
 
 template <bool EXT>
 __global__ void __launch_bounds__(kResidBlock)
@@ -567,34 +580,131 @@ __global__ void __launch_bounds__(kResidBlock)
     }
     __syncthreads();
     if (!s_last) return;
-    // ---- last block: fixed-order sum over blocks (deterministic), unpack, eigen-decompose
+    // ---- last block: fixed-order sum over blocks (deterministic): 4 interleaved slices per value,
+    //      each summed in block order, then combined ((s0+s1)+s2)+s3
     __threadfence();
-    __shared__ double s_sum[NR];
-    if (threadIdx.x < NR) {
-        const volatile double *vp = mb.partials;
-        double v = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) v += vp[(size_t)b * NR + threadIdx.x];
-        s_sum[threadIdx.x] = v;
+    __shared__ double s_sum[4][32];
+    __shared__ double s_fin[NR];
+    for (int base = 0; base < NR; base += 32) {  // block-uniform
+        const int v = base + (threadIdx.x & 31), sl = threadIdx.x >> 5;
+        double acc = 0.0;
+        if (v < NR) {
+            const double *vp = mb.partials;
+            for (unsigned b = sl; b < gridDim.x; b += kResidBlock / 32) acc += __ldcg(vp + (size_t)b * NR + v);
+        }
+        s_sum[sl][threadIdx.x & 31] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32 && v < NR)
+            s_fin[v] = ((s_sum[0][threadIdx.x] + s_sum[1][threadIdx.x]) + s_sum[2][threadIdx.x]) + s_sum[3][threadIdx.x];
+        __syncthreads();
     }
+    // unpack the upper triangle into the 12x12 block of the result
+    double *R = mb.result;
+    for (int k = threadIdx.x; k < 144 + 12; k += kResidBlock) R[k] = 0.0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double *R = mb.result;
-        for (int k = 0; k < 144 + 12; k++) R[k] = 0.0;
         int k = 0;
         for (int a = 0; a < D; a++)
             for (int b = a; b < D; b++) {
-                double v = s_sum[k++];
+                double v = s_fin[k++];
                 R[a * 12 + b] = v;
                 R[b * 12 + a] = v;
             }
-        for (int a = 0; a < D; a++) R[144 + a] = s_sum[k++];
-        R[156] = s_sum[k];
-        R[157] = s_sum[k + 1];
-        double A6[36];
-        for (int a = 0; a < 6; a++)
-            for (int b = 0; b < 6; b++) A6[a * 6 + b] = R[a * 12 + b];
-        jacobi6(A6, R + 158, R + 164);
+        for (int a = 0; a < D; a++) R[144 + a] = s_fin[k++];
+        R[156] = s_fin[k];
+        R[157] = s_fin[k + 1];
         *mb.ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------ degeneracy: eigen-decomposition of H^T H [0:6, 0:6]
+// New output (the reference has no eigen check).  Parallel cyclic Jacobi on one warp:
+// the 15 index pairs of a sweep are visited in 5 rounds of 3 disjoint pairs (round-robin
+// tournament); lanes 0-2 compute the three rotations of a round, then 18 lanes apply them to
+// the columns / rows of A and the columns of V.  Ascending eigenvalues, eigenvectors in columns.
+__global__ void __launch_bounds__(32) k_eigen6(double *__restrict__ result) {
+    __shared__ double A[36], V[36], cs[3][2];
+    __shared__ int pq[3][2];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 36; i += 32) {
+        A[i] = result[(i / 6) * 12 + (i % 6)];
+        V[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 36; i++) {
+            double v = A[i] * A[i];
+            if (i % 7 == 0)
+                diag += v;
+            else
+                off += v;
+        }
+        if (off <= 1e-26 * diag || off == 0.0) break;  // warp-uniform (same data in every lane)
+        for (int round = 0; round < 5; round++) {
+            // round-robin tournament on players {0..5}: player 5 fixed, others rotate
+            if (lane < 3) {
+                int a = (lane == 0) ? 5 : (round + lane) % 5;
+                int b = (lane == 0) ? round % 5 : (round + 5 - lane) % 5;
+                int p = a < b ? a : b, q = a < b ? b : a;
+                pq[lane][0] = p;
+                pq[lane][1] = q;
+                double apq = A[p * 6 + q];
+                double c = 1.0, sn = 0.0;
+                if (apq != 0.0) {
+                    double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+                    double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    c = 1.0 / sqrt(t * t + 1.0);
+                    sn = t * c;
+                }
+                cs[lane][0] = c;
+                cs[lane][1] = sn;
+            }
+            __syncwarp();
+            // columns: A <- A J (and V <- V J); lane = pair * 6 + k
+            if (lane < 18) {
+                const int pr = lane / 6, k = lane % 6;
+                const int p = pq[pr][0], q = pq[pr][1];
+                const double c = cs[pr][0], sn = cs[pr][1];
+                double akp = A[k * 6 + p], akq = A[k * 6 + q];
+                A[k * 6 + p] = c * akp - sn * akq;
+                A[k * 6 + q] = sn * akp + c * akq;
+                double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
+                V[k * 6 + p] = c * vkp - sn * vkq;
+                V[k * 6 + q] = sn * vkp + c * vkq;
+            }
+            __syncwarp();
+            // rows: A <- J^T A
+            if (lane < 18) {
+                const int pr = lane / 6, k = lane % 6;
+                const int p = pq[pr][0], q = pq[pr][1];
+                const double c = cs[pr][0], sn = cs[pr][1];
+                double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+                A[p * 6 + k] = c * apk - sn * aqk;
+                A[q * 6 + k] = sn * apk + c * aqk;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        double ev[6];
+        int ord[6];
+        for (int i = 0; i < 6; i++) {
+            ev[i] = A[i * 6 + i];
+            ord[i] = i;
+        }
+        for (int i = 0; i < 5; i++) {
+            int mn = i;
+            for (int j = i + 1; j < 6; j++)
+                if (ev[ord[j]] < ev[ord[mn]]) mn = j;
+            int t = ord[i];
+            ord[i] = ord[mn];
+            ord[mn] = t;
+        }
+        for (int i = 0; i < 6; i++) {
+            result[158 + i] = ev[ord[i]];
+            for (int k = 0; k < 6; k++) result[164 + k * 6 + i] = V[k * 6 + ord[i]];
+        }
     }
 }
 

@@ -172,6 +172,39 @@ bool invert(const double *A, int n, double *out) {
     return true;
 }
 
+// X (n x m, row-major) = first m columns of A^-1, by LU with partial pivoting on [A | I[:, :m]]
+bool solve_first_columns(const double *A, int n, int m, double *X) {
+    const int W = n + m;
+    std::vector<double> w((size_t)n * W);
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) w[(size_t)i * W + j] = A[(size_t)i * n + j];
+        for (int j = 0; j < m; j++) w[(size_t)i * W + n + j] = (i == j) ? 1.0 : 0.0;
+    }
+    for (int c = 0; c < n; c++) {
+        int p = c;
+        for (int r = c + 1; r < n; r++)
+            if (std::fabs(w[(size_t)r * W + c]) > std::fabs(w[(size_t)p * W + c])) p = r;
+        if (w[(size_t)p * W + c] == 0.0) return false;
+        if (p != c)
+            for (int j = c; j < W; j++) std::swap(w[(size_t)p * W + j], w[(size_t)c * W + j]);
+        const double piv = w[(size_t)c * W + c];
+        for (int r = c + 1; r < n; r++) {
+            const double f = w[(size_t)r * W + c] / piv;
+            if (f == 0.0) continue;
+            for (int j = c + 1; j < W; j++) w[(size_t)r * W + j] -= f * w[(size_t)c * W + j];
+        }
+    }
+    for (int c = n - 1; c >= 0; c--) {
+        const double piv = w[(size_t)c * W + c];
+        for (int j = 0; j < m; j++) {
+            double s = w[(size_t)c * W + n + j];
+            for (int k = c + 1; k < n; k++) s -= w[(size_t)c * W + k] * X[(size_t)k * m + j];
+            X[(size_t)c * m + j] = s / piv;
+        }
+    }
+    return true;
+}
+
 static void set_block3(double *M, int r0, int c0, const Mat3 &B) {
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) M[(r0 + i) * kDim + c0 + j] = B.a[3 * i + j];
@@ -530,6 +563,17 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         double HtH12[144];
         bool have_gain = false;
         dlt_measure_out m;
+        // (state.cov / LASER_POINT_COV).inverse() is the same in every iteration of one scan: the
+        // covariance only changes at :1085, after the loop
+        double Pinv[kDim * kDim];
+        {
+            double Pn[kDim * kDim];
+            for (int i = 0; i < kDim * kDim; i++) Pn[i] = state.cov[i] / LASER_POINT_COV;
+            if (!invert(Pn, kDim, Pinv)) {
+                err = "covariance is singular";
+                return DLT_E_STATE;
+            }
+        }
         for (int iterCount = 0; iterCount < NUM_MAX_ITERATIONS; iterCount++) {  // :820
             dlt_lio_iter rec;
             std::memset(&rec, 0, sizeof(rec));
@@ -559,20 +603,15 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
             // (the `!flg_EKF_inited && !EKF_stop_flg` branch at :986-1011 cannot be reached: INIT_TIME is 0
             //  and flg_EKF_inited is only cleared at :1062, right before the loop breaks at :1095-1100)
             if (!EKF_stop_flg) {  // :1012-1053
-                double A[kDim * kDim], Pn[kDim * kDim], K1[kDim * kDim];
-                for (int i = 0; i < kDim * kDim; i++) Pn[i] = state.cov[i] / LASER_POINT_COV;
-                if (!invert(Pn, kDim, A)) {
-                    err = "covariance is singular";
-                    return DLT_E_STATE;
-                }
+                double A[kDim * kDim];
+                std::memcpy(A, Pinv, sizeof(A));
                 for (int a = 0; a < 12; a++)
                     for (int b = 0; b < 12; b++) A[a * kDim + b] += m.HtH[a * 12 + b];
-                if (!invert(A, kDim, K1)) {
+                // only the first 12 columns of K_1 = A^-1 are ever used (:1019)
+                if (!solve_first_columns(A, kDim, 12, K1c)) {
                     err = "H^T H + (P/R)^-1 is singular";
                     return DLT_E_STATE;
                 }
-                for (int i = 0; i < kDim; i++)
-                    for (int j = 0; j < 12; j++) K1c[i * 12 + j] = K1[i * kDim + j];
                 std::memcpy(HtH12, m.HtH, sizeof(HtH12));
                 have_gain = true;
                 double vec[kDim];
@@ -638,10 +677,9 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
             }
         }
         out->t_iterate = wall() - t0;
-        if (!iters.empty()) {
-            std::memcpy(out->eigvals, m.eigvals, sizeof(out->eigvals));
-            std::memcpy(out->eigvecs, m.eigvecs, sizeof(out->eigvecs));
-            out->degenerate = (m.eigvals[0] < cfg.degeneracy_eig_threshold) ? 1 : 0;
+        if (!iters.empty()) {  // degradation output: eigen-decomposition of the last H^T H pose block, on the device
+            LM_CK(dlt_degeneracy(dev_, out->eigvals, out->eigvecs));
+            out->degenerate = (out->eigvals[0] < cfg.degeneracy_eig_threshold) ? 1 : 0;
         }
 
         // ---- zeta blend, :1105-1129

@@ -153,6 +153,7 @@ class ImuProcess {
 
 // dense n x n inverse, LU with partial pivoting (Eigen's .inverse() for n > 4)
 bool invert(const double *A, int n, double *out);
+bool solve_first_columns(const double *A, int n, int m, double *X);
 
 class LaserMapping {
    public:

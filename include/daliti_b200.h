@@ -58,8 +58,6 @@ typedef struct dlt_measure_out {
     double HtH[144];        /* 12x12 row-major  H^T H   (laserMapping.cpp:1015)                    */
     double Htr[12];         /* H^T meas_vec     (meas_vec = -pd2, laserMapping.cpp:977)            */
     double total_residual;  /* sum of res_last over effective points (laserMapping.cpp:893)        */
-    double eigvals[6];      /* ascending eigenvalues of HtH[0:6,0:6] (new output)    */
-    double eigvecs[36];     /* eigenvectors in columns, row-major 6x6                              */
     int effct_feat_num;     /* laserMapping.cpp:885-896                                            */
     int n_down;             /* feats_down_size                                                     */
     int n_unresolved;       /* queries whose exact neighbours are deferred to map_incremental      */
@@ -116,9 +114,9 @@ int dlt_scan_get_voxel_of_point(dlt_handle h, int *slot, int cap);
  * reduction to H^T H / H^T r.  Nearest_Points, point_selected_surf and the cached planes
  * persist in the handle between calls of one scan.                                              */
 int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_out *out);
-/* Same, but leaves the 200-double result block (HtH[144] Htr[12] count res_sum eigvals[6]
- * eigvecs[36]) in DEVICE memory at result_dev without synchronising -- the partial sums of
- * one map shard, ready for an NCCL all-reduce of the first 158 doubles.                         */
+/* Same, but leaves the result block (HtH[144] Htr[12] count res_sum = 158 doubles, room for 200)
+ * in DEVICE memory at result_dev without synchronising -- the partial sums of one map shard,
+ * ready for an NCCL all-reduce of the 158 doubles.                                              */
 int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev);
 /* laserCloudOri / coeffSel of the last dlt_measure (published as /cloud_effected,
  * laserMapping.cpp:891-892, 1213-1227): body-frame xyzi and (normal, pd2) per effective point   */
@@ -126,7 +124,9 @@ int dlt_effective_points(dlt_handle h, float *xyzi, float *coeff, int cap, int *
 /* Nearest_Points of the last match pass: nbr n_down*5*4 floats (x y z d2), cnt n_down,
  * selected n_down (point_selected_surf after the last dlt_measure)                              */
 int dlt_get_nearest(dlt_handle h, float *nbr, int *cnt, unsigned char *selected, int cap);
-/* degradation output of the last dlt_measure: eigen-decomposition of HtH[0:6,0:6]              */
+/* Degradation output (new; the reference has no eigen check): eigen-decomposition
+ * of HtH[0:6,0:6] of the last dlt_measure, computed on the device (parallel Jacobi, one warp)
+ * when asked for.  Ascending eigenvalues; eigenvectors in the columns of the row-major 6x6.      */
 int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36);
 
 /* ---- map_incremental()                                       laserMapping.cpp:582-630, 1167 - */

@@ -136,6 +136,10 @@ template <typename T>
 static inline T __ldg(const T *p) {
     return *p;
 }
+template <typename T>
+static inline T __ldcg(const T *p) {
+    return *p;
+}
 
 // atomics: the emulator is single-threaded, so these are plain read-modify-writes
 template <typename T>

@@ -48,8 +48,15 @@ def run_sequence(lib, oracle, seq, map_pts, n_scans, ext=False, max_pts=4096, ch
                 assert rel_err(m.HtH, np.array(it.HtH).reshape(12, 12)) < 1e-10
                 assert rel_err(m.Htr, np.array(it.Htr)) < 1e-9
                 assert abs(m.total_residual - it.total_residual) <= 1e-10 * max(1.0, it.total_residual)
-            ev = np.linalg.eigvalsh(m.HtH[:6, :6])
-            np.testing.assert_allclose(m.eigvals, ev, rtol=1e-8, atol=1e-8 * max(1.0, abs(ev).max()))
+            # degradation output: device eigen-decomposition of the 6x6 pose block (property-checked: the
+            # reference has no counterpart) -- eigenvalues vs LAPACK, orthonormal vectors, reconstruction
+            evals, evecs = dm.degeneracy()
+            A6 = m.HtH[:6, :6]
+            ev = np.linalg.eigvalsh(A6)
+            scale = max(1.0, abs(ev).max())
+            np.testing.assert_allclose(evals, ev, rtol=1e-9, atol=1e-9 * scale)
+            np.testing.assert_allclose(evecs.T @ evecs, np.eye(6), atol=1e-10)
+            np.testing.assert_allclose(evecs @ np.diag(evals) @ evecs.T, A6, atol=1e-9 * scale)
         # neighbours of the last match pass + point_selected_surf after the last iteration
         near_o, d2_o, cnt_o, sel_o = lio.nearest()
         nbr_d, cnt_d, sel_d = dm.get_nearest(s.n_down)
