@@ -128,7 +128,32 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def run_cpu(work, n_steps, n_warm, threads_list, want_stage=False):
+class _QuietStdout:
+    """the reference ikd-Tree printf()s from its constructor / rebuild thread: keep fd 1 clean for the JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
+def run_cpu(work, n_steps, n_warm, threads_list):
+    with _QuietStdout():
+        return _run_cpu(work, n_steps, n_warm, threads_list)
+
+
+def _run_cpu(work, n_steps, n_warm, threads_list):
     """the reference's CPU path: unmodified ikd-Tree (oracle/_ref) under the restated loop (oracle/oracle.cpp)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob

@@ -686,16 +686,23 @@ int dlt_get_nearest(dlt_handle h, float *nbr, int *cnt, unsigned char *selected,
     return DLT_OK;
 }
 
-int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
-    if (!h || !eigvals6 || !eigvecs36) return DLT_E_INVALID;
-    if (!h->have_match) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");
+int dlt_degeneracy_begin(dlt_handle h) {
+    if (!h) return DLT_E_INVALID;
+    if (!h->have_match && !h->eig_valid) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");
     rt::set_device(h->cfg.device);
     if (!h->eig_valid) {
         DLT_LAUNCH(k_eigen6, 1, 32, h->stream, h->d_result);
         DLT_RT(h, rt::check_launch());
+        DLT_RT(h, rt::d2h(h->h_result + kNormalEqDoubles, h->d_result + kNormalEqDoubles, 42 * sizeof(double), h->stream));
         h->eig_valid = true;
     }
-    DLT_RT(h, rt::d2h(h->h_result + kNormalEqDoubles, h->d_result + kNormalEqDoubles, 42 * sizeof(double), h->stream));
+    return DLT_OK;
+}
+
+int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
+    if (!h || !eigvals6 || !eigvecs36) return DLT_E_INVALID;
+    int rc = dlt_degeneracy_begin(h);
+    if (rc) return rc;
     DLT_RT(h, rt::sync(h->stream));
     for (int i = 0; i < 6; i++) eigvals6[i] = h->h_result[158 + i];
     for (int i = 0; i < 36; i++) eigvecs36[i] = h->h_result[164 + i];

@@ -68,11 +68,12 @@ DLT_D float axis_gap(float q, int c, float cell_edge, float slack) {
 
 // Merge the staged candidates into the running 5 best, exact version: stated order
 // (d2, x, y, z, id), five rounds of "smallest key greater than the previous pick".
-DLT_D void knn_select_exact(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane) {
+// Rare path (exact d2 ties among the six smallest): kept out of line, state passed through shared memory.
+__device__ __noinline__ void knn_select_exact(Cand *best, int *nbest_io, const float4 *cand, const int *cid, int ncand, int lane) {
+    const int nbest = *nbest_io;
     Cand mine_old = cand_inf();
-#pragma unroll
-    for (int t = 0; t < kK; t++)
-        if (lane == t && t < nbest) mine_old = best[t];
+    if (lane < nbest) mine_old = best[lane];
+    __syncwarp();
     Cand prev;
     prev.d2 = -1.f;
     prev.x = prev.y = prev.z = 0.f;
@@ -93,12 +94,12 @@ DLT_D void knn_select_exact(Cand (&best)[kK], int &nbest, float &d5, const float
             if (cand_less(prev, k) && cand_less(k, loc)) loc = k;
         }
         loc = warp_min_cand(loc);
-        best[t] = loc;
+        if (lane == 0) best[t] = loc;
         if (loc.d2 < INFINITY) nb++;
         prev = loc;
     }
-    nbest = nb;
-    d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
+    if (lane == 0) *nbest_io = nb;
+    __syncwarp();
 }
 
 DLT_D unsigned long long warp_min_u64(unsigned long long k) {
@@ -114,7 +115,8 @@ DLT_D unsigned long long warp_min_u64(unsigned long long k) {
 // its bit pattern orders like the float.  The six smallest keys are extracted; only when two
 // neighbours among them share the same d2 (an exact distance tie, where the stated order looks
 // at x, y, z) does the exact version run instead.
-DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane) {
+DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane, Cand *tie_best,
+                      int *tie_n) {
     const unsigned long long NONE = 0xFFFFFFFFFFFFFFFFull;
     unsigned long long mine_old = NONE;
 #pragma unroll
@@ -138,13 +140,21 @@ DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *can
 #pragma unroll
     for (int t = 0; t < kK; t++)
         if (sel[t + 1] != NONE && (sel[t] >> 32) == (sel[t + 1] >> 32)) tie = true;
+    // stage the previous best in shared memory: the winners are gathered from there by slot
+#pragma unroll
+    for (int t = 0; t < kK; t++)
+        if (lane == t) tie_best[t] = best[t];
+    if (lane == 0) *tie_n = nbest;
+    __syncwarp();
     if (tie) {  // warp-uniform: sel[] is identical in every lane
-        knn_select_exact(best, nbest, d5, cand, cid, ncand, lane);
+        knn_select_exact(tie_best, tie_n, cand, cid, ncand, lane);
+        nbest = *tie_n;
+#pragma unroll
+        for (int t = 0; t < kK; t++) best[t] = tie_best[t];
+        d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
+        __syncwarp();
         return;
     }
-    Cand old[kK];
-#pragma unroll
-    for (int t = 0; t < kK; t++) old[t] = best[t];
     int nb = 0;
 #pragma unroll
     for (int t = 0; t < kK; t++) {
@@ -152,9 +162,7 @@ DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *can
         if (sel[t] != NONE) {
             const int slot = (int)(unsigned)(sel[t] & 0xFFFFFFFFull);
             if (slot >= kCandMax) {
-#pragma unroll
-                for (int u = 0; u < kK; u++)
-                    if (slot - kCandMax == u) r = old[u];
+                r = tie_best[slot - kCandMax];
             } else {
                 float4 e = cand[slot];
                 r.d2 = e.w;
@@ -169,13 +177,16 @@ DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *can
     }
     nbest = nb;
     d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(kKnnWarps * 32)
+__global__ void __launch_bounds__(kKnnWarps * 32, 6)
     k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out) {
     __shared__ float4 s_cand[kKnnWarps][kCandMax];
     __shared__ int s_cid[kKnnWarps][kCandMax];
     __shared__ int s_wl[kKnnWarps][kWlMax];
+    __shared__ Cand s_tie[kKnnWarps][kK];
+    __shared__ int s_tie_n[kKnnWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x * kKnnWarps + warp;
     if (qi >= n) return;  // warp-uniform; the kernel has no block-level barrier
@@ -268,14 +279,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32)
                 }
                 __syncwarp();
                 if (ncand > kCandMax - 32) {  // staging area nearly full: fold it into the running best
-                    knn_select(best, nbest, d5, cand, cid, ncand, lane);
+                    knn_select(best, nbest, d5, cand, cid, ncand, lane, s_tie[warp], &s_tie_n[warp]);
                     ncand = 0;
                     __syncwarp();
                 }
             }
         }
         if (ncand > 0) {
-            knn_select(best, nbest, d5, cand, cid, ncand, lane);
+            knn_select(best, nbest, d5, cand, cid, ncand, lane, s_tie[warp], &s_tie_n[warp]);
             ncand = 0;
             __syncwarp();
         }

@@ -677,10 +677,10 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
             }
         }
         out->t_iterate = wall() - t0;
-        if (!iters.empty()) {  // degradation output: eigen-decomposition of the last H^T H pose block, on the device
-            LM_CK(dlt_degeneracy(dev_, out->eigvals, out->eigvecs));
-            out->degenerate = (out->eigvals[0] < cfg.degeneracy_eig_threshold) ? 1 : 0;
-        }
+        // degradation output: eigen-decomposition of the last H^T H pose block, queued on the device now and
+        // collected after map_incremental (it overlaps the host's zeta blend and the insert kernels)
+        const bool want_eig = !iters.empty();
+        if (want_eig) LM_CK(dlt_degeneracy_begin(dev_));
 
         // ---- zeta blend, :1105-1129
         if ((lidar_cnt < 100) || (!th->tis_online) || (th->tis_online && lidar_cnt % 2 == 1)) {
@@ -715,6 +715,10 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
             out->added = out->n_added_ds + out->n_added_raw;
         }
         out->t_insert = wall() - t0;
+        if (want_eig) {
+            LM_CK(dlt_degeneracy(dev_, out->eigvals, out->eigvecs));
+            out->degenerate = (out->eigvals[0] < cfg.degeneracy_eig_threshold) ? 1 : 0;
+        }
     }
     out->ekf_stop = EKF_stop_flg ? 1 : 0;
     out->n_iters = (int)iters.size();

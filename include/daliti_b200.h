@@ -128,6 +128,9 @@ int dlt_get_nearest(dlt_handle h, float *nbr, int *cnt, unsigned char *selected,
  * of HtH[0:6,0:6] of the last dlt_measure, computed on the device (parallel Jacobi, one warp)
  * when asked for.  Ascending eigenvalues; eigenvectors in the columns of the row-major 6x6.      */
 int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36);
+/* Enqueue that computation and its device->host copy without waiting; a later dlt_degeneracy
+ * (after other work was queued behind it) then only synchronises.                                 */
+int dlt_degeneracy_begin(dlt_handle h);
 
 /* ---- map_incremental()                                       laserMapping.cpp:582-630, 1167 - */
 int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_add_downsample, int *n_add_raw);
