@@ -1,0 +1,39 @@
+"""Multi-GPU glue for the spatially sharded map (BASELINE config C4).
+
+Each rank owns the search-cell tiles `tile_owner(tile) == rank` (plus a halo so that every in-range
+neighbour of an owned query is local) and evaluates the measurement model only on the query points it
+owns; the 158 doubles of partial normal equations (H^T H 144, H^T r 12, effective count, residual sum)
+are summed with ONE all-reduce per IEKF iteration -- NCCL over NVLink on the GPU box, gloo in the CPU
+tests.  torch.distributed is plumbing only: the partials come out of dlt_measure_dev.
+"""
+from __future__ import annotations
+
+N_EQ = 158
+
+
+def allreduce_measure(handle, pose24, do_match: bool, device: str = "cuda", buf=None):
+    """dlt_measure on this rank's shard + all-reduce(SUM) of the partial normal equations.
+
+    device="cuda": the partials stay in device memory (dlt_measure_dev writes into a torch tensor on the
+    handle's stream, NCCL reduces it in place).  device="cpu": host tensor + gloo (tests)."""
+    import torch
+    import torch.distributed as dist
+
+    if device == "cpu":
+        m = handle.measure(pose24, do_match)
+        t = torch.zeros(N_EQ, dtype=torch.float64)
+        t[:144] = torch.from_numpy(m.HtH.reshape(-1).copy())
+        t[144:156] = torch.from_numpy(m.Htr.copy())
+        t[156] = float(m.effct_feat_num)
+        t[157] = m.total_residual
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        r = t.numpy()
+    else:
+        if buf is None:
+            buf = torch.zeros(200, dtype=torch.float64, device=device)
+        handle.measure_dev(pose24, do_match, buf.data_ptr())
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(buf[:N_EQ], op=dist.ReduceOp.SUM)
+        r = buf[:N_EQ].cpu().numpy()
+    return dict(HtH=r[:144].reshape(12, 12).copy(), Htr=r[144:156].copy(), effct_feat_num=int(round(r[156])), total_residual=float(r[157]))

@@ -143,3 +143,32 @@ def test_pipeline_tunnel_degenerate_axis(dev, oracle):
     assert ev[0] < 0.5 * ev[1]  # plane-normal noise leaves a floor of ~N*sigma^2 on the corridor axis
     assert out.degenerate == 1  # min eigenvalue below degeneracy_eig_threshold: the flag for odom.pose.covariance[0]
     lm.close()
+
+
+def test_pipeline_sliding_local_map_box_delete(dev, oracle):
+    """C3-style map maintenance: a small local-map cube so that lasermap_fov_segment (laserMapping.cpp:313-369)
+    shifts the cube and box-deletes the vacated slab while scans keep inserting"""
+    lib, is_gpu = dev
+    seq = helpers.small_sequence(seed=14, half=40.0, beams=16, azimuths=240 if not is_gpu else 900, n_boxes=10, speed=8.0, yaw_rate=0.0)
+    kind = MAP_REF if oracle.ref_ok else MAP_PORT
+    kw = dict(featptsThreshold=5, cube_len=40.0, det_range=10.0)
+    lio = helpers.start_oracle_lio(oracle, seq, None, kind, **kw)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=32768 if is_gpu else 8192, max_map_points=1 << 18), **kw)
+    lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, 0.0]]))
+    lm.set_state(helpers.state612(seq.traj, seq.t_start))
+    deleted_total = 0
+    for k in range(8):
+        pts, t_beg, imu = seq.scan(k)
+        lio.on_lidar_msg()
+        lm.on_lidar_msg()
+        so = lio.process_scan(pts, t_beg, imu)
+        sd = lm.process_scan(pts, t_beg, imu)
+        assert abs(sd.deleted - so.deleted) <= max(3, so.deleted // 50), (k, sd.deleted, so.deleted)
+        deleted_total += so.deleted
+        np.testing.assert_array_equal(lm.localmap(), lio.localmap())
+        n_d, n_o = lm.device.map_valid_count(), lio.map().validnum()
+        assert abs(n_d - n_o) <= max(4, n_o // 100), (k, n_d, n_o)
+        ok, e = pose_close(lm.get_state(), lio.get_state(), 2e-4)
+        assert ok, (k, e)
+    assert deleted_total > 0
+    lm.close()

@@ -1,0 +1,121 @@
+"""Spatially sharded map (BASELINE config C4): every rank holds the tiles it owns plus a
+halo, evaluates only the query points whose tile it owns, and the partial normal equations are summed.
+  * in-process: 2 and 4 shard handles, sum of partials == unsharded result (E exact, fp64 rel 1e-12)
+  * 2 processes over torch.distributed (gloo on CPU with the emulator library here; the same code path
+    runs over NCCL on the GPU box in bench.py --workload c4)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from daliti_b200 import synth
+from daliti_b200.binding import ScanToMap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def scene_scan():
+    seq = helpers.small_sequence(seed=21, half=30.0, beams=16, azimuths=240, n_boxes=8)
+    map_pts = synth.sample_map(seq.scene, seed=21)
+    pts, t_beg, imu = seq.scan(0)
+    return seq, map_pts, pts
+
+
+def downsample_body(lib, pts):
+    dm = ScanToMap(lib, max_scan_points=8192, max_map_points=4096)
+    dm.scan_deskew(pts)
+    n = dm.scan_downsample()
+    down = dm.scan_get_down(n)
+    dm.close()
+    return down
+
+
+@pytest.mark.parametrize("shards", [2, 4])
+def test_sharded_partials_sum_to_unsharded(dev, shards):
+    lib, is_gpu = dev
+    seq, map_pts, pts = scene_scan()
+    down = downsample_body(lib, pts)
+    pose = seq.traj.pose24(0.1)
+    full = ScanToMap(lib, max_scan_points=8192, max_map_points=1 << 17)
+    full.map_build(map_pts)
+    full.scan_set_down(down)
+    m0 = full.measure(pose, True)
+    m1 = full.measure(pose, False)
+    HtH = np.zeros((12, 12))
+    Htr = np.zeros(12)
+    eff = 0
+    res = 0.0
+    live = 0
+    HtH1 = np.zeros((12, 12))
+    for r in range(shards):
+        sh = ScanToMap(lib, max_scan_points=8192, max_map_points=1 << 17, shard_rank=r, shard_count=shards, shard_tile_shift=3)
+        sh.map_build(map_pts)
+        live += sh.map_valid_count()
+        sh.scan_set_down(down)
+        m = sh.measure(pose, True)
+        HtH += m.HtH
+        Htr += m.Htr
+        eff += m.effct_feat_num
+        res += m.total_residual
+        HtH1 += sh.measure(pose, False).HtH
+        sh.close()
+    assert live >= len(map_pts)  # halos are replicated
+    assert live < shards * len(map_pts)
+    assert eff == m0.effct_feat_num
+    np.testing.assert_allclose(HtH, m0.HtH, rtol=1e-12, atol=1e-12 * abs(m0.HtH).max())
+    np.testing.assert_allclose(Htr, m0.Htr, rtol=1e-10, atol=1e-12 * abs(m0.Htr).max())
+    np.testing.assert_allclose(res, m0.total_residual, rtol=1e-12)
+    np.testing.assert_allclose(HtH1, m1.HtH, rtol=1e-12, atol=1e-12 * abs(m1.HtH).max())
+    full.close()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    from daliti_b200.binding import load_library
+    from daliti_b200.sharded import allreduce_measure
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = load_library(os.path.join(ROOT, "tests", "emu", "libdaliti_emu.so"))
+    seq, map_pts, pts = scene_scan()
+    down = downsample_body(lib, pts)
+    pose = seq.traj.pose24(0.1)
+    sh = ScanToMap(lib, max_scan_points=8192, max_map_points=1 << 17, shard_rank=rank, shard_count=world, shard_tile_shift=3)
+    sh.map_build(map_pts)
+    sh.scan_set_down(down)
+    out = allreduce_measure(sh, pose, True, device="cpu")
+    if rank == 0:
+        q.put((out["HtH"], out["Htr"], out["effct_feat_num"], out["total_residual"]))
+    dist.destroy_process_group()
+
+
+def test_two_process_allreduce_gloo(emu_lib):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    HtH, Htr, eff, res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    seq, map_pts, pts = scene_scan()
+    down = downsample_body(emu_lib, pts)
+    full = ScanToMap(emu_lib, max_scan_points=8192, max_map_points=1 << 17)
+    full.map_build(map_pts)
+    full.scan_set_down(down)
+    m0 = full.measure(seq.traj.pose24(0.1), True)
+    assert eff == m0.effct_feat_num
+    np.testing.assert_allclose(HtH, m0.HtH, rtol=1e-12, atol=1e-12 * abs(m0.HtH).max())
+    np.testing.assert_allclose(Htr, m0.Htr, rtol=1e-10, atol=1e-12 * abs(m0.Htr).max())
+    np.testing.assert_allclose(res, m0.total_residual, rtol=1e-12)
+    full.close()
