@@ -66,24 +66,22 @@ DLT_D float axis_gap(float q, int c, float cell_edge, float slack) {
     return g > 0.f ? g : 0.f;
 }
 
-// Merge the staged candidates into the running 5 best, exact version: stated order
-// (d2, x, y, z, id), five rounds of "smallest key greater than the previous pick".
-// Rare path (exact d2 ties among the six smallest): kept out of line, state passed through shared memory.
-__device__ __noinline__ void knn_select_exact(Cand *best, int *nbest_io, const float4 *cand, const int *cid, int ncand, int lane) {
-    const int nbest = *nbest_io;
-    Cand mine_old = cand_inf();
-    if (lane < nbest) mine_old = best[lane];
-    __syncwarp();
+// ---- selection of the 5 best among the staged candidates ------------------------------------
+// The running best lives in shared memory (s_best, ascending) and is appended to the staging list
+// before every selection, so one list holds everything that can still win.
+//
+// Exact version (stated order d2, x, y, z, id): five rounds of "smallest key greater than the
+// previous pick", each a warp-wide lexicographic argmin.  Only runs when the fast path below sees
+// an exact d2 tie among the winners.  Out of line: it is rare.
+__device__ __noinline__ void knn_select_exact(Cand *best, int *nbest_out, const float4 *cand, const int *cid, int n, int lane) {
     Cand prev;
     prev.d2 = -1.f;
     prev.x = prev.y = prev.z = 0.f;
     prev.id = -1;
     int nb = 0;
-#pragma unroll
     for (int t = 0; t < kK; t++) {
         Cand loc = cand_inf();
-        if (cand_less(prev, mine_old)) loc = mine_old;
-        for (int c = lane; c < ncand; c += 32) {
+        for (int c = lane; c < n; c += 32) {
             float4 e = cand[c];
             Cand k;
             k.d2 = e.w;
@@ -94,99 +92,100 @@ __device__ __noinline__ void knn_select_exact(Cand *best, int *nbest_io, const f
             if (cand_less(prev, k) && cand_less(k, loc)) loc = k;
         }
         loc = warp_min_cand(loc);
+        __syncwarp();
         if (lane == 0) best[t] = loc;
         if (loc.d2 < INFINITY) nb++;
         prev = loc;
     }
-    if (lane == 0) *nbest_io = nb;
+    if (lane == 0) *nbest_out = nb;
     __syncwarp();
 }
 
-DLT_D unsigned long long warp_min_u64(unsigned long long k) {
+DLT_D unsigned warp_min_u32(unsigned k) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
-        k = t < k ? t : k;
-    }
+    for (int o = 16; o > 0; o >>= 1) k = min(k, __shfl_xor_sync(0xffffffffu, k, o));
     return k;
 }
 
-// Same result, fast path: order by the 64-bit key (d2 bits << 32 | staging slot).  d2 >= 0, so
-// its bit pattern orders like the float.  The six smallest keys are extracted; only when two
-// neighbours among them share the same d2 (an exact distance tie, where the stated order looks
-// at x, y, z) does the exact version run instead.
-DLT_D void knn_select(Cand (&best)[kK], int &nbest, float &d5, const float4 *cand, const int *cid, int ncand, int lane, Cand *tie_best,
-                      int *tie_n) {
-    const unsigned long long NONE = 0xFFFFFFFFFFFFFFFFull;
-    unsigned long long mine_old = NONE;
-#pragma unroll
-    for (int t = 0; t < kK; t++)
-        if (lane == t && t < nbest) mine_old = ((unsigned long long)__float_as_uint(best[t].d2) << 32) | (unsigned)(kCandMax + t);
-    unsigned long long sel[kK + 1];
-    unsigned long long lo = 0ull;
-#pragma unroll
-    for (int t = 0; t < kK + 1; t++) {
-        unsigned long long loc = NONE;
-        if (mine_old >= lo) loc = mine_old;
-        for (int c = lane; c < ncand; c += 32) {
-            unsigned long long k = ((unsigned long long)__float_as_uint(cand[c].w) << 32) | (unsigned)c;
-            if (k >= lo && k < loc) loc = k;
-        }
-        loc = warp_min_u64(loc);
-        sel[t] = loc;
-        lo = (loc == NONE) ? NONE : loc + 1ull;
+constexpr int kCandSlots = kCandMax + 8;        // staging list + room for the running best
+constexpr int kKeysPerLane = (kCandSlots + 31) / 32;
+
+// Fast path.  d2 >= 0, so its bit pattern orders like the float: every lane keeps the d2 bits of
+// its (at most kKeysPerLane) list entries in registers and five rounds of warp-min extract the
+// five smallest DISTINCT values v0 < ... < v4.  If exactly five entries are <= v4 each value has
+// one owner and the result is the stated order; otherwise two entries share a d2 (a tie inside
+// the winners or at the k-th boundary) and the exact version decides.
+DLT_D void knn_select(Cand *s_best, int *s_nbest, int &nbest, float &d5, float4 *cand, int *cid, int ncand, int lane) {
+    // append the running best to the list
+    if (lane < nbest) {
+        Cand b = s_best[lane];
+        cand[ncand + lane] = make_float4(b.x, b.y, b.z, b.d2);
+        cid[ncand + lane] = b.id;
     }
-    bool tie = false;
-#pragma unroll
-    for (int t = 0; t < kK; t++)
-        if (sel[t + 1] != NONE && (sel[t] >> 32) == (sel[t + 1] >> 32)) tie = true;
-    // stage the previous best in shared memory: the winners are gathered from there by slot
-#pragma unroll
-    for (int t = 0; t < kK; t++)
-        if (lane == t) tie_best[t] = best[t];
-    if (lane == 0) *tie_n = nbest;
+    const int n = ncand + nbest;
     __syncwarp();
-    if (tie) {  // warp-uniform: sel[] is identical in every lane
-        knn_select_exact(tie_best, tie_n, cand, cid, ncand, lane);
-        nbest = *tie_n;
+    unsigned key[kKeysPerLane];
 #pragma unroll
-        for (int t = 0; t < kK; t++) best[t] = tie_best[t];
-        d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
-        __syncwarp();
-        return;
+    for (int j = 0; j < kKeysPerLane; j++) {
+        const int c = lane + 32 * j;
+        key[j] = (c < n) ? __float_as_uint(cand[c].w) : 0xFFFFFFFFu;
+    }
+    unsigned v[kK];
+    unsigned lo = 0u;
+#pragma unroll
+    for (int t = 0; t < kK; t++) {
+        unsigned loc = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < kKeysPerLane; j++)
+            if (key[j] >= lo) loc = min(loc, key[j]);
+        loc = warp_min_u32(loc);
+        v[t] = loc;
+        lo = (loc == 0xFFFFFFFFu) ? loc : loc + 1u;
     }
     int nb = 0;
 #pragma unroll
+    for (int t = 0; t < kK; t++) nb += (v[t] != 0xFFFFFFFFu) ? 1 : 0;
+    // how many entries are <= the largest selected value?  (all finite entries when fewer than 5 exist)
+    const unsigned vmax = (nb == kK) ? v[kK - 1] : 0xFFFFFFFEu;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kKeysPerLane; j++) cnt += __popc(__ballot_sync(0xffffffffu, key[j] <= vmax));
+    if (cnt != nb) {  // warp-uniform
+        knn_select_exact(s_best, s_nbest, cand, cid, n, lane);
+        nbest = *s_nbest;
+        d5 = (nbest == kK) ? s_best[kK - 1].d2 : INFINITY;
+        __syncwarp();
+        return;
+    }
+#pragma unroll
     for (int t = 0; t < kK; t++) {
-        Cand r = cand_inf();
-        if (sel[t] != NONE) {
-            const int slot = (int)(unsigned)(sel[t] & 0xFFFFFFFFull);
-            if (slot >= kCandMax) {
-                r = tie_best[slot - kCandMax];
-            } else {
-                float4 e = cand[slot];
+#pragma unroll
+        for (int j = 0; j < kKeysPerLane; j++) {
+            if (v[t] != 0xFFFFFFFFu && key[j] == v[t]) {  // the unique owner of v[t]
+                const int c = lane + 32 * j;
+                float4 e = cand[c];
+                Cand r;
                 r.d2 = e.w;
                 r.x = e.x;
                 r.y = e.y;
                 r.z = e.z;
-                r.id = cid[slot];
+                r.id = cid[c];
+                s_best[t] = r;
             }
-            nb++;
         }
-        best[t] = r;
     }
     nbest = nb;
-    d5 = (nbest == kK) ? best[kK - 1].d2 : INFINITY;
+    d5 = (nb == kK) ? __uint_as_float(v[kK - 1]) : INFINITY;
     __syncwarp();
 }
 
 __global__ void __launch_bounds__(kKnnWarps * 32, 6)
     k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out) {
-    __shared__ float4 s_cand[kKnnWarps][kCandMax];
-    __shared__ int s_cid[kKnnWarps][kCandMax];
+    __shared__ float4 s_cand[kKnnWarps][kCandSlots];
+    __shared__ int s_cid[kKnnWarps][kCandSlots];
     __shared__ int s_wl[kKnnWarps][kWlMax];
-    __shared__ Cand s_tie[kKnnWarps][kK];
-    __shared__ int s_tie_n[kKnnWarps];
+    __shared__ Cand s_bestw[kKnnWarps][kK];
+    __shared__ int s_nb[kKnnWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x * kKnnWarps + warp;
     if (qi >= n) return;  // warp-uniform; the kernel has no block-level barrier
@@ -211,9 +210,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 6)
     float4 *cand = s_cand[warp];
     int *cid = s_cid[warp];
     int *wl = s_wl[warp];
-    Cand best[kK];
-#pragma unroll
-    for (int t = 0; t < kK; t++) best[t] = cand_inf();
+    Cand *best = s_bestw[warp];
     int nbest = 0, ncand = 0;
     float d5 = INFINITY;
     bool overflow = false, resolved = false;
@@ -222,13 +219,15 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 6)
 
     for (int R = 1; R <= 3 && !resolved; R++) {
         const int side = 2 * R + 1, total = side * side * side;
+        const int mdiv = (R == 1) ? 21846 : (R == 2) ? 13108 : 9363;  // (i * mdiv) >> 16 == i / side for i < 407
         for (int base = 0; base < total; base += 32) {
             // ---- probe up to 32 cells of this ring
             int idx = base + lane;
             if (R == 1) idx = (idx == 0) ? 13 : (idx == 13) ? 0 : idx;  // the query's own cell first: d5 tightens early
             int b = -1;
             if (idx < total) {
-                int dz = idx % side - R, dy = (idx / side) % side - R, dx = idx / (side * side) - R;
+                const int q1 = (idx * mdiv) >> 16, q2 = (q1 * mdiv) >> 16;
+                const int dz = idx - q1 * side - R, dy = q1 - q2 * side - R, dx = q2 - R;
                 int cheb = max(max(abs(dx), abs(dy)), abs(dz));
                 if (cheb == R || (R == 1 && cheb == 0)) {
                     bool prune = false;
@@ -279,16 +278,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 6)
                 }
                 __syncwarp();
                 if (ncand > kCandMax - 32) {  // staging area nearly full: fold it into the running best
-                    knn_select(best, nbest, d5, cand, cid, ncand, lane, s_tie[warp], &s_tie_n[warp]);
+                    knn_select(best, &s_nb[warp], nbest, d5, cand, cid, ncand, lane);
                     ncand = 0;
-                    __syncwarp();
                 }
             }
         }
         if (ncand > 0) {
-            knn_select(best, nbest, d5, cand, cid, ncand, lane, s_tie[warp], &s_tie_n[warp]);
+            knn_select(best, &s_nb[warp], nbest, d5, cand, cid, ncand, lane);
             ncand = 0;
-            __syncwarp();
         }
         // ---- exactness: every unseen point lies outside the (2R+1)^3 block of cells
         if (nbest == kK && !overflow) {
@@ -310,15 +307,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 6)
     // close, or a pathological chain) get their exact neighbours lazily from k_far_* before
     // map_incremental consumes them.
     unsigned char fl = 0;
-    if (resolved && best[kK - 1].d2 <= max_sq_dist) fl |= kFlagMatched;
+    if (resolved && d5 <= max_sq_dist) fl |= kFlagMatched;
     if (!resolved) fl |= kFlagUnresolved;
-#pragma unroll
-    for (int t = 0; t < kK; t++) {
-        if (lane == t) {
-            bool ok = t < nbest;
-            out.nbr[(size_t)qi * kK + t] = ok ? make_float4(best[t].x, best[t].y, best[t].z, best[t].d2) : make_float4(0.f, 0.f, 0.f, -1.f);
-            out.nbr_id[(size_t)qi * kK + t] = ok ? best[t].id : -1;
-        }
+    __syncwarp();
+    if (lane < kK) {
+        const bool ok = lane < nbest;
+        Cand r = best[ok ? lane : 0];
+        out.nbr[(size_t)qi * kK + lane] = ok ? make_float4(r.x, r.y, r.z, r.d2) : make_float4(0.f, 0.f, 0.f, -1.f);
+        out.nbr_id[(size_t)qi * kK + lane] = ok ? r.id : -1;
     }
     if (lane == 0) {
         out.nbr_cnt[qi] = nbest;

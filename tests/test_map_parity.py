@@ -110,3 +110,31 @@ def test_downsample_insert_ties_and_duplicates(dev, oracle):
     assert dm.map_valid_count() == om.validnum()
     assert as_set(dm.map_export()) == as_set(om.flatten())
     dm.close()
+
+
+def test_knn_exact_distance_ties(dev, oracle):
+    """lattice points and lattice-centre queries: many exact d2 ties, also across the k-th boundary, plus
+    duplicated points.  The reference's order under ties depends on its tree shape (strict '<' at
+    ikd_Tree.cpp:1088,1099), so the device is compared with the stated order (d2, x, y, z) as the oracle's
+    PortMap implements it; the distances themselves must also equal the reference's."""
+    lib, _ = dev
+    g = np.arange(-3, 4, dtype=np.float32) * 0.75
+    X, Y, Z = np.meshgrid(g, g, g[:3], indexing="ij")
+    pts = np.column_stack([X.ravel(), Y.ravel(), Z.ravel(), np.ones(X.size)]).astype(np.float32)
+    pts = np.concatenate([pts, pts[:40]])  # exact duplicates
+    q = np.array([[0.375, 0.375, 0.0], [0.0, 0.0, 0.0], [0.375, 0.0, 0.375], [-0.75, 0.75, 0.1], [1.125, -1.125, 0.75]], np.float32)
+    pm = oracle.new_map(MAP_PORT)
+    pm.build(pts)
+    dm = ScanToMap(lib, max_scan_points=1024, max_map_points=8192)
+    dm.map_build(pts)
+    pd_, dd, cd = dm.map_knn(q)
+    po, do, co = pm.knn(q)
+    np.testing.assert_array_equal(cd, co)
+    np.testing.assert_array_equal(dd, do)
+    np.testing.assert_array_equal(pd_[:, :, :3], po[:, :, :3])
+    if oracle.ref_ok:
+        rm = oracle.new_map(MAP_REF)
+        rm.build(pts)
+        _, dr, _ = rm.knn(q)
+        np.testing.assert_array_equal(dd, dr)  # the multiset of distances is tie-break independent
+    dm.close()
