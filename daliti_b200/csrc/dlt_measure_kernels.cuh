@@ -24,6 +24,12 @@ constexpr unsigned char kFlagMatched = 1;     // 5 neighbours found and d2[4] <=
 constexpr unsigned char kFlagUnresolved = 2;  // ring-3 search could not prove exactness (far / crowded)
 constexpr unsigned char kFlagForeign = 4;     // query owned by another shard
 
+#ifndef DLT_KNN_MINBLOCKS
+#define DLT_KNN_MINBLOCKS 8
+#endif
+#ifndef DLT_KNN_BATCH
+#define DLT_KNN_BATCH 1  // bucket load steps (4 buckets each) in flight per warp
+#endif
 constexpr int kKnnWarps = 4;
 constexpr int kCandMax = 128;
 constexpr int kWlMax = 96;
@@ -158,20 +164,22 @@ DLT_D void knn_select(Cand *s_best, int *s_nbest, int &nbest, float &d5, float4 
         return;
     }
 #pragma unroll
-    for (int t = 0; t < kK; t++) {
+    for (int j = 0; j < kKeysPerLane; j++) {
+        // is this entry one of the winners?  (each selected value has exactly one owner)
+        int t = -1;
 #pragma unroll
-        for (int j = 0; j < kKeysPerLane; j++) {
-            if (v[t] != 0xFFFFFFFFu && key[j] == v[t]) {  // the unique owner of v[t]
-                const int c = lane + 32 * j;
-                float4 e = cand[c];
-                Cand r;
-                r.d2 = e.w;
-                r.x = e.x;
-                r.y = e.y;
-                r.z = e.z;
-                r.id = cid[c];
-                s_best[t] = r;
-            }
+        for (int u = 0; u < kK; u++)
+            if (key[j] == v[u]) t = u;
+        if (t >= 0 && key[j] != 0xFFFFFFFFu) {
+            const int c = lane + 32 * j;
+            float4 e = cand[c];
+            Cand r;
+            r.d2 = e.w;
+            r.x = e.x;
+            r.y = e.y;
+            r.z = e.z;
+            r.id = cid[c];
+            s_best[t] = r;
         }
     }
     nbest = nb;
@@ -179,7 +187,7 @@ DLT_D void knn_select(Cand *s_best, int *s_nbest, int &nbest, float &d5, float4 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kKnnWarps * 32, 6)
+__global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
     k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out) {
     __shared__ float4 s_cand[kKnnWarps][kCandSlots];
     __shared__ int s_cid[kKnnWarps][kCandSlots];
@@ -244,43 +252,55 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 6)
             int nwl = __popc(found);
             if (b >= 0) wl[__popc(found & lt_mask)] = b;
             __syncwarp();
-            // ---- stage the buckets: 4 per step, 8 lanes x 16 B = one 128-byte line each
+            // ---- stage the buckets: 8 lanes x 16 B = one 128-byte line each, 4 lines per load step and up to
+            //      4 load steps (16 buckets) in flight before the first one is consumed
             for (int j0 = 0; j0 < nwl;) {
-                const int step = min(4, nwl - j0);  // chain buckets pushed below are picked up by a later step
-                const int j = j0 + grp;
-                const bool act = grp < step;
-                int bidx = act ? wl[j] : 0;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act) v = reinterpret_cast<const float4 *>(&m.buckets[bidx])[sub];
-                int hdr_next = __shfl_sync(FULL, __float_as_int(v.z), lane & ~7);
-                unsigned hdr_mask = __shfl_sync(FULL, __float_as_uint(v.w), lane & ~7);
-                bool pushn = act && sub == 0 && hdr_next >= 0;
-                unsigned pm = __ballot_sync(FULL, pushn);
-                if (pushn) {
-                    int pos = nwl + __popc(pm & lt_mask);
-                    if (pos < kWlMax) wl[pos] = hdr_next;
+                const int batch = min(4 * DLT_KNN_BATCH, nwl - j0);  // chain buckets pushed below are picked up by a later batch
+                float4 vb[DLT_KNN_BATCH];
+                int bi[DLT_KNN_BATCH];
+#pragma unroll
+                for (int u = 0; u < DLT_KNN_BATCH; u++) {
+                    const int k = 4 * u + grp;
+                    bi[u] = (k < batch) ? wl[j0 + k] : -1;
+                    vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bi[u] >= 0) vb[u] = reinterpret_cast<const float4 *>(&m.buckets[bi[u]])[sub];
                 }
-                bool has = act && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u);
-                float d2 = has ? calc_dist(qx, qy, qz, v.x, v.y, v.z) : INFINITY;
-                bool keep = has && (nbest < kK || d2 <= d5);
-                unsigned km = __ballot_sync(FULL, keep);
-                if (keep) {
-                    int pos = ncand + __popc(km & lt_mask);
-                    cand[pos] = make_float4(v.x, v.y, v.z, d2);
-                    cid[pos] = bidx * 8 + sub;
+#pragma unroll
+                for (int u = 0; u < DLT_KNN_BATCH; u++) {
+                    if (4 * u >= batch) break;  // warp-uniform
+                    const float4 v = vb[u];
+                    const int bidx = bi[u];
+                    const bool act = bidx >= 0;
+                    int hdr_next = __shfl_sync(FULL, __float_as_int(v.z), lane & ~7);
+                    unsigned hdr_mask = __shfl_sync(FULL, __float_as_uint(v.w), lane & ~7);
+                    bool pushn = act && sub == 0 && hdr_next >= 0;
+                    unsigned pm = __ballot_sync(FULL, pushn);
+                    if (pushn) {
+                        int pos = nwl + __popc(pm & lt_mask);
+                        if (pos < kWlMax) wl[pos] = hdr_next;
+                    }
+                    bool has = act && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u);
+                    float d2 = has ? calc_dist(qx, qy, qz, v.x, v.y, v.z) : INFINITY;
+                    bool keep = has && (nbest < kK || d2 <= d5);
+                    unsigned km = __ballot_sync(FULL, keep);
+                    if (keep) {
+                        int pos = ncand + __popc(km & lt_mask);
+                        cand[pos] = make_float4(v.x, v.y, v.z, d2);
+                        cid[pos] = bidx * 8 + sub;
+                    }
+                    ncand += __popc(km);
+                    nwl += __popc(pm);
+                    if (nwl > kWlMax) {
+                        overflow = true;  // pathological chain length; exact result comes from k_far_*
+                        nwl = kWlMax;
+                    }
+                    __syncwarp();
+                    if (ncand > kCandMax - 32) {  // staging area nearly full: fold it into the running best
+                        knn_select(best, &s_nb[warp], nbest, d5, cand, cid, ncand, lane);
+                        ncand = 0;
+                    }
                 }
-                ncand += __popc(km);
-                nwl += __popc(pm);
-                j0 += step;
-                if (nwl > kWlMax) {
-                    overflow = true;  // pathological chain length; exact result comes from k_far_*
-                    nwl = kWlMax;
-                }
-                __syncwarp();
-                if (ncand > kCandMax - 32) {  // staging area nearly full: fold it into the running best
-                    knn_select(best, &s_nb[warp], nbest, d5, cand, cid, ncand, lane);
-                    ncand = 0;
-                }
+                j0 += batch;
             }
         }
         if (ncand > 0) {
