@@ -300,7 +300,8 @@ def main():
                 if k >= W:
                     ev[k - W][1].record(stream)
                     host_ms.append(1e3 * (time.perf_counter() - th0))
-                    outs.append((o.n_raw, o.n_down, o.n_iters, o.ekf_stop, o.added, o.map_points_before, lmx.iters()[-1].effct_feat_num if o.n_iters else 0))
+                    outs.append((o.n_raw, o.n_down, o.n_iters, o.ekf_stop, o.added, o.map_points_before, lmx.iters()[-1].effct_feat_num if o.n_iters else 0,
+                                 o.t_deskew, o.t_voxel, o.t_iterate, o.t_insert, o.t_delete, o.t_total))
             barrier()
             launches = lmx.device.launch_count() - launches0
         ms = np.array([a.elapsed_time(b) for a, b in ev])
@@ -404,7 +405,9 @@ def main():
                        "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                        "parallelism": "1 sequence per GPU, no data-path collective" if world > 1 else "single GPU",
                        "value_l2_warm_points_per_s": pts_v / (t_w * 1e-3), "ms_p50_l2_warm": float(np.median(ms_w)),
-                       "host_ms_p50": float(np.median(host_v))},
+                       "host_ms_p50": float(np.median(host_v)),
+                       "host_stage_ms_mean": dict(zip(["deskew_enqueue", "voxelgrid", "iterations", "insert_and_eigen", "delete", "total"],
+                                                      (1e3 * np.mean([o[7:13] for o in outs_v], axis=0)).round(4).tolist()))},
             "e2e": {"value": pts_e / (t_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": t_e / K, "ms_p50": float(np.median(ms_e)), "api": "dlt_lio_process_scan (pinned host buffers)"},
             "gpu_launches": int(launches),
