@@ -646,6 +646,27 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
     return DLT_OK;
 }
 
+int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *out) {
+    if (!h || !result_dev || !out) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    DLT_RT(h, rt::d2h(h->h_result, result_dev, kNormalEqDoubles * sizeof(double), h->stream));
+    DLT_RT(h, rt::d2h(h->h_ints + 8, h->d_counters + 5, sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    const double *R = h->h_result;
+    for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
+    for (int i = 0; i < 12; i++) out->Htr[i] = R[144 + i];
+    out->effct_feat_num = (int)(R[156] + 0.5);
+    out->total_residual = R[157];
+    out->n_down = h->n_down;
+    out->n_unresolved = h->h_ints[8];
+    out->reserved = 0;
+    if (result_dev != h->d_result) {  // keep a copy so that dlt_degeneracy works on the reduced normal equations
+        DLT_RT(h, rt::d2d(h->d_result, result_dev, kNormalEqDoubles * sizeof(double), h->stream));
+        h->eig_valid = false;
+    }
+    return DLT_OK;
+}
+
 int dlt_effective_points(dlt_handle h, float *xyzi, float *coeff, int cap, int *n) {
     if (!h || !n) return DLT_E_INVALID;
     if (!h->have_match) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");

@@ -321,19 +321,28 @@ void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_tim
             Q[(15 + a) * kDim + 15 + a] = 0.0001 * dt * dt;
             Q[(18 + a) * kDim + 18 + a] = 0.0001 * dt * dt;
         }
-        // cov = F cov F^T + Q
-        for (int i = 0; i < kDim; i++)
-            for (int j = 0; j < kDim; j++) {
-                double s = 0;
-                for (int l = 0; l < kDim; l++) s += F[i * kDim + l] * st.cov[l * kDim + j];
-                FP[i * kDim + j] = s;
+        // cov = F cov F^T + Q.  F is the identity plus six 3x3 blocks (:270-276): the products only visit its
+        // non-zeros, in ascending column order so the sums are the dense ones term for term.
+        {
+            int nz_idx[kDim][kDim], nz_n[kDim];
+            for (int i = 0; i < kDim; i++) {
+                nz_n[i] = 0;
+                for (int l = 0; l < kDim; l++)
+                    if (F[i * kDim + l] != 0.0) nz_idx[i][nz_n[i]++] = l;  // at most 10 entries (row block 12)
             }
-        for (int i = 0; i < kDim; i++)
-            for (int j = 0; j < kDim; j++) {
-                double s = 0;
-                for (int l = 0; l < kDim; l++) s += FP[i * kDim + l] * F[j * kDim + l];
-                st.cov[i * kDim + j] = s + Q[i * kDim + j];
-            }
+            for (int i = 0; i < kDim; i++)
+                for (int j = 0; j < kDim; j++) {
+                    double s = 0;
+                    for (int k = 0; k < nz_n[i]; k++) s += F[i * kDim + nz_idx[i][k]] * st.cov[nz_idx[i][k] * kDim + j];
+                    FP[i * kDim + j] = s;
+                }
+            for (int i = 0; i < kDim; i++)
+                for (int j = 0; j < kDim; j++) {
+                    double s = 0;
+                    for (int k = 0; k < nz_n[j]; k++) s += FP[i * kDim + nz_idx[j][k]] * F[j * kDim + nz_idx[j][k]];
+                    st.cov[i * kDim + j] = s + Q[i * kDim + j];
+                }
+        }
 
         R_imu = R_imu * Exp_f;                                      // :291
         acc_imu = R_imu * acc_avr + st.gravity;                     // :294
@@ -580,7 +589,16 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
             rec.iter = iterCount;
             rec.did_match = (iterCount == 0 || rematch_en) ? 1 : 0;  // :847
             state.pose24(rec.pose_in);
-            LM_CK(dlt_measure(dev_, rec.pose_in, rec.did_match, &m));  // :829-979 on the device
+            if (reduce_fn) {  // sharded map: partial sums of this rank -> all-reduce -> host
+                LM_CK(dlt_measure_dev(dev_, rec.pose_in, rec.did_match, reduce_buf_dev));
+                if (reduce_fn(reduce_ctx, reduce_buf_dev, 158) != 0) {
+                    err = "reduce callback failed";
+                    return DLT_E_STATE;
+                }
+                LM_CK(dlt_fetch_result(dev_, reduce_buf_dev, &m));
+            } else {
+                LM_CK(dlt_measure(dev_, rec.pose_in, rec.did_match, &m));  // :829-979 on the device
+            }
             effct_feat_num = m.effct_feat_num;
             const double total_residual = m.total_residual;
             rec.n_down = m.n_down;
@@ -708,7 +726,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
 
         // ---- map_incremental(), :1164-1168
         t0 = wall();
-        if (!EKF_stop_flg) {
+        if (!EKF_stop_flg && cfg.dev.shard_count <= 1) {
             double pose[24];
             state.pose24(pose);
             LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
@@ -831,6 +849,13 @@ int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lid
     if (!h || !out || n < 0 || n_imu < 0 || (n > 0 && !pts48_dev) || (n_imu > 0 && !imu7)) return DLT_E_INVALID;
     return h->lm->process_scan(pts48_dev, n, lidar_beg_time, reinterpret_cast<const ImuSample *>(imu7), n_imu, thermal, out, true,
                                observation_end_time);
+}
+int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *result_dev) {
+    if (!h || (reduce && !result_dev)) return DLT_E_INVALID;
+    h->lm->reduce_fn = reduce;
+    h->lm->reduce_ctx = ctx;
+    h->lm->reduce_buf_dev = result_dev;
+    return DLT_OK;
 }
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap) {
     if (!h) return DLT_E_INVALID;

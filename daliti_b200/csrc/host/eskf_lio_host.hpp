@@ -169,6 +169,9 @@ class LaserMapping {
 
     dlt_lio_config cfg;
     dlt_handle dev_ = nullptr;
+    dlt_lio_reduce_fn reduce_fn = nullptr;  // sharded map: sums the partial normal equations over the ranks
+    void *reduce_ctx = nullptr;
+    double *reduce_buf_dev = nullptr;
     ImuProcess imu_;
     StatesGroup state, last_nodegared_state, last_state;
     std::vector<dlt_lio_iter> iters;

@@ -56,7 +56,7 @@ class LioScanOut(C.Structure):
 _LIO_SYMBOLS = [
     "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
     "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
-    "dlt_lio_get_localmap", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
+    "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
 ]
 
 
@@ -169,6 +169,31 @@ class LaserMapping:
         self._ck(self.lib.dlt_lio_process_scan_dev(self.h, C.c_void_p(pts48_dev_ptr), C.c_int(n), C.c_double(lidar_beg_time),
                                                    C.c_double(observation_end_time), _p(im), C.c_int(im.shape[0]), th, C.byref(self.out)))
         return self.out
+
+    def set_allreduce(self, device: str = "cuda"):
+        """Sharded map: sum the partial normal equations over torch.distributed ranks after every evaluation
+        of the measurement model (NCCL for device="cuda"; gloo on the CPU emulator build for device="cpu")."""
+        import torch
+        import torch.distributed as dist
+
+        if device == "cpu":
+            self._red_np = np.zeros(200, np.float64)
+            self._red_t = torch.from_numpy(self._red_np)
+            ptr = self._red_np.ctypes.data
+        else:
+            self._red_t = torch.zeros(200, dtype=torch.float64, device=device)
+            ptr = self._red_t.data_ptr()
+
+        def _cb(ctx, buf, n):
+            try:
+                if dist.is_initialized() and dist.get_world_size() > 1:
+                    dist.all_reduce(self._red_t[:n], op=dist.ReduceOp.SUM)
+                return 0
+            except Exception:  # never let an exception cross the C ABI
+                return 1
+
+        self._red_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)(_cb)
+        self._ck(self.lib.dlt_lio_set_reduce(self.h, self._red_cb, None, C.c_void_p(ptr)))
 
     def iters(self):
         n = self.out.n_iters

@@ -118,6 +118,8 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
  * in DEVICE memory at result_dev without synchronising -- the partial sums of one map shard,
  * ready for an NCCL all-reduce of the 158 doubles.                                              */
 int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev);
+/* Read a result block produced by dlt_measure_dev (possibly all-reduced in between) back to the host. */
+int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *out);
 /* laserCloudOri / coeffSel of the last dlt_measure (published as /cloud_effected,
  * laserMapping.cpp:891-892, 1213-1227): body-frame xyzi and (normal, pd2) per effective point   */
 int dlt_effective_points(dlt_handle h, float *xyzi, float *coeff, int cap, int *n);
