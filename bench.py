@@ -444,7 +444,8 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
     n_map = len(base) * len(offs)
     per_rank_cap = int(n_map * (1.0 if world == 1 else min(1.0, 1.6 / world + 0.15))) + (1 << 20)
     lm = LaserMapping(dev=dict(device=local_rank, max_scan_points=1 << 18, max_map_points=per_rank_cap, shard_rank=rank, shard_count=world,
-                               shard_tile_shift=5), featptsThreshold=30)
+                               shard_tile_shift=5), featptsThreshold=30,
+                      cube_len=1.0e6)  # the local-map cube must cover the whole tiled area: no lasermap_fov_segment deletes
     stream = torch.cuda.Stream(device=local_rank)
     lm.device.set_stream(stream.cuda_stream)
     s0, mean_acc, last_imu = initial_state(seq)
