@@ -46,7 +46,8 @@ struct dlt_handle_s {
     bool counters_fresh = false;  // h_ints mirrors d_counters (no map mutation since the last read-back)
     bool nfar_known = false;      // h_last_nfar is the far_count of the last match pass
     int h_last_nfar = 0;
-    bool eig_valid = false;       // d_result[158..199] belongs to d_result[0..157]
+    bool eig_valid = false;       // the eigen block of d_result belongs to its normal equations
+    bool sc_clean = true;         // the scan scalars (bounding box, first-point key) are reset
     float4 *d_raw = nullptr, *d_undist = nullptr, *d_down = nullptr;
     ImuPoseDev *d_poses = nullptr;
     ScanScalars *d_sc = nullptr;
@@ -312,6 +313,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
              rt::fill(h->acc.si, 0, cap * 8, h->stream) == 0 && rt::fill(h->acc.cnt, 0, cap * 4, h->stream) == 0 &&
              rt::fill(h->d_ticket, 0, 16, h->stream) == 0 && rt::fill(h->d_sel, 0, cap, h->stream) == 0 &&
              rt::fill(h->d_result, 0, kResultDoubles * sizeof(double), h->stream) == 0;
+    DLT_LAUNCH(k_scan_reset, 1, 32, h->stream, h->d_sc);
     if (!z || map_reset(h) != DLT_OK || rt::sync(h->stream) != 0) {
         dlt_destroy(h);
         return DLT_E_CUDA;
@@ -478,7 +480,8 @@ static int scan_deskew_impl(dlt_handle h, const void *pts48, bool on_device, int
     h->have_raw = true;
     h->have_down = false;
     h->have_match = false;
-    DLT_LAUNCH(k_scan_reset, 1, 32, h->stream, h->d_sc);
+    if (!h->sc_clean) DLT_LAUNCH(k_scan_reset, 1, 32, h->stream, h->d_sc);  // normally k_vox_final already did
+    h->sc_clean = false;
     if (n_raw == 0) return DLT_OK;
     const float4 *d_in = h->d_raw;
     if (on_device)
@@ -526,8 +529,8 @@ int dlt_scan_downsample(dlt_handle h, int *n_down) {
     DLT_LAUNCH(k_vox_scan2, 1, 1024, h->stream, h->d_sc, (const unsigned *)h->d_blksum, h->d_blkoff);
     DLT_LAUNCH(k_vox_accum, G, B, h->stream, (const float4 *)h->d_undist, n, (const ScanScalars *)h->d_sc, (const unsigned *)h->d_bitmap,
                (const unsigned *)h->d_wprefix, (const unsigned *)h->d_blkoff, (const unsigned *)h->d_vidx, h->acc, h->d_vop);
-    DLT_LAUNCH(k_vox_final, G, B, h->stream, (const ScanScalars *)h->d_sc, h->acc, h->d_bitmap, h->d_down, n);
-    DLT_LAUNCH(k_vox_passthrough, G, B, h->stream, (const float4 *)h->d_undist, n, h->d_sc, h->d_down);
+    DLT_LAUNCH(k_vox_final, G, B, h->stream, h->d_sc, h->acc, h->d_bitmap, (const float4 *)h->d_undist, h->d_down, n);
+    h->sc_clean = true;
     delete prof;
     DLT_RT(h, rt::check_launch());
     DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
@@ -613,6 +616,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     mb.eff = h->d_eff;
     mb.partials = h->d_partials;
     mb.ticket = h->d_ticket;
+    mb.far_count = h->d_counters + 5;
     mb.result = result_dev;
     const int G = div_up(n, kResidBlock);
     ProfScope prof(h, 1);
@@ -628,8 +632,7 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
     if (!h || !out) return DLT_E_INVALID;
     int rc = dlt_measure_dev(h, pose24, do_match, h->d_result);
     if (rc) return rc;
-    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kNormalEqDoubles * sizeof(double), h->stream));
-    DLT_RT(h, rt::d2h(h->h_ints + 8, h->d_counters + 5, sizeof(int), h->stream));
+    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kFetchDoubles * sizeof(double), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     const double *R = h->h_result;
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
@@ -638,7 +641,7 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
     out->total_residual = R[157];
     out->n_down = h->n_down;
     if (do_match) {
-        h->h_last_nfar = h->h_ints[8];
+        h->h_last_nfar = (h->n_down > 0) ? (int)(R[158] + 0.5) : 0;
         h->nfar_known = true;
     }
     out->n_unresolved = h->nfar_known ? h->h_last_nfar : 0;
@@ -649,8 +652,7 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
 int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *out) {
     if (!h || !result_dev || !out) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
-    DLT_RT(h, rt::d2h(h->h_result, result_dev, kNormalEqDoubles * sizeof(double), h->stream));
-    DLT_RT(h, rt::d2h(h->h_ints + 8, h->d_counters + 5, sizeof(int), h->stream));
+    DLT_RT(h, rt::d2h(h->h_result, result_dev, kFetchDoubles * sizeof(double), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     const double *R = h->h_result;
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
@@ -658,7 +660,8 @@ int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *ou
     out->effct_feat_num = (int)(R[156] + 0.5);
     out->total_residual = R[157];
     out->n_down = h->n_down;
-    out->n_unresolved = h->h_ints[8];
+    // R[158]: this rank's unresolved-query count (the all-reduce covers the first 158 doubles only)
+    out->n_unresolved = (int)(R[158] + 0.5);
     out->reserved = 0;
     if (result_dev != h->d_result) {  // keep a copy so that dlt_degeneracy works on the reduced normal equations
         DLT_RT(h, rt::d2d(h->d_result, result_dev, kNormalEqDoubles * sizeof(double), h->stream));
@@ -714,7 +717,7 @@ int dlt_degeneracy_begin(dlt_handle h) {
     if (!h->eig_valid) {
         DLT_LAUNCH(k_eigen6, 1, 32, h->stream, h->d_result);
         DLT_RT(h, rt::check_launch());
-        DLT_RT(h, rt::d2h(h->h_result + kNormalEqDoubles, h->d_result + kNormalEqDoubles, 42 * sizeof(double), h->stream));
+        DLT_RT(h, rt::d2h(h->h_result + kEigOffset, h->d_result + kEigOffset, 42 * sizeof(double), h->stream));
         h->eig_valid = true;
     }
     return DLT_OK;
@@ -725,8 +728,8 @@ int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
     int rc = dlt_degeneracy_begin(h);
     if (rc) return rc;
     DLT_RT(h, rt::sync(h->stream));
-    for (int i = 0; i < 6; i++) eigvals6[i] = h->h_result[158 + i];
-    for (int i = 0; i < 36; i++) eigvecs36[i] = h->h_result[164 + i];
+    for (int i = 0; i < 6; i++) eigvals6[i] = h->h_result[kEigOffset + i];
+    for (int i = 0; i < 36; i++) eigvecs36[i] = h->h_result[kEigOffset + 6 + i];
     return DLT_OK;
 }
 

@@ -454,8 +454,10 @@ struct NormalEq {
     static constexpr int NR = TRI + D + 2;  // upper triangle of H^T H, H^T r, effective count, sum |r|
 };
 constexpr int kResidBlock = 128;
-constexpr int kResultDoubles = 144 + 12 + 2 + 6 + 36;  // HtH, Htr, count, res_sum | eigvals, eigvecs (k_eigen6)
-constexpr int kNormalEqDoubles = 158;
+constexpr int kNormalEqDoubles = 158;                 // HtH[144], Htr[12], effective count, residual sum
+constexpr int kFetchDoubles = kNormalEqDoubles + 1;   // + far_count of the last match pass: one device->host copy per iteration
+constexpr int kEigOffset = 160;                       // eigvals[6], eigvecs[36] (k_eigen6)
+constexpr int kResultDoubles = kEigOffset + 42;
 static_assert(kResidBlock == 128, "the final reduce combines exactly 4 warp slices");
 
 struct MeasureBufs {
@@ -468,6 +470,7 @@ struct MeasureBufs {
     unsigned char *eff;       // [n] effective this iteration
     double *partials;         // [blocks][NR]
     unsigned *ticket;
+    const int *far_count;     // unresolved queries of the last match pass
     double *result;           // kResultDoubles
 };
 
@@ -640,6 +643,7 @@ __global__ void __launch_bounds__(kResidBlock)
         for (int a = 0; a < D; a++) R[144 + a] = s_fin[k++];
         R[156] = s_fin[k];
         R[157] = s_fin[k + 1];
+        R[158] = (double)(*mb.far_count);
         *mb.ticket = 0u;
     }
 }
@@ -729,8 +733,8 @@ __global__ void __launch_bounds__(32) k_eigen6(double *__restrict__ result) {
             ord[mn] = t;
         }
         for (int i = 0; i < 6; i++) {
-            result[158 + i] = ev[ord[i]];
-            for (int k = 0; k < 6; k++) result[164 + k * 6 + i] = V[k * 6 + ord[i]];
+            result[kEigOffset + i] = ev[ord[i]];
+            for (int k = 0; k < 6; k++) result[kEigOffset + 6 + k * 6 + i] = V[k * 6 + ord[i]];
         }
     }
 }

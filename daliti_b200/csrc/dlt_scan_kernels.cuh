@@ -359,31 +359,38 @@ __global__ void k_vox_accum(const float4 *__restrict__ pts, int n, const ScanSca
     if (voxel_of_point) voxel_of_point[i] = (int)rank;
 }
 
-// centroid per voxel; leaves the accumulators and the bitmap zeroed for the next scan
-__global__ void k_vox_final(const ScanScalars *sc, VoxAcc acc, unsigned *__restrict__ bitmap, float4 *__restrict__ down, int n_max) {
+// centroid per voxel; leaves the accumulators, the bitmap and the bounding box reset for the next scan.
+// vox_status == 1 (PCL: leaf too small for the data): output = input.
+__global__ void k_vox_final(ScanScalars *sc, VoxAcc acc, unsigned *__restrict__ bitmap, const float4 *__restrict__ pts, float4 *__restrict__ down,
+                            int n) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_max || v >= sc->n_down) return;
-    double c = (double)acc.cnt[v];
-    float4 o;
-    o.x = (float)((double)acc.sx[v] / kFix / c);
-    o.y = (float)((double)acc.sy[v] / kFix / c);
-    o.z = (float)((double)acc.sz[v] / kFix / c);
-    o.w = (float)((double)acc.si[v] / kFix / c);
-    down[v] = o;
-    bitmap[acc.idx[v] >> 5] = 0u;
-    acc.sx[v] = 0;
-    acc.sy[v] = 0;
-    acc.sz[v] = 0;
-    acc.si[v] = 0;
-    acc.cnt[v] = 0u;
-}
-
-// PCL pass-through (leaf too small for the data): output = input
-__global__ void k_vox_passthrough(const float4 *__restrict__ pts, int n, ScanScalars *sc, float4 *__restrict__ down) {
-    if (sc->vox_status != 1) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) down[i] = pts[i];
-    if (i == 0) sc->n_down = n;
+    const int status = sc->vox_status;
+    const int n_down = sc->n_down;
+    if (status == 1) {
+        if (v < n) down[v] = pts[v];
+    } else if (v < n && v < n_down) {
+        double c = (double)acc.cnt[v];
+        float4 o;
+        o.x = (float)((double)acc.sx[v] / kFix / c);
+        o.y = (float)((double)acc.sy[v] / kFix / c);
+        o.z = (float)((double)acc.sz[v] / kFix / c);
+        o.w = (float)((double)acc.si[v] / kFix / c);
+        down[v] = o;
+        bitmap[acc.idx[v] >> 5] = 0u;
+        acc.sx[v] = 0;
+        acc.sy[v] = 0;
+        acc.sz[v] = 0;
+        acc.si[v] = 0;
+        acc.cnt[v] = 0u;
+    }
+    if (v == 0) {  // every consumer of the bounding box (k_vox_mark) ran before this kernel
+        if (status == 1) sc->n_down = n;
+        for (int a = 0; a < 3; a++) {
+            sc->bbox_min[a] = 0xFFFFFFFFu;
+            sc->bbox_max[a] = 0u;
+        }
+        sc->first_key = 0xFFFFFFFFFFFFFFFFull;
+    }
 }
 
 }  // namespace dlt

@@ -286,7 +286,12 @@ void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_tim
     Vec3 acc_imu, angvel_avr, acc_avr, vel_imu = st.vel_end, pos_imu = st.pos_end;
     Mat3 R_imu = st.rot_end;
     double dt = 0;
-    std::vector<double> F(kDim * kDim), Q(kDim * kDim), FP(kDim * kDim);
+    // F = I + six 3x3 blocks, Q = five 3x3 diagonal blocks (:270-286): the structure is fixed, only the block
+    // values change per IMU step, so the buffers are set up once and the products only visit the non-zeros
+    double F[kDim * kDim], Q[kDim * kDim], FP[kDim * kDim];
+    std::memset(F, 0, sizeof(F));
+    std::memset(Q, 0, sizeof(Q));
+    for (int i = 0; i < kDim; i++) F[i * kDim + i] = 1.0;
     for (size_t k = 0; k + 1 < v.size(); k++) {
         const ImuSample &head = v[k], &tail = v[k + 1];
         if (tail.t < last_observation_end_time_) continue;  // :237
@@ -296,15 +301,12 @@ void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_tim
 
         // covariance propagation, :262-288
         const Mat3 Exp_f = so3_exp_rate(angvel_avr, dt);
-        std::fill(F.begin(), F.end(), 0.0);
-        std::fill(Q.begin(), Q.end(), 0.0);
-        for (int i = 0; i < kDim; i++) F[i * kDim + i] = 1.0;
-        set_block3(F.data(), 0, 0, so3_exp_rate(angvel_avr, -dt));
-        set_block3(F.data(), 0, 15, Mat3::identity() * (-dt));
-        set_block3(F.data(), 3, 12, Mat3::identity() * dt);
-        set_block3(F.data(), 12, 0, (R_imu * -1.0) * Mat3::hat(acc_avr) * dt);
-        set_block3(F.data(), 12, 18, R_imu * (-dt));
-        set_block3(F.data(), 12, 21, Mat3::identity() * dt);
+        set_block3(F, 0, 0, so3_exp_rate(angvel_avr, -dt));
+        set_block3(F, 0, 15, Mat3::identity() * (-dt));
+        set_block3(F, 3, 12, Mat3::identity() * dt);
+        set_block3(F, 12, 0, (R_imu * -1.0) * Mat3::hat(acc_avr) * dt);
+        set_block3(F, 12, 18, R_imu * (-dt));
+        set_block3(F, 12, 21, Mat3::identity() * dt);
         Mat3 Ca, Cg;
         Ca.a[0] = cov_acc.x;
         Ca.a[4] = cov_acc.y;
@@ -315,33 +317,49 @@ void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_tim
         Q[0 * kDim + 0] = cov_gyr.x * dt * dt * 10000;
         Q[1 * kDim + 1] = cov_gyr.y * dt * dt * 10000;
         Q[2 * kDim + 2] = cov_gyr.z * dt * dt * 10000;
-        set_block3(Q.data(), 3, 3, R_imu * Cg * R_imu.t() * dt * dt * 10000);
-        set_block3(Q.data(), 12, 12, R_imu * Ca * R_imu.t() * dt * dt * 10000);
+        set_block3(Q, 3, 3, R_imu * Cg * R_imu.t() * dt * dt * 10000);
+        set_block3(Q, 12, 12, R_imu * Ca * R_imu.t() * dt * dt * 10000);
         for (int a = 0; a < 3; a++) {
             Q[(15 + a) * kDim + 15 + a] = 0.0001 * dt * dt;
             Q[(18 + a) * kDim + 18 + a] = 0.0001 * dt * dt;
         }
-        // cov = F cov F^T + Q.  F is the identity plus six 3x3 blocks (:270-276): the products only visit its
-        // non-zeros, in ascending column order so the sums are the dense ones term for term.
+        // cov = F cov F^T + Q with the block structure written out (terms in ascending column order of F, i.e. the
+        // order a dense product would add the non-zeros in).  Rows / columns 0-5 and 12-14 are the only non-identity ones.
         {
-            int nz_idx[kDim][kDim], nz_n[kDim];
-            for (int i = 0; i < kDim; i++) {
-                nz_n[i] = 0;
-                for (int l = 0; l < kDim; l++)
-                    if (F[i * kDim + l] != 0.0) nz_idx[i][nz_n[i]++] = l;  // at most 10 entries (row block 12)
+            const double *E = &F[0];            // F[0:3, 0:3]   = Exp(w, -dt)
+            const double *A = &F[12 * kDim];    // F[12:15, 0:3] = -R a^ dt   (row stride kDim)
+            const double *B = &F[12 * kDim + 18];  // F[12:15, 18:21] = -R dt
+            const double *P = st.cov;
+            std::memcpy(FP, P, sizeof(FP));
+            for (int r = 0; r < 3; r++) {
+                double *o0 = &FP[r * kDim], *o3 = &FP[(3 + r) * kDim], *o12 = &FP[(12 + r) * kDim];
+                const double e0 = E[r * kDim], e1 = E[r * kDim + 1], e2 = E[r * kDim + 2];
+                const double a0 = A[r * kDim], a1 = A[r * kDim + 1], a2 = A[r * kDim + 2];
+                const double b0 = B[r * kDim], b1 = B[r * kDim + 1], b2 = B[r * kDim + 2];
+                for (int j = 0; j < kDim; j++) {
+                    o0[j] = ((e0 * P[j] + e1 * P[kDim + j]) + e2 * P[2 * kDim + j]) + (-dt) * P[(15 + r) * kDim + j];
+                    o3[j] = P[(3 + r) * kDim + j] + dt * P[(12 + r) * kDim + j];
+                    o12[j] = ((((((a0 * P[j] + a1 * P[kDim + j]) + a2 * P[2 * kDim + j]) + P[(12 + r) * kDim + j]) + b0 * P[18 * kDim + j]) +
+                               b1 * P[19 * kDim + j]) + b2 * P[20 * kDim + j]) + dt * P[(21 + r) * kDim + j];
+                }
             }
-            for (int i = 0; i < kDim; i++)
-                for (int j = 0; j < kDim; j++) {
-                    double s = 0;
-                    for (int k = 0; k < nz_n[i]; k++) s += F[i * kDim + nz_idx[i][k]] * st.cov[nz_idx[i][k] * kDim + j];
-                    FP[i * kDim + j] = s;
+            for (int i = 0; i < kDim; i++) {
+                const double *X = &FP[i * kDim];
+                double *o = &st.cov[i * kDim];
+                double c0[3], c3[3], c12[3];
+                for (int c = 0; c < 3; c++) {
+                    c0[c] = ((E[c * kDim] * X[0] + E[c * kDim + 1] * X[1]) + E[c * kDim + 2] * X[2]) + (-dt) * X[15 + c];
+                    c3[c] = X[3 + c] + dt * X[12 + c];
+                    c12[c] = ((((((A[c * kDim] * X[0] + A[c * kDim + 1] * X[1]) + A[c * kDim + 2] * X[2]) + X[12 + c]) + B[c * kDim] * X[18]) +
+                               B[c * kDim + 1] * X[19]) + B[c * kDim + 2] * X[20]) + dt * X[21 + c];
                 }
-            for (int i = 0; i < kDim; i++)
-                for (int j = 0; j < kDim; j++) {
-                    double s = 0;
-                    for (int k = 0; k < nz_n[j]; k++) s += FP[i * kDim + nz_idx[j][k]] * F[j * kDim + nz_idx[j][k]];
-                    st.cov[i * kDim + j] = s + Q[i * kDim + j];
+                for (int j = 0; j < kDim; j++) o[j] = X[j] + Q[i * kDim + j];
+                for (int c = 0; c < 3; c++) {
+                    o[c] = c0[c] + Q[i * kDim + c];
+                    o[3 + c] = c3[c] + Q[i * kDim + 3 + c];
+                    o[12 + c] = c12[c] + Q[i * kDim + 12 + c];
                 }
+            }
         }
 
         R_imu = R_imu * Exp_f;                                      // :291

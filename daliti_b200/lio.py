@@ -177,11 +177,11 @@ class LaserMapping:
         import torch.distributed as dist
 
         if device == "cpu":
-            self._red_np = np.zeros(200, np.float64)
+            self._red_np = np.zeros(256, np.float64)
             self._red_t = torch.from_numpy(self._red_np)
             ptr = self._red_np.ctypes.data
         else:
-            self._red_t = torch.zeros(200, dtype=torch.float64, device=device)
+            self._red_t = torch.zeros(256, dtype=torch.float64, device=device)
             ptr = self._red_t.data_ptr()
 
         def _cb(ctx, buf, n):

@@ -31,7 +31,7 @@ def allreduce_measure(handle, pose24, do_match: bool, device: str = "cuda", buf=
         r = t.numpy()
     else:
         if buf is None:
-            buf = torch.zeros(200, dtype=torch.float64, device=device)
+            buf = torch.zeros(256, dtype=torch.float64, device=device)
         handle.measure_dev(pose24, do_match, buf.data_ptr())
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(buf[:N_EQ], op=dist.ReduceOp.SUM)

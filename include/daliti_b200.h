@@ -114,7 +114,7 @@ int dlt_scan_get_voxel_of_point(dlt_handle h, int *slot, int cap);
  * reduction to H^T H / H^T r.  Nearest_Points, point_selected_surf and the cached planes
  * persist in the handle between calls of one scan.                                              */
 int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_out *out);
-/* Same, but leaves the result block (HtH[144] Htr[12] count res_sum = 158 doubles, room for 200)
+/* Same, but leaves the result block (HtH[144] Htr[12] count res_sum = 158 doubles; the buffer must hold 256)
  * in DEVICE memory at result_dev without synchronising -- the partial sums of one map shard,
  * ready for an NCCL all-reduce of the 158 doubles.                                              */
 int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev);

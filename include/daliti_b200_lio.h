@@ -89,7 +89,7 @@ int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_t
 int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lidar_beg_time, double observation_end_time,
                              const double *imu7, int n_imu, const dlt_lio_thermal *thermal, dlt_lio_scan_out *out);
 /* Sharded map (dev.shard_count > 1): after every evaluation of the measurement model the partial normal
- * equations (n = 158 doubles at result_dev, DEVICE memory owned by the caller, room for 200) are handed to
+ * equations (n = 158 doubles at result_dev, DEVICE memory owned by the caller, 256 doubles) are handed to
  * `reduce`, which must sum them over the ranks in place on the handle's stream (e.g. ncclAllReduce /
  * torch.distributed.all_reduce) and return 0.  map_incremental is skipped on a sharded map.             */
 typedef int (*dlt_lio_reduce_fn)(void *ctx, double *result_dev, int n);
