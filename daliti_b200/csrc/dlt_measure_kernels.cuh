@@ -619,8 +619,16 @@ __global__ void __launch_bounds__(kResidBlock)
         const int v = base + (threadIdx.x & 31), sl = threadIdx.x >> 5;
         double acc = 0.0;
         if (v < NR) {
+            // 8 loads in flight per thread; the adds stay in block order (adding 0.0 for the padding is exact)
             const double *vp = mb.partials;
-            for (unsigned b = sl; b < gridDim.x; b += kResidBlock / 32) acc += __ldcg(vp + (size_t)b * NR + v);
+            constexpr unsigned S = kResidBlock / 32;
+            for (unsigned b = sl; b < gridDim.x; b += S * 8) {
+                double t[8];
+#pragma unroll
+                for (unsigned u = 0; u < 8; u++) t[u] = (b + S * u < gridDim.x) ? __ldcg(vp + (size_t)(b + S * u) * NR + v) : 0.0;
+#pragma unroll
+                for (unsigned u = 0; u < 8; u++) acc += t[u];
+            }
         }
         s_sum[sl][threadIdx.x & 31] = acc;
         __syncthreads();
