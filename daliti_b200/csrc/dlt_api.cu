@@ -35,11 +35,13 @@ struct dlt_handle_s {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     int cap = 0;  // per-point array capacity (max_scan_points)
+    int n_sm = 148;
 
     // map
     MapView map;
     size_t table_cap = 0;
-    int *d_counters = nullptr;  // [0] n_buckets [1] n_live [2] error [3] deleted [4] export counter [5] far_count [6] ds adds [7] raw adds
+    int *d_unres = nullptr;     // queries the thread-per-query pass could not resolve (input of the warp-per-query pass)
+    int *d_counters = nullptr;  // [8] unresolved-after-ring-1 count; [0] n_buckets [1] n_live [2] error [3] deleted [4] export counter [5] far_count [6] ds adds [7] raw adds
     // scan
     int n_raw = 0, n_down = 0;
     bool have_raw = false, have_down = false, have_match = false;
@@ -137,7 +139,21 @@ static Pose pose_from(const double *p) {
 static int map_reset(dlt_handle h) {
     h->counters_fresh = false;
     DLT_RT(h, rt::fill(h->map.table, 0xFF, h->table_cap * sizeof(Slot), h->stream));
-    DLT_RT(h, rt::fill(h->d_counters, 0, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::fill(h->d_counters, 0, 16 * sizeof(int), h->stream));
+    return DLT_OK;
+}
+
+// one match pass: thread-per-query over the 3^3 block, then warp-per-query for what that could not prove exact
+static int launch_knn(dlt_handle h, const float4 *d_q, int n, int body_frame, const Pose &P) {
+    DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));   // far_count
+    DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));   // unresolved after ring 1
+    DLT_LAUNCH(k_knn_ring1, div_up(n, kRing1Block), kRing1Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres,
+               h->d_counters + 8);
+    int grid = div_up(n, kKnnWarps);
+    const int cap_grid = h->n_sm * 8;
+    if (grid > cap_grid) grid = cap_grid;
+    DLT_LAUNCH(k_knn, grid, kKnnWarps * 32, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, (const int *)h->d_unres,
+               (const int *)(h->d_counters + 8));
     return DLT_OK;
 }
 
@@ -251,6 +267,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     dlt_handle h = new dlt_handle_s();
     h->cfg = *cfg;
     h->cap = cfg->max_scan_points;
+    h->n_sm = rt::sm_count();
     bool ok = rt::stream_create(&h->own_stream) == 0;
     h->stream = h->own_stream;
 
@@ -278,7 +295,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     while (sc_cap < 4 * cap) sc_cap <<= 1;
     h->scratch.mask = (unsigned)(sc_cap - 1);
 
-    ok = ok && !dalloc(h, &h->map.table, tcap) && !dalloc(h, &h->map.buckets, bucket_cap) && !dalloc(h, &h->d_counters, 8) &&
+    ok = ok && !dalloc(h, &h->map.table, tcap) && !dalloc(h, &h->map.buckets, bucket_cap) && !dalloc(h, &h->d_counters, 16) && !dalloc(h, &h->d_unres, cap) &&
          !dalloc(h, &h->d_raw, cap * kRawStride4) && !dalloc(h, &h->d_undist, cap) && !dalloc(h, &h->d_down, cap) &&
          !dalloc(h, &h->d_poses, kMaxImuPoses) && !dalloc(h, &h->d_sc, 1) && !dalloc(h, &h->d_bitmap, words) &&
          !dalloc(h, &h->d_wprefix, words) && !dalloc(h, &h->d_blksum, (size_t)h->n_scan_blocks) &&
@@ -447,9 +464,12 @@ int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *ou
             stage[4 * (size_t)i + 2] = q[3 * (size_t)(off + i) + 2];
         }
         DLT_RT(h, rt::h2d(h->d_pw, stage.data(), (size_t)c * sizeof(float4), h->stream));
-        DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
-        DLT_LAUNCH(k_knn, div_up(c, kKnnWarps), kKnnWarps * 32, h->stream, h->map, (const float4 *)h->d_pw, c, 0, P, h->cfg.max_sq_dist, h->knn);
+        {
+            int rk = launch_knn(h, (const float4 *)h->d_pw, c, 0, P);
+            if (rk) return rk;
+        }
         DLT_RT(h, rt::check_launch());
+        h->nfar_known = false;
         int rc = run_far(h, nullptr);
         if (rc) return rc;
         nb.resize((size_t)c * kK);
@@ -601,9 +621,9 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     if (result_dev == h->d_result) h->eig_valid = false;
     if (do_match) {
         h->nfar_known = false;
-        DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
         ProfScope prof(h, 0);
-        DLT_LAUNCH(k_knn, div_up(n, kKnnWarps), kKnnWarps * 32, h->stream, h->map, (const float4 *)h->d_down, n, 1, P, h->cfg.max_sq_dist, h->knn);
+        int rk = launch_knn(h, (const float4 *)h->d_down, n, 1, P);
+        if (rk) return rk;
         h->have_match = true;
     }
     MeasureBufs mb;

@@ -55,6 +55,20 @@ DLT_D Cand warp_min_cand(Cand c) {
     return c;
 }
 
+// keep the kK smallest (stated order) of a stream of candidates, sorted ascending, in registers
+DLT_D void topk_insert(Cand (&b)[kK], const Cand &c) {
+    if (!cand_less(c, b[kK - 1])) return;
+    b[kK - 1] = c;
+#pragma unroll
+    for (int t = kK - 1; t > 0; t--) {
+        if (cand_less(b[t], b[t - 1])) {
+            Cand tmp = b[t];
+            b[t] = b[t - 1];
+            b[t - 1] = tmp;
+        }
+    }
+}
+
 struct KnnOut {
     float4 *qw;            // [n] world-frame query (x y z intensity) of this match pass
     float4 *nbr;           // [n][5] neighbour x y z d2, ascending
@@ -187,16 +201,9 @@ DLT_D void knn_select(Cand *s_best, int *s_nbest, int &nbest, float &d5, float4 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
-    k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out) {
-    __shared__ float4 s_cand[kKnnWarps][kCandSlots];
-    __shared__ int s_cid[kKnnWarps][kCandSlots];
-    __shared__ int s_wl[kKnnWarps][kWlMax];
-    __shared__ Cand s_bestw[kKnnWarps][kK];
-    __shared__ int s_nb[kKnnWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * kKnnWarps + warp;
-    if (qi >= n) return;  // warp-uniform; the kernel has no block-level barrier
+// One query, one warp: rings 3^3 / 5^3 / 7^3 until the 5 best are proven exact.
+DLT_D void knn_warp_query(const MapView &m, const float4 *__restrict__ q_pts, int qi, int body_frame, const Pose &P, float max_sq_dist,
+                          const KnnOut &out, float4 *cand, int *cid, int *wl, Cand *best, int *s_nb_slot, int lane) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
     float4 qb = q_pts[qi];
@@ -215,10 +222,6 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
         return;
     }
 
-    float4 *cand = s_cand[warp];
-    int *cid = s_cid[warp];
-    int *wl = s_wl[warp];
-    Cand *best = s_bestw[warp];
     int nbest = 0, ncand = 0;
     float d5 = INFINITY;
     bool overflow = false, resolved = false;
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
                     }
                     __syncwarp();
                     if (ncand > kCandMax - 32) {  // staging area nearly full: fold it into the running best
-                        knn_select(best, &s_nb[warp], nbest, d5, cand, cid, ncand, lane);
+                        knn_select(best, s_nb_slot, nbest, d5, cand, cid, ncand, lane);
                         ncand = 0;
                     }
                 }
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
             }
         }
         if (ncand > 0) {
-            knn_select(best, &s_nb[warp], nbest, d5, cand, cid, ncand, lane);
+            knn_select(best, s_nb_slot, nbest, d5, cand, cid, ncand, lane);
             ncand = 0;
         }
         // ---- exactness: every unseen point lies outside the (2R+1)^3 block of cells
@@ -346,6 +349,126 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
     }
 }
 
+// Warp-per-query kernel.  list == nullptr: queries 0..n-1, one per warp.  Otherwise the queries list[0..*count)
+// (the ones k_knn_ring1 could not resolve) with a warp-stride loop.
+__global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
+    k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, const int *__restrict__ list,
+          const int *__restrict__ count) {
+    __shared__ float4 s_cand[kKnnWarps][kCandSlots];
+    __shared__ int s_cid[kKnnWarps][kCandSlots];
+    __shared__ int s_wl[kKnnWarps][kWlMax];
+    __shared__ Cand s_bestw[kKnnWarps][kK];
+    __shared__ int s_nb[kKnnWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_warps = gridDim.x * kKnnWarps;
+    const int limit = list ? *count : n;
+    for (int w = blockIdx.x * kKnnWarps + warp; w < limit; w += total_warps) {  // warp-uniform; no block-level barrier
+        const int qi = list ? list[w] : w;
+        knn_warp_query(m, q_pts, qi, body_frame, P, max_sq_dist, out, s_cand[warp], s_cid[warp], s_wl[warp], s_bestw[warp], &s_nb[warp], lane);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ thread-per-query first pass over the 3x3x3 block
+// The downsampled scan comes out of the VoxelGrid in voxel-index order, so neighbouring threads look at
+// neighbouring cells: the 27 hash probes and the bucket lines are shared through L1/L2, each thread keeps its
+// 5 best in registers (stated order d2, x, y, z, id) and there is no cross-lane traffic at all.  A query is
+// finished here when its 5 best are proven exact by the 3^3 block (the common case on a mapped surface);
+// the rest go to `unres_list` for the warp-per-query kernel above, which widens the search.
+constexpr int kRing1Block = 128;
+
+DLT_D int map_find_from(const MapView &m, unsigned long long key, unsigned h) {
+    for (unsigned probe = 0; probe <= m.table_mask; probe++) {
+        Slot s = load_slot(&m.table[h]);
+        if (s.key == key) return s.bucket;
+        if (s.key == kEmptyKey) return -1;
+        h = (h + 1) & m.table_mask;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(kRing1Block)
+    k_knn_ring1(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out,
+                int *__restrict__ unres_list, int *__restrict__ unres_count) {
+    const int qi = blockIdx.x * kRing1Block + threadIdx.x;
+    if (qi >= n) return;
+    float4 qb = q_pts[qi];
+    float qx = qb.x, qy = qb.y, qz = qb.z;
+    if (body_frame) body_to_world(P, qb.x, qb.y, qb.z, qx, qy, qz);
+    const float cell_edge = m.ds * (float)(1 << m.cell_shift);
+    int cx, cy, cz;
+    cell_of_point(m, qx, qy, qz, cx, cy, cz);
+    out.qw[qi] = make_float4(qx, qy, qz, qb.w);
+    if (m.shard_count > 1 && tile_owner(cx, cy, cz, m.tile_shift, m.shard_count) != m.shard_rank) {
+        out.nbr_cnt[qi] = 0;
+        out.flags[qi] = kFlagForeign;
+        return;
+    }
+    Cand best[kK];
+#pragma unroll
+    for (int t = 0; t < kK; t++) best[t] = cand_inf();
+
+    for (int dz = -1; dz <= 1; dz++) {
+        // the 9 home slots of this z-slab are loaded together (independent 16-byte loads)
+        unsigned long long key9[9];
+        unsigned h9[9];
+        Slot s9[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            key9[c] = pack_key(cx + (c % 3) - 1, cy + (c / 3) - 1, cz + dz);
+            h9[c] = hash_key(key9[c]) & m.table_mask;
+            s9[c] = load_slot(&m.table[h9[c]]);
+        }
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            int b = (s9[c].key == key9[c]) ? s9[c].bucket : (s9[c].key == kEmptyKey) ? -1 : map_find_from(m, key9[c], (h9[c] + 1) & m.table_mask);
+            while (b >= 0) {
+                const Bucket *B = &m.buckets[b];
+                const int4 hdr = *reinterpret_cast<const int4 *>(B);  // key (8 B), next, live mask
+                float4 e[kBucketSlots];
+#pragma unroll
+                for (int sl = 0; sl < kBucketSlots; sl++) e[sl] = B->pts[sl];  // one 128-byte line, 7 independent loads
+                const unsigned msk = (unsigned)hdr.w;
+#pragma unroll
+                for (int sl = 0; sl < kBucketSlots; sl++) {
+                    if ((msk >> sl) & 1u) {
+                        Cand cd;
+                        cd.d2 = calc_dist(qx, qy, qz, e[sl].x, e[sl].y, e[sl].z);
+                        cd.x = e[sl].x;
+                        cd.y = e[sl].y;
+                        cd.z = e[sl].z;
+                        cd.id = b * 8 + sl + 1;
+                        topk_insert(best, cd);
+                    }
+                }
+                b = hdr.z;
+            }
+        }
+    }
+    const float d5 = best[kK - 1].d2;  // +inf when fewer than 5 points were seen
+    const float slack = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
+    float cov = INFINITY;
+    cov = fminf(cov, qx - (float)(cx - 1) * cell_edge);
+    cov = fminf(cov, (float)(cx + 2) * cell_edge - qx);
+    cov = fminf(cov, qy - (float)(cy - 1) * cell_edge);
+    cov = fminf(cov, (float)(cy + 2) * cell_edge - qy);
+    cov = fminf(cov, qz - (float)(cz - 1) * cell_edge);
+    cov = fminf(cov, (float)(cz + 2) * cell_edge - qz);
+    cov -= slack;
+    const bool resolved = (d5 < INFINITY) && cov > 0.f && d5 < cov * cov * 0.99999f;
+    if (!resolved) {
+        unres_list[atomicAdd(unres_count, 1)] = qi;
+        return;
+    }
+#pragma unroll
+    for (int t = 0; t < kK; t++) {
+        out.nbr[(size_t)qi * kK + t] = make_float4(best[t].x, best[t].y, best[t].z, best[t].d2);
+        out.nbr_id[(size_t)qi * kK + t] = best[t].id;
+    }
+    out.nbr_cnt[qi] = kK;
+    out.flags[qi] = (d5 <= max_sq_dist) ? kFlagMatched : (unsigned char)0;
+}
+
 // ------------------------------------------------------------------ exact fallback for unresolved queries
 // Streams the whole bucket pool once; lane = query, so a warp serves 32 queries and keeps
 // their running 5 best in registers.  grid = (query groups, map slices); partial results
@@ -354,19 +477,6 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
 // (laserMapping.cpp:593-617), never the residuals.
 constexpr int kFarWarps = 4;
 constexpr int kFarTile = 128;  // buckets per shared-memory tile
-
-DLT_D void topk_insert(Cand (&b)[kK], const Cand &c) {
-    if (!cand_less(c, b[kK - 1])) return;
-    b[kK - 1] = c;
-#pragma unroll
-    for (int t = kK - 1; t > 0; t--) {
-        if (cand_less(b[t], b[t - 1])) {
-            Cand tmp = b[t];
-            b[t] = b[t - 1];
-            b[t - 1] = tmp;
-        }
-    }
-}
 
 __global__ void __launch_bounds__(kFarWarps * 32)
     k_far_scan(MapView m, int n_buckets, const float4 *__restrict__ qw, const int *__restrict__ far_list, int far_off, int nfar,
