@@ -143,11 +143,11 @@ static int map_reset(dlt_handle h) {
     return DLT_OK;
 }
 
-// one match pass: thread-per-query over the 3^3 block, then warp-per-query for what that could not prove exact
+// one match pass: 8 lanes per query over the 3^3 block, then warp-per-query for what that could not prove exact
 static int launch_knn(dlt_handle h, const float4 *d_q, int n, int body_frame, const Pose &P) {
     DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));   // far_count
     DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));   // unresolved after ring 1
-    DLT_LAUNCH(k_knn_ring1, div_up(n, kRing1Block), kRing1Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres,
+    DLT_LAUNCH(k_knn8, div_up(n, kKnn8Block / 8), kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres,
                h->d_counters + 8);
     int grid = div_up(n, kKnnWarps);
     const int cap_grid = h->n_sm * 8;

@@ -369,83 +369,112 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
     }
 }
 
-// ------------------------------------------------------------------ thread-per-query first pass over the 3x3x3 block
-// The downsampled scan comes out of the VoxelGrid in voxel-index order, so neighbouring threads look at
-// neighbouring cells: the 27 hash probes and the bucket lines are shared through L1/L2, each thread keeps its
-// 5 best in registers (stated order d2, x, y, z, id) and there is no cross-lane traffic at all.  A query is
-// finished here when its 5 best are proven exact by the 3^3 block (the common case on a mapped surface);
-// the rest go to `unres_list` for the warp-per-query kernel above, which widens the search.
-constexpr int kRing1Block = 128;
+// ------------------------------------------------------------------ first pass: 8 lanes per query over the 3x3x3 block
+// Four queries per warp.  The 8 lanes of a group probe the 27 cells in 4 rounds, fetch one 128-byte bucket
+// per step (lane 0 the header, lanes 1-7 one point each) and every lane keeps the 5 best of the points it
+// saw in registers (stated order d2, x, y, z, id); the 8 sorted lists are merged with five 8-lane argmins.
+// A query is finished here when the 3^3 block proves its 5 best exact (the common case on a mapped
+// surface); the rest go to `unres_list` for the warp-per-query kernel above, which widens the search.
+constexpr int kKnn8Block = 128;
 
-DLT_D int map_find_from(const MapView &m, unsigned long long key, unsigned h) {
-    for (unsigned probe = 0; probe <= m.table_mask; probe++) {
-        Slot s = load_slot(&m.table[h]);
-        if (s.key == key) return s.bucket;
-        if (s.key == kEmptyKey) return -1;
-        h = (h + 1) & m.table_mask;
+DLT_D Cand group8_min_cand(Cand c) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        Cand t;
+        t.d2 = __shfl_xor_sync(0xffffffffu, c.d2, o);
+        t.x = __shfl_xor_sync(0xffffffffu, c.x, o);
+        t.y = __shfl_xor_sync(0xffffffffu, c.y, o);
+        t.z = __shfl_xor_sync(0xffffffffu, c.z, o);
+        t.id = __shfl_xor_sync(0xffffffffu, c.id, o);
+        if (cand_less(t, c)) c = t;
     }
-    return -1;
+    return c;
 }
 
-__global__ void __launch_bounds__(kRing1Block)
-    k_knn_ring1(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out,
-                int *__restrict__ unres_list, int *__restrict__ unres_count) {
-    const int qi = blockIdx.x * kRing1Block + threadIdx.x;
-    if (qi >= n) return;
-    float4 qb = q_pts[qi];
-    float qx = qb.x, qy = qb.y, qz = qb.z;
-    if (body_frame) body_to_world(P, qb.x, qb.y, qb.z, qx, qy, qz);
+__global__ void __launch_bounds__(kKnn8Block)
+    k_knn8(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
+           int *__restrict__ unres_count) {
+    const unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, sub = lane & 7;
+    const int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4;
+    if (q0 >= n) return;  // warp-uniform
+    const int qi = q0 + grp;
+    const bool live = qi < n;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int cx = 0, cy = 0, cz = 0;
+    bool work = false;
     const float cell_edge = m.ds * (float)(1 << m.cell_shift);
-    int cx, cy, cz;
-    cell_of_point(m, qx, qy, qz, cx, cy, cz);
-    out.qw[qi] = make_float4(qx, qy, qz, qb.w);
-    if (m.shard_count > 1 && tile_owner(cx, cy, cz, m.tile_shift, m.shard_count) != m.shard_rank) {
-        out.nbr_cnt[qi] = 0;
-        out.flags[qi] = kFlagForeign;
-        return;
+    if (live) {
+        float4 qb = q_pts[qi];
+        qx = qb.x;
+        qy = qb.y;
+        qz = qb.z;
+        if (body_frame) body_to_world(P, qb.x, qb.y, qb.z, qx, qy, qz);
+        cell_of_point(m, qx, qy, qz, cx, cy, cz);
+        if (sub == 0) out.qw[qi] = make_float4(qx, qy, qz, qb.w);
+        work = true;
+        if (m.shard_count > 1 && tile_owner(cx, cy, cz, m.tile_shift, m.shard_count) != m.shard_rank) {
+            work = false;
+            if (sub == 0) {
+                out.nbr_cnt[qi] = 0;
+                out.flags[qi] = kFlagForeign;
+            }
+        }
     }
     Cand best[kK];
 #pragma unroll
     for (int t = 0; t < kK; t++) best[t] = cand_inf();
 
-    for (int dz = -1; dz <= 1; dz++) {
-        // the 9 home slots of this z-slab are loaded together (independent 16-byte loads)
-        unsigned long long key9[9];
-        unsigned h9[9];
-        Slot s9[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) {
-            key9[c] = pack_key(cx + (c % 3) - 1, cy + (c / 3) - 1, cz + dz);
-            h9[c] = hash_key(key9[c]) & m.table_mask;
-            s9[c] = load_slot(&m.table[h9[c]]);
-        }
-#pragma unroll
-        for (int c = 0; c < 9; c++) {
-            int b = (s9[c].key == key9[c]) ? s9[c].bucket : (s9[c].key == kEmptyKey) ? -1 : map_find_from(m, key9[c], (h9[c] + 1) & m.table_mask);
-            while (b >= 0) {
-                const Bucket *B = &m.buckets[b];
-                const int4 hdr = *reinterpret_cast<const int4 *>(B);  // key (8 B), next, live mask
-                float4 e[kBucketSlots];
-#pragma unroll
-                for (int sl = 0; sl < kBucketSlots; sl++) e[sl] = B->pts[sl];  // one 128-byte line, 7 independent loads
-                const unsigned msk = (unsigned)hdr.w;
-#pragma unroll
-                for (int sl = 0; sl < kBucketSlots; sl++) {
-                    if ((msk >> sl) & 1u) {
-                        Cand cd;
-                        cd.d2 = calc_dist(qx, qy, qz, e[sl].x, e[sl].y, e[sl].z);
-                        cd.x = e[sl].x;
-                        cd.y = e[sl].y;
-                        cd.z = e[sl].z;
-                        cd.id = b * 8 + sl + 1;
-                        topk_insert(best, cd);
-                    }
+    for (int r = 0; r < 4; r++) {
+        const int ci = r * 8 + sub;
+        int b = -1;
+        if (work && ci < 27) b = map_find(m, pack_key(cx + (ci % 3) - 1, cy + ((ci / 3) % 3) - 1, cz + (ci / 9) - 1));
+        unsigned gb = (__ballot_sync(FULL, b >= 0) >> (grp * 8)) & 0xFFu;  // this group's found cells
+        while (__any_sync(FULL, gb != 0u)) {                                // warp-uniform
+            const int src = gb ? (__ffs((int)gb) - 1) : 0;
+            int bb = __shfl_sync(FULL, b, (grp << 3) + src);
+            if (!gb) bb = -1;
+            gb &= gb - 1u;
+            while (__any_sync(FULL, bb >= 0)) {  // the cell's bucket chain
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bb >= 0) v = reinterpret_cast<const float4 *>(&m.buckets[bb])[sub];  // 8 lanes x 16 B = one line
+                const int hdr_next = __shfl_sync(FULL, __float_as_int(v.z), lane & ~7);
+                const unsigned hdr_mask = __shfl_sync(FULL, __float_as_uint(v.w), lane & ~7);
+                if (bb >= 0 && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u)) {
+                    Cand c;
+                    c.d2 = calc_dist(qx, qy, qz, v.x, v.y, v.z);
+                    c.x = v.x;
+                    c.y = v.y;
+                    c.z = v.z;
+                    c.id = bb * 8 + sub;
+                    topk_insert(best, c);
                 }
-                b = hdr.z;
+                bb = (bb >= 0) ? hdr_next : -1;
             }
         }
     }
-    const float d5 = best[kK - 1].d2;  // +inf when fewer than 5 points were seen
+    // ---- merge the group's 8 sorted lists: five rounds of 8-lane argmin, the owner pops its head
+    int nb = 0;
+    float d5 = INFINITY;
+    Cand mine_out = cand_inf();
+#pragma unroll
+    for (int t = 0; t < kK; t++) {
+        const Cand w = group8_min_cand(best[0]);
+        const bool valid = w.d2 < INFINITY;
+        if (valid && best[0].id == w.id) {
+#pragma unroll
+            for (int u = 0; u < kK - 1; u++) best[u] = best[u + 1];
+            best[kK - 1] = cand_inf();
+        }
+        nb += valid ? 1 : 0;
+        if (t == kK - 1) d5 = w.d2;
+        if (sub == t) {  // lane t of the group keeps result t until the exactness test below
+            mine_out = w;
+            if (!valid) mine_out.id = -1;
+        }
+    }
+    if (!work) return;
     const float slack = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
     float cov = INFINITY;
     cov = fminf(cov, qx - (float)(cx - 1) * cell_edge);
@@ -455,18 +484,19 @@ __global__ void __launch_bounds__(kRing1Block)
     cov = fminf(cov, qz - (float)(cz - 1) * cell_edge);
     cov = fminf(cov, (float)(cz + 2) * cell_edge - qz);
     cov -= slack;
-    const bool resolved = (d5 < INFINITY) && cov > 0.f && d5 < cov * cov * 0.99999f;
+    const bool resolved = (nb == kK) && cov > 0.f && d5 < cov * cov * 0.99999f;
     if (!resolved) {
-        unres_list[atomicAdd(unres_count, 1)] = qi;
+        if (sub == 0) unres_list[atomicAdd(unres_count, 1)] = qi;
         return;
     }
-#pragma unroll
-    for (int t = 0; t < kK; t++) {
-        out.nbr[(size_t)qi * kK + t] = make_float4(best[t].x, best[t].y, best[t].z, best[t].d2);
-        out.nbr_id[(size_t)qi * kK + t] = best[t].id;
+    if (sub < kK) {
+        out.nbr[(size_t)qi * kK + sub] = make_float4(mine_out.x, mine_out.y, mine_out.z, mine_out.d2);
+        out.nbr_id[(size_t)qi * kK + sub] = mine_out.id;
     }
-    out.nbr_cnt[qi] = kK;
-    out.flags[qi] = (d5 <= max_sq_dist) ? kFlagMatched : (unsigned char)0;
+    if (sub == 0) {
+        out.nbr_cnt[qi] = kK;
+        out.flags[qi] = (d5 <= max_sq_dist) ? kFlagMatched : (unsigned char)0;
+    }
 }
 
 // ------------------------------------------------------------------ exact fallback for unresolved queries
