@@ -85,46 +85,92 @@ def initial_state(seq):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in a thread every 5 ms (the timed region of a
+    50-scan run is only ~20-50 ms), falling back to an `nvidia-smi -lms` child when NVML is unavailable."""
+
+    _BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.mode = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.idx])
+                except Exception:
+                    phys = self.idx
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.mode = "smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in self._BAD.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
+    def _read_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 9 and r[1].replace(".", "").isdigit():
+                self.sm.append(float(r[1]))
+                if r[2].replace(".", "").isdigit():
+                    self.mx.append(float(r[2]))
                 for n, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
-                        reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                        self.reasons.add(n)
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        self.stop_flag = True
+        if self.mode == "smi":
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.thread.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.mode}
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -350,18 +396,25 @@ def main():
             peaks = json.load(open(pk))
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        knn_ms, knn_n = prof["knn"]
+        knn_ms, knn_n = prof["knn"]      # whole match pass: k_knn8 + k_knn (+ two 4-byte memsets)
+        k8_ms, k8_n = prof["knn8"]       # k_knn8 alone
         res_ms, res_n = prof["residual"]
         nd_mean = nd_sum / max(1, n_prof)
         # algorithmic bytes per launch: kNN pass  N*(16 + 5*16 + 5*4), residual pass N*(16+16) + 92*8
         knn_bytes = nd_mean * (16 + 5 * 16 + 5 * 4)
         res_bytes = nd_mean * 32 + 92 * 8
-        dom = "k_knn" if knn_ms >= res_ms else "k_residual"
-        d_ms, d_n, d_bytes = (knn_ms, knn_n, knn_bytes) if dom == "k_knn" else (res_ms, res_n, res_bytes)
+        dom = "k_knn8" if k8_ms >= res_ms else "k_residual"
+        d_ms, d_n, d_bytes = (k8_ms, k8_n, knn_bytes) if dom == "k_knn8" else (res_ms, res_n, res_bytes)
         achieved = d_bytes / (1e-3 * d_ms / max(1, d_n)) / 1e9 if d_ms > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "avg_launch_us": 1e3 * d_ms / max(1, d_n), "algorithmic_bytes_per_launch": d_bytes,
-                "note": "single-scan working set is L2-resident and the kernel is latency-bound (SURVEY.md 8d); the fraction is reported, not a target at this size",
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram__bytes_read+write per launch from the committed --set full capture
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if dom in tj:
+                traffic, traffic_src = tj[dom].get("dram_bytes_per_launch"), tj[dom].get("source")
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_us": 1e3 * d_ms / max(1, d_n), "algorithmic_bytes_per_launch": d_bytes,
+                "note": "single-scan working set is L2-resident and the kernel is issue/latency-bound (SURVEY.md 8d); the fraction is reported, not a target at this size",
                 "kernel_ms_per_scan": {k: round(v[0] / max(1, n_prof), 4) for k, v in prof.items() if v[1]},
                 "kernel_launch_groups_per_scan": {k: round(v[1] / max(1, n_prof), 2) for k, v in prof.items() if v[1]}}
     except Exception as e:  # profiling is auxiliary: never lose the headline number over it

@@ -257,7 +257,7 @@ class ScanToMap:
         self._ck(self.lib.dlt_map_incremental(self.h, _p(ps), C.c_int(1 if flg_EKF_inited else 0), C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    PROFILE_GROUPS = ("knn", "residual", "deskew", "voxelgrid", "insert", "far_fallback", "spare6", "spare7")
+    PROFILE_GROUPS = ("knn", "residual", "deskew", "voxelgrid", "insert", "far_fallback", "spare6", "knn8")
 
     def set_profiling(self, on: bool):
         self._ck(self.lib.dlt_set_profiling(self.h, C.c_int(1 if on else 0)))

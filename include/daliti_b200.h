@@ -139,7 +139,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
 
 /* ---- instrumentation (no reference counterpart) ---------------------------------------------- */
 /* Per-kernel-group device time from CUDA events on the launching stream.  Groups: 0 k_knn,
- * 1 k_residual, 2 deskew, 3 VoxelGrid, 4 map insert, 5 exact-neighbour fallback, 6-7 spare.      */
+ * 1 k_residual, 2 deskew, 3 VoxelGrid, 4 map insert, 5 exact-neighbour fallback, 6 spare, 7 k_knn8 alone (inside group 0).      */
 int dlt_set_profiling(dlt_handle h, int on);
 int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset);
 /* kernels launched by this library in this process so far                                         */
