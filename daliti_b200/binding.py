@@ -70,6 +70,7 @@ _SYMBOLS = [
     "dlt_scan_deskew", "dlt_scan_deskew_dev", "dlt_scan_downsample", "dlt_scan_get_undistorted", "dlt_scan_get_down", "dlt_scan_set_down",
     "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
     "dlt_fetch_result", "dlt_degeneracy", "dlt_degeneracy_begin", "dlt_map_incremental", "dlt_set_profiling", "dlt_get_profile", "dlt_launch_count",
+    "dlt_scan_downsample_async", "dlt_iekf_update", "dlt_get_timeline",
 ]
 
 
@@ -257,7 +258,7 @@ class ScanToMap:
         self._ck(self.lib.dlt_map_incremental(self.h, _p(ps), C.c_int(1 if flg_EKF_inited else 0), C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    PROFILE_GROUPS = ("knn", "residual", "deskew", "voxelgrid", "insert", "far_fallback", "spare6", "knn8")
+    PROFILE_GROUPS = ("knn", "residual", "deskew", "voxelgrid", "insert", "far_fallback", "iekf_step", "knn8")
 
     def set_profiling(self, on: bool):
         self._ck(self.lib.dlt_set_profiling(self.h, C.c_int(1 if on else 0)))
@@ -267,6 +268,13 @@ class ScanToMap:
         cnt = np.zeros(8, np.int64)
         self._ck(self.lib.dlt_get_profile(self.h, _p(ms), _p(cnt), C.c_int(1 if reset else 0)))
         return {g: (float(ms[i]), int(cnt[i])) for i, g in enumerate(self.PROFILE_GROUPS)}
+
+    def get_timeline(self, cap=4096):
+        buf = np.zeros((cap, 3), np.float64)
+        n = C.c_int(0)
+        self._ck(self.lib.dlt_get_timeline(self.h, _p(buf), C.c_int(cap), C.byref(n)))
+        names = self.PROFILE_GROUPS + ("eigen6",)
+        return [(names[int(k)], float(a), float(b)) for k, a, b in buf[: min(n.value, cap)]]
 
     def launch_count(self) -> int:
         return int(self.lib.dlt_launch_count())

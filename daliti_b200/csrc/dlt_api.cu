@@ -5,6 +5,7 @@
 // and cached planes of the current IEKF update.  Host buffers in, host buffers out; every
 // kernel is in the three *_kernels.cuh headers.  There is no CPU code path here.
 #include <cmath>
+#include <cstddef>
 #include <string>
 #include <vector>
 
@@ -20,7 +21,7 @@ unsigned long long dlt::rt::g_launches = 0;
 
 namespace {
 constexpr int kMaxImuPoses = 512;
-constexpr int kProfKinds = 8;  // 0 knn, 1 residual, 2 deskew, 3 voxelgrid, 4 insert, 5 far fallback, 6 delete/export, 7 k_knn8 alone
+constexpr int kProfKinds = 9;  // 0 knn, 1 residual, 2 deskew, 3 voxelgrid, 4 insert, 5 far fallback, 6 k_iekf_step, 7 k_knn8 alone, 8 k_eigen6
 struct ProfSpan {
     int kind;
     rt::Event a, b;
@@ -33,6 +34,10 @@ constexpr int kFarGroupsX = 4;
 struct dlt_handle_s {
     dlt_config cfg;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // the degeneracy eigen-decomposition runs on a side stream so that it overlaps the map insert kernels
+    cudaStream_t aux_stream = nullptr;
+    rt::Event ev_fork, ev_join;
+    bool have_aux = false, eig_pending = false;
     std::string err;
     int cap = 0;  // per-point array capacity (max_scan_points)
     int n_sm = 148;
@@ -70,6 +75,11 @@ struct dlt_handle_s {
     unsigned char *d_dsflag = nullptr, *d_addflag = nullptr;
     int *d_cellslot = nullptr, *d_vslot = nullptr;
     DsScratch scratch;
+    // device-resident iteration loop (dlt_iekf_update)
+    IekfDev *d_iekf = nullptr;
+    dlt_iekf_block *h_iekf = nullptr;  // pinned
+    bool n_down_on_device = false;     // dlt_scan_downsample_async ran: h->n_down is only an estimate until the next read-back
+    int n_down_hint = 0;               // feats_down_size of the previous scan (grid sizing for the speculative launches)
     // pinned host staging
     double *h_result = nullptr;
     int *h_ints = nullptr;
@@ -78,8 +88,8 @@ struct dlt_handle_s {
     // optional per-kernel timing with CUDA events on the launching stream
     bool prof_on = false;
     std::vector<ProfSpan> spans;
-    double prof_ms[kProfKinds] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long prof_n[kProfKinds] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double prof_ms[kProfKinds] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_n[kProfKinds] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -87,18 +97,19 @@ struct ProfScope {  // records an event pair around the launches issued inside t
     dlt_handle h;
     ProfSpan sp;
     bool on;
-    ProfScope(dlt_handle h_, int kind) : h(h_), on(h_->prof_on) {
+    cudaStream_t st;
+    ProfScope(dlt_handle h_, int kind, cudaStream_t s = nullptr) : h(h_), on(h_->prof_on), st(s ? s : h_->stream) {
         if (!on) return;
         sp.kind = kind;
         if (rt::event_create(&sp.a) || rt::event_create(&sp.b)) {
             on = false;
             return;
         }
-        rt::event_record(sp.a, h->stream);
+        rt::event_record(sp.a, st);
     }
     ~ProfScope() {
         if (!on) return;
-        rt::event_record(sp.b, h->stream);
+        rt::event_record(sp.b, st);
         h->spans.push_back(sp);
     }
 };
@@ -143,20 +154,44 @@ static int map_reset(dlt_handle h) {
     return DLT_OK;
 }
 
-// one match pass: 8 lanes per query over the 3^3 block, then warp-per-query for what that could not prove exact
-static int launch_knn(dlt_handle h, const float4 *d_q, int n, int body_frame, const Pose &P) {
-    DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));   // far_count
-    DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));   // unresolved after ring 1
+// one match pass: 8 lanes per query over the 3^3 block, then warp-per-query for what that could not prove exact.
+// n_grid sizes the k_knn8 grid (an estimate of n is fine: the kernel strides); with la.ctl the kernels take n, the pose
+// and the do_match decision from device memory.  far_count is zeroed by k_knn8, the hand-over counter by k_residual
+// (the classic callers without a residual pass clear it themselves).
+static int launch_knn(dlt_handle h, const float4 *d_q, int n, int n_grid, int body_frame, const Pose &P, LoopArgs la) {
     {
         ProfScope prof8(h, 7);  // the dominant kernel on its own (group 0 spans the whole match pass)
-        DLT_LAUNCH(k_knn8, div_up(n, kKnn8Block / 8), kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres,
-                   h->d_counters + 8);
+        int g8 = div_up(n_grid, kKnn8Block / 8);
+        if (g8 < 1) g8 = 1;
+        DLT_LAUNCH(k_knn8, g8, kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la);
     }
-    int grid = div_up(n, kKnnWarps);
+    int grid = div_up(n_grid, kKnnWarps);
     const int cap_grid = h->n_sm * 8;
     if (grid > cap_grid) grid = cap_grid;
+    if (grid < 1) grid = 1;
     DLT_LAUNCH(k_knn, grid, kKnnWarps * 32, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, (const int *)h->d_unres,
-               (const int *)(h->d_counters + 8));
+               (const int *)(h->d_counters + 8), la);
+    return DLT_OK;
+}
+
+// the side stream's read of d_result must finish before the main stream overwrites it
+static int eig_join(dlt_handle h) {
+    if (h->eig_pending) {
+        DLT_RT(h, rt::stream_wait(h->stream, h->ev_join));
+        h->eig_pending = false;
+    }
+    return DLT_OK;
+}
+
+// feats_down_size after dlt_scan_downsample_async: fetch it the first time the host needs it
+static int resolve_n_down(dlt_handle h) {
+    if (!h->n_down_on_device) return DLT_OK;
+    DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    h->n_down_on_device = false;
+    if (h->h_sc->vox_status == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    h->n_down = h->h_sc->n_down;
+    h->n_down_hint = h->n_down;
     return DLT_OK;
 }
 
@@ -254,6 +289,13 @@ int dlt_destroy(dlt_handle h) {
     rt::pinned_release(h->h_result);
     rt::pinned_release(h->h_ints);
     rt::pinned_release(h->h_sc);
+    rt::pinned_release(h->h_iekf);
+    if (h->have_aux) {
+        rt::sync(h->aux_stream);
+        rt::event_destroy(h->ev_fork);
+        rt::event_destroy(h->ev_join);
+    }
+    rt::stream_destroy(h->aux_stream);
     rt::stream_destroy(h->own_stream);
     delete h;
     return DLT_OK;
@@ -273,6 +315,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->n_sm = rt::sm_count();
     bool ok = rt::stream_create(&h->own_stream) == 0;
     h->stream = h->own_stream;
+    h->have_aux = rt::stream_create(&h->aux_stream) == 0 && rt::event_create_untimed(&h->ev_fork) == 0 && rt::event_create_untimed(&h->ev_join) == 0;
 
     // search cell edge = ds_map * 2^shift with 3 edges covering sqrt(max_sq_dist)
     int shift = 1;
@@ -311,8 +354,10 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
          !dalloc(h, &h->d_result, (size_t)kResultDoubles) && !dalloc(h, &h->d_ticket, 4) &&
          !dalloc(h, &h->d_far_partial, (size_t)kFarChunk * kFarSlices * kK) && !dalloc(h, &h->d_pw, cap) && !dalloc(h, &h->d_dsflag, cap) &&
          !dalloc(h, &h->d_addflag, cap) && !dalloc(h, &h->d_cellslot, cap) && !dalloc(h, &h->d_vslot, cap) &&
-         !dalloc(h, &h->scratch.vkeys, sc_cap) && !dalloc(h, &h->scratch.vwin, sc_cap);
+         !dalloc(h, &h->scratch.vkeys, sc_cap) && !dalloc(h, &h->scratch.vwin, sc_cap) && !dalloc(h, &h->d_iekf, 1);
     void *p = nullptr;
+    ok = ok && rt::pinned_alloc(&p, sizeof(dlt_iekf_block)) == 0;
+    h->h_iekf = (dlt_iekf_block *)p;
     ok = ok && rt::pinned_alloc(&p, kResultDoubles * sizeof(double)) == 0;
     h->h_result = (double *)p;
     ok = ok && rt::pinned_alloc(&p, 64 * sizeof(int)) == 0;
@@ -370,6 +415,7 @@ int dlt_map_build_from_scan(dlt_handle h, const double *pose24) {
     if (!h || !pose24) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_build_from_scan before a downsampled scan is set");
     rt::set_device(h->cfg.device);
+    if (int rn = resolve_n_down(h)) return rn;
     int rc = map_reset(h);
     if (rc) return rc;
     h->have_match = false;
@@ -468,9 +514,12 @@ int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *ou
         }
         DLT_RT(h, rt::h2d(h->d_pw, stage.data(), (size_t)c * sizeof(float4), h->stream));
         {
-            int rk = launch_knn(h, (const float4 *)h->d_pw, c, 0, P);
+            DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));  // no residual pass here to re-arm it
+            LoopArgs la = {nullptr, nullptr};
+            int rk = launch_knn(h, (const float4 *)h->d_pw, c, c, 0, P, la);
             if (rk) return rk;
         }
+        DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));
         DLT_RT(h, rt::check_launch());
         h->nfar_known = false;
         int rc = run_far(h, nullptr);
@@ -532,20 +581,11 @@ int dlt_scan_deskew_dev(dlt_handle h, const void *pts48_dev, int n_raw, const do
     return scan_deskew_impl(h, pts48_dev, true, n_raw, imu_pose22, n_pose, pose24);
 }
 
-int dlt_scan_downsample(dlt_handle h, int *n_down) {
-    if (!h || !n_down) return DLT_E_INVALID;
-    if (!h->have_raw) DLT_FAIL(h, DLT_E_STATE, "dlt_scan_downsample before dlt_scan_deskew");
-    rt::set_device(h->cfg.device);
+// the five VoxelGrid kernels, enqueued
+static int enqueue_downsample(dlt_handle h) {
     const int n = h->n_raw;
-    h->n_down = 0;
-    *n_down = 0;
-    h->have_match = false;
-    if (n == 0) {
-        h->have_down = true;
-        return DLT_OK;
-    }
     const int B = 256, G = div_up(n, B);
-    ProfScope *prof = new ProfScope(h, 3);
+    ProfScope prof(h, 3);
     DLT_LAUNCH(k_vox_mark, G, B, h->stream, (const float4 *)h->d_undist, n, h->cfg.ds_scan, h->d_sc, h->d_bitmap, h->bitmap_bits, h->d_vidx);
     DLT_LAUNCH(k_vox_scan1, h->n_scan_blocks, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, (const ScanScalars *)h->d_sc, h->d_wprefix,
                h->d_blksum);
@@ -554,14 +594,49 @@ int dlt_scan_downsample(dlt_handle h, int *n_down) {
                (const unsigned *)h->d_wprefix, (const unsigned *)h->d_blkoff, (const unsigned *)h->d_vidx, h->acc, h->d_vop);
     DLT_LAUNCH(k_vox_final, G, B, h->stream, h->d_sc, h->acc, h->d_bitmap, (const float4 *)h->d_undist, h->d_down, n);
     h->sc_clean = true;
-    delete prof;
+    return DLT_OK;
+}
+
+int dlt_scan_downsample(dlt_handle h, int *n_down) {
+    if (!h || !n_down) return DLT_E_INVALID;
+    if (!h->have_raw) DLT_FAIL(h, DLT_E_STATE, "dlt_scan_downsample before dlt_scan_deskew");
+    rt::set_device(h->cfg.device);
+    const int n = h->n_raw;
+    h->n_down = 0;
+    *n_down = 0;
+    h->have_match = false;
+    h->n_down_on_device = false;
+    if (n == 0) {
+        h->have_down = true;
+        return DLT_OK;
+    }
+    enqueue_downsample(h);
     DLT_RT(h, rt::check_launch());
     DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     if (h->h_sc->vox_status == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
     h->n_down = h->h_sc->n_down;
+    h->n_down_hint = h->n_down;
     *n_down = h->n_down;
     h->have_down = true;
+    return DLT_OK;
+}
+
+int dlt_scan_downsample_async(dlt_handle h) {
+    if (!h) return DLT_E_INVALID;
+    if (!h->have_raw) DLT_FAIL(h, DLT_E_STATE, "dlt_scan_downsample_async before dlt_scan_deskew");
+    rt::set_device(h->cfg.device);
+    h->have_match = false;
+    h->have_down = true;
+    if (h->n_raw == 0) {
+        h->n_down = 0;
+        h->n_down_on_device = false;
+        return DLT_OK;
+    }
+    enqueue_downsample(h);
+    DLT_RT(h, rt::check_launch());
+    h->n_down = h->n_raw;  // upper bound until dlt_iekf_update reads feats_down_size back
+    h->n_down_on_device = true;
     return DLT_OK;
 }
 
@@ -579,6 +654,7 @@ int dlt_scan_get_undistorted(dlt_handle h, float *xyzi, int cap, int *n) {
 int dlt_scan_get_down(dlt_handle h, float *xyzi, int cap, int *n) {
     if (!h || !n) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "no downsampled scan");
+    if (int rn = resolve_n_down(h)) return rn;
     *n = h->n_down;
     int m = h->n_down < cap ? h->n_down : cap;
     if (m > 0 && xyzi) {
@@ -614,6 +690,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_measure before a downsampled scan is set");
     if (!do_match && !h->have_match) DLT_FAIL(h, DLT_E_STATE, "dlt_measure(do_match=0) before any match pass");
     rt::set_device(h->cfg.device);
+    if (int rn = resolve_n_down(h)) return rn;
     const int n = h->n_down;
     Pose P = pose_from(pose24);
     if (n == 0) {
@@ -621,11 +698,15 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
         h->have_match = true;
         return DLT_OK;
     }
-    if (result_dev == h->d_result) h->eig_valid = false;
+    if (result_dev == h->d_result) {
+        h->eig_valid = false;
+        if (int rj = eig_join(h)) return rj;
+    }
     if (do_match) {
         h->nfar_known = false;
         ProfScope prof(h, 0);
-        int rk = launch_knn(h, (const float4 *)h->d_down, n, 1, P);
+        LoopArgs la0 = {nullptr, nullptr};
+        int rk = launch_knn(h, (const float4 *)h->d_down, n, n, 1, P, la0);
         if (rk) return rk;
         h->have_match = true;
     }
@@ -640,14 +721,107 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     mb.partials = h->d_partials;
     mb.ticket = h->d_ticket;
     mb.far_count = h->d_counters + 5;
+    mb.unres_count = h->d_counters + 8;
     mb.result = result_dev;
     const int G = div_up(n, kResidBlock);
+    LoopArgs la = {nullptr, nullptr};
     ProfScope prof(h, 1);
     if (h->cfg.extrinsic_est_en)
-        DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr);
+        DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr, la);
     else
-        DLT_LAUNCH(k_residual<false>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr);
+        DLT_LAUNCH(k_residual<false>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr, la);
     DLT_RT(h, rt::check_launch());
+    return DLT_OK;
+}
+
+// ------------------------------------------------------------------ the iteration loop on the device
+int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, void *reduce_ctx, double *result_dev) {
+    if (!h || !blk) return DLT_E_INVALID;
+    if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_iekf_update before a downsampled scan is set");
+    if (blk->max_iteration < 1 || blk->max_iteration > DLT_IEKF_MAX_ITER) DLT_FAIL(h, DLT_E_INVALID, "max_iteration out of range");
+    rt::set_device(h->cfg.device);
+    const int n_iter = blk->max_iteration;
+    // host -> device: everything up to (not including) the out fields
+    blk->n_iters = blk->converged = blk->ekf_stop = blk->have_gain = blk->status = 0;
+    blk->n_down = blk->n_unresolved = blk->reserved1 = 0;
+    blk->iter = blk->rematch_num = blk->rematch_en = blk->done = 0;
+    const size_t up_bytes = offsetof(dlt_iekf_block, reserved3);
+    std::memcpy(h->h_iekf, blk, up_bytes);
+    DLT_RT(h, rt::h2d(&h->d_iekf->b, h->h_iekf, up_bytes, h->stream));
+
+    // speculative grids: feats_down_size may still be on the device
+    int n_grid = h->n_down;
+    if (h->n_down_on_device) {
+        n_grid = h->n_down_hint > 0 ? (int)(1.25 * h->n_down_hint) + 1024 : h->n_raw;
+        if (n_grid > h->n_raw) n_grid = h->n_raw;
+    }
+    const int n_upper = h->n_down_on_device ? h->n_raw : h->n_down;  // k_residual: one point per thread, surplus blocks exit
+    Pose P = {};
+    MeasureBufs mb;
+    mb.down = h->d_down;
+    mb.nbr = h->knn.nbr;
+    mb.flags = h->knn.flags;
+    mb.plane = h->d_plane;
+    mb.coeff = h->d_coeff;
+    mb.sel = h->d_sel;
+    mb.eff = h->d_eff;
+    mb.partials = h->d_partials;
+    mb.ticket = h->d_ticket;
+    mb.far_count = h->d_counters + 5;
+    mb.unres_count = h->d_counters + 8;
+    double *res = result_dev ? result_dev : h->d_result;
+    mb.result = res;
+    LoopArgs la = {h->d_iekf, &h->d_sc->n_down};
+    if (!h->n_down_on_device) {  // the scan was set with a host-known size: publish it where the kernels look
+        DLT_RT(h, rt::h2d(&h->d_sc->n_down, &h->n_down, sizeof(int), h->stream));
+    }
+    h->eig_valid = false;
+    h->nfar_known = false;
+    if (int rj = eig_join(h)) return rj;
+    int G = div_up(n_upper, kResidBlock);
+    if (G < 1) G = 1;
+    for (int it = 0; it < n_iter; it++) {
+        {
+            ProfScope prof(h, 0);
+            int rk = launch_knn(h, (const float4 *)h->d_down, 0, n_grid, 1, P, la);
+            if (rk) return rk;
+        }
+        {
+            ProfScope prof(h, 1);
+            if (h->cfg.extrinsic_est_en)
+                DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, 0, 0, P, h->cfg.plane_thr, la);
+            else
+                DLT_LAUNCH(k_residual<false>, G, kResidBlock, h->stream, mb, 0, 0, P, h->cfg.plane_thr, la);
+        }
+        if (reduce && reduce(reduce_ctx, res, kNormalEqDoubles) != 0) DLT_FAIL(h, DLT_E_STATE, "reduce callback failed");
+        ProfScope profs(h, 6);
+        DLT_LAUNCH(k_iekf_step, 1, kIekfBlock, h->stream, h->d_iekf, (const double *)res, (const int *)&h->d_sc->n_down,
+                   (const int *)&h->d_sc->vox_status, h->cfg.extrinsic_est_en ? 12 : 6);
+    }
+    if (res != h->d_result) DLT_RT(h, rt::d2d(h->d_result, res, kNormalEqDoubles * sizeof(double), h->stream));  // for dlt_degeneracy
+    DLT_RT(h, rt::check_launch());
+    // degeneracy output: fork the eigen-decomposition of the last normal equations onto the side stream now, so that
+    // it runs while the host waits for / digests the block below
+    h->have_match = true;
+    if (int re = dlt_degeneracy_begin(h)) return re;
+    // device -> host: in/out + out fields + the iteration records that can have been written
+    const size_t lo = offsetof(dlt_iekf_block, state);
+    const size_t hi = offsetof(dlt_iekf_block, iters) + (size_t)n_iter * sizeof(dlt_iekf_iter);
+    DLT_RT(h, rt::d2h((char *)h->h_iekf + lo, (const char *)&h->d_iekf->b + lo, hi - lo, h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    std::memcpy((char *)blk + lo, (const char *)h->h_iekf + lo, hi - lo);
+    if (h->n_down_on_device && blk->n_iters == 0) {  // the loop never ran: fetch feats_down_size the plain way
+        if (int rn = resolve_n_down(h)) return rn;
+        blk->n_down = h->n_down;
+    }
+    h->n_down = blk->n_down;
+    h->n_down_hint = blk->n_down;
+    h->n_down_on_device = false;
+    h->have_match = blk->n_iters > 0;
+    h->h_last_nfar = blk->n_unresolved;
+    h->nfar_known = blk->n_iters > 0;
+    if (blk->reserved1 == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    if (blk->status == 1) DLT_FAIL(h, DLT_E_STATE, "H^T H + (P/R)^-1 is singular");
     return DLT_OK;
 }
 
@@ -687,6 +861,7 @@ int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *ou
     out->n_unresolved = (int)(R[158] + 0.5);
     out->reserved = 0;
     if (result_dev != h->d_result) {  // keep a copy so that dlt_degeneracy works on the reduced normal equations
+        if (int rj = eig_join(h)) return rj;
         DLT_RT(h, rt::d2d(h->d_result, result_dev, kNormalEqDoubles * sizeof(double), h->stream));
         h->eig_valid = false;
     }
@@ -696,6 +871,7 @@ int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *ou
 int dlt_effective_points(dlt_handle h, float *xyzi, float *coeff, int cap, int *n) {
     if (!h || !n) return DLT_E_INVALID;
     if (!h->have_match) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");
+    if (int rn = resolve_n_down(h)) return rn;
     const int nd = h->n_down;
     std::vector<unsigned char> eff(nd);
     std::vector<float4> pts(nd), cf(nd);
@@ -738,9 +914,22 @@ int dlt_degeneracy_begin(dlt_handle h) {
     if (!h->have_match && !h->eig_valid) DLT_FAIL(h, DLT_E_STATE, "no measurement yet");
     rt::set_device(h->cfg.device);
     if (!h->eig_valid) {
-        DLT_LAUNCH(k_eigen6, 1, 32, h->stream, h->d_result);
+        cudaStream_t s = h->stream;
+        if (h->have_aux) {  // fork: the decomposition overlaps whatever the caller queues next (map_incremental)
+            DLT_RT(h, rt::event_record(h->ev_fork, h->stream));
+            DLT_RT(h, rt::stream_wait(h->aux_stream, h->ev_fork));
+            s = h->aux_stream;
+        }
+        {
+            ProfScope profe(h, 8, s);
+            DLT_LAUNCH(k_eigen6, 1, 32, s, (const double *)h->d_result, h->d_result + kEigOffset);
+        }
         DLT_RT(h, rt::check_launch());
-        DLT_RT(h, rt::d2h(h->h_result + kEigOffset, h->d_result + kEigOffset, 42 * sizeof(double), h->stream));
+        DLT_RT(h, rt::d2h(h->h_result + kEigOffset, h->d_result + kEigOffset, 42 * sizeof(double), s));
+        if (h->have_aux) {
+            DLT_RT(h, rt::event_record(h->ev_join, h->aux_stream));
+            h->eig_pending = true;
+        }
         h->eig_valid = true;
     }
     return DLT_OK;
@@ -750,7 +939,12 @@ int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
     if (!h || !eigvals6 || !eigvecs36) return DLT_E_INVALID;
     int rc = dlt_degeneracy_begin(h);
     if (rc) return rc;
-    DLT_RT(h, rt::sync(h->stream));
+    if (h->eig_pending) {
+        DLT_RT(h, rt::sync(h->aux_stream));
+        h->eig_pending = false;
+    } else {
+        DLT_RT(h, rt::sync(h->stream));
+    }
     for (int i = 0; i < 6; i++) eigvals6[i] = h->h_result[kEigOffset + i];
     for (int i = 0; i < 36; i++) eigvecs36[i] = h->h_result[kEigOffset + 6 + i];
     return DLT_OK;
@@ -762,6 +956,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental before a scan");
     if (h->map.shard_count > 1) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental is not supported on a sharded map yet");
     rt::set_device(h->cfg.device);
+    if (int rn = resolve_n_down(h)) return rn;
     const int n = h->n_down;
     if (n_ds) *n_ds = 0;
     if (n_raw) *n_raw = 0;
@@ -802,8 +997,10 @@ int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset) {
     }
     h->spans.clear();
     for (int k = 0; k < kProfKinds; k++) {
-        ms8[k] = h->prof_ms[k];
-        count8[k] = h->prof_n[k];
+        if (k < 8) {
+            ms8[k] = h->prof_ms[k];
+            count8[k] = h->prof_n[k];
+        }
         if (reset) {
             h->prof_ms[k] = 0;
             h->prof_n[k] = 0;
@@ -812,5 +1009,18 @@ int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset) {
     return DLT_OK;
 }
 unsigned long long dlt_launch_count(void) { return rt::g_launches; }
+
+int dlt_get_timeline(dlt_handle h, double *kind_start_end, int cap, int *n) {
+    if (!h || !n || cap < 0 || (cap > 0 && !kind_start_end)) return DLT_E_INVALID;
+    DLT_RT(h, rt::sync(h->stream));
+    if (h->have_aux) DLT_RT(h, rt::sync(h->aux_stream));
+    *n = (int)h->spans.size();
+    for (int i = 0; i < *n && i < cap; i++) {
+        kind_start_end[3 * i] = (double)h->spans[i].kind;
+        kind_start_end[3 * i + 1] = (double)rt::event_elapsed_ms(h->spans[0].a, h->spans[i].a);
+        kind_start_end[3 * i + 2] = (double)rt::event_elapsed_ms(h->spans[0].a, h->spans[i].b);
+    }
+    return DLT_OK;
+}
 
 }  // extern "C"

@@ -338,22 +338,23 @@ DLT_HD void body_to_world(const Pose &P, float bx, float by, float bz, float &wx
     wy = (float)(gy + P.pos_end[1]);
     wz = (float)(gz + P.pos_end[2]);
 }
+// Eye3 + sin(ang) K + (1 - cos(ang)) K K with K = skew(unit axis): so3_math.h:41-48, 62-68
+DLT_HD void so3_rodrigues(double ax, double ay, double az, double ang, double *R) {
+    double s = sin(ang), c1 = 1.0 - cos(ang);
+    double K[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double kk = (c1 * K[3 * i]) * K[j] + (c1 * K[3 * i + 1]) * K[3 + j] + (c1 * K[3 * i + 2]) * K[6 + j];
+            R[3 * i + j] = ((i == j) ? 1.0 : 0.0) + K[3 * i + j] * s + kk;
+        }
+}
 // R = Exp(ang_vel, dt): so3_math.h:32-52
 DLT_HD void so3_exp(const double *w, double dt, double *R) {
     double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     if (n > 0.0000001) {
-        double ax = w[0] / n, ay = w[1] / n, az = w[2] / n;
-        double ang = n * dt;
-        double s = sin(ang), c1 = 1.0 - cos(ang);
-        // K = skew(axis);  I + s K + (c1 K) K
-        double K[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                double kk = (c1 * K[3 * i]) * K[j] + (c1 * K[3 * i + 1]) * K[3 + j] + (c1 * K[3 * i + 2]) * K[6 + j];
-                R[3 * i + j] = ((i == j) ? 1.0 : 0.0) + K[3 * i + j] * s + kk;
-            }
+        so3_rodrigues(w[0] / n, w[1] / n, w[2] / n, n * dt, R);
     } else {
 #pragma unroll
         for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;

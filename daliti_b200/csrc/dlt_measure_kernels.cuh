@@ -14,10 +14,47 @@
 //              deterministically across blocks; the last block also runs the 6x6 Jacobi
 //              eigen-decomposition of the pose block (the new degeneracy output).
 #pragma once
+#include "../../include/daliti_b200.h"
 #include "dlt_common.cuh"
 #include "dlt_map_kernels.cuh"
 
 namespace dlt {
+
+// Device-resident iteration loop (dlt_iekf_update): the kernels of one enqueued iteration take the
+// pose, the do_match decision and the scan size from device memory instead of from their
+// parameters, and return at once when the loop has already ended.  ctl == nullptr: classic path.
+struct IekfDev {
+    dlt_iekf_block b;
+    double K1c[24 * 12];  // K_1[:, :12] of the last Kalman update (laserMapping.cpp:1019)
+    double HtH12[144];    // its H^T H (for G = K H at :1084)
+};
+struct LoopArgs {
+    const IekfDev *ctl;
+    const int *n_ptr;  // feats_down_size on the device (ScanScalars::n_down)
+};
+// Block-wide: resolve (n, do_match, pose) for this launch; false = nothing to do.  The pose ends
+// up in shared memory either way so that both paths run the same code.
+DLT_D bool loop_resolve(const LoopArgs &la, const Pose &P_param, Pose *sP, int &n, int *do_match) {
+    bool go = true;
+    if (la.ctl) {
+        const dlt_iekf_block &c = la.ctl->b;
+        const int dm = (c.iter == 0 || c.rematch_en) ? 1 : 0;
+        if (c.done) go = false;
+        if (do_match) {
+            if (*do_match < 0) {  // a match-pass kernel: only runs when this iteration (re)matches
+                if (!dm) go = false;
+            } else {
+                *do_match = dm;
+            }
+        }
+        n = *la.n_ptr;
+        if (go && threadIdx.x < 24) reinterpret_cast<double *>(sP)[threadIdx.x] = c.state[threadIdx.x];
+    } else {
+        if (threadIdx.x < 24) reinterpret_cast<double *>(sP)[threadIdx.x] = reinterpret_cast<const double *>(&P_param)[threadIdx.x];
+    }
+    __syncthreads();
+    return go;
+}
 
 // per-point flag bits
 constexpr unsigned char kFlagMatched = 1;     // 5 neighbours found and d2[4] <= max_sq_dist
@@ -353,52 +390,87 @@ DLT_D void knn_warp_query(const MapView &m, const float4 *__restrict__ q_pts, in
 // (the ones k_knn_ring1 could not resolve) with a warp-stride loop.
 __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
     k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, const int *__restrict__ list,
-          const int *__restrict__ count) {
+          const int *__restrict__ count, LoopArgs la) {
     __shared__ float4 s_cand[kKnnWarps][kCandSlots];
     __shared__ int s_cid[kKnnWarps][kCandSlots];
     __shared__ int s_wl[kKnnWarps][kWlMax];
     __shared__ Cand s_bestw[kKnnWarps][kK];
     __shared__ int s_nb[kKnnWarps];
+    __shared__ Pose sP;
+    int is_match = -1;
+    if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_warps = gridDim.x * kKnnWarps;
     const int limit = list ? *count : n;
     for (int w = blockIdx.x * kKnnWarps + warp; w < limit; w += total_warps) {  // warp-uniform; no block-level barrier
         const int qi = list ? list[w] : w;
-        knn_warp_query(m, q_pts, qi, body_frame, P, max_sq_dist, out, s_cand[warp], s_cid[warp], s_wl[warp], s_bestw[warp], &s_nb[warp], lane);
+        knn_warp_query(m, q_pts, qi, body_frame, sP, max_sq_dist, out, s_cand[warp], s_cid[warp], s_wl[warp], s_bestw[warp], &s_nb[warp], lane);
         __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------ first pass: 8 lanes per query over the 3x3x3 block
-// Four queries per warp.  The 8 lanes of a group probe the 27 cells in 4 rounds, fetch one 128-byte bucket
-// per step (lane 0 the header, lanes 1-7 one point each) and every lane keeps the 5 best of the points it
-// saw in registers (stated order d2, x, y, z, id); the 8 sorted lists are merged with five 8-lane argmins.
-// A query is finished here when the 3^3 block proves its 5 best exact (the common case on a mapped
-// surface); the rest go to `unres_list` for the warp-per-query kernel above, which widens the search.
+// Four queries per warp.  The 8 lanes of a group probe the 27 cells in 4 rounds and fetch two 128-byte
+// buckets per step (lane 0 the header, lanes 1-7 one point each; both loads in flight before the first
+// is consumed).  Every lane keeps the 5 best of the points it saw as 64-bit keys (d2 bits << 32 | id;
+// d2 >= 0, so the bit pattern orders like the float) plus the smallest d2 it ever dropped; the 8 sorted
+// lists are merged with five 8-lane mins and the winners' coordinates are re-read from their (L1-hot)
+// buckets.  Keys order by (d2, id), the stated order is (d2, x, y, z, id): whenever two of the six best
+// share a d2 -- inside the winners or at the k-th boundary -- the query is left to the warp-per-query
+// kernel above, which applies the stated order exactly.  A query is finished here when the 3^3 block
+// proves its 5 best exact (the common case on a mapped surface); the rest go to `unres_list`.
 constexpr int kKnn8Block = 128;
+#ifndef DLT_KNN8_MINBLOCKS
+#define DLT_KNN8_MINBLOCKS 12
+#endif
+constexpr unsigned long long kKeyInf = (0x7F800000ull << 32) | 0x7FFFFFFFull;
 
-DLT_D Cand group8_min_cand(Cand c) {
+DLT_D unsigned long long group8_min_u64(unsigned long long k) {
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
-        Cand t;
-        t.d2 = __shfl_xor_sync(0xffffffffu, c.d2, o);
-        t.x = __shfl_xor_sync(0xffffffffu, c.x, o);
-        t.y = __shfl_xor_sync(0xffffffffu, c.y, o);
-        t.z = __shfl_xor_sync(0xffffffffu, c.z, o);
-        t.id = __shfl_xor_sync(0xffffffffu, c.id, o);
-        if (cand_less(t, c)) c = t;
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
+        k = t < k ? t : k;
     }
-    return c;
+    return k;
+}
+DLT_D unsigned group8_min_u32(unsigned k) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) k = min(k, __shfl_xor_sync(0xffffffffu, k, o));
+    return k;
+}
+// keep the kK smallest keys, ascending; `dropped` <- smallest d2 bits that ever fell off the list
+DLT_D void topk_insert_key(unsigned long long (&b)[kK], unsigned long long k, unsigned &dropped) {
+    if (k < b[kK - 1]) {
+        dropped = min(dropped, (unsigned)(b[kK - 1] >> 32));
+        b[kK - 1] = k;
+#pragma unroll
+        for (int t = kK - 1; t > 0; t--) {
+            const unsigned long long lo = b[t] < b[t - 1] ? b[t] : b[t - 1];
+            const unsigned long long hi = b[t] < b[t - 1] ? b[t - 1] : b[t];
+            b[t - 1] = lo;
+            b[t] = hi;
+        }
+    } else {
+        dropped = min(dropped, (unsigned)(k >> 32));
+    }
+}
+// one staged bucket line: lane `sub` of the group holds 16 bytes of bucket bb (sub 0 = header)
+DLT_D void knn8_consume(const float4 v, int &bb, int lane, int sub, float qx, float qy, float qz, unsigned long long (&best)[kK],
+                        unsigned &dropped) {
+    const int hdr_next = __shfl_sync(0xffffffffu, __float_as_int(v.z), lane & ~7);
+    const unsigned hdr_mask = __shfl_sync(0xffffffffu, __float_as_uint(v.w), lane & ~7);
+    if (bb >= 0 && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u)) {
+        const float d2 = calc_dist(qx, qy, qz, v.x, v.y, v.z);
+        topk_insert_key(best, ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(unsigned)(bb * 8 + sub), dropped);
+    }
+    bb = (bb >= 0) ? hdr_next : -1;
 }
 
-__global__ void __launch_bounds__(kKnn8Block)
-    k_knn8(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
-           int *__restrict__ unres_count) {
+// the four queries q0 .. q0+3 of one warp
+DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n, int body_frame, const Pose &P, float max_sq_dist, const KnnOut &out,
+                      int *__restrict__ unres_list, int *__restrict__ unres_count, int q0, int lane) {
     const unsigned FULL = 0xffffffffu;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, sub = lane & 7;
-    const int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4;
-    if (q0 >= n) return;  // warp-uniform
     const int qi = q0 + grp;
     const bool live = qi < n;
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -422,9 +494,10 @@ __global__ void __launch_bounds__(kKnn8Block)
             }
         }
     }
-    Cand best[kK];
+    unsigned long long best[kK];
 #pragma unroll
-    for (int t = 0; t < kK; t++) best[t] = cand_inf();
+    for (int t = 0; t < kK; t++) best[t] = kKeyInf;
+    unsigned dropped = 0x7F800000u;
 
     for (int r = 0; r < 4; r++) {
         const int ci = r * 8 + sub;
@@ -432,49 +505,48 @@ __global__ void __launch_bounds__(kKnn8Block)
         if (work && ci < 27) b = map_find(m, pack_key(cx + (ci % 3) - 1, cy + ((ci / 3) % 3) - 1, cz + (ci / 9) - 1));
         unsigned gb = (__ballot_sync(FULL, b >= 0) >> (grp * 8)) & 0xFFu;  // this group's found cells
         while (__any_sync(FULL, gb != 0u)) {                                // warp-uniform
-            const int src = gb ? (__ffs((int)gb) - 1) : 0;
-            int bb = __shfl_sync(FULL, b, (grp << 3) + src);
-            if (!gb) bb = -1;
+            const int s0 = gb ? (__ffs((int)gb) - 1) : -1;
+            gb &= gb - 1u;  // (0 stays 0)
+            const int s1 = gb ? (__ffs((int)gb) - 1) : -1;
             gb &= gb - 1u;
-            while (__any_sync(FULL, bb >= 0)) {  // the cell's bucket chain
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bb >= 0) v = reinterpret_cast<const float4 *>(&m.buckets[bb])[sub];  // 8 lanes x 16 B = one line
-                const int hdr_next = __shfl_sync(FULL, __float_as_int(v.z), lane & ~7);
-                const unsigned hdr_mask = __shfl_sync(FULL, __float_as_uint(v.w), lane & ~7);
-                if (bb >= 0 && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u)) {
-                    Cand c;
-                    c.d2 = calc_dist(qx, qy, qz, v.x, v.y, v.z);
-                    c.x = v.x;
-                    c.y = v.y;
-                    c.z = v.z;
-                    c.id = bb * 8 + sub;
-                    topk_insert(best, c);
-                }
-                bb = (bb >= 0) ? hdr_next : -1;
+            int bb0 = __shfl_sync(FULL, b, (grp << 3) + (s0 < 0 ? 0 : s0));
+            int bb1 = __shfl_sync(FULL, b, (grp << 3) + (s1 < 0 ? 0 : s1));
+            if (s0 < 0) bb0 = -1;
+            if (s1 < 0) bb1 = -1;
+            while (__any_sync(FULL, bb0 >= 0 || bb1 >= 0)) {  // the two cells' bucket chains
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (bb0 >= 0) v0 = reinterpret_cast<const float4 *>(&m.buckets[bb0])[sub];  // 8 lanes x 16 B = one line
+                if (bb1 >= 0) v1 = reinterpret_cast<const float4 *>(&m.buckets[bb1])[sub];
+                knn8_consume(v0, bb0, lane, sub, qx, qy, qz, best, dropped);
+                knn8_consume(v1, bb1, lane, sub, qx, qy, qz, best, dropped);
             }
         }
     }
-    // ---- merge the group's 8 sorted lists: five rounds of 8-lane argmin, the owner pops its head
+    // ---- merge the group's 8 sorted lists: five rounds of 8-lane min, the owner pops its head
     int nb = 0;
-    float d5 = INFINITY;
-    Cand mine_out = cand_inf();
+    unsigned prevd = 0xFFFFFFFFu;
+    bool tie = false;
+    unsigned long long mine = kKeyInf;
 #pragma unroll
     for (int t = 0; t < kK; t++) {
-        const Cand w = group8_min_cand(best[0]);
-        const bool valid = w.d2 < INFINITY;
-        if (valid && best[0].id == w.id) {
+        const unsigned long long w = group8_min_u64(best[0]);
+        const bool valid = (unsigned)(w >> 32) < 0x7F800000u;
+        if (valid && best[0] == w) {  // ids are unique: exactly one owner
 #pragma unroll
             for (int u = 0; u < kK - 1; u++) best[u] = best[u + 1];
-            best[kK - 1] = cand_inf();
+            best[kK - 1] = kKeyInf;
         }
         nb += valid ? 1 : 0;
-        if (t == kK - 1) d5 = w.d2;
-        if (sub == t) {  // lane t of the group keeps result t until the exactness test below
-            mine_out = w;
-            if (!valid) mine_out.id = -1;
-        }
+        const unsigned wd = (unsigned)(w >> 32);
+        if (valid && wd == prevd) tie = true;
+        prevd = wd;
+        if (sub == t) mine = w;
     }
+    // the group's 6th-smallest d2: a remaining list head or something a lane dropped earlier
+    const unsigned sixth = group8_min_u32(min((unsigned)(best[0] >> 32), dropped));
     if (!work) return;
+    const float d5 = (nb == kK) ? __uint_as_float(prevd) : INFINITY;
+    if (nb == kK && sixth == prevd) tie = true;
     const float slack = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
     float cov = INFINITY;
     cov = fminf(cov, qx - (float)(cx - 1) * cell_edge);
@@ -484,19 +556,37 @@ __global__ void __launch_bounds__(kKnn8Block)
     cov = fminf(cov, qz - (float)(cz - 1) * cell_edge);
     cov = fminf(cov, (float)(cz + 2) * cell_edge - qz);
     cov -= slack;
-    const bool resolved = (nb == kK) && cov > 0.f && d5 < cov * cov * 0.99999f;
+    const bool resolved = (nb == kK) && !tie && cov > 0.f && d5 < cov * cov * 0.99999f;
     if (!resolved) {
         if (sub == 0) unres_list[atomicAdd(unres_count, 1)] = qi;
         return;
     }
     if (sub < kK) {
-        out.nbr[(size_t)qi * kK + sub] = make_float4(mine_out.x, mine_out.y, mine_out.z, mine_out.d2);
-        out.nbr_id[(size_t)qi * kK + sub] = mine_out.id;
+        const int id = (int)(unsigned)(mine & 0xFFFFFFFFull);
+        const float4 p = m.buckets[id >> 3].pts[(id & 7) - 1];
+        out.nbr[(size_t)qi * kK + sub] = make_float4(p.x, p.y, p.z, __uint_as_float((unsigned)(mine >> 32)));
+        out.nbr_id[(size_t)qi * kK + sub] = id;
     }
     if (sub == 0) {
         out.nbr_cnt[qi] = kK;
         out.flags[qi] = (d5 <= max_sq_dist) ? kFlagMatched : (unsigned char)0;
     }
+}
+
+// Warp-stride over groups of four queries, so the grid may be sized from an estimate of n (the
+// device-resident loop launches before the host knows feats_down_size).  Also zeroes far_count for
+// the warp-per-query pass that follows in stream order.
+__global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
+    k_knn8(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
+           int *__restrict__ unres_count, LoopArgs la) {
+    __shared__ Pose sP;
+    int is_match = -1;
+    if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out.far_count = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = gridDim.x * (kKnn8Block / 32) * 4;
+    for (int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4; q0 < n; q0 += stride)  // warp-uniform
+        knn8_group(m, q_pts, n, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane);
 }
 
 // ------------------------------------------------------------------ exact fallback for unresolved queries
@@ -611,16 +701,33 @@ struct MeasureBufs {
     double *partials;         // [blocks][NR]
     unsigned *ticket;
     const int *far_count;     // unresolved queries of the last match pass
+    int *unres_count;         // k_knn8 -> k_knn hand-over counter, re-armed here for the next match pass
     double *result;           // kResultDoubles
 };
 
 template <bool EXT>
 __global__ void __launch_bounds__(kResidBlock)
-    k_residual(MeasureBufs mb, int n, int do_match, Pose P, float plane_thr) {
+    k_residual(MeasureBufs mb, int n, int do_match, Pose P_param, float plane_thr, LoopArgs la) {
     using NE = NormalEq<EXT>;
     constexpr int D = NE::D, NR = NE::NR;
     __shared__ double s_part[kResidBlock / 32][NR];
     __shared__ int s_last;
+    __shared__ Pose sP;
+    if (!loop_resolve(la, P_param, &sP, n, &do_match)) return;  // block-uniform
+    // the grid may be larger than needed (sized before the host knows n): only the first n_blocks blocks work
+    const unsigned n_blocks = (unsigned)((n + kResidBlock - 1) / kResidBlock);
+    if (n_blocks == 0u) {  // empty scan: the normal equations are zero
+        if (blockIdx.x == 0) {
+            for (int k = threadIdx.x; k < kNormalEqDoubles; k += kResidBlock) mb.result[k] = 0.0;
+            if (threadIdx.x == 0) {
+                mb.result[158] = (double)(*mb.far_count);
+                *mb.unres_count = 0;
+            }
+        }
+        return;
+    }
+    if (blockIdx.x >= n_blocks) return;
+    const Pose &P = sP;
     const int i = blockIdx.x * kResidBlock + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -746,7 +853,7 @@ __global__ void __launch_bounds__(kResidBlock)
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned t = atomicAdd(mb.ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        s_last = (t == n_blocks - 1u) ? 1 : 0;
     }
     __syncthreads();
     if (!s_last) return;
@@ -762,10 +869,10 @@ __global__ void __launch_bounds__(kResidBlock)
             // 8 loads in flight per thread; the adds stay in block order (adding 0.0 for the padding is exact)
             const double *vp = mb.partials;
             constexpr unsigned S = kResidBlock / 32;
-            for (unsigned b = sl; b < gridDim.x; b += S * 8) {
+            for (unsigned b = sl; b < n_blocks; b += S * 8) {
                 double t[8];
 #pragma unroll
-                for (unsigned u = 0; u < 8; u++) t[u] = (b + S * u < gridDim.x) ? __ldcg(vp + (size_t)(b + S * u) * NR + v) : 0.0;
+                for (unsigned u = 0; u < 8; u++) t[u] = (b + S * u < n_blocks) ? __ldcg(vp + (size_t)(b + S * u) * NR + v) : 0.0;
 #pragma unroll
                 for (unsigned u = 0; u < 8; u++) acc += t[u];
             }
@@ -793,6 +900,7 @@ __global__ void __launch_bounds__(kResidBlock)
         R[157] = s_fin[k + 1];
         R[158] = (double)(*mb.far_count);
         *mb.ticket = 0u;
+        *mb.unres_count = 0;
     }
 }
 
@@ -801,7 +909,7 @@ __global__ void __launch_bounds__(kResidBlock)
 // the 15 index pairs of a sweep are visited in 5 rounds of 3 disjoint pairs (round-robin
 // tournament); lanes 0-2 compute the three rotations of a round, then 18 lanes apply them to
 // the columns / rows of A and the columns of V.  Ascending eigenvalues, eigenvectors in columns.
-__global__ void __launch_bounds__(32) k_eigen6(double *__restrict__ result) {
+__global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result, double *__restrict__ eig_out /* eigvals[6], eigvecs[36] */) {
     __shared__ double A[36], V[36], cs[3][2];
     __shared__ int pq[3][2];
     const int lane = threadIdx.x;
@@ -881,10 +989,345 @@ __global__ void __launch_bounds__(32) k_eigen6(double *__restrict__ result) {
             ord[mn] = t;
         }
         for (int i = 0; i < 6; i++) {
-            result[kEigOffset + i] = ev[ord[i]];
-            for (int k = 0; k < 6; k++) result[kEigOffset + 6 + k * 6 + i] = V[k * 6 + ord[i]];
+            eig_out[i] = ev[ord[i]];
+            for (int k = 0; k < 6; k++) eig_out[6 + k * 6 + i] = V[k * 6 + ord[i]];
         }
     }
+}
+
+// ------------------------------------------------------------------ the iteration loop on the device
+// One launch per enqueued iteration, after that iteration's k_residual: laserMapping.cpp:899-918
+// (degradation window), :1012-1053 (Kalman update in the reduced form of SURVEY.md 8b), :1054-1063
+// (stop branch), :1069-1101 (rematch / convergence control) and :1084-1085 (covariance update).
+// One block; the 24 x 24 solve is a Gauss-Jordan elimination in shared
+// memory, the SO(3) pieces run on one thread.  Mirrors dlt_host::LaserMapping::process_scan.
+namespace iekf {
+DLT_D void mat3_mul(const double *a, const double *b, double *r) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+DLT_D void mat3T_mul(const double *a, const double *b, double *r) {  // a^T b
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
+}
+// Exp(v1, v2, v3), so3_math.h:54-72
+DLT_D void exp3(double v1, double v2, double v3, double *R) {
+    const double n = sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+    if (n > 0.00001) {
+        so3_rodrigues(v1 / n, v2 / n, v3 / n, n, R);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    }
+}
+// Log(R), so3_math.h:75-81
+DLT_D void log3(const double *R, double *o) {
+    const double tr = R[0] + R[4] + R[8];
+    const double theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1));
+    const double K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+    const double f = (fabs(theta) < 0.001) ? 0.5 : (0.5 * theta / sin(theta));
+    o[0] = K[0] * f;
+    o[1] = K[1] * f;
+    o[2] = K[2] * f;
+}
+// a (-) b over the 24-dim error state, common_lib.h:173-187
+DLT_D void boxminus(const double *a, const double *b, double *o) {
+    double M[9];
+    mat3T_mul(b, a, M);
+    log3(M, o);
+    mat3T_mul(b + 12, a + 12, M);
+    log3(M, o + 6);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o[3 + k] = a[9 + k] - b[9 + k];
+        o[9 + k] = a[21 + k] - b[21 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) o[12 + k] = a[24 + k] - b[24 + k];
+}
+// s (+)= d, common_lib.h:147-158
+DLT_D void boxplus_inplace(double *s, const double *d) {
+    double E[9], M[9];
+    exp3(d[0], d[1], d[2], E);
+    mat3_mul(s, E, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) s[k] = M[k];
+    exp3(d[6], d[7], d[8], E);
+    mat3_mul(s + 12, E, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) s[12 + k] = M[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        s[9 + k] += d[3 + k];
+        s[21 + k] += d[9 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[24 + k] += d[12 + k];
+}
+}  // namespace iekf
+
+constexpr int kIekfBlock = 576;  // one thread per covariance element
+
+// Kalman gain in covariance (Woodbury) form.  The reference inverts twice, K_1 = (H^T H + (P/R)^-1)^-1
+// (laserMapping.cpp:1017-1018); with P' = P/R, U = [I_12; 0] and H^T H = U H U^T the same matrix is
+//     K_1 = P' - P' U (I + H P'_11)^-1 H U^T P',     so     K_1[:, :12] = P'_1 - P'_1 Y,   (I + Q) Y = Q,   Q = H P'_11
+// (P'_1 = first 12 columns, P'_11 = top-left 12 x 12).  Without extrinsic estimation only the top-left D = 6 block of
+// H is non-zero, rows D..11 of Q and Y vanish and the system is D x D with 12 right-hand sides: 6 elimination steps
+// instead of two 24 x 24 inversions.  Equal to the reference form up to fp64 round-off (tests: 1e-7 on the solution).
+__global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const double *__restrict__ result, const int *__restrict__ n_down_ptr,
+                                                           const int *__restrict__ vox_status_ptr, int D /* 6 or 12 */) {
+    dlt_iekf_block &c = dev->b;
+    if (c.done) return;  // block-uniform
+    constexpr int N = 24;
+    __shared__ double PN[N * N];                      // P' = cov / LASER_POINT_COV
+    __shared__ double W[12 * 24];                     // [I + Q[:, :D] | Q], later G = K H (24 x 12)
+    __shared__ double T[N * 12];                      // K_1[:, :12]
+    __shared__ double C12[12 * N];                    // the first 12 rows of the covariance
+    __shared__ double R[kNormalEqDoubles + 2];        // the normal equations of this iteration
+    __shared__ double st[36], sprop[36], sother[36];  // state, state_propagat | thermal delta, last_nodegared (non-covariance parts)
+    __shared__ double vec[N], rhs[12], sol[N];
+    __shared__ int s_i[16];
+    __shared__ int s_q[10];
+    __shared__ int s_fail, s_piv;
+    enum { I_QLEN, I_THR, I_CONV, I_RNUM, I_MAXIT, I_INITED, I_GAIN, I_NDOWN, I_VOX };
+    const int tid = threadIdx.x;
+    const int it = c.iter;
+    dlt_iekf_iter &rec = c.iters[it];
+    const int did_match = (it == 0 || c.rematch_en) ? 1 : 0;
+    const int AW = D + 12;
+
+    // ---- one round trip to global memory for everything the step needs
+    for (int k = tid; k < kNormalEqDoubles + 1; k += kIekfBlock) R[k] = result[k];
+    double cov_own = c.state[36 + tid];
+    const double lpc = c.laser_point_cov;
+    if (tid < 36) {
+        st[tid] = c.state[tid];
+        sprop[tid] = c.state_propagat[tid];
+    } else if (tid >= 64 && tid < 74) {
+        s_q[tid - 64] = c.effct_queue[tid - 64];
+    } else if (tid == 96) {
+        s_i[I_QLEN] = c.queue_len;
+        s_i[I_THR] = c.threshold;
+        s_i[I_CONV] = c.converged;
+    } else if (tid == 97) {
+        s_i[I_RNUM] = c.rematch_num;
+        s_i[I_MAXIT] = c.max_iteration;
+        s_i[I_INITED] = c.flg_EKF_inited;
+    } else if (tid == 98) {
+        s_i[I_GAIN] = c.have_gain;
+        s_i[I_NDOWN] = *n_down_ptr;
+        s_i[I_VOX] = *vox_status_ptr;
+    }
+    if (tid == 0) s_fail = 0;
+    PN[tid] = cov_own / lpc;
+    if (tid < 12 * N) C12[tid] = cov_own;
+    __syncthreads();
+
+    // effct_feat_numQueue, :899-918 -- every thread derives the same decision from shared memory
+    const int effct = (int)(R[156] + 0.5);
+    int ql = s_i[I_QLEN];
+    const int shift = (ql >= 10) ? 1 : 0;
+    ql -= shift;
+    int stop = (effct <= s_i[I_THR]) ? 1 : 0;
+    for (int k = 0; k < ql; k++)
+        if (s_q[k + shift] <= s_i[I_THR]) stop = 1;
+    if (tid < 10) c.effct_queue[tid] = (tid < ql) ? s_q[tid + shift] : (tid == ql ? effct : 0);
+    for (int k = tid; k < 144; k += kIekfBlock) rec.HtH[k] = R[k];
+    if (tid < 12) rec.Htr[tid] = R[144 + tid];
+    if (tid < 24) rec.pose_in[tid] = st[tid];
+    if (tid == 0) {
+        rec.iter = it;
+        rec.effct_feat_num = effct;
+        rec.total_residual = R[157];
+        rec.did_match = did_match;
+        rec.reserved = 0;
+        rec.ekf_stop = stop;
+        c.n_down = s_i[I_NDOWN];
+        c.reserved1 = s_i[I_VOX];  // VoxelGrid status of this scan (2 = bitmap capacity exceeded)
+        if (did_match) c.n_unresolved = (int)(R[158] + 0.5);
+        c.queue_len = ql + 1;
+        c.ekf_stop = stop;
+    }
+    int conv = s_i[I_CONV];
+    int have_gain = s_i[I_GAIN];
+    int inited = s_i[I_INITED];
+
+    if (!stop) {  // ---- Kalman update, :1012-1053
+        c.last_nodegared[36 + tid] = cov_own;  // :1050 (the covariance does not change inside the loop)
+        if (tid < D * 12) {                    // Q = H P'_11 (rows 0..D-1)
+            const int i = tid / 12, j = tid % 12;
+            double q = 0;
+            for (int a = 0; a < D; a++) q += R[i * 12 + a] * PN[a * N + j];
+            W[i * AW + D + j] = q;
+            if (j < D) W[i * AW + j] = q + ((i == j) ? 1.0 : 0.0);
+        }
+        if (tid == 320) iekf::boxminus(sprop, st, vec);  // :1028 (its own warp)
+        __syncthreads();
+        // (I + Q[:, :D]) Y = Q by Gauss-Jordan with partial pivoting, the row exchange folded into the update
+        for (int col = 0; col < D; col++) {
+            if (tid < 32) {
+                const int r = col + tid;
+                double v = (r < D) ? fabs(W[r * AW + col]) : -1.0;
+                int idx = r;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {  // D <= 12 rows: 16 lanes suffice
+                    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                    if (ov > v || (ov == v && oi < idx)) {
+                        v = ov;
+                        idx = oi;
+                    }
+                }
+                if (tid == 0) {
+                    s_piv = idx;
+                    if (!(v > 1e-300) || !(v < 1e300)) s_fail = 1;
+                }
+            }
+            __syncthreads();
+            if (s_fail) break;  // block-uniform
+            const int p = s_piv;
+            const int ncols = AW - 1 - col;
+            double v = 0.0;
+            int dst = -1;
+            if (tid < D * ncols) {
+                const int r = tid / ncols, j = col + 1 + tid % ncols;
+                const int src = (r == col) ? p : (r == p) ? col : r;  // row it comes from (rows p / col exchanged)
+                v = W[src * AW + j];
+                if (r != col) v = v - (W[src * AW + col] / W[p * AW + col]) * W[p * AW + j];
+                dst = r * AW + j;
+            }
+            double dcol = 0.0;  // the pivot moves to the diagonal; the rest of the column is never read again
+            if (tid == 0) dcol = W[p * AW + col];
+            __syncthreads();
+            if (dst >= 0) W[dst] = v;
+            if (tid == 0) W[col * AW + col] = dcol;
+            __syncthreads();
+        }
+        if (s_fail) {
+            if (tid == 0) {
+                c.status = 1;
+                c.done = 1;
+                c.n_iters = it;
+            }
+            return;
+        }
+        if (tid < N * 12) {  // K_1[:, :12] = P'_1 - P'_1[:, :D] Y
+            const int i = tid / 12, j = tid % 12;
+            double x = PN[i * N + j];
+            for (int a = 0; a < D; a++) x -= PN[i * N + a] * (W[a * AW + D + j] / W[a * AW + a]);
+            T[tid] = x;
+            dev->K1c[tid] = x;
+        }
+        for (int k = tid; k < 144; k += kIekfBlock) dev->HtH12[k] = R[k];
+        if (tid >= 320 && tid < 332) {  // solution = K_1[:, :12] (H^T r - H^T H vec_12) + vec, :1032
+            const int a = tid - 320;
+            double sacc = 0;
+            for (int b = 0; b < 12; b++) sacc += R[a * 12 + b] * vec[b];
+            rhs[a] = R[144 + a] - sacc;
+        }
+        __syncthreads();
+        if (tid < N) {
+            double sacc = 0;
+            for (int a = 0; a < 12; a++) sacc += T[tid * 12 + a] * rhs[a];
+            sol[tid] = sacc + vec[tid];
+            rec.solution[tid] = sol[tid];
+        }
+        __syncthreads();
+        // state (+)= solution, :1033 -- the two rotations on two warps, the vector parts on a third
+        if (tid == 0 || tid == 32) {
+            const int o = (tid == 0) ? 0 : 12, d = (tid == 0) ? 0 : 6;
+            double E[9], M[9];
+            iekf::exp3(sol[d], sol[d + 1], sol[d + 2], E);
+            iekf::mat3_mul(st + o, E, M);
+#pragma unroll
+            for (int k = 0; k < 9; k++) st[o + k] = M[k];
+        } else if (tid >= 64 && tid < 67) {
+            st[9 + tid - 64] += sol[3 + tid - 64];
+            st[21 + tid - 64] += sol[9 + tid - 64];
+        } else if (tid >= 96 && tid < 108) {
+            st[24 + tid - 96] += sol[12 + tid - 96];
+        }
+        const double rn = sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
+        const double tn = sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
+        conv = ((rn * 57.3 < 0.01) && (tn * 100 < 0.015)) ? 1 : 0;  // :1040
+        have_gain = 1;
+        __syncthreads();
+        if (tid < 36) {
+            c.state[tid] = st[tid];
+            c.last_nodegared[tid] = st[tid];  // :1050
+        }
+    } else {  // ---- stop branch, :1054-1063: state = last_nodegared_state + odomToStateGruop(delta)
+        if (tid < N) rec.solution[tid] = 0.0;
+        if (tid < 36) sother[tid] = c.last_nodegared[tid];
+        if (tid >= 64 && tid < 100) sprop[tid - 64] = c.thermal_delta[tid - 64];  // state_propagat is not needed on this branch
+        cov_own = c.last_nodegared[36 + tid];
+        c.state[36 + tid] = cov_own;
+        __syncthreads();  // (block-uniform branch)
+        if (tid == 0) {
+            const double *L = sother, *Dl = sprop;
+            iekf::mat3_mul(L, Dl, st);
+            iekf::mat3_mul(L + 12, Dl + 12, st + 12);
+            for (int k = 0; k < 3; k++) {
+                st[9 + k] = L[9 + k] + Dl[9 + k];
+                st[21 + k] = L[21 + k] + Dl[21 + k];
+                st[24 + k] = L[24 + k] + Dl[24 + k];
+            }
+            for (int k = 27; k < 36; k++) st[k] = L[k];  // bias_g, bias_a, gravity of the left operand
+        }
+        inited = 0;
+        __syncthreads();
+        if (tid < 36) c.state[tid] = st[tid];
+    }
+    if (tid < 36) rec.state_out[tid] = st[tid];
+    // ---- :1069-1101, every thread derives the same control decisions
+    int rematch_en = 0, rematch_num = s_i[I_RNUM];
+    if (conv || (rematch_num == 0 && it == s_i[I_MAXIT] - 2)) {
+        rematch_en = 1;
+        rematch_num++;
+    }
+    int fin = 0, upd = 0;
+    if (rematch_num >= 2 || it == s_i[I_MAXIT] - 1) {
+        fin = 1;
+        upd = (inited && have_gain) ? 1 : 0;
+    } else if (stop) {
+        fin = 1;
+    }
+    if (tid == 0) {
+        rec.converged = conv;
+        c.converged = conv;
+        c.have_gain = have_gain;
+        c.flg_EKF_inited = inited;
+        c.rematch_en = rematch_en;
+        c.rematch_num = rematch_num;
+        c.iter = it + 1;
+        c.n_iters = it + 1;
+    }
+    if (fin && upd) {  // G[:, :12] = K_1[:, :12] H^T H;  cov = (I - G) cov, :1084-1085   (block-uniform)
+        if (stop) {  // the gain of an earlier iteration: back from global memory (unreachable today: a stop clears inited)
+            for (int k = tid; k < N * 12; k += kIekfBlock) T[k] = dev->K1c[k];
+            for (int k = tid; k < 144; k += kIekfBlock) R[k] = dev->HtH12[k];
+        }
+        __syncthreads();
+        double *G = W;  // 24 x 12
+        if (tid < N * 12) {
+            const int i = tid / 12, j = tid % 12;
+            double sacc = 0;
+            for (int a = 0; a < 12; a++) sacc += T[i * 12 + a] * R[a * 12 + j];
+            G[tid] = sacc;
+        }
+        __syncthreads();
+        {
+            const int i = tid / N, j = tid % N;
+            double sacc = cov_own;
+            for (int a = 0; a < 12; a++) sacc -= G[i * 12 + a] * C12[a * N + j];
+            c.state[36 + tid] = sacc;
+        }
+    }
+    if (tid == 0 && fin) c.done = 1;
 }
 
 // ------------------------------------------------------------------ map_incremental classification

@@ -429,6 +429,7 @@ LaserMapping::LaserMapping(const dlt_lio_config &c) : cfg(c) {
 }
 LaserMapping::~LaserMapping() {
     if (dev_) dlt_destroy(dev_);
+    delete iekf_blk_;
 }
 void LaserMapping::on_lidar_msg() {
     lidar_frame_counter_num++;
@@ -487,6 +488,37 @@ int LaserMapping::fov_segment(const Vec3 &pos, int *deleted) {
     std::memcpy(LocalMap_max, nmax, sizeof(nmax));
     if (!boxes.empty() && map_built) return dlt_map_delete_boxes(dev_, boxes.data(), (int)(boxes.size() / 6), deleted);
     return 0;
+}
+
+// zeta blend, laserMapping.cpp:1105-1131
+void LaserMapping::zeta_blend(int effct_feat_num, const StatesGroup &state_propagat, const dlt_lio_thermal *th) {
+    if ((lidar_cnt < 100) || (!th->tis_online) || (th->tis_online && lidar_cnt % 2 == 1)) {
+        const double alpha_l = effct_feat_num / (cfg.beta * 65536.0);  // Nla, :106
+        zeta_l = 2.0 / (1.0 + std::exp(-alpha_l)) - 1;
+        double zeta_l_norm = zeta_l / (zeta_l + zeta_t);
+        if (lidar_cnt < 100) zeta_l_norm = 1;
+        double v1[kDim], v2[kDim];
+        state_propagat.boxminus(last_state, v1);
+        state.boxminus(last_state, v2);
+        for (int i = 0; i < kDim; i++) {
+            v1[i] *= (1 - zeta_l_norm);
+            v2[i] *= zeta_l_norm;
+        }
+        state = last_state.boxplus(v1).boxplus(v2);  // :1119 -- the result carries last_state.cov (reference quirk)
+    } else {
+        const double zeta_t_norm = zeta_t / (zeta_l + zeta_t);
+        double v1[kDim];
+        state.boxminus(last_state, v1);
+        for (int i = 0; i < kDim; i++) v1[i] *= (1 - zeta_t_norm);
+        StatesGroup o = odom_to_state(th->l2l_pos, th->l2l_quat, th->l2l_vel, th->l2l_cov_slots);
+        state = last_state.boxplus(v1).compose(o.scaled(zeta_t_norm));  // :1127
+    }
+    last_state = state;  // :1131
+}
+
+int LaserMapping::reduce_trampoline(void *self, double *result_dev, int n) {
+    LaserMapping *lm = static_cast<LaserMapping *>(self);
+    return lm->reduce_fn(lm->reduce_ctx, result_dev, n);
 }
 
 #define LM_CK(expr)                               \
@@ -554,17 +586,22 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     LM_CK(fov_segment(pos_lid, &out->deleted));  // :772
     out->t_delete = wall() - t0;
 
-    t0 = wall();
-    int feats_down_size = 0;
-    LM_CK(dlt_scan_downsample(dev_, &feats_down_size));  // :775-778
-    out->t_voxel = wall() - t0;
-    out->n_down = feats_down_size;
-
     if (!map_built) {  // a map built directly through the device handle (dlt_map_build) also counts as a root
         int c = 0;
         LM_CK(dlt_map_valid_count(dev_, &c));
         if (c > 0) map_built = true;
     }
+    // the device-resident loop needs no host copy of feats_down_size before it has run
+    const bool device_loop = cfg.device_loop && map_built && NUM_MAX_ITERATIONS >= 1 && NUM_MAX_ITERATIONS <= DLT_IEKF_MAX_ITER;
+    t0 = wall();
+    int feats_down_size = 0;
+    if (device_loop)
+        LM_CK(dlt_scan_downsample_async(dev_));
+    else
+        LM_CK(dlt_scan_downsample(dev_, &feats_down_size));  // :775-778
+    out->t_voxel = wall() - t0;
+    out->n_down = feats_down_size;
+
     if (!map_built) {  // ikdtree.Root_Node == nullptr, :780-793
         if (feats_down_size > 5) {
             double pose[24];
@@ -581,7 +618,78 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     out->map_points_before = featsFromMapNum;
 
     int effct_feat_num = 0;
-    if (featsFromMapNum >= 5) {  // :804
+    if (featsFromMapNum < 5 && device_loop) {  // no update: still report feats_down_size
+        int nd = 0;
+        LM_CK(dlt_scan_get_down(dev_, nullptr, 0, &nd));
+        out->n_down = nd;
+    }
+    if (featsFromMapNum >= 5 && device_loop) {  // :804, the loop :820-1102 resident on the device
+        out->did_update = 1;
+        t0 = wall();
+        if (!iekf_blk_) iekf_blk_ = new dlt_iekf_block();
+        dlt_iekf_block &B = *iekf_blk_;
+        {
+            double f[36 + kDim * kDim];
+            state_propagat.to_flat(f);
+            std::memcpy(B.state_propagat, f, sizeof(B.state_propagat));
+            StatesGroup d = odom_to_state(th->delta_pos, th->delta_quat, th->delta_vel, th->cov_slots);
+            d.to_flat(f);
+            std::memcpy(B.thermal_delta, f, sizeof(B.thermal_delta));
+            B.laser_point_cov = LASER_POINT_COV;
+            state.to_flat(B.state);
+            last_nodegared_state.to_flat(B.last_nodegared);
+        }
+        B.threshold = dynamic_effect_featurepoints_threshold;
+        B.max_iteration = NUM_MAX_ITERATIONS;
+        B.reserved2 = 0;
+        B.reserved0 = 0;
+        B.queue_len = (int)effct_q.size();
+        for (int i = 0; i < 10; i++) B.effct_queue[i] = i < B.queue_len ? effct_q[i] : 0;
+        B.flg_EKF_inited = flg_EKF_inited ? 1 : 0;
+        LM_CK(dlt_iekf_update(dev_, &B, reduce_fn ? &LaserMapping::reduce_trampoline : nullptr, this, reduce_fn ? reduce_buf_dev : nullptr));
+        // mirror the device's bookkeeping back into the host members
+        state.from_flat(B.state);
+        last_nodegared_state.from_flat(B.last_nodegared);
+        effct_q.assign(B.effct_queue, B.effct_queue + B.queue_len);
+        flg_EKF_inited = B.flg_EKF_inited != 0;
+        if (B.n_iters > 0) EKF_stop_flg = B.ekf_stop != 0;
+        out->n_down = B.n_down;
+        for (int k = 0; k < B.n_iters; k++) {
+            const dlt_iekf_iter &r = B.iters[k];
+            dlt_lio_iter rec;
+            std::memset(&rec, 0, sizeof(rec));
+            rec.iter = r.iter;
+            rec.effct_feat_num = r.effct_feat_num;
+            rec.converged = r.converged;
+            rec.ekf_stop = r.ekf_stop;
+            rec.did_match = r.did_match;
+            rec.n_down = B.n_down;
+            rec.total_residual = r.total_residual;
+            rec.res_mean_last = r.total_residual / r.effct_feat_num;  // :932
+            std::memcpy(rec.HtH, r.HtH, sizeof(rec.HtH));
+            std::memcpy(rec.Htr, r.Htr, sizeof(rec.Htr));
+            std::memcpy(rec.pose_in, r.pose_in, sizeof(rec.pose_in));
+            std::memcpy(rec.state_out, r.state_out, sizeof(rec.state_out));
+            std::memcpy(rec.solution, r.solution, sizeof(rec.solution));
+            iters.push_back(rec);
+            effct_feat_num = r.effct_feat_num;
+        }
+        out->t_iterate = wall() - t0;
+        const bool want_eig = B.n_iters > 0;
+        zeta_blend(effct_feat_num, state_propagat, th);  // (the eigen-decomposition was forked onto the side stream by dlt_iekf_update)
+        t0 = wall();
+        if (!EKF_stop_flg && cfg.dev.shard_count <= 1) {
+            double pose[24];
+            state.pose24(pose);
+            LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
+            out->added = out->n_added_ds + out->n_added_raw;
+        }
+        out->t_insert = wall() - t0;
+        if (want_eig) {
+            LM_CK(dlt_degeneracy(dev_, out->eigvals, out->eigvecs));
+            out->degenerate = (out->eigvals[0] < cfg.degeneracy_eig_threshold) ? 1 : 0;
+        }
+    } else if (featsFromMapNum >= 5) {  // :804, one host round trip per iteration
         out->did_update = 1;
         t0 = wall();
         int rematch_num = 0;
@@ -718,29 +826,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         const bool want_eig = !iters.empty();
         if (want_eig) LM_CK(dlt_degeneracy_begin(dev_));
 
-        // ---- zeta blend, :1105-1129
-        if ((lidar_cnt < 100) || (!th->tis_online) || (th->tis_online && lidar_cnt % 2 == 1)) {
-            const double alpha_l = effct_feat_num / (cfg.beta * 65536.0);  // Nla, :106
-            zeta_l = 2.0 / (1.0 + std::exp(-alpha_l)) - 1;
-            double zeta_l_norm = zeta_l / (zeta_l + zeta_t);
-            if (lidar_cnt < 100) zeta_l_norm = 1;
-            double v1[kDim], v2[kDim];
-            state_propagat.boxminus(last_state, v1);
-            state.boxminus(last_state, v2);
-            for (int i = 0; i < kDim; i++) {
-                v1[i] *= (1 - zeta_l_norm);
-                v2[i] *= zeta_l_norm;
-            }
-            state = last_state.boxplus(v1).boxplus(v2);  // :1119 -- the result carries last_state.cov (reference quirk)
-        } else {
-            const double zeta_t_norm = zeta_t / (zeta_l + zeta_t);
-            double v1[kDim];
-            state.boxminus(last_state, v1);
-            for (int i = 0; i < kDim; i++) v1[i] *= (1 - zeta_t_norm);
-            StatesGroup o = odom_to_state(th->l2l_pos, th->l2l_quat, th->l2l_vel, th->l2l_cov_slots);
-            state = last_state.boxplus(v1).compose(o.scaled(zeta_t_norm));  // :1127
-        }
-        last_state = state;  // :1131
+        zeta_blend(effct_feat_num, state_propagat, th);
 
         // ---- map_incremental(), :1164-1168
         t0 = wall();
@@ -780,6 +866,8 @@ void dlt_lio_default_config(dlt_lio_config *c) {
     for (int i = 0; i < 3; i++) c->extrinT[i] = 0.0;
     for (int i = 0; i < 9; i++) c->extrinR[i] = (i % 4 == 0) ? 1.0 : 0.0;
     c->degeneracy_eig_threshold = 100.0;
+    c->device_loop = 1;
+    c->reserved = 0;
 }
 
 int dlt_lio_create(const dlt_lio_config *cfg, dlt_lio *out) {

@@ -184,6 +184,9 @@ class LaserMapping {
 
    private:
     int fov_segment(const Vec3 &pos_LiD, int *deleted);  // lasermap_fov_segment, :313-369
+    void zeta_blend(int effct_feat_num, const StatesGroup &state_propagat, const dlt_lio_thermal *th);  // :1105-1131
+    static int reduce_trampoline(void *self, double *result_dev, int n);
+    dlt_iekf_block *iekf_blk_ = nullptr;  // host copy of the device-resident loop's block
     bool flg_first_scan = true;
     double first_lidar_time = 0.0;
     double zeta_l = 0.0, zeta_t = 0.0;

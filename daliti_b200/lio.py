@@ -20,6 +20,8 @@ class LioConfig(C.Structure):
         ("extrinT", C.c_double * 3),
         ("extrinR", C.c_double * 9),
         ("degeneracy_eig_threshold", C.c_double),
+        ("device_loop", C.c_int),
+        ("reserved", C.c_int),
     ]
 
 

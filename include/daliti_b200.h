@@ -130,18 +130,74 @@ int dlt_get_nearest(dlt_handle h, float *nbr, int *cnt, unsigned char *selected,
  * of HtH[0:6,0:6] of the last dlt_measure, computed on the device (parallel Jacobi, one warp)
  * when asked for.  Ascending eigenvalues; eigenvectors in the columns of the row-major 6x6.      */
 int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36);
-/* Enqueue that computation and its device->host copy without waiting; a later dlt_degeneracy
- * (after other work was queued behind it) then only synchronises.                                 */
+/* Enqueue that computation and its device->host copy on the handle's side stream without waiting: it
+ * overlaps whatever is queued next on the main stream (dlt_map_incremental); a later dlt_degeneracy
+ * then only synchronises.                                                                          */
 int dlt_degeneracy_begin(dlt_handle h);
+
+/* ---- the iteration loop resident on the device ------------------------
+ * laserMapping.cpp:820-1102 without a host round trip between iterations: per iteration the
+ * measurement model above, the degradation window (:899-918), the Kalman update (:1012-1053, with
+ * the gain K_1 = (H^T H + (P/R)^-1)^-1 evaluated in the algebraically equal covariance form
+ * P' - P' U (I + H P'_11)^-1 H U^T P', P' = P/R: one 6 x 6 or 12 x 12 solve, no inversions) or
+ * the stop branch (:1054-1063), the rematch / convergence control (:1069-1101) and, at loop
+ * exit, the covariance update (:1084-1085).  The caller fills the `in` and `in / out` parts of
+ * one block; dlt_iekf_update copies it to the device, enqueues max_iteration rounds of
+ * {match pass, residual pass, solve} whose kernels turn into no-ops once the loop has ended,
+ * and reads the block back with ONE synchronisation.  State layout = StatesGroup flat:
+ * rot_end[9] pos_end[3] R_L_I[9] T_L_I[3] vel_end[3] bias_g[3] bias_a[3] gravity[3] (+ cov[576]). */
+#define DLT_IEKF_MAX_ITER 16
+typedef struct dlt_iekf_iter {          /* one row of Log/mat_out.txt (:936-937) + the algebra  */
+    int iter, effct_feat_num, converged, ekf_stop, did_match, reserved;
+    double total_residual;
+    double HtH[144], Htr[12], pose_in[24], state_out[36], solution[24];
+} dlt_iekf_iter;
+typedef struct dlt_iekf_block {
+    /* in */
+    double state_propagat[36];          /* :752                                                  */
+    double thermal_delta[36];           /* odomToStateGruop(g_tis_odom_delta), :1057, flat state */
+    double laser_point_cov;             /* LASER_POINT_COV, :76 (the gain uses state.cov / this) */
+    int threshold;                      /* dynamic_effect_featurepoints_threshold, :908          */
+    int max_iteration;                  /* NUM_MAX_ITERATIONS (<= DLT_IEKF_MAX_ITER)             */
+    int reserved2;
+    int reserved0;
+    /* in / out, updated in place */
+    double state[612];                  /* state at loop entry -> state at loop exit             */
+    double last_nodegared[612];         /* last_nodegared_state, :1050                           */
+    int effct_queue[10];                /* effct_feat_numQueue, oldest first, :899-905           */
+    int queue_len, flg_EKF_inited;
+    /* out */
+    int n_iters, converged, ekf_stop, have_gain;
+    int status;                         /* 0 ok, 1 = H^T H + (P/R)^-1 singular                   */
+    int n_down, n_unresolved;
+    int reserved1;                      /* VoxelGrid status of the scan (2 = capacity exceeded -> DLT_E_CAPACITY) */
+    /* loop control, owned by the device (zeroed by dlt_iekf_update)                              */
+    int iter, rematch_num, rematch_en, done;
+    double reserved3[42];
+    dlt_iekf_iter iters[DLT_IEKF_MAX_ITER];
+} dlt_iekf_block;
+/* downSizeFilterSurf.filter enqueued without waiting: feats_down_size stays on the device and is
+ * reported by the next dlt_iekf_update (n_down).                                                 */
+int dlt_scan_downsample_async(dlt_handle h);
+/* reduce/reduce_ctx (optional): called once per enqueued iteration between the residual pass and the solve
+ * with the 158-double partial normal equations in DEVICE memory; it must sum them over the ranks
+ * in place on the handle's stream without blocking the host (sharded map, NCCL all-reduce).      */
+typedef int (*dlt_reduce_fn)(void *ctx, double *result_dev, int n);
+/* result_dev: where the residual pass leaves the 158 doubles handed to `reduce` (DEVICE memory, 256
+ * doubles, caller-owned); NULL = the handle's own buffer.                                         */
+int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, void *reduce_ctx, double *result_dev);
 
 /* ---- map_incremental()                                       laserMapping.cpp:582-630, 1167 - */
 int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_add_downsample, int *n_add_raw);
 
 /* ---- instrumentation (no reference counterpart) ---------------------------------------------- */
 /* Per-kernel-group device time from CUDA events on the launching stream.  Groups: 0 k_knn,
- * 1 k_residual, 2 deskew, 3 VoxelGrid, 4 map insert, 5 exact-neighbour fallback, 6 spare, 7 k_knn8 alone (inside group 0).      */
+ * 1 k_residual, 2 deskew, 3 VoxelGrid, 4 map insert, 5 exact-neighbour fallback, 6 k_iekf_step, 7 k_knn8 alone (inside group 0).      */
 int dlt_set_profiling(dlt_handle h, int on);
 int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset);
+/* Spans recorded since the last dlt_get_profile(reset): (group, start ms, end ms) triples relative to the
+ * first span, device time from the CUDA events (group 6 = k_iekf_step, 8 = k_eigen6 on the side stream). */
+int dlt_get_timeline(dlt_handle h, double *kind_start_end, int cap, int *n);
 /* kernels launched by this library in this process so far                                         */
 unsigned long long dlt_launch_count(void);
 

@@ -32,6 +32,10 @@ typedef struct dlt_lio_config {
     double extrinT[3];       /* mapping/extrinsic_T              laserMapping.cpp:661              */
     double extrinR[9];       /* mapping/extrinsic_R (row-major)  laserMapping.cpp:662              */
     double degeneracy_eig_threshold; /* new: flag when min eigenvalue of HtH[0:6,0:6] is below     */
+    int device_loop;         /* 1 (default): the iteration loop :820-1102 runs resident on the device
+                                (dlt_iekf_update, one synchronisation per scan); 0: one host round trip
+                                per iteration (dlt_measure + host Kalman algebra)                   */
+    int reserved;
 } dlt_lio_config;
 
 /* State left behind by tis_cbk / tn_cbk (laserMapping.cpp:471-498): g_tis_odom_delta and
@@ -91,7 +95,9 @@ int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lid
 /* Sharded map (dev.shard_count > 1): after every evaluation of the measurement model the partial normal
  * equations (n = 158 doubles at result_dev, DEVICE memory owned by the caller, 256 doubles) are handed to
  * `reduce`, which must sum them over the ranks in place on the handle's stream (e.g. ncclAllReduce /
- * torch.distributed.all_reduce) and return 0.  map_incremental is skipped on a sharded map.             */
+ * torch.distributed.all_reduce) and return 0.  With device_loop it is called max_iteration times per scan
+ * on every rank and must only ENQUEUE the reduction (no host wait).  map_incremental is skipped on a
+ * sharded map.                                                                                           */
 typedef int (*dlt_lio_reduce_fn)(void *ctx, double *result_dev, int n);
 int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *result_dev);
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap);

@@ -136,10 +136,20 @@ class OracleMap:
         b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
         return self.o.lib.orc_map_delete_boxes(C.c_void_p(self.h), _p(b), C.c_int(len(b)))
 
+    def _settle(self):
+        """The reference ikd-Tree rebuilds unbalanced sub-trees on a background pthread (ikd_Tree.cpp:229-367) and
+        its flatten / validnum are not atomic against it (the reference itself races here, laserMapping.cpp:1172).
+        Give that thread a moment before reading whole-tree contents so set comparisons are deterministic."""
+        import time
+
+        time.sleep(0.05)
+
     def validnum(self) -> int:
+        self._settle()
         return self.o.lib.orc_map_validnum(C.c_void_p(self.h))
 
     def flatten(self) -> np.ndarray:
+        self._settle()
         n = self.o.lib.orc_map_flatten(C.c_void_p(self.h), None, C.c_int(0))
         out = np.zeros((max(n, 1), 4), np.float32)
         m = self.o.lib.orc_map_flatten(C.c_void_p(self.h), _p(out), C.c_int(len(out)))

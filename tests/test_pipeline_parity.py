@@ -172,3 +172,58 @@ def test_pipeline_sliding_local_map_box_delete(dev, oracle):
         assert ok, (k, e)
     assert deleted_total > 0
     lm.close()
+
+
+@pytest.mark.parametrize("stop", [False, True])
+def test_device_resident_loop_equals_host_loop(dev, stop):
+    """dlt_iekf_update (the iteration loop :820-1102 resident on the device, one sync per scan) against the host
+    loop over dlt_measure (one round trip per iteration) on the same scans: same control flow, same counts,
+    states equal to fp64 round-off (covariance-form gain on the device vs two LU inversions on the host, CUDA vs glibc sin/cos)."""
+    lib, is_gpu = dev
+    seq = helpers.small_sequence(seed=21, half=25.0, beams=16, azimuths=900 if is_gpu else 240, n_boxes=8, speed=2.0, yaw_rate=0.2)
+    map_pts = synth.sample_map(seq.scene, seed=21)
+    kw = dict(featptsThreshold=1000000 if stop else 5, max_iteration=4)
+    lms = []
+    for device_loop in (1, 0):
+        lm = LaserMapping(lib, dev=dict(max_scan_points=32768 if is_gpu else 8192, max_map_points=4 * len(map_pts)), device_loop=device_loop, **kw)
+        lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
+        lm.set_state(helpers.state612(seq.traj, seq.t_start))
+        lm.device.map_build(map_pts)
+        lms.append(lm)
+    th = LioThermal()
+    th.tis_online = 1
+    th.delta_pos[0], th.delta_pos[1] = 0.03, -0.02
+    th.delta_quat[0], th.delta_quat[3] = np.cos(0.005), np.sin(0.005)
+    th.l2l_pos[0] = 0.02
+    th.l2l_quat[0] = 1.0
+    th.cov_slots[7] = -9.8
+    th.l2l_cov_slots[7] = -9.8
+    n_stop = 0
+    for k in range(4):
+        pts, t_beg, imu = seq.scan(k)
+        outs = []
+        for lm in lms:
+            for _ in range(101 if (stop and k == 0) else 1):  # past the first 100 messages the window uses featptsThreshold
+                lm.on_lidar_msg()
+            outs.append(lm.process_scan(pts, t_beg, imu, th))
+        a, b = outs
+        assert (a.n_raw, a.n_down, a.n_iters, a.ekf_stop, a.did_update, a.added) == (b.n_raw, b.n_down, b.n_iters, b.ekf_stop, b.did_update, b.added), k
+        n_stop += a.ekf_stop
+        for ra, rb in zip(lms[0].iters(), lms[1].iters()):
+            assert (ra.iter, ra.did_match, ra.ekf_stop, ra.converged, ra.effct_feat_num, ra.n_down) == \
+                   (rb.iter, rb.did_match, rb.ekf_stop, rb.converged, rb.effct_feat_num, rb.n_down), (k, ra.iter)
+            # the gain is evaluated in covariance (Woodbury) form on the device and by two LU inversions on the host:
+            # equal up to fp64 round-off times the conditioning of P/R (~2e-9 absolute on the state here, far inside the 1e-5 pose tolerance)
+            hs = max(1.0, np.abs(np.array(rb.HtH)).max())
+            np.testing.assert_allclose(np.array(ra.HtH), np.array(rb.HtH), rtol=1e-7, atol=1e-8 * hs)
+            np.testing.assert_allclose(np.array(ra.Htr), np.array(rb.Htr), rtol=1e-7, atol=1e-8 * hs)
+            np.testing.assert_allclose(np.array(ra.pose_in), np.array(rb.pose_in), rtol=0, atol=2e-8)
+            np.testing.assert_allclose(np.array(ra.solution), np.array(rb.solution), rtol=1e-5, atol=2e-8)
+            np.testing.assert_allclose(np.array(ra.state_out), np.array(rb.state_out), rtol=0, atol=2e-8)
+        np.testing.assert_allclose(lms[0].get_state(), lms[1].get_state(), rtol=1e-6, atol=2e-8)
+        np.testing.assert_allclose(np.array(a.eigvals), np.array(b.eigvals), rtol=1e-6, atol=1e-6)
+        assert lms[0].flags() == lms[1].flags()
+        assert lms[0].device.map_valid_count() == lms[1].device.map_valid_count()
+    assert (n_stop > 0) == stop
+    for lm in lms:
+        lm.close()

@@ -42,7 +42,7 @@ def main():
             torch.cuda.synchronize()
             m = dm.measure(pose, True)
         prof = dm.get_profile(reset=True)
-        print(f"{os.path.basename(path):24s} n_down={len(down)} effct={m.effct_feat_num} knn {1e3*prof['knn'][0]/prof['knn'][1]:7.1f} us  residual {1e3*prof['residual'][0]/prof['residual'][1]:7.1f} us", flush=True)
+        print(f"{os.path.basename(path):24s} n_down={len(down)} effct={m.effct_feat_num} knn {1e3*prof['knn'][0]/prof['knn'][1]:7.1f} us  knn8 {1e3*prof['knn8'][0]/max(1,prof['knn8'][1]):7.1f} us  residual {1e3*prof['residual'][0]/prof['residual'][1]:7.1f} us", flush=True)
         dm.close()
 
 

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Device timeline of one per-scan update (CUDA events around every kernel group, on the launching streams) next to
+the host-side stage clocks: where the gaps between kernels are.  Development tool; profiling events add ~1 us each."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    import bench
+    from daliti_b200.lio import LaserMapping
+
+    n = 8
+    work = bench.build_workload(0, n, "c2")
+    seq, scans = work["seq"], work["scans"]
+    lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30)
+    s0, mean_acc, last_imu = bench.initial_state(seq)
+    lm.force_imu_ready(mean_acc, last_imu)
+    lm.set_state(s0)
+    lm.device.map_build(work["map_pts"])
+    lm.device.set_profiling(True)
+    devs = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p, _, _ in scans]
+    for k in range(n):
+        pts, t_beg, imu = scans[k]
+        lm.on_lidar_msg()
+        lm.device.get_profile(reset=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o = lm.process_scan_dev(devs[k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
+        host_ms = 1e3 * (time.perf_counter() - t0)
+        tl = lm.device.get_timeline()
+        if k >= n - 2:
+            print(f"--- scan {k}: host {host_ms:.3f} ms; stages deskew {1e3*o.t_deskew:.3f} voxel {1e3*o.t_voxel:.3f} iterate {1e3*o.t_iterate:.3f} insert {1e3*o.t_insert:.3f}")
+            prev_end = 0.0
+            busy = 0.0
+            for name, a, b in tl:
+                if name == "knn8":
+                    continue  # nested inside knn
+                gap = a - prev_end
+                print(f"  {name:12s} start {1e3*a:8.1f} us  dur {1e3*(b-a):7.1f} us  gap before {1e3*gap:7.1f} us")
+                if name != "eigen6":
+                    prev_end = b
+                    busy += b - a
+            print(f"  device span {1e3*prev_end:.1f} us, busy {1e3*busy:.1f} us")
+    lm.close()
+
+
+if __name__ == "__main__":
+    main()
