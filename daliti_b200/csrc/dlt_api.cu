@@ -75,11 +75,13 @@ struct dlt_handle_s {
     unsigned char *d_dsflag = nullptr, *d_addflag = nullptr;
     int *d_cellslot = nullptr, *d_vslot = nullptr;
     DsScratch scratch;
+    size_t scratch_cap = 0;
     // device-resident iteration loop (dlt_iekf_update)
     IekfDev *d_iekf = nullptr;
     dlt_iekf_block *h_iekf = nullptr;  // pinned
     bool n_down_on_device = false;     // dlt_scan_downsample_async ran: h->n_down is only an estimate until the next read-back
     int n_down_hint = 0;               // feats_down_size of the previous scan (grid sizing for the speculative launches)
+    int far_hint = 1;                  // unresolved queries of the previous scan: queue the exact-neighbour fallback behind the loop?
     // pinned host staging
     double *h_result = nullptr;
     int *h_ints = nullptr;
@@ -204,22 +206,29 @@ static int map_check_error(dlt_handle h) {
     return DLT_OK;
 }
 
-// claim | (bid, resolve) | append over n device points with per-point flags
-static int insert_points(dlt_handle h, const float4 *d_pts, int n, bool any_ds) {
+// claim | (bid, resolve) | append over n device points with per-point flags.  With a gate (device-resident loop) n is
+// only the grid size: the kernels read the real count, and whether to run at all, from device memory.
+static int insert_points(dlt_handle h, const float4 *d_pts, int n, bool any_ds, InsertGate gate = {nullptr, nullptr}) {
     if (n <= 0) return DLT_OK;
     h->counters_fresh = false;
     ProfScope prof(h, 4);
     const int B = 256, G = div_up(n, B);
     DLT_LAUNCH(k_map_claim, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
-               h->d_cellslot, h->map.shard_count > 1 ? 1 : 0);
+               h->d_cellslot, h->map.shard_count > 1 ? 1 : 0, gate);
     if (any_ds) {
-        DLT_RT(h, rt::fill(h->scratch.vkeys, 0xFF, ((size_t)h->scratch.mask + 1) * sizeof(unsigned long long), h->stream));
-        DLT_RT(h, rt::fill(h->scratch.vwin, 0xFF, ((size_t)h->scratch.mask + 1) * sizeof(unsigned long long), h->stream));
-        DLT_LAUNCH(k_ds_bid, G, B, h->stream, h->map, h->scratch, d_pts, n, (const unsigned char *)h->d_dsflag, h->d_vslot);
-        DLT_LAUNCH(k_ds_resolve, G, B, h->stream, h->map, h->scratch, d_pts, n, (const unsigned char *)h->d_dsflag, (const int *)h->d_vslot,
-                   (const int *)h->d_cellslot, h->d_addflag);
+        // the voxel scratch only has to be clean where this batch can hash to: size it to the batch (power of two >= 4 n)
+        size_t sc = 1024;
+        while (sc < (gate.go ? 2 : 4) * (size_t)n) sc <<= 1;  // gated: n is an upper bound of the batch, load factor <= 0.5 either way
+        if (sc > (size_t)h->scratch_cap) sc = h->scratch_cap;
+        DsScratch scr = h->scratch;
+        scr.mask = (unsigned)(sc - 1);
+        DLT_RT(h, rt::fill(scr.vkeys, 0xFF, sc * sizeof(unsigned long long), h->stream));
+        DLT_RT(h, rt::fill(scr.vwin, 0xFF, sc * sizeof(unsigned long long), h->stream));
+        DLT_LAUNCH(k_ds_bid, G, B, h->stream, h->map, scr, d_pts, n, (const unsigned char *)h->d_dsflag, h->d_vslot, gate);
+        DLT_LAUNCH(k_ds_resolve, G, B, h->stream, h->map, scr, d_pts, n, (const unsigned char *)h->d_dsflag, (const int *)h->d_vslot,
+                   (const int *)h->d_cellslot, h->d_addflag, gate);
     }
-    DLT_LAUNCH(k_map_append, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_addflag, (const int *)h->d_cellslot);
+    DLT_LAUNCH(k_map_append, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_addflag, (const int *)h->d_cellslot, gate);
     DLT_RT(h, rt::check_launch());
     return DLT_OK;
 }
@@ -253,9 +262,9 @@ static int run_far(dlt_handle h, int *n_far_out) {
     for (int off = 0; off < nfar; off += kFarChunk) {
         int c = nfar - off < kFarChunk ? nfar - off : kFarChunk;
         DLT_LAUNCH(k_far_scan, dim3(kFarGroupsX, kFarSlices), kFarWarps * 32, h->stream, h->map, n_buckets, (const float4 *)h->knn.qw,
-                   (const int *)h->knn.far_list, off, c, kFarSlices, h->d_far_partial);
+                   (const int *)h->knn.far_list, off, c, kFarSlices, h->d_far_partial, (const int *)nullptr, (IekfDev *)nullptr, 0);
         DLT_LAUNCH(k_far_merge, div_up(c, 128), 128, h->stream, (const int *)h->knn.far_list, off, c, kFarSlices,
-                   (const Cand *)h->d_far_partial, h->cfg.max_sq_dist, h->knn);
+                   (const Cand *)h->d_far_partial, h->cfg.max_sq_dist, h->knn, (const int *)nullptr, (IekfDev *)nullptr, 0);
     }
     DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::check_launch());
@@ -340,6 +349,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     size_t sc_cap = 1;
     while (sc_cap < 4 * cap) sc_cap <<= 1;
     h->scratch.mask = (unsigned)(sc_cap - 1);
+    h->scratch_cap = sc_cap;
 
     ok = ok && !dalloc(h, &h->map.table, tcap) && !dalloc(h, &h->map.buckets, bucket_cap) && !dalloc(h, &h->d_counters, 16) && !dalloc(h, &h->d_unres, cap) &&
          !dalloc(h, &h->d_raw, cap * kRawStride4) && !dalloc(h, &h->d_undist, cap) && !dalloc(h, &h->d_down, cap) &&
@@ -745,7 +755,13 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     blk->n_iters = blk->converged = blk->ekf_stop = blk->have_gain = blk->status = 0;
     blk->n_down = blk->n_unresolved = blk->reserved1 = 0;
     blk->iter = blk->rematch_num = blk->rematch_en = blk->done = 0;
-    const size_t up_bytes = offsetof(dlt_iekf_block, reserved3);
+    blk->insert_status = 0;
+    // the device-side finish needs the bucket count for the exact-neighbour fallback and an unsharded map
+    const bool finish = blk->finish && h->map.shard_count <= 1 && h->counters_fresh;
+    blk->finish = finish ? 1 : 0;
+    const bool far_q = finish && h->far_hint > 0;
+    blk->far_enqueued = far_q ? 1 : 0;
+    const size_t up_bytes = offsetof(dlt_iekf_block, blend_state);
     std::memcpy(h->h_iekf, blk, up_bytes);
     DLT_RT(h, rt::h2d(&h->d_iekf->b, h->h_iekf, up_bytes, h->stream));
 
@@ -804,6 +820,24 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     // it runs while the host waits for / digests the block below
     h->have_match = true;
     if (int re = dlt_degeneracy_begin(h)) return re;
+    if (finish) {  // ---- map_incremental (:582-630, 1164-1168) behind the loop, armed by the last k_iekf_step
+        const int n_buckets = h->h_ints[0];
+        IekfDev *ctl = h->d_iekf;
+        if (far_q) {
+            ProfScope prof(h, 5);
+            DLT_LAUNCH(k_far_scan, dim3(kFarGroupsX, kFarSlices), kFarWarps * 32, h->stream, h->map, n_buckets, (const float4 *)h->knn.qw,
+                       (const int *)h->knn.far_list, 0, 0, kFarSlices, h->d_far_partial, (const int *)(h->d_counters + 5), ctl, kFarChunk);
+            DLT_LAUNCH(k_far_merge, div_up(kFarChunk, 128), 128, h->stream, (const int *)h->knn.far_list, 0, 0, kFarSlices,
+                       (const Cand *)h->d_far_partial, h->cfg.max_sq_dist, h->knn, (const int *)(h->d_counters + 5), ctl, kFarChunk);
+        }
+        DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));  // downsample adds, raw adds (far_count is re-armed by the next k_knn8)
+        DLT_LAUNCH(k_incr_classify, div_up(n_upper, 256), 256, h->stream, (const float4 *)h->d_down, 0, P, (const float4 *)h->knn.nbr,
+                   (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, la);
+        InsertGate gate = {&h->d_iekf->b.insert_status, &h->d_sc->n_down};
+        int ri = insert_points(h, h->d_pw, n_upper, true, gate);
+        if (ri) return ri;
+        DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    }
     // device -> host: in/out + out fields + the iteration records that can have been written
     const size_t lo = offsetof(dlt_iekf_block, state);
     const size_t hi = offsetof(dlt_iekf_block, iters) + (size_t)n_iter * sizeof(dlt_iekf_iter);
@@ -818,7 +852,22 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     h->n_down_hint = blk->n_down;
     h->n_down_on_device = false;
     h->have_match = blk->n_iters > 0;
-    h->h_last_nfar = blk->n_unresolved;
+    if (finish) {
+        if (blk->insert_status == 1) {  // the map changed: neighbour sets are stale, the counters are fresh
+            h->have_match = false;
+            h->counters_fresh = true;
+            blk->n_added_ds = h->h_ints[6];
+            blk->n_added_raw = h->h_ints[7];
+            for (int i = 0; i < 5; i++) blk->map_counters[i] = h->h_ints[i];
+            if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
+            if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
+        } else {
+            h->counters_fresh = true;  // nothing was inserted: the read-back still mirrors the counters
+            blk->n_added_ds = blk->n_added_raw = 0;
+        }
+    }
+    h->h_last_nfar = (finish && far_q && blk->insert_status == 1) ? 0 : blk->n_unresolved;  // 0: the fallback already made them exact
+    h->far_hint = blk->n_unresolved;
     h->nfar_known = blk->n_iters > 0;
     if (blk->reserved1 == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
     if (blk->status == 1) DLT_FAIL(h, DLT_E_STATE, "H^T H + (P/R)^-1 is singular");
@@ -970,7 +1019,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     Pose P = pose_from(pose24);
     DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
-               (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6);
+               (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, LoopArgs{nullptr, nullptr});
     int rc = insert_points(h, h->d_pw, n, true);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
@@ -1009,6 +1058,13 @@ int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset) {
     return DLT_OK;
 }
 unsigned long long dlt_launch_count(void) { return rt::g_launches; }
+
+int dlt_get_iekf_clocks(dlt_handle h, long long *clocks, int n_iter) {
+    if (!h || !clocks || n_iter < 0 || n_iter > DLT_IEKF_MAX_ITER) return DLT_E_INVALID;
+    DLT_RT(h, rt::d2h(clocks, h->d_iekf->clocks, (size_t)n_iter * 16 * sizeof(long long), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    return DLT_OK;
+}
 
 int dlt_get_timeline(dlt_handle h, double *kind_start_end, int cap, int *n) {
     if (!h || !n || cap < 0 || (cap > 0 && !kind_start_end)) return DLT_E_INVALID;

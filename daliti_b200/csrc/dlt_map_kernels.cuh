@@ -123,11 +123,25 @@ DLT_D bool shard_keeps_cell(const MapView &m, int cx, int cy, int cz, int halo) 
 }
 constexpr int kShardHalo = 4;  // cells: ring-3 search + 1
 
+// Kernels enqueued behind the device-resident IEKF loop take their point count and a go/no-go flag from device
+// memory (both null on the classic path): go == 1 runs, anything else returns at once.
+struct InsertGate {
+    const int *go;
+    const int *n_ptr;
+};
+DLT_D bool gate_open(const InsertGate &g, int &n) {
+    if (!g.go) return true;
+    if (*g.go != 1) return false;
+    n = *g.n_ptr;
+    return true;
+}
+
 // ------------------------------------------------------------------ phase 1: claim cells
 // Points with neither flag set (dropped by map_incremental) take no part.
 // cell_slot[i] <- table slot of the point's cell (-1: not taking part / not kept by this shard).
 __global__ void k_map_claim(MapView m, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
-                            const unsigned char *__restrict__ add_flag, int *__restrict__ cell_slot, int apply_shard_filter) {
+                            const unsigned char *__restrict__ add_flag, int *__restrict__ cell_slot, int apply_shard_filter, InsertGate gate) {
+    if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (!ds_flag[i] && !add_flag[i]) {
@@ -146,7 +160,8 @@ __global__ void k_map_claim(MapView m, const float4 *__restrict__ pts, int n, co
 
 // ------------------------------------------------------------------ phase 3: append
 __global__ void k_map_append(MapView m, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ add_flag,
-                             const int *__restrict__ cell_slot) {
+                             const int *__restrict__ cell_slot, InsertGate gate) {
+    if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (add_flag && !add_flag[i]) return;
@@ -179,7 +194,8 @@ DLT_D void voxel_box(float x, float ds, float &mn, float &mx, float &mid) {
 
 // phase 1b: per ds point, claim a scratch entry for its voxel and bid for it
 __global__ void k_ds_bid(MapView m, DsScratch sc, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
-                         int *__restrict__ vslot) {
+                         int *__restrict__ vslot, InsertGate gate) {
+    if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     vslot[i] = -1;
@@ -205,7 +221,8 @@ __global__ void k_ds_bid(MapView m, DsScratch sc, const float4 *__restrict__ pts
 // phase 2: the winning incoming point of each voxel resolves the voxel against the map.
 // Clears the live bits of the points it removes; sets add_flag[i] when it must be added.
 __global__ void k_ds_resolve(MapView m, DsScratch sc, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
-                             const int *__restrict__ vslot, const int *__restrict__ cell_slot, unsigned char *__restrict__ add_flag) {
+                             const int *__restrict__ vslot, const int *__restrict__ cell_slot, unsigned char *__restrict__ add_flag, InsertGate gate) {
+    if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (!ds_flag[i]) return;  // raw points keep the add_flag the caller set

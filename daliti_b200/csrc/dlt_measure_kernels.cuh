@@ -27,7 +27,16 @@ struct IekfDev {
     dlt_iekf_block b;
     double K1c[24 * 12];  // K_1[:, :12] of the last Kalman update (laserMapping.cpp:1019)
     double HtH12[144];    // its H^T H (for G = K H at :1084)
+    long long clocks[DLT_IEKF_MAX_ITER][16];  // instrumentation: SM clock at the stages of k_iekf_step (dlt_get_iekf_clocks)
 };
+#if defined(DLT_EMU)
+#define DLT_STAMP(i)
+#else
+#define DLT_STAMP(i)                                          \
+    do {                                                      \
+        if (threadIdx.x == 0) dev->clocks[it][i] = clock64(); \
+    } while (0)
+#endif
 struct LoopArgs {
     const IekfDev *ctl;
     const int *n_ptr;  // feats_down_size on the device (ScanScalars::n_down)
@@ -121,6 +130,14 @@ DLT_D float axis_gap(float q, int c, float cell_edge, float slack) {
     float lo = (float)c * cell_edge, hi = (float)(c + 1) * cell_edge;
     float g = fmaxf(fmaxf(lo - q, q - hi), 0.f) - slack;
     return g > 0.f ? g : 0.f;
+}
+
+// map_incremental kernels enqueued behind the device-resident loop: run only when the loop armed them
+DLT_D bool insert_gate(const LoopArgs &la, int &n) {
+    if (!la.ctl) return true;
+    if (la.ctl->b.insert_status != 1) return false;
+    n = *la.n_ptr;
+    return true;
 }
 
 // ---- selection of the 5 best among the staged candidates ------------------------------------
@@ -600,8 +617,13 @@ constexpr int kFarTile = 128;  // buckets per shared-memory tile
 
 __global__ void __launch_bounds__(kFarWarps * 32)
     k_far_scan(MapView m, int n_buckets, const float4 *__restrict__ qw, const int *__restrict__ far_list, int far_off, int nfar,
-               int n_slices, Cand *__restrict__ partial /* [far][slice][5] */) {
+               int n_slices, Cand *__restrict__ partial /* [far][slice][5] */, const int *__restrict__ nfar_ptr, IekfDev *ctl, int chunk_cap) {
     __shared__ float4 tile[kFarTile * 8];
+    if (nfar_ptr) {  // behind the device-resident loop: the count lives on the device; one chunk only
+        nfar = *nfar_ptr;
+        if (ctl->b.insert_status != 1 || nfar == 0) return;
+        if (nfar > chunk_cap) return;  // k_far_merge flags it; the host then runs the chunked fallback
+    }
     const int groups = (nfar + kFarWarps * 32 - 1) / (kFarWarps * 32);
     const int slice = blockIdx.y;
     const int per = (n_buckets + n_slices - 1) / n_slices;
@@ -650,7 +672,15 @@ __global__ void __launch_bounds__(kFarWarps * 32)
 }
 
 __global__ void k_far_merge(const int *__restrict__ far_list, int far_off, int nfar, int n_slices, const Cand *__restrict__ partial,
-                            float max_sq_dist, KnnOut out) {
+                            float max_sq_dist, KnnOut out, const int *__restrict__ nfar_ptr, IekfDev *ctl, int chunk_cap) {
+    if (nfar_ptr) {
+        nfar = *nfar_ptr;
+        if (ctl->b.insert_status != 1 || nfar == 0) return;
+        if (nfar > chunk_cap) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->b.insert_status = 2;  // read by the kernels that follow in stream order
+            return;
+        }
+    }
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfar; f += gridDim.x * blockDim.x) {
         Cand best[kK];
 #pragma unroll
@@ -1068,9 +1098,42 @@ DLT_D void boxplus_inplace(double *s, const double *d) {
 #pragma unroll
     for (int k = 0; k < 12; k++) s[24 + k] += d[12 + k];
 }
+// o = a * s, common_lib.h:190-205 (R_L_I is not scaled)
+DLT_D void scaled(const double *a, double s, double *o) {
+    double so3[3];
+    log3(a, so3);
+    exp3(so3[0] * s, so3[1] * s, so3[2] * s, o);
+#pragma unroll
+    for (int k = 0; k < 9; k++) o[12 + k] = a[12 + k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o[9 + k] = a[9 + k] * s;
+        o[21 + k] = a[21 + k] * s;
+    }
+#pragma unroll
+    for (int k = 24; k < 36; k++) o[k] = a[k] * s;
+}
+// a <- a + b (StatesGroup + StatesGroup), common_lib.h:131-144: biases and gravity of the left operand
+DLT_D void compose_inplace(double *a, const double *b) {
+    double M[9];
+    mat3_mul(a, b, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) a[k] = M[k];
+    mat3_mul(a + 12, b + 12, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) a[12 + k] = M[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        a[9 + k] += b[9 + k];
+        a[21 + k] += b[21 + k];
+        a[24 + k] += b[24 + k];
+    }
+}
 }  // namespace iekf
 
 constexpr int kIekfBlock = 576;  // one thread per covariance element
+// state_propagat: the shared copy, unless the stop branch reused that buffer for the thermal delta
+DLT_D const double *sprop_or(const double *shared_copy, const double *global_copy, int stop) { return stop ? global_copy : shared_copy; }
 
 // Kalman gain in covariance (Woodbury) form.  The reference inverts twice, K_1 = (H^T H + (P/R)^-1)^-1
 // (laserMapping.cpp:1017-1018); with P' = P/R, U = [I_12; 0] and H^T H = U H U^T the same matrix is
@@ -1100,6 +1163,7 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
     const int did_match = (it == 0 || c.rematch_en) ? 1 : 0;
     const int AW = D + 12;
 
+    DLT_STAMP(0);
     // ---- one round trip to global memory for everything the step needs
     for (int k = tid; k < kNormalEqDoubles + 1; k += kIekfBlock) R[k] = result[k];
     double cov_own = c.state[36 + tid];
@@ -1122,10 +1186,14 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
         s_i[I_NDOWN] = *n_down_ptr;
         s_i[I_VOX] = *vox_status_ptr;
     }
-    if (tid == 0) s_fail = 0;
+    if (tid == 0) {
+        s_fail = 0;
+        if (it == 0) c.insert_status = 0;  // map_incremental stays disarmed until the loop ends cleanly
+    }
     PN[tid] = cov_own / lpc;
     if (tid < 12 * N) C12[tid] = cov_own;
     __syncthreads();
+    DLT_STAMP(1);
 
     // effct_feat_numQueue, :899-918 -- every thread derives the same decision from shared memory
     const int effct = (int)(R[156] + 0.5);
@@ -1166,7 +1234,9 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
             if (j < D) W[i * AW + j] = q + ((i == j) ? 1.0 : 0.0);
         }
         if (tid == 320) iekf::boxminus(sprop, st, vec);  // :1028 (its own warp)
+        DLT_STAMP(2);
         __syncthreads();
+        DLT_STAMP(3);
         // (I + Q[:, :D]) Y = Q by Gauss-Jordan with partial pivoting, the row exchange folded into the update
         for (int col = 0; col < D; col++) {
             if (tid < 32) {
@@ -1215,6 +1285,7 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
             }
             return;
         }
+        DLT_STAMP(4);
         if (tid < N * 12) {  // K_1[:, :12] = P'_1 - P'_1[:, :D] Y
             const int i = tid / 12, j = tid % 12;
             double x = PN[i * N + j];
@@ -1237,6 +1308,7 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
             rec.solution[tid] = sol[tid];
         }
         __syncthreads();
+        DLT_STAMP(5);
         // state (+)= solution, :1033 -- the two rotations on two warps, the vector parts on a third
         if (tid == 0 || tid == 32) {
             const int o = (tid == 0) ? 0 : 12, d = (tid == 0) ? 0 : 6;
@@ -1256,6 +1328,7 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
         conv = ((rn * 57.3 < 0.01) && (tn * 100 < 0.015)) ? 1 : 0;  // :1040
         have_gain = 1;
         __syncthreads();
+        DLT_STAMP(6);
         if (tid < 36) {
             c.state[tid] = st[tid];
             c.last_nodegared[tid] = st[tid];  // :1050
@@ -1327,15 +1400,72 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
             c.state[36 + tid] = sacc;
         }
     }
+    DLT_STAMP(7);
+    if (fin && c.finish) {  // ---- zeta blend, :1105-1131, then arm map_incremental (block-uniform)
+        __syncthreads();
+        __shared__ double lastS[36], v1[N], v2[N], bl[36];
+        if (tid < 36) lastS[tid] = c.last_state[tid];
+        if (tid >= 64 && tid < 100 && c.blend_mode != 1) sother[tid - 64] = c.l2l_state[tid - 64];
+        __syncthreads();
+        const double zeta_t = c.zeta_t;
+        if (c.blend_mode == 1) {
+            const double alpha_l = effct / (c.beta * 65536.0);  // Nla, :106
+            const double zeta_l = 2.0 / (1.0 + exp(-alpha_l)) - 1;
+            double zn = zeta_l / (zeta_l + zeta_t);
+            if (c.lidar_cnt_lt_100) zn = 1;
+            if (tid == 0) {
+                iekf::boxminus(sprop_or(sprop, c.state_propagat, stop), lastS, v1);
+                for (int k = 0; k < N; k++) v1[k] *= (1 - zn);
+                c.zeta_l = zeta_l;
+            } else if (tid == 32) {
+                iekf::boxminus(st, lastS, v2);
+                for (int k = 0; k < N; k++) v2[k] *= zn;
+            }
+            __syncthreads();
+            if (tid == 0) {  // state = (last_state + v1) + v2, :1119
+                for (int k = 0; k < 36; k++) bl[k] = lastS[k];
+                iekf::boxplus_inplace(bl, v1);
+                iekf::boxplus_inplace(bl, v2);
+            }
+        } else {
+            if (tid == 0) {  // state = (last_state + v1) + l2l * zeta_t_norm, :1122-1127
+                const double ztn = zeta_t / (c.zeta_l + zeta_t);
+                iekf::boxminus(st, lastS, v1);
+                for (int k = 0; k < N; k++) v1[k] *= (1 - ztn);
+                for (int k = 0; k < 36; k++) bl[k] = lastS[k];
+                iekf::boxplus_inplace(bl, v1);
+                double o[36];
+                iekf::scaled(sother, ztn, o);
+                iekf::compose_inplace(bl, o);
+            }
+        }
+        __syncthreads();
+        if (tid < 36) c.blend_state[tid] = bl[tid];
+        // :1165: no map update while the EKF is stopped.  Unresolved queries need the exact-neighbour fallback first:
+        // when its kernels were not queued (no such queries in the recent scans) the host runs map_incremental itself.
+        if (tid == 0) c.insert_status = stop ? 0 : ((c.n_unresolved > 0 && !c.far_enqueued) ? 2 : 1);
+    }
+    DLT_STAMP(8);
     if (tid == 0 && fin) c.done = 1;
 }
 
 // ------------------------------------------------------------------ map_incremental classification
 // laserMapping.cpp:582-630: decide per downsampled point whether it is added raw
 // (PointNoNeedDownsample), through downsample-on-insert (PointToAdd) or dropped.
-__global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P, const float4 *__restrict__ nbr, const int *__restrict__ nbr_cnt,
+__global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_param, const float4 *__restrict__ nbr, const int *__restrict__ nbr_cnt,
                                 double fs, int ekf_inited, float4 *__restrict__ pw, unsigned char *__restrict__ ds_flag,
-                                unsigned char *__restrict__ add_flag, int *__restrict__ class_counts /* [0] downsample adds, [1] raw adds */) {
+                                unsigned char *__restrict__ add_flag, int *__restrict__ class_counts /* [0] downsample adds, [1] raw adds */,
+                                LoopArgs la) {
+    __shared__ Pose sP;
+    if (!insert_gate(la, n)) return;  // block-uniform
+    if (la.ctl) {  // pose after the zeta blend, flg_EKF_inited after the loop
+        if (threadIdx.x < 24) reinterpret_cast<double *>(&sP)[threadIdx.x] = la.ctl->b.blend_state[threadIdx.x];
+        ekf_inited = la.ctl->b.flg_EKF_inited;
+    } else {
+        if (threadIdx.x < 24) reinterpret_cast<double *>(&sP)[threadIdx.x] = reinterpret_cast<const double *>(&P_param)[threadIdx.x];
+    }
+    __syncthreads();
+    const Pose &P = sP;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned char ds = 0, add = 0;
     if (i < n) {

@@ -641,8 +641,22 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         }
         B.threshold = dynamic_effect_featurepoints_threshold;
         B.max_iteration = NUM_MAX_ITERATIONS;
-        B.reserved2 = 0;
-        B.reserved0 = 0;
+        // zeta blend + map_incremental behind the loop on the device (one synchronisation per scan)
+        B.finish = cfg.device_loop == 2 ? 0 : 1;  // device_loop == 2: loop on the device, blend + insert driven by the host (A/B measurements)
+        B.blend_mode = ((lidar_cnt < 100) || (!th->tis_online) || (th->tis_online && lidar_cnt % 2 == 1)) ? 1 : 2;  // :1107
+        {
+            double f[36 + kDim * kDim];
+            last_state.to_flat(f);
+            std::memcpy(B.last_state, f, sizeof(B.last_state));
+            StatesGroup o = odom_to_state(th->l2l_pos, th->l2l_quat, th->l2l_vel, th->l2l_cov_slots);
+            o.to_flat(f);
+            std::memcpy(B.l2l_state, f, sizeof(B.l2l_state));
+        }
+        B.zeta_t = zeta_t;
+        B.zeta_l = zeta_l;
+        B.beta = cfg.beta;
+        B.lidar_cnt_lt_100 = lidar_cnt < 100 ? 1 : 0;
+        B.far_enqueued = 0;
         B.queue_len = (int)effct_q.size();
         for (int i = 0; i < 10; i++) B.effct_queue[i] = i < B.queue_len ? effct_q[i] : 0;
         B.flg_EKF_inited = flg_EKF_inited ? 1 : 0;
@@ -676,9 +690,28 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         }
         out->t_iterate = wall() - t0;
         const bool want_eig = B.n_iters > 0;
-        zeta_blend(effct_feat_num, state_propagat, th);  // (the eigen-decomposition was forked onto the side stream by dlt_iekf_update)
         t0 = wall();
-        if (!EKF_stop_flg && cfg.dev.shard_count <= 1) {
+        if (B.finish && B.n_iters > 0 && B.done) {  // the blend ran on the device: adopt it (covariance of last_state, :1119)
+            if (B.blend_mode == 1) zeta_l = B.zeta_l;
+            double f[36 + kDim * kDim];
+            last_state.to_flat(f);
+            std::memcpy(f, B.blend_state, sizeof(B.blend_state));
+            state.from_flat(f);
+            last_state = state;  // :1131
+            if (B.insert_status == 1) {
+                out->n_added_ds = B.n_added_ds;
+                out->n_added_raw = B.n_added_raw;
+                out->added = out->n_added_ds + out->n_added_raw;
+            } else if (B.insert_status == 2) {  // more unresolved queries than one fallback chunk: the chunked host-driven path
+                double pose[24];
+                state.pose24(pose);
+                LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
+                out->added = out->n_added_ds + out->n_added_raw;
+            }
+        } else {
+            zeta_blend(effct_feat_num, state_propagat, th);
+        }
+        if (B.insert_status == 0 && !EKF_stop_flg && cfg.dev.shard_count <= 1) {  // not armed on the device (e.g. stale map counters)
             double pose[24];
             state.pose24(pose);
             LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));

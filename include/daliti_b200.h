@@ -159,8 +159,15 @@ typedef struct dlt_iekf_block {
     double laser_point_cov;             /* LASER_POINT_COV, :76 (the gain uses state.cov / this) */
     int threshold;                      /* dynamic_effect_featurepoints_threshold, :908          */
     int max_iteration;                  /* NUM_MAX_ITERATIONS (<= DLT_IEKF_MAX_ITER)             */
-    int reserved2;
-    int reserved0;
+    int finish;                         /* 1: also run the zeta blend (:1105-1131) and map_incremental (:1164-1168)
+                                           on the device behind the loop, before the one synchronisation; cleared
+                                           on return when that was not possible (sharded map, stale counters) */
+    int blend_mode;                     /* which branch of :1107 applies: 1 = LiDAR/IMU blend, 2 = thermal  */
+    double last_state[36];              /* last_state, :1131 (finish only)                        */
+    double l2l_state[36];               /* odomToStateGruop(g_tis_odom_delta_lframe2lframe), :1125 */
+    double zeta_t, beta;                /* :1112, feat.yaml:8                                     */
+    int lidar_cnt_lt_100;               /* :1113                                                  */
+    int far_enqueued;                   /* set by dlt_iekf_update: the exact-neighbour fallback kernels are queued behind the loop */
     /* in / out, updated in place */
     double state[612];                  /* state at loop entry -> state at loop exit             */
     double last_nodegared[612];         /* last_nodegared_state, :1050                           */
@@ -173,7 +180,12 @@ typedef struct dlt_iekf_block {
     int reserved1;                      /* VoxelGrid status of the scan (2 = capacity exceeded -> DLT_E_CAPACITY) */
     /* loop control, owned by the device (zeroed by dlt_iekf_update)                              */
     int iter, rematch_num, rematch_en, done;
-    double reserved3[42];
+    double zeta_l;                      /* in / out: :1110 (finish only)                          */
+    double blend_state[36];             /* state after the zeta blend (its covariance is last_state's, :1119) */
+    int insert_status;                  /* 0 not run (EKF stop / sharded / !finish), 1 done, 2 not done: more unresolved
+                                           queries than one fallback chunk -- call dlt_map_incremental instead */
+    int n_added_ds, n_added_raw;        /* PointToAdd / PointNoNeedDownsample sizes, :627-628     */
+    int map_counters[5];                /* buckets, live points, map error, -, -                   */
     dlt_iekf_iter iters[DLT_IEKF_MAX_ITER];
 } dlt_iekf_block;
 /* downSizeFilterSurf.filter enqueued without waiting: feats_down_size stays on the device and is
@@ -198,6 +210,8 @@ int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset);
 /* Spans recorded since the last dlt_get_profile(reset): (group, start ms, end ms) triples relative to the
  * first span, device time from the CUDA events (group 6 = k_iekf_step, 8 = k_eigen6 on the side stream). */
 int dlt_get_timeline(dlt_handle h, double *kind_start_end, int cap, int *n);
+/* SM clock stamps of the stages of k_iekf_step in the last dlt_iekf_update: n_iter x 16 values (kernel tuning)  */
+int dlt_get_iekf_clocks(dlt_handle h, long long *clocks, int n_iter);
 /* kernels launched by this library in this process so far                                         */
 unsigned long long dlt_launch_count(void);
 

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""A/B of the per-scan update latency between configurations of the host loop (device_loop = 0 host loop, 2 device loop +
+host-driven blend/insert, 1 device loop + device-side finish) on the C2 workload: p50 of per-scan CUDA-event times with
+the L2 flushed between scans, and the host wall clock.  Development tool."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    import bench
+    from daliti_b200.lio import LaserMapping
+
+    n, warm = 45, 5
+    work = bench.build_workload(0, n, "c2")
+    seq, scans = work["seq"], work["scans"]
+    devs = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p, _, _ in scans]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    stream = torch.cuda.Stream()
+    modes = [int(a) for a in sys.argv[1:]] or [0, 2, 1]
+    for rep in range(2):
+        for mode in modes:
+            lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30,
+                              device_loop=mode)
+            lm.device.set_stream(stream.cuda_stream)
+            s0, mean_acc, last_imu = bench.initial_state(seq)
+            lm.force_imu_ready(mean_acc, last_imu)
+            lm.set_state(s0)
+            lm.device.map_build(work["map_pts"])
+            ev, host = [], []
+            with torch.cuda.stream(stream):
+                for k in range(n):
+                    pts, t_beg, imu = scans[k]
+                    lm.on_lidar_msg()
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    t0 = time.perf_counter()
+                    lm.process_scan_dev(devs[k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
+                    host.append(1e3 * (time.perf_counter() - t0))
+                    b.record(stream)
+                    ev.append((a, b))
+                torch.cuda.synchronize()
+            ms = np.array([a.elapsed_time(b) for a, b in ev])[warm:]
+            print(f"device_loop={mode}: p50 {np.median(ms):.4f} ms  mean {ms.mean():.4f}  host p50 {np.median(host[warm:]):.4f} ms", flush=True)
+            lm.close()
+
+
+if __name__ == "__main__":
+    main()

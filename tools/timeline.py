@@ -49,6 +49,12 @@ def main():
                     prev_end = b
                     busy += b - a
             print(f"  device span {1e3*prev_end:.1f} us, busy {1e3*busy:.1f} us")
+            import ctypes as C
+            ck = np.zeros((4, 16), np.int64)
+            lm.lib.dlt_get_iekf_clocks(lm.device.h, ck.ctypes.data_as(C.c_void_p), C.c_int(4))
+            for it in range(4):
+                d = ck[it, 1:9] - ck[it, 0:8]
+                print("  k_iekf_step iter", it, "stage cycles:", d.tolist(), "total", int(ck[it, 8] - ck[it, 0]))
     lm.close()
 
 
