@@ -39,12 +39,27 @@ def build_workload(rank: int, n_scans: int, workload: str):
     """scene + map + n_scans raw scans with IMU, deterministic per rank"""
     from daliti_b200 import synth
 
+    lm_kwargs = {}
+
     if workload == "c1":  # VLP-16, ~30 k raw points, 200 k-point local map
         scene = synth.make_box_world(half=110.0, n_boxes=60, seed=10 + rank, keep_clear=6.0)
         traj = synth.Trajectory(speed=1.0, yaw_rate=0.1, z0=1.5)
         spec = synth.VLP16
         map_pts = synth.sample_map(scene, seed=10 + rank, max_points=200_000)
         name = "C1: synthetic VLP-16 scan (16x1800) vs ~200k-pt map"
+    elif workload == "c3":  # degenerate tunnel, 64 x 1024, small local-map cube so that lasermap_fov_segment box-deletes fire
+        scene = synth.make_tunnel(length=400.0)
+        traj = synth.Trajectory(speed=5.0, yaw_rate=0.0, x0=-150.0, z0=1.5)
+        spec = synth.ScanSpec(64, 1024, (-22.5, 22.5), max_range=60.0)
+        map_pts = synth.sample_map(scene, seed=30 + rank)
+        name = "C3: synthetic degenerate tunnel (3x3x400 m, ~19k-pt surface map at 0.5 m), 64x1024 scan at 5 m/s, insert every scan, cube 40 m / DET_RANGE 13 m so box deletes fire"
+        lm_kwargs = dict(cube_len=40.0, det_range=13.0)
+    elif workload == "c5":  # one of the independent 32-beam sequences: 32 x 1024 scan, ~0.5 M-point map
+        scene = synth.make_box_world(half=160.0, n_boxes=260, seed=50 + rank, keep_clear=8.0, height=(8.0, 40.0), max_size=25.0)
+        traj = synth.Trajectory(speed=2.0, yaw_rate=0.15, z0=1.8)
+        spec = synth.ScanSpec(32, 1024, (-22.5, 22.5), max_range=100.0)
+        map_pts = synth.sample_map(scene, seed=50 + rank, region=(-85.0, 85.0, -85.0, 85.0))
+        name = "C5: independent synthetic 32-beam sequences (32x1024 scans, ~0.5M-pt map each)"
     else:  # c2 (default): OS1-64, ~125 k raw points, ~2 M-point map
         scene = synth.make_box_world(half=300.0, n_boxes=900, seed=20 + rank, keep_clear=8.0, height=(12.0, 70.0), max_size=30.0)
         traj = synth.Trajectory(speed=2.0, yaw_rate=0.2, z0=1.8)
@@ -63,7 +78,7 @@ def build_workload(rank: int, n_scans: int, workload: str):
             scans = [seq.scan(k) for k in range(n_scans)]
     except Exception:
         scans = [seq.scan(k) for k in range(n_scans)]
-    return dict(name=name, seq=seq, map_pts=map_pts, scans=scans)
+    return dict(name=name, seq=seq, map_pts=map_pts, scans=scans, lm_kwargs=lm_kwargs)
 
 
 def _gen_scan(a):
@@ -248,7 +263,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--seqs-per-gpu", type=int, default=8, help="c5: independent sequences driven concurrently on every GPU (one stream + host thread each)")
+    ap.add_argument("--device-loop", type=int, default=1, choices=[0, 1, 2],
+                    help="1: iteration loop, zeta blend and map insert resident on the device (one sync per scan); 2: loop on the device, "
+                         "blend/insert host-driven; 0: one host round trip per iteration")
     ap.add_argument("--tiles", type=int, default=5, help="c4: the map is tiles x tiles shifted copies of the C2 map")
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans of the same workload timed on the host cores (cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -296,6 +315,8 @@ def main():
 
     if args.workload == "c4":
         return main_c4(args, K, W, rank, local_rank, world, dist)
+    if args.workload == "c5":
+        return main_c5(args, K, W, rank, local_rank, world, dist)
 
     work = build_workload(rank, K + W, args.workload)
     seq, scans = work["seq"], work["scans"]
@@ -303,10 +324,10 @@ def main():
     stream = torch.cuda.Stream(device=local_rank)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
-    def reset(device_loop=1):
+    def reset(device_loop=args.device_loop):
         s0, mean_acc, last_imu = initial_state(seq)
         lm2 = LaserMapping(dev=dict(device=local_rank, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * n_map)), featptsThreshold=30,
-                           device_loop=device_loop)
+                           device_loop=device_loop, **work["lm_kwargs"])
         lm2.device.set_stream(stream.cuda_stream)
         lm2.force_imu_ready(mean_acc, last_imu)
         lm2.set_state(s0)
@@ -352,7 +373,7 @@ def main():
                     ev[k - W][1].record(stream)
                     host_ms.append(1e3 * (time.perf_counter() - th0))
                     outs.append((o.n_raw, o.n_down, o.n_iters, o.ekf_stop, o.added, o.map_points_before, lmx.iters()[-1].effct_feat_num if o.n_iters else 0,
-                                 o.t_deskew, o.t_voxel, o.t_iterate, o.t_insert, o.t_delete, o.t_total))
+                                 o.t_deskew, o.t_voxel, o.t_iterate, o.t_insert, o.t_delete, o.t_total, o.deleted, o.degenerate))
             barrier()
             launches = lmx.device.launch_count() - launches0
         ms = np.array([a.elapsed_time(b) for a, b in ev])
@@ -459,7 +480,10 @@ def main():
             "ms_per_step": t_v / K, "ms_p50": float(np.median(ms_v)), "ms_p99": float(np.percentile(ms_v, 99)),
             "scans_per_s": world * K / (t_v * 1e-3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
-            "config": {"workload": work["name"], "iterations": 4, "iterations_run_mean": iters_mean, "loop": "device-resident (dlt_iekf_update), 2 host syncs per scan",
+            "config": {"workload": work["name"], "iterations": 4, "iterations_run_mean": iters_mean, "loop": {1: "device-resident loop + zeta blend + map insert (dlt_iekf_update), 1 host sync per scan",
+                                2: "device-resident loop (dlt_iekf_update), blend/insert host-driven, 2 host syncs per scan",
+                                0: "host loop over dlt_measure, 1 host sync per iteration"}[args.device_loop],
+                       "deleted_total": int(sum(o[13] for o in outs_v)), "degenerate_scans": int(sum(o[14] for o in outs_v)),
                        "n_raw_mean": n_raw_mean, "n_down_mean": n_down_mean, "map_points": n_map, "effct_feat_mean": float(np.mean([o[6] for o in outs_v])),
                        "ekf_stops": int(sum(o[3] for o in outs_v)), "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
                        "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
@@ -599,6 +623,129 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
         }
         print(json.dumps(line))
     lm.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main_c5(args, K, W, rank, local_rank, world, dist):
+    """BASELINE config C5: independent 32-beam sequences, S per GPU driven concurrently (one handle + stream + host thread
+    each), no data-path collective.  A step = one scan of every sequence; value = aggregate raw points / s."""
+    import threading
+
+    import torch
+
+    from daliti_b200.lio import LaserMapping
+
+    S = max(1, args.seqs_per_gpu)
+    works = [build_workload(rank * S + i, K + W, "c5") for i in range(S)]
+    dev = f"cuda:{local_rank}"
+    streams, dev_scans, pin_scans = [], [], []
+    for w in works:
+        streams.append(torch.cuda.Stream(device=local_rank))
+        dev_scans.append([torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p, _, _ in w["scans"]])
+        pin_scans.append([torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p, _, _ in w["scans"]])
+
+    def run(mode):
+        lms = []
+        for w, st in zip(works, streams):
+            lm = LaserMapping(dev=dict(device=local_rank, max_scan_points=1 << 16, max_map_points=max(1 << 20, 2 * len(w["map_pts"])),
+                                       voxel_bitmap_bits=1 << 25), featptsThreshold=30, device_loop=args.device_loop)
+            lm.device.set_stream(st.cuda_stream)
+            s0, mean_acc, last_imu = initial_state(w["seq"])
+            lm.force_imu_ready(mean_acc, last_imu)
+            lm.set_state(s0)
+            lm.device.map_build(w["map_pts"])
+            lms.append(lm)
+        torch.cuda.synchronize()
+        gate = threading.Barrier(S + 1)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
+        stats = [None] * S
+        errs = []
+
+        def worker(i):
+            try:
+                lm, st, w = lms[i], streams[i], works[i]
+                pts_total, nd, eff = 0, 0, 0
+                with torch.cuda.stream(st):
+                    for k in range(W + K):
+                        pts, t_beg, imu = w["scans"][k]
+                        if k == W:
+                            gate.wait()   # warm-up done everywhere
+                            gate.wait()   # start event recorded
+                        lm.on_lidar_msg()
+                        if mode == "dev":
+                            o = lm.process_scan_dev(dev_scans[i][k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
+                        else:
+                            o = lm.process_scan(pin_scans[i][k], t_beg, imu)
+                        if k >= W:
+                            pts_total += o.n_raw
+                            nd += o.n_down
+                            eff += lm.iters()[-1].effct_feat_num if o.n_iters else 0
+                    ends[i].record(st)
+                stats[i] = (pts_total, nd, eff)
+            except Exception as e:  # surface worker failures in the main thread
+                errs.append(repr(e))
+                try:
+                    gate.abort()
+                except Exception:
+                    pass
+
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(S)]
+        for t in ths:
+            t.start()
+        gate.wait()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        start = torch.cuda.Event(enable_timing=True)
+        start.record(torch.cuda.current_stream())
+        l0 = lms[0].device.launch_count()
+        gate.wait()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize()
+        if errs:
+            raise RuntimeError("; ".join(errs))
+        ms = max(start.elapsed_time(e) for e in ends)
+        n_launch = lms[0].device.launch_count() - l0
+        for lm in lms:
+            lm.close()
+        return ms, stats, n_launch
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_v, st_v, launches = run("dev")
+    clocks = sampler.stop()
+    ms_e, st_e, _ = run("host")
+    pts_v, pts_e = float(sum(s[0] for s in st_v)), float(sum(s[0] for s in st_e))
+    if dist is not None:
+        buf = torch.tensor([pts_v, pts_e, float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        mx = torch.tensor([ms_v, ms_e], dtype=torch.float64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        pts_v, pts_e, launches = float(buf[0]), float(buf[1]), int(buf[2])
+        ms_v, ms_e = float(mx[0]), float(mx[1])
+    if rank == 0:
+        n_seq = S * world
+        line = {
+            "metric": METRIC, "value": pts_v / (ms_v * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_v / K,
+            "scans_per_s": n_seq * K / (ms_v * 1e-3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
+            "config": {"workload": f"{works[0]['name']}: {n_seq} sequences, {S} per GPU driven concurrently (one handle + CUDA stream + host thread each), "
+                                   f"{K} scans per sequence timed (BASELINE names 1000: bounded here by scan synthesis time)",
+                       "iterations": 4, "sequences": n_seq, "seqs_per_gpu": S, "n_raw_mean": pts_v / (n_seq * K),
+                       "n_down_mean": float(sum(s[1] for s in st_v)) / (S * K), "effct_feat_mean": float(sum(s[2] for s in st_v)) / (S * K),
+                       "map_points_per_sequence": int(np.mean([len(w["map_pts"]) for w in works])),
+                       "l2": "not flushed: the concurrent sequences' maps (S x ~70 MB of buckets + tables) exceed the 126 MB L2 for S >= 2",
+                       "timing": "one CUDA event before the workers are released to the last worker's end event (max over sequences and ranks)",
+                       "parallelism": "independent sequences, no data-path collective"},
+            "e2e": {"value": pts_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(pts_e / (world * K) * 48), "d2h_bytes_per_step": int(S * 18064),
+                    "ms_per_step": ms_e / K, "api": "dlt_lio_process_scan (pinned host buffers), one host thread per sequence"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

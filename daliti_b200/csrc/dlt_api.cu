@@ -29,6 +29,7 @@ struct ProfSpan {
 constexpr int kFarChunk = 4096;
 constexpr int kFarSlices = 64;
 constexpr int kFarGroupsX = 4;
+constexpr int kNn1GroupsX = 2;
 }  // namespace
 
 struct dlt_handle_s {
@@ -359,7 +360,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
          !dalloc(h, &h->acc.sy, cap) && !dalloc(h, &h->acc.sz, cap) && !dalloc(h, &h->acc.si, cap) && !dalloc(h, &h->acc.cnt, cap) &&
          !dalloc(h, &h->acc.idx, cap) && !dalloc(h, &h->d_vop, cap) && !dalloc(h, &h->knn.qw, cap) && !dalloc(h, &h->knn.nbr, cap * kK) &&
          !dalloc(h, &h->knn.nbr_id, cap * kK) && !dalloc(h, &h->knn.nbr_cnt, cap) && !dalloc(h, &h->knn.flags, cap) &&
-         !dalloc(h, &h->knn.far_list, cap) && !dalloc(h, &h->d_plane, cap) && !dalloc(h, &h->d_coeff, cap) && !dalloc(h, &h->d_sel, cap) &&
+         !dalloc(h, &h->knn.far_list, cap) && !dalloc(h, &h->knn.nn_list, cap) && !dalloc(h, &h->knn.nn_pos, cap) && !dalloc(h, &h->knn.nn_key, cap) && !dalloc(h, &h->d_plane, cap) && !dalloc(h, &h->d_coeff, cap) && !dalloc(h, &h->d_sel, cap) &&
          !dalloc(h, &h->d_eff, cap) && !dalloc(h, &h->d_partials, (size_t)blocks_max * NormalEq<true>::NR) &&
          !dalloc(h, &h->d_result, (size_t)kResultDoubles) && !dalloc(h, &h->d_ticket, 4) &&
          !dalloc(h, &h->d_far_partial, (size_t)kFarChunk * kFarSlices * kK) && !dalloc(h, &h->d_pw, cap) && !dalloc(h, &h->d_dsflag, cap) &&
@@ -382,6 +383,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->map.n_live = h->d_counters + 1;
     h->map.error = h->d_counters + 2;
     h->knn.far_count = h->d_counters + 5;
+    h->knn.nn_count = h->d_counters + 9;  // [9] queries needing their nearest point, [10] ring-search overflows
     // accumulators and bitmap are kept zero between scans by k_vox_final
     bool z = rt::fill(h->d_bitmap, 0, words * 4, h->stream) == 0 && rt::fill(h->acc.sx, 0, cap * 8, h->stream) == 0 &&
              rt::fill(h->acc.sy, 0, cap * 8, h->stream) == 0 && rt::fill(h->acc.sz, 0, cap * 8, h->stream) == 0 &&
@@ -756,8 +758,8 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     blk->n_down = blk->n_unresolved = blk->reserved1 = 0;
     blk->iter = blk->rematch_num = blk->rematch_en = blk->done = 0;
     blk->insert_status = 0;
-    // the device-side finish needs the bucket count for the exact-neighbour fallback and an unsharded map
-    const bool finish = blk->finish && h->map.shard_count <= 1 && h->counters_fresh;
+    // the device-side finish needs an unsharded map (a sharded map_incremental exchanges the per-point decisions first)
+    const bool finish = blk->finish && h->map.shard_count <= 1;
     blk->finish = finish ? 1 : 0;
     const bool far_q = finish && h->far_hint > 0;
     blk->far_enqueued = far_q ? 1 : 0;
@@ -821,18 +823,16 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     h->have_match = true;
     if (int re = dlt_degeneracy_begin(h)) return re;
     if (finish) {  // ---- map_incremental (:582-630, 1164-1168) behind the loop, armed by the last k_iekf_step
-        const int n_buckets = h->h_ints[0];
         IekfDev *ctl = h->d_iekf;
         if (far_q) {
             ProfScope prof(h, 5);
-            DLT_LAUNCH(k_far_scan, dim3(kFarGroupsX, kFarSlices), kFarWarps * 32, h->stream, h->map, n_buckets, (const float4 *)h->knn.qw,
-                       (const int *)h->knn.far_list, 0, 0, kFarSlices, h->d_far_partial, (const int *)(h->d_counters + 5), ctl, kFarChunk);
-            DLT_LAUNCH(k_far_merge, div_up(kFarChunk, 128), 128, h->stream, (const int *)h->knn.far_list, 0, 0, kFarSlices,
-                       (const Cand *)h->d_far_partial, h->cfg.max_sq_dist, h->knn, (const int *)(h->d_counters + 5), ctl, kFarChunk);
+            DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 2 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
+                       (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
         }
         DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));  // downsample adds, raw adds (far_count is re-armed by the next k_knn8)
         DLT_LAUNCH(k_incr_classify, div_up(n_upper, 256), 256, h->stream, (const float4 *)h->d_down, 0, P, (const float4 *)h->knn.nbr,
-                   (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, la);
+                   (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, la, h->map,
+                   (const int *)h->map.n_live, (const unsigned char *)h->knn.flags, (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key);
         InsertGate gate = {&h->d_iekf->b.insert_status, &h->d_sc->n_down};
         int ri = insert_points(h, h->d_pw, n_upper, true, gate);
         if (ri) return ri;
@@ -866,7 +866,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
             blk->n_added_ds = blk->n_added_raw = 0;
         }
     }
-    h->h_last_nfar = (finish && far_q && blk->insert_status == 1) ? 0 : blk->n_unresolved;  // 0: the fallback already made them exact
+    h->h_last_nfar = blk->n_unresolved;
     h->far_hint = blk->n_unresolved;
     h->nfar_known = blk->n_iters > 0;
     if (blk->reserved1 == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
@@ -1010,16 +1010,27 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     if (n_ds) *n_ds = 0;
     if (n_raw) *n_raw = 0;
     if (n == 0) return DLT_OK;
-    if (h->have_match) {
-        int rc = run_far(h, nullptr);
-        if (rc) return rc;
-    } else {
-        DLT_RT(h, rt::fill(h->knn.nbr_cnt, 0, (size_t)n * sizeof(int), h->stream));  // Nearest_Points empty
+    if (h->have_match && !(h->nfar_known && h->h_last_nfar == 0)) {
+        // unresolved queries: map_incremental only needs the nearest point of those that saw nothing at all (k_nn1);
+        // a ring-search overflow (pathological chains) takes the full exact fallback
+        DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 16 * sizeof(int), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+        if (h->h_ints[10] > 0) {
+            h->nfar_known = false;
+            int rc = run_far(h, nullptr);
+            if (rc) return rc;
+        } else if (h->h_ints[9] > 0) {
+            ProfScope prof(h, 5);
+            DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 2 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
+                       (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, (int *)nullptr);
+        }
     }
     Pose P = pose_from(pose24);
     DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
-               (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, LoopArgs{nullptr, nullptr});
+               (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
+               LoopArgs{nullptr, nullptr}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
+               (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key);
     int rc = insert_points(h, h->d_pw, n, true);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale

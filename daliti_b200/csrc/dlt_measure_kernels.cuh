@@ -69,6 +69,7 @@ DLT_D bool loop_resolve(const LoopArgs &la, const Pose &P_param, Pose *sP, int &
 constexpr unsigned char kFlagMatched = 1;     // 5 neighbours found and d2[4] <= max_sq_dist
 constexpr unsigned char kFlagUnresolved = 2;  // ring-3 search could not prove exactness (far / crowded)
 constexpr unsigned char kFlagForeign = 4;     // query owned by another shard
+constexpr unsigned char kFlagNeedNN = 8;      // unresolved AND nothing at all within the 7^3 block: map_incremental needs the true nearest point
 
 #ifndef DLT_KNN_MINBLOCKS
 #define DLT_KNN_MINBLOCKS 8
@@ -123,6 +124,13 @@ struct KnnOut {
     unsigned char *flags;  // [n]
     int *far_list;         // indices of unresolved queries
     int *far_count;
+    // The subset of them that map_incremental cannot classify from what the rings saw (see k_nn1): their single
+    // nearest map point is searched for by brute force.  nn_count[0] = size, nn_count[1] = queries whose bucket
+    // chains overflowed the work list (pathological; they need the full exact fallback).
+    int *nn_list;
+    int *nn_pos;           // [n] position of a query in nn_list
+    unsigned long long *nn_key;  // [.] (d2 bits << 32 | id) of the nearest point, all-ones = none yet
+    int *nn_count;
 };
 
 // distance from q to the slab of cell c along one axis (conservative: shrunk by a rounding slack)
@@ -395,11 +403,32 @@ DLT_D void knn_warp_query(const MapView &m, const float4 *__restrict__ q_pts, in
     }
     if (lane == 0) {
         out.nbr_cnt[qi] = nbest;
-        out.flags[qi] = fl;
         if (!resolved) {
             int pos = atomicAdd(out.far_count, 1);
             out.far_list[pos] = qi;
+            // What map_incremental (laserMapping.cpp:593-617) reads of Nearest_Points: the nearest point, and which of the
+            // five lie within half a voxel diagonal of the voxel centre.  Every point closer than the distance `cov3` to the
+            // faces of the 7^3 block was seen, so once ONE candidate is closer than that the nearest point is exact and every
+            // unseen point is too far to matter.  Otherwise the true nearest point has to be searched for.
+            float cov3 = INFINITY;
+            cov3 = fminf(cov3, qx - (float)(cx - 3) * cell_edge);
+            cov3 = fminf(cov3, (float)(cx + 4) * cell_edge - qx);
+            cov3 = fminf(cov3, qy - (float)(cy - 3) * cell_edge);
+            cov3 = fminf(cov3, (float)(cy + 4) * cell_edge - qy);
+            cov3 = fminf(cov3, qz - (float)(cz - 3) * cell_edge);
+            cov3 = fminf(cov3, (float)(cz + 4) * cell_edge - qz);
+            cov3 -= slack;
+            const bool have_near = !overflow && nbest > 0 && cov3 > 0.f && best[0].d2 < cov3 * cov3 * 0.99999f;
+            if (overflow) atomicAdd(out.nn_count + 1, 1);
+            if (!have_near) {
+                fl |= kFlagNeedNN;
+                int np = atomicAdd(out.nn_count, 1);
+                out.nn_list[np] = qi;
+                out.nn_pos[qi] = np;
+                out.nn_key[np] = 0xFFFFFFFFFFFFFFFFull;
+            }
         }
+        out.flags[qi] = fl;
     }
 }
 
@@ -599,7 +628,11 @@ __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
     __shared__ Pose sP;
     int is_match = -1;
     if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
-    if (blockIdx.x == 0 && threadIdx.x == 0) *out.far_count = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *out.far_count = 0;
+        out.nn_count[0] = 0;
+        out.nn_count[1] = 0;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * (kKnn8Block / 32) * 4;
     for (int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4; q0 < n; q0 += stride)  // warp-uniform
@@ -703,6 +736,63 @@ __global__ void k_far_merge(const int *__restrict__ far_list, int far_off, int n
         unsigned char fl = 0;
         if (nb == kK && best[kK - 1].d2 <= max_sq_dist) fl |= kFlagMatched;
         out.flags[qi] = fl;  // now exact
+    }
+}
+
+// ------------------------------------------------------------------ nearest map point of the kFlagNeedNN queries
+// Brute force, k = 1: lane = query, the bucket pool is split into gridDim.y slices that are streamed through shared
+// memory, slices combine with a 64-bit atomicMin on (d2 bits << 32 | id).  Sized to fill the machine (the full exact
+// fallback above keeps five candidates with coordinates per lane and runs at a fraction of this rate).
+constexpr int kNn1Block = 128;
+constexpr int kNn1Tile = 64;  // buckets per shared-memory tile
+
+__global__ void __launch_bounds__(kNn1Block)
+    k_nn1(MapView m, const int *__restrict__ n_buckets_ptr, const float4 *__restrict__ qw, const int *__restrict__ nn_list,
+          const int *__restrict__ nn_count, unsigned long long *__restrict__ nn_key, int *gate) {
+    __shared__ float4 tile[kNn1Tile * 8];
+    if (gate && *gate != 1) return;
+    if (gate && nn_count[1] > 0) {  // a bucket chain overflowed the ring search: the host runs the full exact fallback instead
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *gate = 2;
+        return;
+    }
+    const int nn = nn_count[0];
+    if (nn == 0) return;
+    const int n_buckets = min(*n_buckets_ptr, m.bucket_cap);
+    const int n_slices = gridDim.y;
+    const int per = (n_buckets + n_slices - 1) / n_slices;
+    const int b0 = blockIdx.y * per, b1 = min(n_buckets, b0 + per);
+    const int groups = (nn + kNn1Block - 1) / kNn1Block;
+    for (int g = blockIdx.x; g < groups; g += gridDim.x) {  // block-uniform
+        const int f = g * kNn1Block + threadIdx.x;
+        const bool live = f < nn;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (live) {
+            const float4 q = qw[nn_list[f]];
+            qx = q.x;
+            qy = q.y;
+            qz = q.z;
+        }
+        unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
+        for (int tb = b0; tb < b1; tb += kNn1Tile) {
+            const int nb = min(kNn1Tile, b1 - tb);
+            __syncthreads();
+            for (int k = threadIdx.x; k < nb * 8; k += kNn1Block) tile[k] = reinterpret_cast<const float4 *>(&m.buckets[tb])[k];
+            __syncthreads();
+            if (live) {
+                for (int k = 0; k < nb; k++) {
+                    unsigned msk = __float_as_uint(tile[k * 8].w) & 0x7Fu;
+                    while (msk) {
+                        const int sl = __ffs((int)msk) - 1;
+                        msk &= msk - 1u;
+                        const float4 e = tile[k * 8 + 1 + sl];
+                        const float d2 = calc_dist(qx, qy, qz, e.x, e.y, e.z);
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)((tb + k) * 8 + 1 + sl);
+                        best = key < best ? key : best;
+                    }
+                }
+            }
+        }
+        if (live && best != 0xFFFFFFFFFFFFFFFFull) atomicMin(&nn_key[f], best);
     }
 }
 
@@ -1455,7 +1545,8 @@ __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const do
 __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_param, const float4 *__restrict__ nbr, const int *__restrict__ nbr_cnt,
                                 double fs, int ekf_inited, float4 *__restrict__ pw, unsigned char *__restrict__ ds_flag,
                                 unsigned char *__restrict__ add_flag, int *__restrict__ class_counts /* [0] downsample adds, [1] raw adds */,
-                                LoopArgs la) {
+                                LoopArgs la, MapView m, const int *__restrict__ live_ptr, const unsigned char *__restrict__ flags,
+                                const int *__restrict__ nn_pos, const unsigned long long *__restrict__ nn_key) {
     __shared__ Pose sP;
     if (!insert_gate(la, n)) return;  // block-uniform
     if (la.ctl) {  // pose after the zeta blend, flg_EKF_inited after the loop
@@ -1473,21 +1564,39 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_p
     float wx, wy, wz;
     body_to_world(P, pb.x, pb.y, pb.z, wx, wy, wz);  // :591
     pw[i] = make_float4(wx, wy, wz, pb.w);
-    int cnt = nbr_cnt[i];
+    // Nearest_Points[i].size(): what the reference's search returned = min(5, live map points).  The rings may have seen
+    // fewer (unresolved query): the unseen ones are farther than the 7^3 block's faces, too far to decide anything below.
+    int seen = nbr_cnt[i];
+    const int live_pts = *live_ptr;
+    int cnt = live_pts < kK ? (live_pts < seen ? seen : live_pts) : kK;
+    float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (seen > 0) n0 = nbr[(size_t)i * kK];
+    if (!flags || (flags[i] & kFlagForeign)) {  // no match pass behind this scan (Nearest_Points empty) / another shard's query
+        cnt = 0;
+        seen = 0;
+    } else if (flags[i] & kFlagNeedNN) {  // nothing within the block: the true nearest point from k_nn1
+        const unsigned long long key = nn_key[nn_pos[i]];
+        seen = 0;
+        if (key == 0xFFFFFFFFFFFFFFFFull) {
+            cnt = 0;
+        } else {
+            const int id = (int)(unsigned)(key & 0xFFFFFFFFull);
+            n0 = m.buckets[id >> 3].pts[(id & 7) - 1];
+        }
+    }
     ds = 1;  // default: PointToAdd (:621-624)
     if (cnt > 0 && ekf_inited) {    // :593
         float mx = (float)(floor((double)wx / fs) * fs + 0.5 * fs);  // :599-601
         float my = (float)(floor((double)wy / fs) * fs + 0.5 * fs);
         float mz = (float)(floor((double)wz / fs) * fs + 0.5 * fs);
         float dist = calc_dist(wx, wy, wz, mx, my, mz);  // :602
-        float4 n0 = nbr[(size_t)i * kK];
         if ((double)fabsf(n0.x - mx) > 0.5 * fs && (double)fabsf(n0.y - my) > 0.5 * fs && (double)fabsf(n0.z - mz) > 0.5 * fs) {  // :603
             ds = 0;
             add = 1;  // PointNoNeedDownsample
         } else {
             bool need_add = true;
             if (cnt >= kK) {  // :610
-                for (int j = 0; j < kK; j++) {
+                for (int j = 0; j < seen; j++) {
                     float4 e = nbr[(size_t)i * kK + j];
                     if (calc_dist(e.x, e.y, e.z, mx, my, mz) < dist) {  // :612
                         need_add = false;

@@ -18,9 +18,10 @@ def main():
     from daliti_b200.lio import LaserMapping
 
     n = 8
-    work = bench.build_workload(0, n, "c2")
+    wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
+    work = bench.build_workload(0, n, wl)
     seq, scans = work["seq"], work["scans"]
-    lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30)
+    lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30, **work["lm_kwargs"])
     s0, mean_acc, last_imu = bench.initial_state(seq)
     lm.force_imu_ready(mean_acc, last_imu)
     lm.set_state(s0)
@@ -37,6 +38,7 @@ def main():
         host_ms = 1e3 * (time.perf_counter() - t0)
         tl = lm.device.get_timeline()
         if k >= n - 2:
+            print(f"--- scan {k}: n_raw {o.n_raw} n_down {o.n_down} iters {o.n_iters} added {o.added} deleted {o.deleted} unresolved {[it.effct_feat_num for it in lm.iters()]}")
             print(f"--- scan {k}: host {host_ms:.3f} ms; stages deskew {1e3*o.t_deskew:.3f} voxel {1e3*o.t_voxel:.3f} iterate {1e3*o.t_iterate:.3f} insert {1e3*o.t_insert:.3f}")
             prev_end = 0.0
             busy = 0.0
