@@ -524,7 +524,7 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
     n_map = len(base) * len(offs)
     per_rank_cap = int(n_map * (1.0 if world == 1 else min(1.0, 1.6 / world + 0.15))) + (1 << 20)
     lm = LaserMapping(dev=dict(device=local_rank, max_scan_points=1 << 18, max_map_points=per_rank_cap, shard_rank=rank, shard_count=world,
-                               shard_tile_shift=5), featptsThreshold=30,
+                               shard_tile_shift=5), featptsThreshold=30, device_loop=args.device_loop,
                       cube_len=1.0e6)  # the local-map cube must cover the whole tiled area: no lasermap_fov_segment deletes
     stream = torch.cuda.Stream(device=local_rank)
     lm.device.set_stream(stream.cuda_stream)
@@ -608,7 +608,7 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
             "ms_per_step": t_v / K, "ms_p50": float(np.median(ms_v)), "ms_p99": float(np.percentile(ms_v, 99)), "scans_per_s": K / (t_v * 1e-3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
             "config": {"workload": f"C4: {n_map / 1e6:.1f}M-pt voxel-hash map ({T}x{T} tiles of the C2 map) spatially sharded over {world} GPU(s), "
-                                   "C2 scans at poses hopping between tiles, all-reduce of H^T H / H^T r per iteration, no insert",
+                                   "C2 scans at poses hopping between tiles, all-reduce of H^T H / H^T r per iteration inside the device-resident loop, map_incremental with the owners' decisions exchanged",
                        "iterations": 4, "n_raw_mean": float(np.mean([o[0] for o in outs_v])), "n_down_mean": float(np.mean([o[1] for o in outs_v])),
                        "map_points": n_map, "live_points_incl_halos": live_sum, "map_build_s": t_build,
                        "effct_feat_mean": float(np.mean([o[3] for o in outs_v])),

@@ -82,6 +82,10 @@ struct dlt_handle_s {
     dlt_iekf_block *h_iekf = nullptr;  // pinned
     bool n_down_on_device = false;     // dlt_scan_downsample_async ran: h->n_down is only an estimate until the next read-back
     int n_down_hint = 0;               // feats_down_size of the previous scan (grid sizing for the speculative launches)
+    // sharded map_incremental: exchange of the per-point decisions
+    dlt_reduce_fn shard_reduce = nullptr;
+    void *shard_reduce_ctx = nullptr;
+    double *d_flagbuf = nullptr;
     int far_hint = 1;                  // unresolved queries of the previous scan: queue the exact-neighbour fallback behind the loop?
     // pinned host staging
     double *h_result = nullptr;
@@ -366,6 +370,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
          !dalloc(h, &h->d_far_partial, (size_t)kFarChunk * kFarSlices * kK) && !dalloc(h, &h->d_pw, cap) && !dalloc(h, &h->d_dsflag, cap) &&
          !dalloc(h, &h->d_addflag, cap) && !dalloc(h, &h->d_cellslot, cap) && !dalloc(h, &h->d_vslot, cap) &&
          !dalloc(h, &h->scratch.vkeys, sc_cap) && !dalloc(h, &h->scratch.vwin, sc_cap) && !dalloc(h, &h->d_iekf, 1);
+    if (cfg->shard_count > 1) ok = ok && !dalloc(h, &h->d_flagbuf, cap);
     void *p = nullptr;
     ok = ok && rt::pinned_alloc(&p, sizeof(dlt_iekf_block)) == 0;
     h->h_iekf = (dlt_iekf_block *)p;
@@ -1003,7 +1008,8 @@ int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
 int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_ds, int *n_raw) {
     if (!h || !pose24) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental before a scan");
-    if (h->map.shard_count > 1) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental is not supported on a sharded map yet");
+    const bool sharded = h->map.shard_count > 1;
+    if (sharded && !h->shard_reduce) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental on a sharded map needs dlt_set_shard_reduce");
     rt::set_device(h->cfg.device);
     if (int rn = resolve_n_down(h)) return rn;
     const int n = h->n_down;
@@ -1031,6 +1037,14 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
                (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
                LoopArgs{nullptr, nullptr}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
                (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key);
+    if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
+                                     // (without a match pass every rank already agrees: all points are PointToAdd)
+        DLT_LAUNCH(k_incr_pack, div_up(n, 256), 256, h->stream, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag, n, h->d_flagbuf);
+        DLT_RT(h, rt::check_launch());
+        if (h->shard_reduce(h->shard_reduce_ctx, h->d_flagbuf, n) != 0) DLT_FAIL(h, DLT_E_STATE, "shard reduce callback failed");
+        DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
+        DLT_LAUNCH(k_incr_unpack, div_up(n, 256), 256, h->stream, (const double *)h->d_flagbuf, n, h->d_dsflag, h->d_addflag, h->d_counters + 6);
+    }
     int rc = insert_points(h, h->d_pw, n, true);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
@@ -1038,6 +1052,15 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     if (n_ds) *n_ds = h->h_ints[6];
     if (n_raw) *n_raw = h->h_ints[7];
     return rc;
+}
+
+double *dlt_result_dev(dlt_handle h) { return h ? h->d_result : nullptr; }
+
+int dlt_set_shard_reduce(dlt_handle h, dlt_reduce_fn reduce, void *ctx) {
+    if (!h) return DLT_E_INVALID;
+    h->shard_reduce = reduce;
+    h->shard_reduce_ctx = ctx;
+    return DLT_OK;
 }
 
 // ------------------------------------------------------------------ instrumentation

@@ -1571,7 +1571,8 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_p
     int cnt = live_pts < kK ? (live_pts < seen ? seen : live_pts) : kK;
     float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (seen > 0) n0 = nbr[(size_t)i * kK];
-    if (!flags || (flags[i] & kFlagForeign)) {  // no match pass behind this scan (Nearest_Points empty) / another shard's query
+    const bool foreign = flags && (flags[i] & kFlagForeign);  // another shard owns this query and decides for it (k_incr_pack / unpack)
+    if (!flags || foreign) {  // no match pass behind this scan: Nearest_Points empty
         cnt = 0;
         seen = 0;
     } else if (flags[i] & kFlagNeedNN) {  // nothing within the block: the true nearest point from k_nn1
@@ -1607,10 +1608,34 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_p
             ds = need_add ? 1 : 0;
         }
     }
+    if (foreign) ds = 0;
     ds_flag[i] = ds;
     add_flag[i] = add;
     }
     unsigned bd = __ballot_sync(0xffffffffu, ds != 0), ba = __ballot_sync(0xffffffffu, add != 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (bd) atomicAdd(&class_counts[0], __popc(bd));
+        if (ba) atomicAdd(&class_counts[1], __popc(ba));
+    }
+}
+
+// Sharded map: every rank classifies the queries it owns; the decisions (0 drop, 1 PointToAdd, 2 PointNoNeedDownsample) are
+// exchanged as doubles so that the same sum all-reduce that carries the normal equations can carry them (one owner per
+// query, so the sum IS the decision); afterwards every rank knows every decision and inserts what falls into its tiles + halo.
+__global__ void k_incr_pack(const unsigned char *__restrict__ ds_flag, const unsigned char *__restrict__ add_flag, int n, double *__restrict__ buf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = ds_flag[i] ? 1.0 : (add_flag[i] ? 2.0 : 0.0);
+}
+__global__ void k_incr_unpack(const double *__restrict__ buf, int n, unsigned char *__restrict__ ds_flag, unsigned char *__restrict__ add_flag,
+                              int *__restrict__ class_counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int code = 0;
+    if (i < n) {
+        code = (int)(buf[i] + 0.5);
+        ds_flag[i] = code == 1 ? 1 : 0;
+        add_flag[i] = code == 2 ? 1 : 0;
+    }
+    unsigned bd = __ballot_sync(0xffffffffu, code == 1), ba = __ballot_sync(0xffffffffu, code == 2);
     if ((threadIdx.x & 31) == 0) {
         if (bd) atomicAdd(&class_counts[0], __popc(bd));
         if (ba) atomicAdd(&class_counts[1], __popc(ba));

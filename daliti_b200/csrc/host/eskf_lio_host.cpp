@@ -711,7 +711,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         } else {
             zeta_blend(effct_feat_num, state_propagat, th);
         }
-        if (B.insert_status == 0 && !EKF_stop_flg && cfg.dev.shard_count <= 1) {  // not armed on the device (e.g. stale map counters)
+        if (B.insert_status == 0 && !EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn)) {  // not armed on the device (sharded map)
             double pose[24];
             state.pose24(pose);
             LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
@@ -863,7 +863,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
 
         // ---- map_incremental(), :1164-1168
         t0 = wall();
-        if (!EKF_stop_flg && cfg.dev.shard_count <= 1) {
+        if (!EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn)) {
             double pose[24];
             state.pose24(pose);
             LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
@@ -990,11 +990,13 @@ int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lid
                                observation_end_time);
 }
 int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *result_dev) {
-    if (!h || (reduce && !result_dev)) return DLT_E_INVALID;
+    if (!h) return DLT_E_INVALID;
+    if (reduce && !result_dev) result_dev = dlt_result_dev(h->lm->dev_);  // the handle's own buffer
     h->lm->reduce_fn = reduce;
     h->lm->reduce_ctx = ctx;
     h->lm->reduce_buf_dev = result_dev;
-    return DLT_OK;
+    // the same sum over the ranks also carries the per-point map_incremental decisions of a sharded map
+    return dlt_set_shard_reduce(h->lm->dev_, reduce ? &dlt_host::LaserMapping::reduce_trampoline : nullptr, h->lm);
 }
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap) {
     if (!h) return DLT_E_INVALID;

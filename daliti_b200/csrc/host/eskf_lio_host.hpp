@@ -166,6 +166,7 @@ class LaserMapping {
                      dlt_lio_scan_out *out, bool pts_on_device = false, double observation_end_time_in = 0.0);
     void on_lidar_msg();       // feat_points_cbk, laserMapping.cpp:424-446
     void on_edge_count(int n); // tn_cbk, :491-498
+    static int reduce_trampoline(void *self, double *result_dev, int n);  // forwards to reduce_fn
 
     dlt_lio_config cfg;
     dlt_handle dev_ = nullptr;
@@ -185,7 +186,6 @@ class LaserMapping {
    private:
     int fov_segment(const Vec3 &pos_LiD, int *deleted);  // lasermap_fov_segment, :313-369
     void zeta_blend(int effct_feat_num, const StatesGroup &state_propagat, const dlt_lio_thermal *th);  // :1105-1131
-    static int reduce_trampoline(void *self, double *result_dev, int n);
     dlt_iekf_block *iekf_blk_ = nullptr;  // host copy of the device-resident loop's block
     bool flg_first_scan = true;
     double first_lidar_time = 0.0;

@@ -173,29 +173,40 @@ class LaserMapping:
         return self.out
 
     def set_allreduce(self, device: str = "cuda"):
-        """Sharded map: sum the partial normal equations over torch.distributed ranks after every evaluation
-        of the measurement model (NCCL for device="cuda"; gloo on the CPU emulator build for device="cpu")."""
+        """Sharded map: sum over torch.distributed ranks whatever the library hands to the callback (the partial normal
+        equations after every evaluation of the measurement model, the per-point map_incremental decisions) in place, on
+        the current stream (NCCL for device="cuda"; gloo on the CPU emulator build for device="cpu")."""
         import torch
         import torch.distributed as dist
 
-        if device == "cpu":
-            self._red_np = np.zeros(256, np.float64)
-            self._red_t = torch.from_numpy(self._red_np)
-            ptr = self._red_np.ctypes.data
-        else:
-            self._red_t = torch.zeros(256, dtype=torch.float64, device=device)
-            ptr = self._red_t.data_ptr()
+        class _DevPtr:  # wrap a raw device pointer as a tensor without copying
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        cpu = device == "cpu"
+        views = {}  # (pointer, n) -> tensor view: the library hands over the same few buffers every scan
 
         def _cb(ctx, buf, n):
             try:
                 if dist.is_initialized() and dist.get_world_size() > 1:
-                    dist.all_reduce(self._red_t[:n], op=dist.ReduceOp.SUM)
+                    t = views.get((buf, n))
+                    if t is None:
+                        if cpu:
+                            t = torch.from_numpy(np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(n,)))
+                        else:
+                            t = torch.as_tensor(_DevPtr(buf, n), device=device)
+                        if len(views) < 64:
+                            views[(buf, n)] = t
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 return 0
             except Exception:  # never let an exception cross the C ABI
+                import traceback
+
+                traceback.print_exc()
                 return 1
 
         self._red_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)(_cb)
-        self._ck(self.lib.dlt_lio_set_reduce(self.h, self._red_cb, None, C.c_void_p(ptr)))
+        self._ck(self.lib.dlt_lio_set_reduce(self.h, self._red_cb, None, None))
 
     def iters(self):
         n = self.out.n_iters

@@ -118,6 +118,8 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
  * in DEVICE memory at result_dev without synchronising -- the partial sums of one map shard,
  * ready for an NCCL all-reduce of the 158 doubles.                                              */
 int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev);
+/* The handle's own 256-double result buffer in DEVICE memory (a valid result_dev for the calls around it).        */
+double *dlt_result_dev(dlt_handle h);
 /* Read a result block produced by dlt_measure_dev (possibly all-reduced in between) back to the host. */
 int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *out);
 /* laserCloudOri / coeffSel of the last dlt_measure (published as /cloud_effected,
@@ -201,6 +203,11 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
 
 /* ---- map_incremental()                                       laserMapping.cpp:582-630, 1167 - */
 int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_add_downsample, int *n_add_raw);
+/* Sharded map (shard_count > 1): the rank that owns a query point decides whether it is added (it holds the
+ * point's neighbours); `reduce` sums the n per-point decision codes (doubles in DEVICE memory) over the ranks in
+ * place on the handle's stream, after which every rank inserts the accepted points that fall into its tiles + halo.
+ * Unresolved far points are classified against this rank's tiles + halo only.                               */
+int dlt_set_shard_reduce(dlt_handle h, dlt_reduce_fn reduce, void *ctx);
 
 /* ---- instrumentation (no reference counterpart) ---------------------------------------------- */
 /* Per-kernel-group device time from CUDA events on the launching stream.  Groups: 0 k_knn,

@@ -96,10 +96,11 @@ int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lid
  * equations (n = 158 doubles at result_dev, DEVICE memory owned by the caller, 256 doubles) are handed to
  * `reduce`, which must sum them over the ranks in place on the handle's stream (e.g. ncclAllReduce /
  * torch.distributed.all_reduce) and return 0.  With device_loop it is called max_iteration times per scan
- * on every rank and must only ENQUEUE the reduction (no host wait).  map_incremental is skipped on a
- * sharded map.                                                                                           */
+ * on every rank and must only ENQUEUE the reduction (no host wait).  The same callback then sums the per-point
+ * map_incremental decisions (n = feats_down_size doubles at the pointer it is given -- it must reduce THAT buffer,
+ * not one of its own): the owner of a query decides, every rank inserts into its tiles + halo.                     */
 typedef int (*dlt_lio_reduce_fn)(void *ctx, double *result_dev, int n);
-int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *result_dev);
+int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *result_dev /* NULL: the handle's own buffer */);
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap);
 /* IMUpose list of the last scan's forward propagation (22 doubles each)                          */
 int dlt_lio_get_imu_poses(dlt_lio h, double *pose22, int cap);

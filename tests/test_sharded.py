@@ -138,7 +138,22 @@ def _lio_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def _run_lio(lib, rank, world):
+def _tile_owner(xyz, shards, ds=0.5, cell_shift=1, tile_shift=3):
+    """numpy restatement of dlt::tile_owner (dlt_common.cuh) for the cell of each point"""
+    v = np.floor(xyz.astype(np.float32) / np.float32(ds)).astype(np.int64)
+    t = (v >> cell_shift) >> tile_shift
+    m = np.uint64(0x1FFFFF)
+    k = ((t[:, 0].astype(np.uint64) & m) << np.uint64(42)) | ((t[:, 1].astype(np.uint64) & m) << np.uint64(21)) | (t[:, 2].astype(np.uint64) & m)
+    with np.errstate(over="ignore"):
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xFF51AFD7ED558CCD)
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xC4CEB9FE1A85EC53)
+        k ^= k >> np.uint64(33)
+    return ((k & np.uint64(0xFFFFFFFF)) % np.uint64(shards)).astype(np.int64)
+
+
+def _run_lio(lib, rank, world, n_scans=3):
     from daliti_b200.lio import LaserMapping
 
     seq = helpers.small_sequence(seed=22, half=30.0, beams=16, azimuths=240, n_boxes=8)
@@ -151,47 +166,65 @@ def _run_lio(lib, rank, world):
     if world > 1:
         lm.set_allreduce("cpu")
     states = []
-    for k in range(3):
+    for k in range(n_scans):
         pts, t_beg, imu = seq.scan(k)
         lm.on_lidar_msg()
         o = lm.process_scan(pts, t_beg, imu)
-        states.append((lm.get_state()[:36].copy(), [it.effct_feat_num for it in lm.iters()], o.n_iters))
+        m = lm.device.map_export()
+        if world > 1:  # only the points of the tiles this rank owns (halos are replicas)
+            m = m[_tile_owner(m[:, :3], world) == rank]
+        states.append((lm.get_state()[:36].copy(), [it.effct_feat_num for it in lm.iters()], o.n_iters, o.added, m.astype(np.float64)))
     lm.close()
     return states
 
 
+def _lio_worker_all(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    from daliti_b200.binding import load_library
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = load_library(os.path.join(ROOT, "tests", "emu", "libdaliti_emu.so"))
+    states = _run_lio(lib, rank, world)
+    q.put((rank, states))
+    dist.destroy_process_group()
+
+
 def test_sharded_per_scan_update_two_processes(emu_lib):
-    """the full per-scan update on a 2-way sharded map (all-reduce of the normal equations every iteration, replicated
-    24-state solve) follows the unsharded update: effective counts exact, states to fp64 rounding.  The unsharded run
-    skips map_incremental too (a sharded map cannot insert yet), so both see the same map throughout."""
+    """the full per-scan update on a 2-way sharded map -- all-reduce of the normal equations every iteration inside the
+    device-resident loop, replicated 24-state solve, map_incremental with the owners' decisions exchanged -- follows the
+    unsharded update: effective counts exact, states to fp64 rounding, and the union of the owned tiles holds exactly
+    the unsharded map after every scan."""
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_lio_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    sharded = q.get(timeout=600)
+    got = dict(q.get(timeout=600) for _ in range(2))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    # unsharded reference run on the same build, with inserts disabled the same way: shard_count=1 inserts, so
-    # rebuild the map before every scan instead
-    from daliti_b200.lio import LaserMapping
+    ref = _run_lio(emu_lib, 0, 1)
+    for k in range(len(ref)):
+        st, eff, n_it, added, pts = ref[k]
+        for r in range(2):
+            st_r, eff_r, n_it_r, added_r, _ = got[r][k]
+            assert n_it_r == n_it and eff_r == eff, (k, r)
+            assert added_r == added, (k, r, added_r, added)
+            np.testing.assert_allclose(st_r, st, rtol=1e-8, atol=1e-8, err_msg=f"scan {k} rank {r}")
+        # the sharded run's poses differ from the unsharded ones by the summation order of the partial normal equations
+        # (~1e-10), so inserted points may differ in their last float32 bit: match point for point within 1e-5 m
+        from scipy.spatial import cKDTree
 
-    seq = helpers.small_sequence(seed=22, half=30.0, beams=16, azimuths=240, n_boxes=8)
-    map_pts = synth.sample_map(seq.scene, seed=22)
-    lm = LaserMapping(emu_lib, dev=dict(max_scan_points=8192, max_map_points=1 << 17), featptsThreshold=5)
-    lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
-    lm.set_state(helpers.state612(seq.traj, seq.t_start))
-    for k in range(3):
-        lm.device.map_build(map_pts)
-        pts, t_beg, imu = seq.scan(k)
-        lm.on_lidar_msg()
-        o = lm.process_scan(pts, t_beg, imu)
-        st, eff, n_it = sharded[k]
-        assert n_it == o.n_iters
-        assert eff == [it.effct_feat_num for it in lm.iters()]
-        np.testing.assert_allclose(st, lm.get_state()[:36], rtol=1e-9, atol=1e-10)
-    lm.close()
+        owned = np.concatenate([got[0][k][4], got[1][k][4]], 0)
+        assert len(owned) == len(pts), (k, len(owned), len(pts))
+        d, idx = cKDTree(pts[:, :3]).query(owned[:, :3])
+        assert d.max() < 1e-5, (k, d.max())
+        assert len(np.unique(idx)) == len(pts)  # a bijection: no tile is held twice, none is missing
+        np.testing.assert_allclose(owned[:, 3], pts[idx, 3], rtol=1e-5)
