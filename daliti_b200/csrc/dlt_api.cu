@@ -532,7 +532,7 @@ int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *ou
         DLT_RT(h, rt::h2d(h->d_pw, stage.data(), (size_t)c * sizeof(float4), h->stream));
         {
             DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));  // no residual pass here to re-arm it
-            LoopArgs la = {nullptr, nullptr};
+            LoopArgs la = {nullptr, nullptr, nullptr, 0};
             int rk = launch_knn(h, (const float4 *)h->d_pw, c, c, 0, P, la);
             if (rk) return rk;
         }
@@ -722,7 +722,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     if (do_match) {
         h->nfar_known = false;
         ProfScope prof(h, 0);
-        LoopArgs la0 = {nullptr, nullptr};
+        LoopArgs la0 = {nullptr, nullptr, nullptr, 0};
         int rk = launch_knn(h, (const float4 *)h->d_down, n, n, 1, P, la0);
         if (rk) return rk;
         h->have_match = true;
@@ -741,7 +741,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     mb.unres_count = h->d_counters + 8;
     mb.result = result_dev;
     const int G = div_up(n, kResidBlock);
-    LoopArgs la = {nullptr, nullptr};
+    LoopArgs la = {nullptr, nullptr, nullptr, 0};
     ProfScope prof(h, 1);
     if (h->cfg.extrinsic_est_en)
         DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr, la);
@@ -794,7 +794,8 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     mb.unres_count = h->d_counters + 8;
     double *res = result_dev ? result_dev : h->d_result;
     mb.result = res;
-    LoopArgs la = {h->d_iekf, &h->d_sc->n_down};
+    // without a reduction over ranks between them the solve step rides in the last block of k_residual
+    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, reduce ? 0 : 1};
     if (!h->n_down_on_device) {  // the scan was set with a host-known size: publish it where the kernels look
         DLT_RT(h, rt::h2d(&h->d_sc->n_down, &h->n_down, sizeof(int), h->stream));
     }
@@ -816,10 +817,12 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
             else
                 DLT_LAUNCH(k_residual<false>, G, kResidBlock, h->stream, mb, 0, 0, P, h->cfg.plane_thr, la);
         }
-        if (reduce && reduce(reduce_ctx, res, kNormalEqDoubles) != 0) DLT_FAIL(h, DLT_E_STATE, "reduce callback failed");
-        ProfScope profs(h, 6);
-        DLT_LAUNCH(k_iekf_step, 1, kIekfBlock, h->stream, h->d_iekf, (const double *)res, (const int *)&h->d_sc->n_down,
-                   (const int *)&h->d_sc->vox_status, h->cfg.extrinsic_est_en ? 12 : 6);
+        if (reduce) {
+            if (reduce(reduce_ctx, res, kNormalEqDoubles) != 0) DLT_FAIL(h, DLT_E_STATE, "reduce callback failed");
+            ProfScope profs(h, 6);
+            DLT_LAUNCH(k_iekf_step, 1, kIekfBlock, h->stream, h->d_iekf, (const double *)res, (const int *)&h->d_sc->n_down,
+                       (const int *)&h->d_sc->vox_status, h->cfg.extrinsic_est_en ? 12 : 6);
+        }
     }
     if (res != h->d_result) DLT_RT(h, rt::d2d(h->d_result, res, kNormalEqDoubles * sizeof(double), h->stream));  // for dlt_degeneracy
     DLT_RT(h, rt::check_launch());
@@ -1035,7 +1038,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
                (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
-               LoopArgs{nullptr, nullptr}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
+               LoopArgs{nullptr, nullptr, nullptr, 0}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
                (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key);
     if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
                                      // (without a match pass every rank already agrees: all points are PointToAdd)

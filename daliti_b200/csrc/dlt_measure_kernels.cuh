@@ -39,7 +39,9 @@ struct IekfDev {
 #endif
 struct LoopArgs {
     const IekfDev *ctl;
-    const int *n_ptr;  // feats_down_size on the device (ScanScalars::n_down)
+    const int *n_ptr;    // feats_down_size on the device (ScanScalars::n_down)
+    const int *vox_ptr;  // VoxelGrid status of the scan (ScanScalars::vox_status)
+    int fuse_step;       // k_residual: its last block also runs the iteration's solve / control step (iekf_step_block)
 };
 // Block-wide: resolve (n, do_match, pose) for this launch; false = nothing to do.  The pose ends
 // up in shared memory either way so that both paths run the same code.
@@ -796,6 +798,483 @@ __global__ void __launch_bounds__(kNn1Block)
     }
 }
 
+constexpr int kNormalEqDoubles = 158;                 // HtH[144], Htr[12], effective count, residual sum
+constexpr int kFetchDoubles = kNormalEqDoubles + 1;   // + far_count of the last match pass: one device->host copy per iteration
+constexpr int kEigOffset = 160;                       // eigvals[6], eigvecs[36] (k_eigen6)
+constexpr int kResultDoubles = kEigOffset + 42;
+
+// ------------------------------------------------------------------ the iteration loop on the device
+// One launch per enqueued iteration, after that iteration's k_residual: laserMapping.cpp:899-918
+// (degradation window), :1012-1053 (Kalman update in the reduced form of SURVEY.md 8b), :1054-1063
+// (stop branch), :1069-1101 (rematch / convergence control) and :1084-1085 (covariance update).
+// One block; the 24 x 24 solve is a Gauss-Jordan elimination in shared
+// memory, the SO(3) pieces run on one thread.  Mirrors dlt_host::LaserMapping::process_scan.
+namespace iekf {
+DLT_D void mat3_mul(const double *a, const double *b, double *r) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+DLT_D void mat3T_mul(const double *a, const double *b, double *r) {  // a^T b
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
+}
+// Exp(v1, v2, v3), so3_math.h:54-72
+DLT_D void exp3(double v1, double v2, double v3, double *R) {
+    const double n = sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+    if (n > 0.00001) {
+        so3_rodrigues(v1 / n, v2 / n, v3 / n, n, R);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    }
+}
+// Log(R), so3_math.h:75-81
+DLT_D void log3(const double *R, double *o) {
+    const double tr = R[0] + R[4] + R[8];
+    const double theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1));
+    const double K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+    const double f = (fabs(theta) < 0.001) ? 0.5 : (0.5 * theta / sin(theta));
+    o[0] = K[0] * f;
+    o[1] = K[1] * f;
+    o[2] = K[2] * f;
+}
+// a (-) b over the 24-dim error state, common_lib.h:173-187
+DLT_D void boxminus(const double *a, const double *b, double *o) {
+    double M[9];
+    mat3T_mul(b, a, M);
+    log3(M, o);
+    mat3T_mul(b + 12, a + 12, M);
+    log3(M, o + 6);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o[3 + k] = a[9 + k] - b[9 + k];
+        o[9 + k] = a[21 + k] - b[21 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) o[12 + k] = a[24 + k] - b[24 + k];
+}
+// s (+)= d, common_lib.h:147-158
+DLT_D void boxplus_inplace(double *s, const double *d) {
+    double E[9], M[9];
+    exp3(d[0], d[1], d[2], E);
+    mat3_mul(s, E, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) s[k] = M[k];
+    exp3(d[6], d[7], d[8], E);
+    mat3_mul(s + 12, E, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) s[12 + k] = M[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        s[9 + k] += d[3 + k];
+        s[21 + k] += d[9 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[24 + k] += d[12 + k];
+}
+// o = a * s, common_lib.h:190-205 (R_L_I is not scaled)
+DLT_D void scaled(const double *a, double s, double *o) {
+    double so3[3];
+    log3(a, so3);
+    exp3(so3[0] * s, so3[1] * s, so3[2] * s, o);
+#pragma unroll
+    for (int k = 0; k < 9; k++) o[12 + k] = a[12 + k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o[9 + k] = a[9 + k] * s;
+        o[21 + k] = a[21 + k] * s;
+    }
+#pragma unroll
+    for (int k = 24; k < 36; k++) o[k] = a[k] * s;
+}
+// a <- a + b (StatesGroup + StatesGroup), common_lib.h:131-144: biases and gravity of the left operand
+DLT_D void compose_inplace(double *a, const double *b) {
+    double M[9];
+    mat3_mul(a, b, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) a[k] = M[k];
+    mat3_mul(a + 12, b + 12, M);
+#pragma unroll
+    for (int k = 0; k < 9; k++) a[12 + k] = M[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        a[9 + k] += b[9 + k];
+        a[21 + k] += b[21 + k];
+        a[24 + k] += b[24 + k];
+    }
+}
+}  // namespace iekf
+
+constexpr int kIekfBlock = 256;
+// state_propagat: the shared copy, unless the stop branch reused that buffer for the thermal delta
+DLT_D const double *sprop_or(const double *shared_copy, const double *global_copy, int stop) { return stop ? global_copy : shared_copy; }
+
+// Kalman gain in covariance (Woodbury) form.  The reference inverts twice, K_1 = (H^T H + (P/R)^-1)^-1
+// (laserMapping.cpp:1017-1018); with P' = P/R, U = [I_12; 0] and H^T H = U H U^T the same matrix is
+//     K_1 = P' - P' U (I + H P'_11)^-1 H U^T P',     so     K_1[:, :12] = P'_1 - P'_1 Y,   (I + Q) Y = Q,   Q = H P'_11
+// (P'_1 = first 12 columns, P'_11 = top-left 12 x 12).  Without extrinsic estimation only the top-left D = 6 block of
+// H is non-zero, rows D..11 of Q and Y vanish and the system is D x D with 12 right-hand sides: 6 elimination steps
+// instead of two 24 x 24 inversions.  Equal to the reference form up to fp64 round-off (tests: 1e-7 on the solution).
+// The step as a block-wide device function (any block size >= 128 that is a multiple of 32): called by the last block
+// of k_residual (fused: no launch, no extra round trip for the normal equations) or by k_iekf_step when a reduction
+// over ranks has to run in between.
+DLT_D void iekf_step_block(IekfDev *dev, const double *__restrict__ result, const int *__restrict__ n_down_ptr,
+                           const int *__restrict__ vox_status_ptr, int D /* 6 or 12 */) {
+    dlt_iekf_block &c = dev->b;
+    constexpr int N = 24;
+    __shared__ double PN[N * N];                      // P' = cov / LASER_POINT_COV
+    __shared__ double W[12 * 24];                     // [I + Q[:, :D] | Q], later G = K H (24 x 12)
+    __shared__ double T[N * 12];                      // K_1[:, :12]
+    __shared__ double C12[12 * N];                    // the first 12 rows of the covariance
+    __shared__ double R[kNormalEqDoubles + 2];        // the normal equations of this iteration
+    __shared__ double st[36], sprop[36], sother[36];  // state, state_propagat | thermal delta, last_nodegared (non-covariance parts)
+    __shared__ double vec[N], rhs[12], sol[N];
+    __shared__ int s_i[16];
+    __shared__ int s_q[10];
+    __shared__ int s_fail, s_piv;
+    enum { I_QLEN, I_THR, I_CONV, I_RNUM, I_MAXIT, I_INITED, I_GAIN, I_NDOWN, I_VOX };
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int it = c.iter;
+    dlt_iekf_iter &rec = c.iters[it];
+    const int did_match = (it == 0 || c.rematch_en) ? 1 : 0;
+    const int AW = D + 12;
+    constexpr int kCovPer = 5;  // covariance elements per thread at the smallest block size (128)
+
+    DLT_STAMP(0);
+    // ---- one round trip to global memory for everything the step needs
+    for (int k = tid; k < kNormalEqDoubles + 1; k += NT) R[k] = result[k];
+    double cov_own[kCovPer];
+#pragma unroll
+    for (int q = 0; q < kCovPer; q++) {
+        const int k = tid + q * NT;
+        cov_own[q] = (k < N * N) ? c.state[36 + k] : 0.0;
+    }
+    const double lpc = c.laser_point_cov;
+    if (tid < 36) {
+        st[tid] = c.state[tid];
+        sprop[tid] = c.state_propagat[tid];
+    } else if (tid >= 64 && tid < 74) {
+        s_q[tid - 64] = c.effct_queue[tid - 64];
+    } else if (tid == 96) {
+        s_i[I_QLEN] = c.queue_len;
+        s_i[I_THR] = c.threshold;
+        s_i[I_CONV] = c.converged;
+    } else if (tid == 97) {
+        s_i[I_RNUM] = c.rematch_num;
+        s_i[I_MAXIT] = c.max_iteration;
+        s_i[I_INITED] = c.flg_EKF_inited;
+    } else if (tid == 98) {
+        s_i[I_GAIN] = c.have_gain;
+        s_i[I_NDOWN] = *n_down_ptr;
+        s_i[I_VOX] = *vox_status_ptr;
+    }
+    if (tid == 0) {
+        s_fail = 0;
+        if (it == 0) c.insert_status = 0;  // map_incremental stays disarmed until the loop ends cleanly
+    }
+#pragma unroll
+    for (int q = 0; q < kCovPer; q++) {
+        const int k = tid + q * NT;
+        if (k < N * N) {
+            PN[k] = cov_own[q] / lpc;
+            if (k < 12 * N) C12[k] = cov_own[q];
+        }
+    }
+    __syncthreads();
+    DLT_STAMP(1);
+
+    // effct_feat_numQueue, :899-918 -- every thread derives the same decision from shared memory
+    const int effct = (int)(R[156] + 0.5);
+    int ql = s_i[I_QLEN];
+    const int shift = (ql >= 10) ? 1 : 0;
+    ql -= shift;
+    int stop = (effct <= s_i[I_THR]) ? 1 : 0;
+    for (int k = 0; k < ql; k++)
+        if (s_q[k + shift] <= s_i[I_THR]) stop = 1;
+    if (tid < 10) c.effct_queue[tid] = (tid < ql) ? s_q[tid + shift] : (tid == ql ? effct : 0);
+    for (int k = tid; k < 144; k += NT) rec.HtH[k] = R[k];
+    if (tid < 12) rec.Htr[tid] = R[144 + tid];
+    if (tid < 24) rec.pose_in[tid] = st[tid];
+    if (tid == 0) {
+        rec.iter = it;
+        rec.effct_feat_num = effct;
+        rec.total_residual = R[157];
+        rec.did_match = did_match;
+        rec.reserved = 0;
+        rec.ekf_stop = stop;
+        c.n_down = s_i[I_NDOWN];
+        c.reserved1 = s_i[I_VOX];  // VoxelGrid status of this scan (2 = bitmap capacity exceeded)
+        if (did_match) c.n_unresolved = (int)(R[158] + 0.5);
+        c.queue_len = ql + 1;
+        c.ekf_stop = stop;
+    }
+    int conv = s_i[I_CONV];
+    int have_gain = s_i[I_GAIN];
+    int inited = s_i[I_INITED];
+
+    if (!stop) {  // ---- Kalman update, :1012-1053
+#pragma unroll
+        for (int q = 0; q < kCovPer; q++) {
+            const int k = tid + q * NT;
+            if (k < N * N) c.last_nodegared[36 + k] = cov_own[q];  // :1050 (the covariance does not change inside the loop)
+        }
+        for (int k = tid; k < D * 12; k += NT) {  // Q = H P'_11 (rows 0..D-1)
+            const int i = k / 12, j = k % 12;
+            double qv = 0;
+            for (int a = 0; a < D; a++) qv += R[i * 12 + a] * PN[a * N + j];
+            W[i * AW + D + j] = qv;
+            if (j < D) W[i * AW + j] = qv + ((i == j) ? 1.0 : 0.0);
+        }
+        if (tid == NT - 32) iekf::boxminus(sprop, st, vec);  // :1028 (lane 0 of the last warp)
+        DLT_STAMP(2);
+        __syncthreads();
+        DLT_STAMP(3);
+        // (I + Q[:, :D]) Y = Q by Gauss-Jordan with partial pivoting, the row exchange folded into the update
+        for (int col = 0; col < D; col++) {
+            if (tid < 32) {
+                const int r = col + tid;
+                double v = (r < D) ? fabs(W[r * AW + col]) : -1.0;
+                int idx = r;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {  // D <= 12 rows: 16 lanes suffice
+                    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                    if (ov > v || (ov == v && oi < idx)) {
+                        v = ov;
+                        idx = oi;
+                    }
+                }
+                if (tid == 0) {
+                    s_piv = idx;
+                    if (!(v > 1e-300) || !(v < 1e300)) s_fail = 1;
+                }
+            }
+            __syncthreads();
+            if (s_fail) break;  // block-uniform
+            const int p = s_piv;
+            const int ncols = AW - 1 - col;
+            const double inv = 1.0 / W[p * AW + col];
+            double upd[3];
+            int dst[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {  // D * ncols <= 12 * 23 elements
+                const int k = tid + q * NT;
+                dst[q] = -1;
+                upd[q] = 0.0;
+                if (k < D * ncols) {
+                    const int r = k / ncols, j = col + 1 + k % ncols;
+                    const int src = (r == col) ? p : (r == p) ? col : r;  // row it comes from (rows p / col exchanged)
+                    double v = W[src * AW + j];
+                    if (r != col) v = v - (W[src * AW + col] * inv) * W[p * AW + j];
+                    upd[q] = v;
+                    dst[q] = r * AW + j;
+                }
+            }
+            double dcol = 0.0;  // the pivot moves to the diagonal; the rest of the column is never read again
+            if (tid == 0) dcol = W[p * AW + col];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                if (dst[q] >= 0) W[dst[q]] = upd[q];
+            if (tid == 0) W[col * AW + col] = dcol;
+            __syncthreads();
+        }
+        if (s_fail) {
+            if (tid == 0) {
+                c.status = 1;
+                c.done = 1;
+                c.n_iters = it;
+            }
+            return;
+        }
+        DLT_STAMP(4);
+        if (tid < D) rhs[tid] = 1.0 / W[tid * AW + tid];  // (rhs doubles as the pivots' reciprocals for a moment)
+        __syncthreads();
+        for (int k = tid; k < N * 12; k += NT) {  // K_1[:, :12] = P'_1 - P'_1[:, :D] Y
+            const int i = k / 12, j = k % 12;
+            double x = PN[i * N + j];
+            for (int a = 0; a < D; a++) x -= PN[i * N + a] * (W[a * AW + D + j] * rhs[a]);
+            T[k] = x;
+            dev->K1c[k] = x;
+        }
+        for (int k = tid; k < 144; k += NT) dev->HtH12[k] = R[k];
+        __syncthreads();
+        if (tid >= 32 && tid < 44) {  // solution = K_1[:, :12] (H^T r - H^T H vec_12) + vec, :1032
+            const int a = tid - 32;
+            double sacc = 0;
+            for (int b = 0; b < 12; b++) sacc += R[a * 12 + b] * vec[b];
+            rhs[a] = R[144 + a] - sacc;
+        }
+        __syncthreads();
+        if (tid < N) {
+            double sacc = 0;
+            for (int a = 0; a < 12; a++) sacc += T[tid * 12 + a] * rhs[a];
+            sol[tid] = sacc + vec[tid];
+            rec.solution[tid] = sol[tid];
+        }
+        __syncthreads();
+        DLT_STAMP(5);
+        // state (+)= solution, :1033 -- the two rotations on two warps, the vector parts on a third
+        if (tid == 0 || tid == 32) {
+            const int o = (tid == 0) ? 0 : 12, d = (tid == 0) ? 0 : 6;
+            double E[9], M[9];
+            iekf::exp3(sol[d], sol[d + 1], sol[d + 2], E);
+            iekf::mat3_mul(st + o, E, M);
+#pragma unroll
+            for (int k = 0; k < 9; k++) st[o + k] = M[k];
+        } else if (tid >= 64 && tid < 67) {
+            st[9 + tid - 64] += sol[3 + tid - 64];
+            st[21 + tid - 64] += sol[9 + tid - 64];
+        } else if (tid >= 96 && tid < 108) {
+            st[24 + tid - 96] += sol[12 + tid - 96];
+        }
+        const double rn = sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
+        const double tn = sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
+        conv = ((rn * 57.3 < 0.01) && (tn * 100 < 0.015)) ? 1 : 0;  // :1040
+        have_gain = 1;
+        __syncthreads();
+        DLT_STAMP(6);
+        if (tid < 36) {
+            c.state[tid] = st[tid];
+            c.last_nodegared[tid] = st[tid];  // :1050
+        }
+    } else {  // ---- stop branch, :1054-1063: state = last_nodegared_state + odomToStateGruop(delta)
+        if (tid < N) rec.solution[tid] = 0.0;
+        if (tid < 36) sother[tid] = c.last_nodegared[tid];
+        if (tid >= 64 && tid < 100) sprop[tid - 64] = c.thermal_delta[tid - 64];  // state_propagat is not needed on this branch
+#pragma unroll
+        for (int q = 0; q < kCovPer; q++) {
+            const int k = tid + q * NT;
+            if (k < N * N) {
+                cov_own[q] = c.last_nodegared[36 + k];
+                c.state[36 + k] = cov_own[q];
+            }
+        }
+        __syncthreads();  // (block-uniform branch)
+        if (tid == 0) {
+            const double *L = sother, *Dl = sprop;
+            iekf::mat3_mul(L, Dl, st);
+            iekf::mat3_mul(L + 12, Dl + 12, st + 12);
+            for (int k = 0; k < 3; k++) {
+                st[9 + k] = L[9 + k] + Dl[9 + k];
+                st[21 + k] = L[21 + k] + Dl[21 + k];
+                st[24 + k] = L[24 + k] + Dl[24 + k];
+            }
+            for (int k = 27; k < 36; k++) st[k] = L[k];  // bias_g, bias_a, gravity of the left operand
+        }
+        inited = 0;
+        __syncthreads();
+        if (tid < 36) c.state[tid] = st[tid];
+    }
+    if (tid < 36) rec.state_out[tid] = st[tid];
+    // ---- :1069-1101, every thread derives the same control decisions
+    int rematch_en = 0, rematch_num = s_i[I_RNUM];
+    if (conv || (rematch_num == 0 && it == s_i[I_MAXIT] - 2)) {
+        rematch_en = 1;
+        rematch_num++;
+    }
+    int fin = 0, upd = 0;
+    if (rematch_num >= 2 || it == s_i[I_MAXIT] - 1) {
+        fin = 1;
+        upd = (inited && have_gain) ? 1 : 0;
+    } else if (stop) {
+        fin = 1;
+    }
+    if (tid == 0) {
+        rec.converged = conv;
+        c.converged = conv;
+        c.have_gain = have_gain;
+        c.flg_EKF_inited = inited;
+        c.rematch_en = rematch_en;
+        c.rematch_num = rematch_num;
+        c.iter = it + 1;
+        c.n_iters = it + 1;
+    }
+    if (fin && upd) {  // G[:, :12] = K_1[:, :12] H^T H;  cov = (I - G) cov, :1084-1085   (block-uniform)
+        if (stop) {  // the gain of an earlier iteration: back from global memory (unreachable today: a stop clears inited)
+            for (int k = tid; k < N * 12; k += NT) T[k] = dev->K1c[k];
+            for (int k = tid; k < 144; k += NT) R[k] = dev->HtH12[k];
+        }
+        __syncthreads();
+        double *G = W;  // 24 x 12
+        for (int k = tid; k < N * 12; k += NT) {
+            const int i = k / 12, j = k % 12;
+            double sacc = 0;
+            for (int a = 0; a < 12; a++) sacc += T[i * 12 + a] * R[a * 12 + j];
+            G[k] = sacc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kCovPer; q++) {
+            const int k = tid + q * NT;
+            if (k < N * N) {
+                const int i = k / N, j = k % N;
+                double sacc = cov_own[q];
+                for (int a = 0; a < 12; a++) sacc -= G[i * 12 + a] * C12[a * N + j];
+                c.state[36 + k] = sacc;
+            }
+        }
+    }
+    DLT_STAMP(7);
+    if (fin && c.finish) {  // ---- zeta blend, :1105-1131, then arm map_incremental (block-uniform)
+        __syncthreads();
+        __shared__ double lastS[36], v1[N], v2[N], bl[36];
+        if (tid < 36) lastS[tid] = c.last_state[tid];
+        if (tid >= 64 && tid < 100 && c.blend_mode != 1) sother[tid - 64] = c.l2l_state[tid - 64];
+        __syncthreads();
+        const double zeta_t = c.zeta_t;
+        if (c.blend_mode == 1) {
+            const double alpha_l = effct / (c.beta * 65536.0);  // Nla, :106
+            const double zeta_l = 2.0 / (1.0 + exp(-alpha_l)) - 1;
+            double zn = zeta_l / (zeta_l + zeta_t);
+            if (c.lidar_cnt_lt_100) zn = 1;
+            if (tid == 0) {
+                iekf::boxminus(sprop_or(sprop, c.state_propagat, stop), lastS, v1);
+                for (int k = 0; k < N; k++) v1[k] *= (1 - zn);
+                c.zeta_l = zeta_l;
+            } else if (tid == 32) {
+                iekf::boxminus(st, lastS, v2);
+                for (int k = 0; k < N; k++) v2[k] *= zn;
+            }
+            __syncthreads();
+            if (tid == 0) {  // state = (last_state + v1) + v2, :1119
+                for (int k = 0; k < 36; k++) bl[k] = lastS[k];
+                iekf::boxplus_inplace(bl, v1);
+                iekf::boxplus_inplace(bl, v2);
+            }
+        } else {
+            if (tid == 0) {  // state = (last_state + v1) + l2l * zeta_t_norm, :1122-1127
+                const double ztn = zeta_t / (c.zeta_l + zeta_t);
+                iekf::boxminus(st, lastS, v1);
+                for (int k = 0; k < N; k++) v1[k] *= (1 - ztn);
+                for (int k = 0; k < 36; k++) bl[k] = lastS[k];
+                iekf::boxplus_inplace(bl, v1);
+                double o[36];
+                iekf::scaled(sother, ztn, o);
+                iekf::compose_inplace(bl, o);
+            }
+        }
+        __syncthreads();
+        if (tid < 36) c.blend_state[tid] = bl[tid];
+        // :1165: no map update while the EKF is stopped.  Unresolved queries need the exact-neighbour fallback first:
+        // when its kernels were not queued (no such queries in the recent scans) the host runs map_incremental itself.
+        if (tid == 0) c.insert_status = stop ? 0 : ((c.n_unresolved > 0 && !c.far_enqueued) ? 2 : 1);
+    }
+    DLT_STAMP(8);
+    if (tid == 0 && fin) c.done = 1;
+}
+
+
+__global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const double *__restrict__ result, const int *__restrict__ n_down_ptr,
+                                                           const int *__restrict__ vox_status_ptr, int D /* 6 or 12 */) {
+    if (dev->b.done) return;  // block-uniform
+    iekf_step_block(dev, result, n_down_ptr, vox_status_ptr, D);
+}
+
 // ------------------------------------------------------------------ residual / Jacobian / reduction
 template <bool EXT>
 struct NormalEq {
@@ -803,12 +1282,8 @@ struct NormalEq {
     static constexpr int TRI = D * (D + 1) / 2;
     static constexpr int NR = TRI + D + 2;  // upper triangle of H^T H, H^T r, effective count, sum |r|
 };
-constexpr int kResidBlock = 128;
-constexpr int kNormalEqDoubles = 158;                 // HtH[144], Htr[12], effective count, residual sum
-constexpr int kFetchDoubles = kNormalEqDoubles + 1;   // + far_count of the last match pass: one device->host copy per iteration
-constexpr int kEigOffset = 160;                       // eigvals[6], eigvecs[36] (k_eigen6)
-constexpr int kResultDoubles = kEigOffset + 42;
-static_assert(kResidBlock == 128, "the final reduce combines exactly 4 warp slices");
+constexpr int kResidBlock = 256;
+static_assert(kResidBlock == 256, "the final reduce combines exactly 8 warp slices");
 
 struct MeasureBufs {
     const float4 *down;       // [n] body-frame downsampled scan (x y z intensity)
@@ -977,50 +1452,65 @@ __global__ void __launch_bounds__(kResidBlock)
     }
     __syncthreads();
     if (!s_last) return;
-    // ---- last block: fixed-order sum over blocks (deterministic): 4 interleaved slices per value,
-    //      each summed in block order, then combined ((s0+s1)+s2)+s3
+    // ---- last block: fixed-order sum over blocks (deterministic): 8 interleaved slices per value (one per warp),
+    //      each summed in block order with 16 loads in flight, then combined in slice order
     __threadfence();
-    __shared__ double s_sum[4][32];
+    constexpr unsigned S = kResidBlock / 32;
+    __shared__ double s_sum[S][32];
     __shared__ double s_fin[NR];
     for (int base = 0; base < NR; base += 32) {  // block-uniform
         const int v = base + (threadIdx.x & 31), sl = threadIdx.x >> 5;
         double acc = 0.0;
         if (v < NR) {
-            // 8 loads in flight per thread; the adds stay in block order (adding 0.0 for the padding is exact)
             const double *vp = mb.partials;
-            constexpr unsigned S = kResidBlock / 32;
-            for (unsigned b = sl; b < n_blocks; b += S * 8) {
-                double t[8];
+            for (unsigned b = sl; b < n_blocks; b += S * 16) {  // (adding 0.0 for the padding is exact)
+                double t[16];
 #pragma unroll
-                for (unsigned u = 0; u < 8; u++) t[u] = (b + S * u < n_blocks) ? __ldcg(vp + (size_t)(b + S * u) * NR + v) : 0.0;
+                for (unsigned u = 0; u < 16; u++) t[u] = (b + S * u < n_blocks) ? __ldcg(vp + (size_t)(b + S * u) * NR + v) : 0.0;
 #pragma unroll
-                for (unsigned u = 0; u < 8; u++) acc += t[u];
+                for (unsigned u = 0; u < 16; u++) acc += t[u];
             }
         }
         s_sum[sl][threadIdx.x & 31] = acc;
         __syncthreads();
-        if (threadIdx.x < 32 && v < NR)
-            s_fin[v] = ((s_sum[0][threadIdx.x] + s_sum[1][threadIdx.x]) + s_sum[2][threadIdx.x]) + s_sum[3][threadIdx.x];
+        if (threadIdx.x < 32 && v < NR) {
+            double f = s_sum[0][threadIdx.x];
+#pragma unroll
+            for (unsigned w = 1; w < S; w++) f += s_sum[w][threadIdx.x];
+            s_fin[v] = f;
+        }
         __syncthreads();
     }
     // unpack the upper triangle into the 12x12 block of the result
     double *R = mb.result;
     for (int k = threadIdx.x; k < 144 + 12; k += kResidBlock) R[k] = 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int k = 0;
-        for (int a = 0; a < D; a++)
-            for (int b = a; b < D; b++) {
-                double v = s_fin[k++];
-                R[a * 12 + b] = v;
-                R[b * 12 + a] = v;
+    if (threadIdx.x < NR) {
+        const int k = threadIdx.x;
+        if (k < NE::TRI) {  // k-th element of the row-major upper triangle -> (a, b)
+            int a = 0, rem = k;
+            while (rem >= D - a) {
+                rem -= D - a;
+                a++;
             }
-        for (int a = 0; a < D; a++) R[144 + a] = s_fin[k++];
-        R[156] = s_fin[k];
-        R[157] = s_fin[k + 1];
+            const int b = a + rem;
+            const double v = s_fin[k];
+            R[a * 12 + b] = v;
+            R[b * 12 + a] = v;
+        } else if (k < NE::TRI + D) {
+            R[144 + (k - NE::TRI)] = s_fin[k];
+        } else {
+            R[156 + (k - NE::TRI - D)] = s_fin[k];
+        }
+    }
+    if (threadIdx.x == 0) {
         R[158] = (double)(*mb.far_count);
         *mb.ticket = 0u;
         *mb.unres_count = 0;
+    }
+    if (la.ctl && la.fuse_step) {  // block-uniform: the solve / control step of this iteration, no launch in between
+        __syncthreads();           // the block's own global writes to R are visible to it after the barrier
+        iekf_step_block(const_cast<IekfDev *>(la.ctl), R, la.n_ptr, la.vox_ptr, D);
     }
 }
 
@@ -1113,430 +1603,6 @@ __global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result
             for (int k = 0; k < 6; k++) eig_out[6 + k * 6 + i] = V[k * 6 + ord[i]];
         }
     }
-}
-
-// ------------------------------------------------------------------ the iteration loop on the device
-// One launch per enqueued iteration, after that iteration's k_residual: laserMapping.cpp:899-918
-// (degradation window), :1012-1053 (Kalman update in the reduced form of SURVEY.md 8b), :1054-1063
-// (stop branch), :1069-1101 (rematch / convergence control) and :1084-1085 (covariance update).
-// One block; the 24 x 24 solve is a Gauss-Jordan elimination in shared
-// memory, the SO(3) pieces run on one thread.  Mirrors dlt_host::LaserMapping::process_scan.
-namespace iekf {
-DLT_D void mat3_mul(const double *a, const double *b, double *r) {
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
-}
-DLT_D void mat3T_mul(const double *a, const double *b, double *r) {  // a^T b
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) r[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
-}
-// Exp(v1, v2, v3), so3_math.h:54-72
-DLT_D void exp3(double v1, double v2, double v3, double *R) {
-    const double n = sqrt(v1 * v1 + v2 * v2 + v3 * v3);
-    if (n > 0.00001) {
-        so3_rodrigues(v1 / n, v2 / n, v3 / n, n, R);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-    }
-}
-// Log(R), so3_math.h:75-81
-DLT_D void log3(const double *R, double *o) {
-    const double tr = R[0] + R[4] + R[8];
-    const double theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1));
-    const double K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
-    const double f = (fabs(theta) < 0.001) ? 0.5 : (0.5 * theta / sin(theta));
-    o[0] = K[0] * f;
-    o[1] = K[1] * f;
-    o[2] = K[2] * f;
-}
-// a (-) b over the 24-dim error state, common_lib.h:173-187
-DLT_D void boxminus(const double *a, const double *b, double *o) {
-    double M[9];
-    mat3T_mul(b, a, M);
-    log3(M, o);
-    mat3T_mul(b + 12, a + 12, M);
-    log3(M, o + 6);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        o[3 + k] = a[9 + k] - b[9 + k];
-        o[9 + k] = a[21 + k] - b[21 + k];
-    }
-#pragma unroll
-    for (int k = 0; k < 12; k++) o[12 + k] = a[24 + k] - b[24 + k];
-}
-// s (+)= d, common_lib.h:147-158
-DLT_D void boxplus_inplace(double *s, const double *d) {
-    double E[9], M[9];
-    exp3(d[0], d[1], d[2], E);
-    mat3_mul(s, E, M);
-#pragma unroll
-    for (int k = 0; k < 9; k++) s[k] = M[k];
-    exp3(d[6], d[7], d[8], E);
-    mat3_mul(s + 12, E, M);
-#pragma unroll
-    for (int k = 0; k < 9; k++) s[12 + k] = M[k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        s[9 + k] += d[3 + k];
-        s[21 + k] += d[9 + k];
-    }
-#pragma unroll
-    for (int k = 0; k < 12; k++) s[24 + k] += d[12 + k];
-}
-// o = a * s, common_lib.h:190-205 (R_L_I is not scaled)
-DLT_D void scaled(const double *a, double s, double *o) {
-    double so3[3];
-    log3(a, so3);
-    exp3(so3[0] * s, so3[1] * s, so3[2] * s, o);
-#pragma unroll
-    for (int k = 0; k < 9; k++) o[12 + k] = a[12 + k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        o[9 + k] = a[9 + k] * s;
-        o[21 + k] = a[21 + k] * s;
-    }
-#pragma unroll
-    for (int k = 24; k < 36; k++) o[k] = a[k] * s;
-}
-// a <- a + b (StatesGroup + StatesGroup), common_lib.h:131-144: biases and gravity of the left operand
-DLT_D void compose_inplace(double *a, const double *b) {
-    double M[9];
-    mat3_mul(a, b, M);
-#pragma unroll
-    for (int k = 0; k < 9; k++) a[k] = M[k];
-    mat3_mul(a + 12, b + 12, M);
-#pragma unroll
-    for (int k = 0; k < 9; k++) a[12 + k] = M[k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        a[9 + k] += b[9 + k];
-        a[21 + k] += b[21 + k];
-        a[24 + k] += b[24 + k];
-    }
-}
-}  // namespace iekf
-
-constexpr int kIekfBlock = 576;  // one thread per covariance element
-// state_propagat: the shared copy, unless the stop branch reused that buffer for the thermal delta
-DLT_D const double *sprop_or(const double *shared_copy, const double *global_copy, int stop) { return stop ? global_copy : shared_copy; }
-
-// Kalman gain in covariance (Woodbury) form.  The reference inverts twice, K_1 = (H^T H + (P/R)^-1)^-1
-// (laserMapping.cpp:1017-1018); with P' = P/R, U = [I_12; 0] and H^T H = U H U^T the same matrix is
-//     K_1 = P' - P' U (I + H P'_11)^-1 H U^T P',     so     K_1[:, :12] = P'_1 - P'_1 Y,   (I + Q) Y = Q,   Q = H P'_11
-// (P'_1 = first 12 columns, P'_11 = top-left 12 x 12).  Without extrinsic estimation only the top-left D = 6 block of
-// H is non-zero, rows D..11 of Q and Y vanish and the system is D x D with 12 right-hand sides: 6 elimination steps
-// instead of two 24 x 24 inversions.  Equal to the reference form up to fp64 round-off (tests: 1e-7 on the solution).
-__global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const double *__restrict__ result, const int *__restrict__ n_down_ptr,
-                                                           const int *__restrict__ vox_status_ptr, int D /* 6 or 12 */) {
-    dlt_iekf_block &c = dev->b;
-    if (c.done) return;  // block-uniform
-    constexpr int N = 24;
-    __shared__ double PN[N * N];                      // P' = cov / LASER_POINT_COV
-    __shared__ double W[12 * 24];                     // [I + Q[:, :D] | Q], later G = K H (24 x 12)
-    __shared__ double T[N * 12];                      // K_1[:, :12]
-    __shared__ double C12[12 * N];                    // the first 12 rows of the covariance
-    __shared__ double R[kNormalEqDoubles + 2];        // the normal equations of this iteration
-    __shared__ double st[36], sprop[36], sother[36];  // state, state_propagat | thermal delta, last_nodegared (non-covariance parts)
-    __shared__ double vec[N], rhs[12], sol[N];
-    __shared__ int s_i[16];
-    __shared__ int s_q[10];
-    __shared__ int s_fail, s_piv;
-    enum { I_QLEN, I_THR, I_CONV, I_RNUM, I_MAXIT, I_INITED, I_GAIN, I_NDOWN, I_VOX };
-    const int tid = threadIdx.x;
-    const int it = c.iter;
-    dlt_iekf_iter &rec = c.iters[it];
-    const int did_match = (it == 0 || c.rematch_en) ? 1 : 0;
-    const int AW = D + 12;
-
-    DLT_STAMP(0);
-    // ---- one round trip to global memory for everything the step needs
-    for (int k = tid; k < kNormalEqDoubles + 1; k += kIekfBlock) R[k] = result[k];
-    double cov_own = c.state[36 + tid];
-    const double lpc = c.laser_point_cov;
-    if (tid < 36) {
-        st[tid] = c.state[tid];
-        sprop[tid] = c.state_propagat[tid];
-    } else if (tid >= 64 && tid < 74) {
-        s_q[tid - 64] = c.effct_queue[tid - 64];
-    } else if (tid == 96) {
-        s_i[I_QLEN] = c.queue_len;
-        s_i[I_THR] = c.threshold;
-        s_i[I_CONV] = c.converged;
-    } else if (tid == 97) {
-        s_i[I_RNUM] = c.rematch_num;
-        s_i[I_MAXIT] = c.max_iteration;
-        s_i[I_INITED] = c.flg_EKF_inited;
-    } else if (tid == 98) {
-        s_i[I_GAIN] = c.have_gain;
-        s_i[I_NDOWN] = *n_down_ptr;
-        s_i[I_VOX] = *vox_status_ptr;
-    }
-    if (tid == 0) {
-        s_fail = 0;
-        if (it == 0) c.insert_status = 0;  // map_incremental stays disarmed until the loop ends cleanly
-    }
-    PN[tid] = cov_own / lpc;
-    if (tid < 12 * N) C12[tid] = cov_own;
-    __syncthreads();
-    DLT_STAMP(1);
-
-    // effct_feat_numQueue, :899-918 -- every thread derives the same decision from shared memory
-    const int effct = (int)(R[156] + 0.5);
-    int ql = s_i[I_QLEN];
-    const int shift = (ql >= 10) ? 1 : 0;
-    ql -= shift;
-    int stop = (effct <= s_i[I_THR]) ? 1 : 0;
-    for (int k = 0; k < ql; k++)
-        if (s_q[k + shift] <= s_i[I_THR]) stop = 1;
-    if (tid < 10) c.effct_queue[tid] = (tid < ql) ? s_q[tid + shift] : (tid == ql ? effct : 0);
-    for (int k = tid; k < 144; k += kIekfBlock) rec.HtH[k] = R[k];
-    if (tid < 12) rec.Htr[tid] = R[144 + tid];
-    if (tid < 24) rec.pose_in[tid] = st[tid];
-    if (tid == 0) {
-        rec.iter = it;
-        rec.effct_feat_num = effct;
-        rec.total_residual = R[157];
-        rec.did_match = did_match;
-        rec.reserved = 0;
-        rec.ekf_stop = stop;
-        c.n_down = s_i[I_NDOWN];
-        c.reserved1 = s_i[I_VOX];  // VoxelGrid status of this scan (2 = bitmap capacity exceeded)
-        if (did_match) c.n_unresolved = (int)(R[158] + 0.5);
-        c.queue_len = ql + 1;
-        c.ekf_stop = stop;
-    }
-    int conv = s_i[I_CONV];
-    int have_gain = s_i[I_GAIN];
-    int inited = s_i[I_INITED];
-
-    if (!stop) {  // ---- Kalman update, :1012-1053
-        c.last_nodegared[36 + tid] = cov_own;  // :1050 (the covariance does not change inside the loop)
-        if (tid < D * 12) {                    // Q = H P'_11 (rows 0..D-1)
-            const int i = tid / 12, j = tid % 12;
-            double q = 0;
-            for (int a = 0; a < D; a++) q += R[i * 12 + a] * PN[a * N + j];
-            W[i * AW + D + j] = q;
-            if (j < D) W[i * AW + j] = q + ((i == j) ? 1.0 : 0.0);
-        }
-        if (tid == 320) iekf::boxminus(sprop, st, vec);  // :1028 (its own warp)
-        DLT_STAMP(2);
-        __syncthreads();
-        DLT_STAMP(3);
-        // (I + Q[:, :D]) Y = Q by Gauss-Jordan with partial pivoting, the row exchange folded into the update
-        for (int col = 0; col < D; col++) {
-            if (tid < 32) {
-                const int r = col + tid;
-                double v = (r < D) ? fabs(W[r * AW + col]) : -1.0;
-                int idx = r;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {  // D <= 12 rows: 16 lanes suffice
-                    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-                    if (ov > v || (ov == v && oi < idx)) {
-                        v = ov;
-                        idx = oi;
-                    }
-                }
-                if (tid == 0) {
-                    s_piv = idx;
-                    if (!(v > 1e-300) || !(v < 1e300)) s_fail = 1;
-                }
-            }
-            __syncthreads();
-            if (s_fail) break;  // block-uniform
-            const int p = s_piv;
-            const int ncols = AW - 1 - col;
-            double v = 0.0;
-            int dst = -1;
-            if (tid < D * ncols) {
-                const int r = tid / ncols, j = col + 1 + tid % ncols;
-                const int src = (r == col) ? p : (r == p) ? col : r;  // row it comes from (rows p / col exchanged)
-                v = W[src * AW + j];
-                if (r != col) v = v - (W[src * AW + col] / W[p * AW + col]) * W[p * AW + j];
-                dst = r * AW + j;
-            }
-            double dcol = 0.0;  // the pivot moves to the diagonal; the rest of the column is never read again
-            if (tid == 0) dcol = W[p * AW + col];
-            __syncthreads();
-            if (dst >= 0) W[dst] = v;
-            if (tid == 0) W[col * AW + col] = dcol;
-            __syncthreads();
-        }
-        if (s_fail) {
-            if (tid == 0) {
-                c.status = 1;
-                c.done = 1;
-                c.n_iters = it;
-            }
-            return;
-        }
-        DLT_STAMP(4);
-        if (tid < N * 12) {  // K_1[:, :12] = P'_1 - P'_1[:, :D] Y
-            const int i = tid / 12, j = tid % 12;
-            double x = PN[i * N + j];
-            for (int a = 0; a < D; a++) x -= PN[i * N + a] * (W[a * AW + D + j] / W[a * AW + a]);
-            T[tid] = x;
-            dev->K1c[tid] = x;
-        }
-        for (int k = tid; k < 144; k += kIekfBlock) dev->HtH12[k] = R[k];
-        if (tid >= 320 && tid < 332) {  // solution = K_1[:, :12] (H^T r - H^T H vec_12) + vec, :1032
-            const int a = tid - 320;
-            double sacc = 0;
-            for (int b = 0; b < 12; b++) sacc += R[a * 12 + b] * vec[b];
-            rhs[a] = R[144 + a] - sacc;
-        }
-        __syncthreads();
-        if (tid < N) {
-            double sacc = 0;
-            for (int a = 0; a < 12; a++) sacc += T[tid * 12 + a] * rhs[a];
-            sol[tid] = sacc + vec[tid];
-            rec.solution[tid] = sol[tid];
-        }
-        __syncthreads();
-        DLT_STAMP(5);
-        // state (+)= solution, :1033 -- the two rotations on two warps, the vector parts on a third
-        if (tid == 0 || tid == 32) {
-            const int o = (tid == 0) ? 0 : 12, d = (tid == 0) ? 0 : 6;
-            double E[9], M[9];
-            iekf::exp3(sol[d], sol[d + 1], sol[d + 2], E);
-            iekf::mat3_mul(st + o, E, M);
-#pragma unroll
-            for (int k = 0; k < 9; k++) st[o + k] = M[k];
-        } else if (tid >= 64 && tid < 67) {
-            st[9 + tid - 64] += sol[3 + tid - 64];
-            st[21 + tid - 64] += sol[9 + tid - 64];
-        } else if (tid >= 96 && tid < 108) {
-            st[24 + tid - 96] += sol[12 + tid - 96];
-        }
-        const double rn = sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
-        const double tn = sqrt(sol[3] * sol[3] + sol[4] * sol[4] + sol[5] * sol[5]);
-        conv = ((rn * 57.3 < 0.01) && (tn * 100 < 0.015)) ? 1 : 0;  // :1040
-        have_gain = 1;
-        __syncthreads();
-        DLT_STAMP(6);
-        if (tid < 36) {
-            c.state[tid] = st[tid];
-            c.last_nodegared[tid] = st[tid];  // :1050
-        }
-    } else {  // ---- stop branch, :1054-1063: state = last_nodegared_state + odomToStateGruop(delta)
-        if (tid < N) rec.solution[tid] = 0.0;
-        if (tid < 36) sother[tid] = c.last_nodegared[tid];
-        if (tid >= 64 && tid < 100) sprop[tid - 64] = c.thermal_delta[tid - 64];  // state_propagat is not needed on this branch
-        cov_own = c.last_nodegared[36 + tid];
-        c.state[36 + tid] = cov_own;
-        __syncthreads();  // (block-uniform branch)
-        if (tid == 0) {
-            const double *L = sother, *Dl = sprop;
-            iekf::mat3_mul(L, Dl, st);
-            iekf::mat3_mul(L + 12, Dl + 12, st + 12);
-            for (int k = 0; k < 3; k++) {
-                st[9 + k] = L[9 + k] + Dl[9 + k];
-                st[21 + k] = L[21 + k] + Dl[21 + k];
-                st[24 + k] = L[24 + k] + Dl[24 + k];
-            }
-            for (int k = 27; k < 36; k++) st[k] = L[k];  // bias_g, bias_a, gravity of the left operand
-        }
-        inited = 0;
-        __syncthreads();
-        if (tid < 36) c.state[tid] = st[tid];
-    }
-    if (tid < 36) rec.state_out[tid] = st[tid];
-    // ---- :1069-1101, every thread derives the same control decisions
-    int rematch_en = 0, rematch_num = s_i[I_RNUM];
-    if (conv || (rematch_num == 0 && it == s_i[I_MAXIT] - 2)) {
-        rematch_en = 1;
-        rematch_num++;
-    }
-    int fin = 0, upd = 0;
-    if (rematch_num >= 2 || it == s_i[I_MAXIT] - 1) {
-        fin = 1;
-        upd = (inited && have_gain) ? 1 : 0;
-    } else if (stop) {
-        fin = 1;
-    }
-    if (tid == 0) {
-        rec.converged = conv;
-        c.converged = conv;
-        c.have_gain = have_gain;
-        c.flg_EKF_inited = inited;
-        c.rematch_en = rematch_en;
-        c.rematch_num = rematch_num;
-        c.iter = it + 1;
-        c.n_iters = it + 1;
-    }
-    if (fin && upd) {  // G[:, :12] = K_1[:, :12] H^T H;  cov = (I - G) cov, :1084-1085   (block-uniform)
-        if (stop) {  // the gain of an earlier iteration: back from global memory (unreachable today: a stop clears inited)
-            for (int k = tid; k < N * 12; k += kIekfBlock) T[k] = dev->K1c[k];
-            for (int k = tid; k < 144; k += kIekfBlock) R[k] = dev->HtH12[k];
-        }
-        __syncthreads();
-        double *G = W;  // 24 x 12
-        if (tid < N * 12) {
-            const int i = tid / 12, j = tid % 12;
-            double sacc = 0;
-            for (int a = 0; a < 12; a++) sacc += T[i * 12 + a] * R[a * 12 + j];
-            G[tid] = sacc;
-        }
-        __syncthreads();
-        {
-            const int i = tid / N, j = tid % N;
-            double sacc = cov_own;
-            for (int a = 0; a < 12; a++) sacc -= G[i * 12 + a] * C12[a * N + j];
-            c.state[36 + tid] = sacc;
-        }
-    }
-    DLT_STAMP(7);
-    if (fin && c.finish) {  // ---- zeta blend, :1105-1131, then arm map_incremental (block-uniform)
-        __syncthreads();
-        __shared__ double lastS[36], v1[N], v2[N], bl[36];
-        if (tid < 36) lastS[tid] = c.last_state[tid];
-        if (tid >= 64 && tid < 100 && c.blend_mode != 1) sother[tid - 64] = c.l2l_state[tid - 64];
-        __syncthreads();
-        const double zeta_t = c.zeta_t;
-        if (c.blend_mode == 1) {
-            const double alpha_l = effct / (c.beta * 65536.0);  // Nla, :106
-            const double zeta_l = 2.0 / (1.0 + exp(-alpha_l)) - 1;
-            double zn = zeta_l / (zeta_l + zeta_t);
-            if (c.lidar_cnt_lt_100) zn = 1;
-            if (tid == 0) {
-                iekf::boxminus(sprop_or(sprop, c.state_propagat, stop), lastS, v1);
-                for (int k = 0; k < N; k++) v1[k] *= (1 - zn);
-                c.zeta_l = zeta_l;
-            } else if (tid == 32) {
-                iekf::boxminus(st, lastS, v2);
-                for (int k = 0; k < N; k++) v2[k] *= zn;
-            }
-            __syncthreads();
-            if (tid == 0) {  // state = (last_state + v1) + v2, :1119
-                for (int k = 0; k < 36; k++) bl[k] = lastS[k];
-                iekf::boxplus_inplace(bl, v1);
-                iekf::boxplus_inplace(bl, v2);
-            }
-        } else {
-            if (tid == 0) {  // state = (last_state + v1) + l2l * zeta_t_norm, :1122-1127
-                const double ztn = zeta_t / (c.zeta_l + zeta_t);
-                iekf::boxminus(st, lastS, v1);
-                for (int k = 0; k < N; k++) v1[k] *= (1 - ztn);
-                for (int k = 0; k < 36; k++) bl[k] = lastS[k];
-                iekf::boxplus_inplace(bl, v1);
-                double o[36];
-                iekf::scaled(sother, ztn, o);
-                iekf::compose_inplace(bl, o);
-            }
-        }
-        __syncthreads();
-        if (tid < 36) c.blend_state[tid] = bl[tid];
-        // :1165: no map update while the EKF is stopped.  Unresolved queries need the exact-neighbour fallback first:
-        // when its kernels were not queued (no such queries in the recent scans) the host runs map_incremental itself.
-        if (tid == 0) c.insert_status = stop ? 0 : ((c.n_unresolved > 0 && !c.far_enqueued) ? 2 : 1);
-    }
-    DLT_STAMP(8);
-    if (tid == 0 && fin) c.done = 1;
 }
 
 // ------------------------------------------------------------------ map_incremental classification
