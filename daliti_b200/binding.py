@@ -70,7 +70,7 @@ _SYMBOLS = [
     "dlt_scan_deskew", "dlt_scan_deskew_dev", "dlt_scan_downsample", "dlt_scan_get_undistorted", "dlt_scan_get_down", "dlt_scan_set_down",
     "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
     "dlt_fetch_result", "dlt_degeneracy", "dlt_degeneracy_begin", "dlt_map_incremental", "dlt_set_profiling", "dlt_get_profile", "dlt_launch_count",
-    "dlt_scan_downsample_async", "dlt_iekf_update", "dlt_get_timeline", "dlt_get_iekf_clocks", "dlt_set_shard_reduce", "dlt_result_dev",
+    "dlt_scan_downsample_async", "dlt_iekf_update", "dlt_get_timeline", "dlt_get_iekf_clocks", "dlt_set_shard_reduce", "dlt_result_dev", "dlt_frontend_sample", "dlt_frontend_read",
 ]
 
 
@@ -177,6 +177,27 @@ class ScanToMap:
         cnt = np.zeros(nq, np.int32)
         self._ck(self.lib.dlt_map_knn(self.h, _p(q), C.c_int(nq), _p(pts), _p(d2), _p(cnt)))
         return pts, d2, cnt
+
+    # ---- front end (feature_extract.cpp:264-450 with feature_enabled = 0)
+    SENSORS = {"velodyne": 0, "livox": 1, "ouster": 2, "robosense": 3}
+
+    def frontend_sample(self, cloud: np.ndarray, layout, sensor, point_filter_num=5, min_range=0.5, max_range=1000.0):
+        """cloud: the PointCloud2 data as uint8 (n_points * point_step); layout: (point_step, off_x, off_y, off_z, off_intensity, off_ring,
+        off_time).  Returns (device pointer to the 48-byte records, n, timespan, sweep_span, stamp_shift)."""
+        buf = np.ascontiguousarray(cloud, dtype=np.uint8).reshape(-1)
+        lay = (C.c_int * 7)(*[int(v) for v in layout])
+        n_points = buf.size // int(layout[0])
+        ptr, n = C.c_void_p(), C.c_int(0)
+        ts, sp, sh = C.c_double(0), C.c_double(0), C.c_double(0)
+        code = self.SENSORS[sensor] if isinstance(sensor, str) else int(sensor)
+        self._ck(self.lib.dlt_frontend_sample(self.h, _p(buf), C.c_int(n_points), lay, C.c_int(code), C.c_int(point_filter_num), C.c_float(min_range),
+                                              C.c_float(max_range), C.byref(ptr), C.byref(n), C.byref(ts), C.byref(sp), C.byref(sh)))
+        return ptr.value, n.value, ts.value, sp.value, sh.value
+
+    def frontend_read(self, n) -> np.ndarray:
+        out = np.zeros((max(n, 1), 12), np.float32)
+        self._ck(self.lib.dlt_frontend_read(self.h, _p(out), C.c_int(n)))
+        return out[:n]
 
     # ---- scan
     def scan_deskew(self, pts48, imu_pose22=None, pose24=None):

@@ -6,10 +6,13 @@
 // kernel is in the three *_kernels.cuh headers.  There is no CPU code path here.
 #include <cmath>
 #include <cstddef>
+#include <cstring>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
 #include "../../include/daliti_b200.h"
+#include "dlt_frontend_kernels.cuh"
 #include "dlt_map_kernels.cuh"
 #include "dlt_measure_kernels.cuh"
 #include "dlt_rt.h"
@@ -87,6 +90,14 @@ struct dlt_handle_s {
     void *shard_reduce_ctx = nullptr;
     double *d_flagbuf = nullptr;
     int far_hint = 1;                  // unresolved queries of the previous scan: queue the exact-neighbour fallback behind the loop?
+    // front end (dlt_frontend_sample): sensor cloud staging, grown on demand
+    unsigned char *d_sensor = nullptr;
+    size_t sensor_cap = 0;
+    float4 *d_fe_tmp = nullptr;
+    unsigned char *d_fe_keep = nullptr;
+    unsigned *d_fe_pos = nullptr, *d_fe_blk = nullptr, *d_fe_blkoff = nullptr;
+    int *d_fe_index = nullptr;
+    size_t fe_cap = 0;
     // pinned host staging
     double *h_result = nullptr;
     int *h_ints = nullptr;
@@ -300,6 +311,9 @@ int dlt_destroy(dlt_handle h) {
     rt::set_device(h->cfg.device);
     if (h->own_stream) rt::sync(h->own_stream);
     for (void *p : h->allocs) rt::release(p);
+    for (void *p : {(void *)h->d_sensor, (void *)h->d_fe_tmp, (void *)h->d_fe_keep, (void *)h->d_fe_pos, (void *)h->d_fe_blk, (void *)h->d_fe_blkoff,
+                    (void *)h->d_fe_index})
+        rt::release(p);
     rt::pinned_release(h->h_result);
     rt::pinned_release(h->h_ints);
     rt::pinned_release(h->h_sc);
@@ -696,6 +710,133 @@ int dlt_scan_get_voxel_of_point(dlt_handle h, int *slot, int cap) {
     int m = h->n_raw < cap ? h->n_raw : cap;
     if (m > 0) {
         DLT_RT(h, rt::d2h(slot, h->d_vop, (size_t)m * sizeof(int), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+    }
+    return DLT_OK;
+}
+
+// ------------------------------------------------------------------ front end
+int dlt_frontend_sample(dlt_handle h, const void *cloud_data, int n_points, const dlt_cloud_layout *lay, int sensor, int point_filter_num,
+                        float lidar_min_range, float lidar_max_range, void **pts48_dev, int *n_out, double *timespan_out, double *sweep_span_out,
+                        double *stamp_shift_out) {
+    if (!h || !lay || !pts48_dev || !n_out || n_points < 0 || (n_points > 0 && !cloud_data) || point_filter_num < 1) return DLT_E_INVALID;
+    if (sensor < DLT_SENSOR_VELODYNE || sensor > DLT_SENSOR_ROBOSENSE) return DLT_E_INVALID;
+    const int offs[6] = {lay->off_x, lay->off_y, lay->off_z, lay->off_intensity, lay->off_ring, lay->off_time};
+    const int t_bytes = sensor == DLT_SENSOR_ROBOSENSE ? 8 : 4;
+    if (lay->point_step < 16 || (lay->point_step & 3)) DLT_FAIL(h, DLT_E_INVALID, "point_step must be a multiple of 4");
+    for (int k = 0; k < 6; k++) {
+        const int width = k == 4 ? 2 : (k == 5 ? t_bytes : (k == 3 && sensor == DLT_SENSOR_ROBOSENSE ? 1 : 4));
+        const int align = width >= 4 ? 4 : width;
+        if (offs[k] < 0 || offs[k] + width > lay->point_step || (offs[k] % align)) DLT_FAIL(h, DLT_E_INVALID, "field offset outside the record or misaligned");
+    }
+    rt::set_device(h->cfg.device);
+    *pts48_dev = h->d_raw;
+    *n_out = 0;
+    if (timespan_out) *timespan_out = 0.0;
+    if (sweep_span_out) *sweep_span_out = 0.0;
+    if (stamp_shift_out) *stamp_shift_out = 0.0;
+    if (n_points == 0) return DLT_OK;
+    const unsigned char *src = static_cast<const unsigned char *>(cloud_data);
+    auto rec = [&](long long i) { return src + (size_t)i * lay->point_step; };
+    auto f32 = [](const unsigned char *p) { float v; std::memcpy(&v, p, 4); return v; };
+    auto u32 = [](const unsigned char *p) { unsigned v; std::memcpy(&v, p, 4); return v; };
+    auto f64 = [](const unsigned char *p) { double v; std::memcpy(&v, p, 8); return v; };
+    FeParams P;
+    P.lay = *lay;
+    P.sensor = sensor;
+    P.n_points = n_points;
+    P.filter_num = point_filter_num;
+    P.min_range = lidar_min_range;
+    P.max_range = lidar_max_range;
+    P.t0 = 0.0;
+    P.vel_time0 = 0.f;
+    double timespan = 0.0, ret_timespan = 0.0, shift = 0.0;
+    std::vector<int> rs_index;  // RoboSense: indices of the finite records that survive i % point_filter_num
+    if (sensor == DLT_SENSOR_VELODYNE) {  // :279: timespan = back().time - points[0].time (float arithmetic), zeroed after use (:299)
+        const float tb = f32(rec(n_points - 1) + lay->off_time), t0 = f32(rec(0) + lay->off_time);
+        timespan = (double)(tb - t0);
+        ret_timespan = 0.0;
+    } else if (sensor == DLT_SENSOR_LIVOX) {  // :311
+        timespan = (double)f32(rec(n_points - 1) + lay->off_time);
+        ret_timespan = timespan;
+    } else if (sensor == DLT_SENSOR_OUSTER) {  // :333 (the second to last record), :346
+        if (n_points < 2) DLT_FAIL(h, DLT_E_INVALID, "an Ouster cloud needs at least two records");
+        timespan = (double)u32(rec(n_points - 2) + lay->off_time);
+        ret_timespan = timespan * (double)1e-9f;
+    } else {  // :360, :383
+        P.t0 = f64(rec(0) + lay->off_time);
+        timespan = f64(rec(n_points - 1) + lay->off_time) - P.t0;
+        ret_timespan = timespan;
+        shift = timespan;
+        int kept = 0;
+        for (int i = 0; i < n_points; i++) {  // inputCloud->push_back skips non-finite records (:369-370) before the 1-in-N sampling
+            const unsigned char *r = rec(i);
+            const float x = f32(r + lay->off_x), y = f32(r + lay->off_y), z = f32(r + lay->off_z);
+            if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z)) continue;
+            if (kept % point_filter_num == 0) rs_index.push_back(i);
+            kept++;
+        }
+    }
+    P.timespan = timespan;
+    const int n_cand = sensor == DLT_SENSOR_ROBOSENSE ? (int)rs_index.size() : (n_points + point_filter_num - 1) / point_filter_num;
+    P.n_cand = n_cand;
+    if (timespan_out) *timespan_out = ret_timespan;
+    if (stamp_shift_out) *stamp_shift_out = shift;
+    if (sweep_span_out) *sweep_span_out = (double)(sensor == DLT_SENSOR_OUSTER ? (float)(timespan * (double)1e-9f) : (float)timespan);
+    if (n_cand == 0) return DLT_OK;
+    if (n_cand > h->cap) DLT_FAIL(h, DLT_E_CAPACITY, "sampled cloud larger than max_scan_points");
+    // staging (grown on demand; the sensor cloud is the only thing that crosses PCIe)
+    const size_t bytes = (size_t)n_points * lay->point_step;
+    if (bytes > h->sensor_cap) {
+        DLT_RT(h, rt::sync(h->stream));
+        rt::release(h->d_sensor);
+        void *v = nullptr;
+        size_t want = bytes + bytes / 4;
+        if (rt::alloc(&v, want) != 0) DLT_FAIL(h, DLT_E_CUDA, "sensor cloud staging allocation failed");
+        h->d_sensor = (unsigned char *)v;
+        h->sensor_cap = want;
+    }
+    if ((size_t)n_cand > h->fe_cap) {
+        DLT_RT(h, rt::sync(h->stream));
+        for (void *q : {(void *)h->d_fe_tmp, (void *)h->d_fe_keep, (void *)h->d_fe_pos, (void *)h->d_fe_blk, (void *)h->d_fe_blkoff, (void *)h->d_fe_index}) rt::release(q);
+        const size_t c = (size_t)h->cap;
+        void *v[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        const size_t nblk = (c + kFeBlock - 1) / kFeBlock;
+        if (rt::alloc(&v[0], c * 3 * sizeof(float4)) || rt::alloc(&v[1], c) || rt::alloc(&v[2], c * 4) || rt::alloc(&v[3], nblk * 4) ||
+            rt::alloc(&v[4], nblk * 4) || rt::alloc(&v[5], c * 4))
+            DLT_FAIL(h, DLT_E_CUDA, "front end scratch allocation failed");
+        h->d_fe_tmp = (float4 *)v[0];
+        h->d_fe_keep = (unsigned char *)v[1];
+        h->d_fe_pos = (unsigned *)v[2];
+        h->d_fe_blk = (unsigned *)v[3];
+        h->d_fe_blkoff = (unsigned *)v[4];
+        h->d_fe_index = (int *)v[5];
+        h->fe_cap = c;
+    }
+    DLT_RT(h, rt::h2d(h->d_sensor, cloud_data, bytes, h->stream));
+    const int *d_index = nullptr;
+    if (sensor == DLT_SENSOR_ROBOSENSE) {
+        DLT_RT(h, rt::h2d(h->d_fe_index, rs_index.data(), rs_index.size() * sizeof(int), h->stream));
+        DLT_RT(h, rt::sync(h->stream));  // rs_index is a local
+        d_index = h->d_fe_index;
+    }
+    const int G = div_up(n_cand, kFeBlock);
+    DLT_LAUNCH(k_fe_convert, G, kFeBlock, h->stream, P, (const unsigned char *)h->d_sensor, d_index, h->d_fe_tmp, h->d_fe_keep, h->d_fe_pos, h->d_fe_blk);
+    DLT_LAUNCH(k_fe_offsets, 1, 1024, h->stream, (const unsigned *)h->d_fe_blk, G, h->d_fe_blkoff, h->d_counters + 11);
+    DLT_LAUNCH(k_fe_scatter, G, kFeBlock, h->stream, n_cand, (const float4 *)h->d_fe_tmp, (const unsigned char *)h->d_fe_keep,
+               (const unsigned *)h->d_fe_pos, (const unsigned *)h->d_fe_blkoff, h->d_raw, h->cap);
+    DLT_RT(h, rt::check_launch());
+    DLT_RT(h, rt::d2h(h->h_ints + 32, h->d_counters + 11, sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    *n_out = h->h_ints[32];
+    return DLT_OK;
+}
+
+int dlt_frontend_read(dlt_handle h, void *pts48, int n) {
+    if (!h || n < 0 || (n > 0 && !pts48) || n > h->cap) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    if (n > 0) {
+        DLT_RT(h, rt::d2h(pts48, h->d_raw, (size_t)n * 48, h->stream));
         DLT_RT(h, rt::sync(h->stream));
     }
     return DLT_OK;

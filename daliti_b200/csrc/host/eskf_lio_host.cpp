@@ -989,6 +989,24 @@ int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lid
     return h->lm->process_scan(pts48_dev, n, lidar_beg_time, reinterpret_cast<const ImuSample *>(imu7), n_imu, thermal, out, true,
                                observation_end_time);
 }
+int dlt_lio_process_cloud(dlt_lio h, const void *cloud_data, int n_points, const dlt_cloud_layout *layout, int sensor, int point_filter_num,
+                          float lidar_min_range, float lidar_max_range, double header_stamp, const double *imu7, int n_imu,
+                          const dlt_lio_thermal *thermal, dlt_lio_scan_out *out, int *n_sampled) {
+    if (!h || !out || !layout || n_points < 0 || n_imu < 0 || (n_points > 0 && !cloud_data) || (n_imu > 0 && !imu7)) return DLT_E_INVALID;
+    void *pts_dev = nullptr;
+    int n = 0;
+    double timespan = 0, sweep = 0, shift = 0;
+    int rc = dlt_frontend_sample(h->lm->dev_, cloud_data, n_points, layout, sensor, point_filter_num, lidar_min_range, lidar_max_range, &pts_dev, &n,
+                                 &timespan, &sweep, &shift);
+    if (rc != 0) {
+        h->lm->err = dlt_last_error(h->lm->dev_);
+        return rc;
+    }
+    if (n_sampled) *n_sampled = n;
+    const double lidar_beg_time = header_stamp - shift;  // feature_extract.cpp:383 (RoboSense), else the header stamp
+    // observation_end_time = lidar_beg_time + points.back().normal_z, laserMapping.cpp:546
+    return h->lm->process_scan(pts_dev, n, lidar_beg_time, reinterpret_cast<const ImuSample *>(imu7), n_imu, thermal, out, true, lidar_beg_time + sweep);
+}
 int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *result_dev) {
     if (!h) return DLT_E_INVALID;
     if (reduce && !result_dev) result_dev = dlt_result_dev(h->lm->dev_);  // the handle's own buffer

@@ -58,7 +58,7 @@ class LioScanOut(C.Structure):
 _LIO_SYMBOLS = [
     "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
     "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
-    "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
+    "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_process_cloud", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
 ]
 
 
@@ -171,6 +171,19 @@ class LaserMapping:
         self._ck(self.lib.dlt_lio_process_scan_dev(self.h, C.c_void_p(pts48_dev_ptr), C.c_int(n), C.c_double(lidar_beg_time),
                                                    C.c_double(observation_end_time), _p(im), C.c_int(im.shape[0]), th, C.byref(self.out)))
         return self.out
+
+    def process_cloud(self, cloud, layout, sensor, header_stamp, imu7, point_filter_num=5, min_range=0.5, max_range=1000.0, thermal=None):
+        """sensor PointCloud2 payload (uint8) -> front end on the device -> the per-scan update (dlt_lio_process_cloud)"""
+        buf = np.ascontiguousarray(cloud, dtype=np.uint8).reshape(-1)
+        lay = (C.c_int * 7)(*[int(v) for v in layout])
+        im = _f64(imu7).reshape(-1, 7)
+        th = C.byref(thermal) if thermal is not None else None
+        code = ScanToMap.SENSORS[sensor] if isinstance(sensor, str) else int(sensor)
+        ns = C.c_int(0)
+        self._ck(self.lib.dlt_lio_process_cloud(self.h, _p(buf), C.c_int(buf.size // int(layout[0])), lay, C.c_int(code), C.c_int(point_filter_num),
+                                                C.c_float(min_range), C.c_float(max_range), C.c_double(header_stamp), _p(im), C.c_int(im.shape[0]), th,
+                                                C.byref(self.out), C.byref(ns)))
+        return self.out, ns.value
 
     def set_allreduce(self, device: str = "cuda"):
         """Sharded map: sum over torch.distributed ranks whatever the library hands to the callback (the partial normal

@@ -108,6 +108,33 @@ int dlt_scan_set_down(dlt_handle h, const float *xyzi, int n);
 /* output slot of every raw point of the last dlt_scan_downsample (voxel assignment)             */
 int dlt_scan_get_voxel_of_point(dlt_handle h, int *slot, int cap);
 
+/* ---- LiDAR front end with feature_enabled = 0 --------------------------
+ * FeatureExtract::cachePointCloud (eskf_lio/src/feature_extract.cpp:264-423) fused with samplePointCloud
+ * (:425-450): the sensor's PointCloud2 records (HOST memory, `layout` = point_step and field offsets of the
+ * message) become the PointXYZINormal records of /laser_cloud_surf -- normal_x = time ratio, normal_y = ring,
+ * normal_z = sweep span; every point_filter_num-th record (feat.yaml:21), range gate (:445), order preserved --
+ * directly in DEVICE memory, where dlt_scan_deskew_dev / dlt_lio_process_scan_dev read them.
+ * Field types per sensor (eskf_lio/include/my_utility.h:19-54): Velodyne / Livox x y z intensity f32, ring u16,
+ * time f32; Ouster the same with t u32 [ns]; RoboSense intensity u8, timestamp f64 (non-finite points dropped).   */
+#define DLT_SENSOR_VELODYNE 0
+#define DLT_SENSOR_LIVOX 1
+#define DLT_SENSOR_OUSTER 2
+#define DLT_SENSOR_ROBOSENSE 3
+typedef struct dlt_cloud_layout {
+    int point_step;                                  /* sensor_msgs/PointCloud2.point_step                       */
+    int off_x, off_y, off_z, off_intensity, off_ring, off_time; /* PointField offsets                            */
+} dlt_cloud_layout;
+/* pts48_dev: the handle's record buffer (valid until the next scan call); n_out: sampleCloud->size();
+ * timespan: what cachePointCloud leaves in `timespan` (timeScanEnd = stamp + timespan, :387);
+ * sweep_span: normal_z of the records (laserMapping's observation_end_time = lidar_beg_time + points.back().normal_z);
+ * stamp_shift: what it subtracts from the header stamp (RoboSense, :383), else 0.                                  */
+int dlt_frontend_sample(dlt_handle h, const void *cloud_data, int n_points, const dlt_cloud_layout *layout, int sensor, int point_filter_num,
+                        float lidar_min_range, float lidar_max_range, void **pts48_dev, int *n_out, double *timespan, double *sweep_span,
+                        double *stamp_shift);
+
+/* the first n records of the last dlt_frontend_sample, back on the host (publishing /laser_cloud_surf, tests)        */
+int dlt_frontend_read(dlt_handle h, void *pts48, int n);
+
 /* ---- the measurement model, one IEKF iteration ---------------------------------------------- */
 /* laserMapping.cpp:829-979 at the given state: transform, (re)match when do_match
  * (iterCount == 0 || rematch_en, :847), plane fit, residual + gates, Jacobian, and the

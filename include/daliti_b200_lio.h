@@ -92,6 +92,13 @@ int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_t
  * passed explicitly (the host cannot read points.back().normal_z, laserMapping.cpp:546).            */
 int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lidar_beg_time, double observation_end_time,
                              const double *imu7, int n_imu, const dlt_lio_thermal *thermal, dlt_lio_scan_out *out);
+/* The same starting one node earlier: the sensor's PointCloud2 payload (HOST memory) goes through the
+ * front end of feature_extract.cpp:264-450 (feature_enabled = 0; dlt_frontend_sample) on the device and straight into the
+ * update -- the /laser_cloud_surf hop and its 48-byte AoS round trip disappear.  header_stamp = cloudHeader.stamp (:268);
+ * n_sampled (optional) <- sampleCloud->size().                                                                          */
+int dlt_lio_process_cloud(dlt_lio h, const void *cloud_data, int n_points, const dlt_cloud_layout *layout, int sensor, int point_filter_num,
+                          float lidar_min_range, float lidar_max_range, double header_stamp, const double *imu7, int n_imu,
+                          const dlt_lio_thermal *thermal, dlt_lio_scan_out *out, int *n_sampled);
 /* Sharded map (dev.shard_count > 1): after every evaluation of the measurement model the partial normal
  * equations (n = 158 doubles at result_dev, DEVICE memory owned by the caller, 256 doubles) are handed to
  * `reduce`, which must sum them over the ranks in place on the handle's stream (e.g. ncclAllReduce /

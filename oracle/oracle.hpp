@@ -315,6 +315,121 @@ inline int voxel_grid(const Pt *in, int n, float leaf, std::vector<Pt> &out, boo
 }
 
 // ======================================================================== IMU process / deskew
+// ------------------------------------------------------------------ LiDAR front end, feature_enabled = 0
+// FeatureExtract::cachePointCloud (eskf_lio/src/feature_extract.cpp:264-423) + samplePointCloud (:425-450), restated
+// over raw PointCloud2 records (point_step + field offsets) with the sensor structs of eskf_lio/include/my_utility.h:19-54.
+// TEST_LIO_SAM_6AXIS_DATA is #defined in the reference (:262), so the Velodyne branch is the 6-axis one.
+struct CloudLayout {
+    int point_step, off_x, off_y, off_z, off_intensity, off_ring, off_time;
+};
+enum { SENSOR_VELODYNE = 0, SENSOR_LIVOX = 1, SENSOR_OUSTER = 2, SENSOR_ROBOSENSE = 3 };
+
+inline float pointDistance(const Pt &p) {  // my_utility.h:76-79 (sqrt of a float sum: correctly rounded either way)
+    float s = p.x * p.x + p.y * p.y;
+    s = s + p.z * p.z;
+    return std::sqrt(s);
+}
+
+inline int frontend_sample(const unsigned char *data, int n, const CloudLayout &L, int sensor, int point_filter_num, float lidarMinRange,
+                           float lidarMaxRange, std::vector<Pt> &sampleCloud, double &timespan_out, double &stamp_shift) {
+    auto rec = [&](size_t i) { return data + i * (size_t)L.point_step; };
+    auto f32 = [](const unsigned char *p) { float v; std::memcpy(&v, p, 4); return v; };
+    auto u32 = [](const unsigned char *p) { uint32_t v; std::memcpy(&v, p, 4); return v; };
+    auto u16 = [](const unsigned char *p) { uint16_t v; std::memcpy(&v, p, 2); return v; };
+    auto f64 = [](const unsigned char *p) { double v; std::memcpy(&v, p, 8); return v; };
+    std::vector<Pt> inputCloud;
+    double timespan = 0.0;
+    stamp_shift = 0.0;
+    sampleCloud.clear();
+    if (n == 0) {
+        timespan_out = 0.0;
+        return 0;
+    }
+    auto blank = []() {
+        Pt d;
+        std::memset(&d, 0, sizeof(d));
+        d.d3 = 1.0f;  // PCL_ADD_POINT4D
+        return d;
+    };
+    if (sensor == SENSOR_VELODYNE) {  // :271-302
+        inputCloud.resize(n, blank());
+        timespan = f32(rec(n - 1) + L.off_time) - f32(rec(0) + L.off_time);  // :279 (float - float)
+        for (int i = 0; i < n; i++) {
+            Pt &dst = inputCloud[i];
+            dst.x = f32(rec(i) + L.off_x);
+            dst.y = f32(rec(i) + L.off_y);
+            dst.z = f32(rec(i) + L.off_z);
+            dst.intensity = f32(rec(i) + L.off_intensity);
+            dst.ny = u16(rec(i) + L.off_ring);
+            dst.nz = timespan;
+            dst.nx = (f32(rec(i) + L.off_time) + timespan) / timespan;  // :296
+        }
+        timespan = 0.0;  // :299
+    } else if (sensor == SENSOR_LIVOX) {  // :306-323
+        inputCloud.resize(n, blank());
+        timespan = f32(rec(n - 1) + L.off_time);
+        for (int i = 0; i < n; i++) {
+            Pt &dst = inputCloud[i];
+            dst.x = f32(rec(i) + L.off_x);
+            dst.y = f32(rec(i) + L.off_y);
+            dst.z = f32(rec(i) + L.off_z);
+            dst.intensity = f32(rec(i) + L.off_intensity);
+            dst.ny = u16(rec(i) + L.off_ring);
+            dst.nz = timespan;
+            dst.nx = f32(rec(i) + L.off_time) / timespan;
+        }
+    } else if (sensor == SENSOR_OUSTER) {  // :324-347
+        inputCloud.resize(n, blank());
+        timespan = u32(rec(n - 2) + L.off_time);  // :333
+        for (int i = 0; i < n; i++) {
+            Pt &dst = inputCloud[i];
+            dst.x = f32(rec(i) + L.off_x);
+            dst.y = f32(rec(i) + L.off_y);
+            dst.z = f32(rec(i) + L.off_z);
+            dst.intensity = f32(rec(i) + L.off_intensity);
+            dst.ny = u16(rec(i) + L.off_ring);
+            dst.nz = timespan * 1e-9f;
+            dst.nx = u32(rec(i) + L.off_time) / timespan;
+        }
+        timespan = timespan * 1e-9f;  // :346
+    } else {  // SENSOR_ROBOSENSE, :348-383
+        const double t0 = f64(rec(0) + L.off_time);
+        timespan = f64(rec(n - 1) + L.off_time) - t0;
+        for (int i = 0; i < n; i++) {
+            const float x = f32(rec(i) + L.off_x), y = f32(rec(i) + L.off_y), z = f32(rec(i) + L.off_z);
+            if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z)) continue;
+            Pt dst = blank();
+            dst.x = x;
+            dst.y = y;
+            dst.z = z;
+            dst.intensity = *(rec(i) + L.off_intensity);  // uint8_t
+            dst.ny = u16(rec(i) + L.off_ring);
+            dst.nz = timespan;
+            dst.nx = (f64(rec(i) + L.off_time) - t0) / timespan;
+            inputCloud.push_back(dst);
+        }
+        stamp_shift = timespan;  // :383
+    }
+    timespan_out = timespan;  // timeScanEnd = timeScanCur + timespan, :387
+    // samplePointCloud, :425-450
+    const int cloudSize = (int)inputCloud.size();
+    for (int i = 0; i < cloudSize; ++i) {
+        if (i % point_filter_num != 0) continue;
+        Pt thisPoint = blank();
+        thisPoint.x = inputCloud[i].x;
+        thisPoint.y = inputCloud[i].y;
+        thisPoint.z = inputCloud[i].z;
+        thisPoint.intensity = inputCloud[i].intensity;
+        thisPoint.nx = inputCloud[i].nx;
+        thisPoint.ny = inputCloud[i].ny;
+        thisPoint.nz = inputCloud[i].nz;
+        float range = pointDistance(thisPoint);
+        if (range < lidarMinRange || range > lidarMaxRange) continue;
+        sampleCloud.push_back(thisPoint);
+    }
+    return (int)sampleCloud.size();
+}
+
 struct ImuSample {
     double t;
     double acc[3];

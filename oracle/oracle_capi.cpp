@@ -114,6 +114,19 @@ static MapBackend *make_map(int kind, float ds) {
     }
     return new PortMap(ds);
 }
+// front end: layout7 = point_step, off_x, off_y, off_z, off_intensity, off_ring, off_time; out48: cap records
+int orc_frontend_sample(const void *data, int n, const int *layout7, int sensor, int point_filter_num, float min_range, float max_range,
+                        void *out48, int cap, double *timespan, double *stamp_shift) {
+    orc::CloudLayout L = {layout7[0], layout7[1], layout7[2], layout7[3], layout7[4], layout7[5], layout7[6]};
+    std::vector<orc::Pt> s;
+    double ts = 0, sh = 0;
+    int m = orc::frontend_sample(static_cast<const unsigned char *>(data), n, L, sensor, point_filter_num, min_range, max_range, s, ts, sh);
+    if (timespan) *timespan = ts;
+    if (stamp_shift) *stamp_shift = sh;
+    for (int i = 0; i < m && i < cap; i++) std::memcpy(static_cast<char *>(out48) + 48 * (size_t)i, &s[i], 48);
+    return m;
+}
+
 void *orc_map_create(int kind, float ds) { return make_map(kind, ds); }
 void orc_map_destroy(void *h) { delete static_cast<MapBackend *>(h); }
 void orc_map_build(void *h, const float *p4, int n) {

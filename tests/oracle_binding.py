@@ -280,6 +280,17 @@ class Oracle:
         self.lib.orc_esti_plane_batch(_p(a), C.c_int(n), C.c_float(thr), _p(pabcd), _p(ok))
         return pabcd, ok.astype(bool)
 
+    def frontend_sample(self, cloud, layout, sensor, point_filter_num=5, min_range=0.5, max_range=1000.0):
+        """cachePointCloud + samplePointCloud restated (oracle.hpp): returns (records (m,12) float32, timespan, stamp_shift)"""
+        buf = np.ascontiguousarray(cloud, np.uint8).reshape(-1)
+        lay = (C.c_int * 7)(*[int(v) for v in layout])
+        n = buf.size // int(layout[0])
+        out = np.zeros((max(n, 1), 12), np.float32)
+        ts, sh = C.c_double(0), C.c_double(0)
+        m = self.lib.orc_frontend_sample(_p(buf), C.c_int(n), lay, C.c_int(sensor), C.c_int(point_filter_num), C.c_float(min_range),
+                                         C.c_float(max_range), _p(out), C.c_int(len(out)), C.byref(ts), C.byref(sh))
+        return out[:m], ts.value, sh.value
+
     def voxel_grid(self, pts48, leaf=0.5, stable=False):
         a = np.ascontiguousarray(pts48, np.float32).reshape(-1, 12)
         n = len(a)
