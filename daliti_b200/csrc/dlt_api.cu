@@ -89,6 +89,14 @@ struct dlt_handle_s {
     dlt_reduce_fn shard_reduce = nullptr;
     void *shard_reduce_ctx = nullptr;
     double *d_flagbuf = nullptr;
+    // the iteration loop as a CUDA graph with conditional nodes (built lazily, once: every kernel in it has a fixed grid and
+    // takes its sizes from device memory)
+#if !defined(DLT_EMU)
+    cudaGraph_t loop_graph = nullptr;
+    cudaGraphExec_t loop_exec = nullptr;
+#endif
+    int loop_graph_state = 0;  // 0 not tried, 1 ready, -1 unavailable (stream launches are used instead)
+    int use_graph = 0;  // measured slower than stream launches with early-exit kernels: opt-in via DLT_LOOP_GRAPH=1
     int far_hint = 1;                  // unresolved queries of the previous scan: queue the exact-neighbour fallback behind the loop?
     // front end (dlt_frontend_sample): sensor cloud staging, grown on demand
     unsigned char *d_sensor = nullptr;
@@ -318,6 +326,10 @@ int dlt_destroy(dlt_handle h) {
     rt::pinned_release(h->h_ints);
     rt::pinned_release(h->h_sc);
     rt::pinned_release(h->h_iekf);
+#if !defined(DLT_EMU)
+    if (h->loop_exec) cudaGraphExecDestroy(h->loop_exec);
+    if (h->loop_graph) cudaGraphDestroy(h->loop_graph);
+#endif
     if (h->have_aux) {
         rt::sync(h->aux_stream);
         rt::event_destroy(h->ev_fork);
@@ -343,6 +355,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->n_sm = rt::sm_count();
     bool ok = rt::stream_create(&h->own_stream) == 0;
     h->stream = h->own_stream;
+    if (const char *e = std::getenv("DLT_LOOP_GRAPH")) h->use_graph = (e[0] == '1') ? 1 : 0;  // A/B switch for measurements
     h->have_aux = rt::stream_create(&h->aux_stream) == 0 && rt::event_create_untimed(&h->ev_fork) == 0 && rt::event_create_untimed(&h->ev_join) == 0;
 
     // search cell edge = ds_map * 2^shift with 3 edges covering sqrt(max_sq_dist)
@@ -546,7 +559,7 @@ int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *ou
         DLT_RT(h, rt::h2d(h->d_pw, stage.data(), (size_t)c * sizeof(float4), h->stream));
         {
             DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));  // no residual pass here to re-arm it
-            LoopArgs la = {nullptr, nullptr, nullptr, 0};
+            LoopArgs la = {nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull};
             int rk = launch_knn(h, (const float4 *)h->d_pw, c, c, 0, P, la);
             if (rk) return rk;
         }
@@ -863,7 +876,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     if (do_match) {
         h->nfar_known = false;
         ProfScope prof(h, 0);
-        LoopArgs la0 = {nullptr, nullptr, nullptr, 0};
+        LoopArgs la0 = {nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull};
         int rk = launch_knn(h, (const float4 *)h->d_down, n, n, 1, P, la0);
         if (rk) return rk;
         h->have_match = true;
@@ -882,7 +895,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     mb.unres_count = h->d_counters + 8;
     mb.result = result_dev;
     const int G = div_up(n, kResidBlock);
-    LoopArgs la = {nullptr, nullptr, nullptr, 0};
+    LoopArgs la = {nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull};
     ProfScope prof(h, 1);
     if (h->cfg.extrinsic_est_en)
         DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr, la);
@@ -893,6 +906,79 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
 }
 
 // ------------------------------------------------------------------ the iteration loop on the device
+#if !defined(DLT_EMU)
+// WHILE(cond_while) { IF(cond_match) { k_knn8; k_knn }  k_residual (+ fused solve / control step) }
+// Both conditions default to 1 at every launch (iteration 0 always matches) and are then driven by the fused step.
+static bool build_loop_graph(dlt_handle h, const MeasureBufs &mb) {
+    cudaGraph_t g = nullptr;
+    cudaGraphConditionalHandle hw = 0, hm = 0;
+    cudaStream_t cs = h->own_stream;
+    bool capturing = false;
+    auto fail = [&]() {
+        if (capturing) {
+            cudaGraph_t junk = nullptr;
+            cudaStreamEndCapture(cs, &junk);
+        }
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        return false;
+    };
+    if (cudaGraphCreate(&g, 0) != cudaSuccess) return fail();
+    if (cudaGraphConditionalHandleCreate(&hw, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) return fail();
+    if (cudaGraphConditionalHandleCreate(&hm, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) return fail();
+    cudaGraphNodeParams wp = {};
+    wp.type = cudaGraphNodeTypeConditional;
+    wp.conditional.handle = hw;
+    wp.conditional.type = cudaGraphCondTypeWhile;
+    wp.conditional.size = 1;
+    cudaGraphNode_t wnode = nullptr;
+    if (cudaGraphAddNode(&wnode, g, nullptr, 0, &wp) != cudaSuccess) return fail();
+    cudaGraph_t wbody = wp.conditional.phGraph_out[0];
+    cudaGraphNodeParams ip = {};
+    ip.type = cudaGraphNodeTypeConditional;
+    ip.conditional.handle = hm;
+    ip.conditional.type = cudaGraphCondTypeIf;
+    ip.conditional.size = 1;
+    cudaGraphNode_t inode = nullptr;
+    if (cudaGraphAddNode(&inode, wbody, nullptr, 0, &ip) != cudaSuccess) return fail();
+    cudaGraph_t ibody = ip.conditional.phGraph_out[0];
+
+    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, 1, 1, (unsigned long long)hw, (unsigned long long)hm};
+    Pose P = {};
+    const unsigned long long launches_before = rt::g_launches;
+    // fixed grids: two full waves of k_knn8 (no stride pass up to 24 * SMs * 16 queries), surplus blocks return at once
+    const int g8 = 24 * h->n_sm, gk = 8 * h->n_sm, gr = div_up(h->cap, kResidBlock);
+    if (cudaStreamBeginCaptureToGraph(cs, ibody, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail();
+    capturing = true;
+    k_knn8<<<g8, kKnn8Block, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la);
+    k_knn<<<gk, kKnnWarps * 32, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, (const int *)h->d_unres,
+                                           (const int *)(h->d_counters + 8), la);
+    cudaGraph_t out = nullptr;
+    if (cudaStreamEndCapture(cs, &out) != cudaSuccess) {
+        capturing = false;
+        return fail();
+    }
+    capturing = false;
+    if (cudaStreamBeginCaptureToGraph(cs, wbody, &inode, nullptr, 1, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail();
+    capturing = true;
+    if (h->cfg.extrinsic_est_en)
+        k_residual<true><<<gr, kResidBlock, 0, cs>>>(mb, 0, 0, P, h->cfg.plane_thr, la);
+    else
+        k_residual<false><<<gr, kResidBlock, 0, cs>>>(mb, 0, 0, P, h->cfg.plane_thr, la);
+    if (cudaStreamEndCapture(cs, &out) != cudaSuccess) {
+        capturing = false;
+        return fail();
+    }
+    capturing = false;
+    rt::g_launches = launches_before;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) return fail();
+    h->loop_graph = g;
+    h->loop_exec = exec;
+    return true;
+}
+#endif
+
 int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, void *reduce_ctx, double *result_dev) {
     if (!h || !blk) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_iekf_update before a downsampled scan is set");
@@ -936,7 +1022,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     double *res = result_dev ? result_dev : h->d_result;
     mb.result = res;
     // without a reduction over ranks between them the solve step rides in the last block of k_residual
-    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, reduce ? 0 : 1};
+    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, reduce ? 0 : 1, 0, 0ull, 0ull};
     if (!h->n_down_on_device) {  // the scan was set with a host-known size: publish it where the kernels look
         DLT_RT(h, rt::h2d(&h->d_sc->n_down, &h->n_down, sizeof(int), h->stream));
     }
@@ -945,7 +1031,24 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     if (int rj = eig_join(h)) return rj;
     int G = div_up(n_upper, kResidBlock);
     if (G < 1) G = 1;
-    for (int it = 0; it < n_iter; it++) {
+    bool graph_run = false;
+#if !defined(DLT_EMU)
+    if (!reduce && res == h->d_result && h->use_graph && !h->prof_on) {
+        if (h->loop_graph_state == 0) {
+            DLT_RT(h, rt::sync(h->own_stream));
+            h->loop_graph_state = build_loop_graph(h, mb) ? 1 : -1;
+        }
+        if (h->loop_graph_state == 1) {
+            if (cudaGraphLaunch(h->loop_exec, h->stream) != cudaSuccess) {
+                cudaGetLastError();
+                h->loop_graph_state = -1;
+            } else {
+                graph_run = true;
+            }
+        }
+    }
+#endif
+    for (int it = 0; it < n_iter && !graph_run; it++) {
         {
             ProfScope prof(h, 0);
             int rk = launch_knn(h, (const float4 *)h->d_down, 0, n_grid, 1, P, la);
@@ -993,6 +1096,11 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     DLT_RT(h, rt::d2h((char *)h->h_iekf + lo, (const char *)&h->d_iekf->b + lo, hi - lo, h->stream));
     DLT_RT(h, rt::sync(h->stream));
     std::memcpy((char *)blk + lo, (const char *)h->h_iekf + lo, hi - lo);
+    if (graph_run) {  // kernels the graph actually ran: one residual pass per iteration, two kNN kernels per match pass
+        int n_match = 0;
+        for (int k = 0; k < blk->n_iters && k < DLT_IEKF_MAX_ITER; k++) n_match += blk->iters[k].did_match ? 1 : 0;
+        rt::g_launches += (unsigned long long)(blk->n_iters + 2 * n_match);
+    }
     if (h->n_down_on_device && blk->n_iters == 0) {  // the loop never ran: fetch feats_down_size the plain way
         if (int rn = resolve_n_down(h)) return rn;
         blk->n_down = h->n_down;
@@ -1179,7 +1287,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
                (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
-               LoopArgs{nullptr, nullptr, nullptr, 0}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
+               LoopArgs{nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
                (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key);
     if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
                                      // (without a match pass every rank already agrees: all points are PointToAdd)

@@ -42,6 +42,10 @@ struct LoopArgs {
     const int *n_ptr;    // feats_down_size on the device (ScanScalars::n_down)
     const int *vox_ptr;  // VoxelGrid status of the scan (ScanScalars::vox_status)
     int fuse_step;       // k_residual: its last block also runs the iteration's solve / control step (iekf_step_block)
+    // CUDA-graph form of the loop: a WHILE node around {IF(match) {k_knn8, k_knn}, k_residual}; the fused step drives both
+    // conditions from the device (cudaGraphSetConditional), so iterations that do not run are never launched.
+    int use_cond;
+    unsigned long long cond_while, cond_match;
 };
 // Block-wide: resolve (n, do_match, pose) for this launch; false = nothing to do.  The pose ends
 // up in shared memory either way so that both paths run the same code.
@@ -467,7 +471,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
 // share a d2 -- inside the winners or at the k-th boundary -- the query is left to the warp-per-query
 // kernel above, which applies the stated order exactly.  A query is finished here when the 3^3 block
 // proves its 5 best exact (the common case on a mapped surface); the rest go to `unres_list`.
-constexpr int kKnn8Block = 128;
+#ifndef DLT_KNN8_BLOCK
+#define DLT_KNN8_BLOCK 128
+#endif
+constexpr int kKnn8Block = DLT_KNN8_BLOCK;
 #ifndef DLT_KNN8_MINBLOCKS
 #define DLT_KNN8_MINBLOCKS 12
 #endif
@@ -1511,6 +1518,12 @@ __global__ void __launch_bounds__(kResidBlock)
     if (la.ctl && la.fuse_step) {  // block-uniform: the solve / control step of this iteration, no launch in between
         __syncthreads();           // the block's own global writes to R are visible to it after the barrier
         iekf_step_block(const_cast<IekfDev *>(la.ctl), R, la.n_ptr, la.vox_ptr, D);
+#if !defined(DLT_EMU)
+        if (la.use_cond && threadIdx.x == 0) {  // (the step's own writes of done / rematch_en by this thread)
+            cudaGraphSetConditional((cudaGraphConditionalHandle)la.cond_while, la.ctl->b.done ? 0u : 1u);
+            cudaGraphSetConditional((cudaGraphConditionalHandle)la.cond_match, la.ctl->b.rematch_en ? 1u : 0u);
+        }
+#endif
     }
 }
 

@@ -24,9 +24,11 @@ def main():
     devs = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p, _, _ in scans]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
     stream = torch.cuda.Stream()
-    modes = [int(a) for a in sys.argv[1:]] or [0, 2, 1]
+    modes = [a for a in sys.argv[1:]] or ["0", "2", "1", "1g"]  # "1g" / "2g": device loop as a CUDA graph with conditional nodes
     for rep in range(2):
-        for mode in modes:
+        for mtag in modes:
+            mode = int(mtag[0])
+            os.environ["DLT_LOOP_GRAPH"] = "1" if mtag.endswith("g") else "0"
             lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30,
                               device_loop=mode)
             lm.device.set_stream(stream.cuda_stream)
@@ -49,7 +51,7 @@ def main():
                     ev.append((a, b))
                 torch.cuda.synchronize()
             ms = np.array([a.elapsed_time(b) for a, b in ev])[warm:]
-            print(f"device_loop={mode}: p50 {np.median(ms):.4f} ms  mean {ms.mean():.4f}  host p50 {np.median(host[warm:]):.4f} ms", flush=True)
+            print(f"device_loop={mtag}: p50 {np.median(ms):.4f} ms  mean {ms.mean():.4f}  host p50 {np.median(host[warm:]):.4f} ms", flush=True)
             lm.close()
 
 
