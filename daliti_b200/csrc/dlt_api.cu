@@ -20,7 +20,7 @@
 
 using namespace dlt;
 
-unsigned long long dlt::rt::g_launches = 0;
+std::atomic<unsigned long long> dlt::rt::g_launches{0};
 
 namespace {
 constexpr int kMaxImuPoses = 512;
@@ -286,9 +286,9 @@ static int run_far(dlt_handle h, int *n_far_out) {
     for (int off = 0; off < nfar; off += kFarChunk) {
         int c = nfar - off < kFarChunk ? nfar - off : kFarChunk;
         DLT_LAUNCH(k_far_scan, dim3(kFarGroupsX, kFarSlices), kFarWarps * 32, h->stream, h->map, n_buckets, (const float4 *)h->knn.qw,
-                   (const int *)h->knn.far_list, off, c, kFarSlices, h->d_far_partial, (const int *)nullptr, (IekfDev *)nullptr, 0);
+                   (const int *)h->knn.far_list, off, c, kFarSlices, h->d_far_partial);
         DLT_LAUNCH(k_far_merge, div_up(c, 128), 128, h->stream, (const int *)h->knn.far_list, off, c, kFarSlices,
-                   (const Cand *)h->d_far_partial, h->cfg.max_sq_dist, h->knn, (const int *)nullptr, (IekfDev *)nullptr, 0);
+                   (const Cand *)h->d_far_partial, h->cfg.max_sq_dist, h->knn);
     }
     DLT_RT(h, rt::fill(h->d_counters + 5, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::check_launch());
@@ -945,7 +945,7 @@ static bool build_loop_graph(dlt_handle h, const MeasureBufs &mb) {
 
     LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, 1, 1, (unsigned long long)hw, (unsigned long long)hm};
     Pose P = {};
-    const unsigned long long launches_before = rt::g_launches;
+    const unsigned long long launches_before = rt::g_launches.load();
     // fixed grids: two full waves of k_knn8 (no stride pass up to 24 * SMs * 16 queries), surplus blocks return at once
     const int g8 = 24 * h->n_sm, gk = 8 * h->n_sm, gr = div_up(h->cap, kResidBlock);
     if (cudaStreamBeginCaptureToGraph(cs, ibody, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail();
@@ -1343,7 +1343,7 @@ int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset) {
     }
     return DLT_OK;
 }
-unsigned long long dlt_launch_count(void) { return rt::g_launches; }
+unsigned long long dlt_launch_count(void) { return rt::g_launches.load(); }
 
 int dlt_get_iekf_clocks(dlt_handle h, long long *clocks, int n_iter) {
     if (!h || !clocks || n_iter < 0 || n_iter > DLT_IEKF_MAX_ITER) return DLT_E_INVALID;

@@ -659,13 +659,8 @@ constexpr int kFarTile = 128;  // buckets per shared-memory tile
 
 __global__ void __launch_bounds__(kFarWarps * 32)
     k_far_scan(MapView m, int n_buckets, const float4 *__restrict__ qw, const int *__restrict__ far_list, int far_off, int nfar,
-               int n_slices, Cand *__restrict__ partial /* [far][slice][5] */, const int *__restrict__ nfar_ptr, IekfDev *ctl, int chunk_cap) {
+               int n_slices, Cand *__restrict__ partial /* [far][slice][5] */) {
     __shared__ float4 tile[kFarTile * 8];
-    if (nfar_ptr) {  // behind the device-resident loop: the count lives on the device; one chunk only
-        nfar = *nfar_ptr;
-        if (ctl->b.insert_status != 1 || nfar == 0) return;
-        if (nfar > chunk_cap) return;  // k_far_merge flags it; the host then runs the chunked fallback
-    }
     const int groups = (nfar + kFarWarps * 32 - 1) / (kFarWarps * 32);
     const int slice = blockIdx.y;
     const int per = (n_buckets + n_slices - 1) / n_slices;
@@ -714,15 +709,7 @@ __global__ void __launch_bounds__(kFarWarps * 32)
 }
 
 __global__ void k_far_merge(const int *__restrict__ far_list, int far_off, int nfar, int n_slices, const Cand *__restrict__ partial,
-                            float max_sq_dist, KnnOut out, const int *__restrict__ nfar_ptr, IekfDev *ctl, int chunk_cap) {
-    if (nfar_ptr) {
-        nfar = *nfar_ptr;
-        if (ctl->b.insert_status != 1 || nfar == 0) return;
-        if (nfar > chunk_cap) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->b.insert_status = 2;  // read by the kernels that follow in stream order
-            return;
-        }
-    }
+                            float max_sq_dist, KnnOut out) {
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfar; f += gridDim.x * blockDim.x) {
         Cand best[kK];
 #pragma unroll

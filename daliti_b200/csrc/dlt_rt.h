@@ -3,6 +3,7 @@
 // sources compile as plain C++ against the test emulator so kernel logic can be exercised
 // without a GPU; that build is test infrastructure and is never loaded by the package.
 #pragma once
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,7 +14,7 @@
 
 namespace dlt {
 namespace rt {
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 struct Event {};
 inline int event_create(Event *) { return 0; }
 inline void event_destroy(Event) {}
@@ -62,7 +63,7 @@ inline int check_launch() { return 0; }
 
 #else  // ------------------------------------------------------------------ CUDA
 
-namespace dlt { namespace rt { extern unsigned long long g_launches; } }
+namespace dlt { namespace rt { extern std::atomic<unsigned long long> g_launches; } }
 #define DLT_LAUNCH(kernel, grid, block, stream, ...)                      \
     do {                                                                  \
         kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);            \

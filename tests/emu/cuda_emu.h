@@ -194,7 +194,8 @@ static inline T atomicAnd(T *a, T v) {
 using std::max;
 using std::min;
 
-namespace dlt { namespace rt { extern unsigned long long g_launches; } }
+#include <atomic>
+namespace dlt { namespace rt { extern std::atomic<unsigned long long> g_launches; } }
 #define DLT_LAUNCH(kernel, grid, block, stream, ...)                              \
     do {                                                                          \
         emu::launch(dim3(grid), dim3(block), [=]() { kernel(__VA_ARGS__); });     \
