@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--seqs-per-gpu", type=int, default=8, help="c5: independent sequences driven concurrently on every GPU (one stream + host thread each)")
-    ap.add_argument("--device-loop", type=int, default=1, choices=[0, 1, 2],
+    ap.add_argument("--device-loop", type=int, default=2, choices=[0, 1, 2],
                     help="1: iteration loop, zeta blend and map insert resident on the device (one sync per scan); 2: loop on the device, "
                          "blend/insert host-driven; 0: one host round trip per iteration")
     ap.add_argument("--tiles", type=int, default=5, help="c4: the map is tiles x tiles shifted copies of the C2 map")

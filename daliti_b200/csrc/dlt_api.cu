@@ -230,25 +230,40 @@ static int map_check_error(dlt_handle h) {
     return DLT_OK;
 }
 
+// the voxel scratch of one insert batch: only has to be clean where the batch can hash to, so it is sized to the batch
+// (power of two >= 4 n, or >= 2 n when n is an upper bound of the batch) and cleared with ONE memset (vwin sits right behind vkeys)
+static int prepare_scratch(dlt_handle h, int n, bool n_is_upper_bound, DsScratch *out) {
+    size_t sc = 1024;
+    while (sc < (n_is_upper_bound ? 2 : 4) * (size_t)n) sc <<= 1;
+    if (sc > h->scratch_cap) sc = h->scratch_cap;
+    DsScratch scr = h->scratch;
+    scr.mask = (unsigned)(sc - 1);
+    scr.vwin = scr.vkeys + sc;
+    DLT_RT(h, rt::fill(scr.vkeys, 0xFF, 2 * sc * sizeof(unsigned long long), h->stream));
+    *out = scr;
+    return DLT_OK;
+}
+
 // claim | (bid, resolve) | append over n device points with per-point flags.  With a gate (device-resident loop) n is
-// only the grid size: the kernels read the real count, and whether to run at all, from device memory.
-static int insert_points(dlt_handle h, const float4 *d_pts, int n, bool any_ds, InsertGate gate = {nullptr, nullptr}) {
+// only the grid size: the kernels read the real count, and whether to run at all, from device memory.  front_done: the
+// caller's classification kernel already claimed the cells and placed the bids (scratch `pre`).
+static int insert_points(dlt_handle h, const float4 *d_pts, int n, bool any_ds, InsertGate gate = {nullptr, nullptr}, const DsScratch *pre = nullptr) {
     if (n <= 0) return DLT_OK;
     h->counters_fresh = false;
     ProfScope prof(h, 4);
     const int B = 256, G = div_up(n, B);
-    DLT_LAUNCH(k_map_claim, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
-               h->d_cellslot, h->map.shard_count > 1 ? 1 : 0, gate);
+    if (!pre)
+        DLT_LAUNCH(k_map_claim, G, B, h->stream, h->map, d_pts, n, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
+                   h->d_cellslot, h->map.shard_count > 1 ? 1 : 0, gate);
     if (any_ds) {
-        // the voxel scratch only has to be clean where this batch can hash to: size it to the batch (power of two >= 4 n)
-        size_t sc = 1024;
-        while (sc < (gate.go ? 2 : 4) * (size_t)n) sc <<= 1;  // gated: n is an upper bound of the batch, load factor <= 0.5 either way
-        if (sc > (size_t)h->scratch_cap) sc = h->scratch_cap;
-        DsScratch scr = h->scratch;
-        scr.mask = (unsigned)(sc - 1);
-        DLT_RT(h, rt::fill(scr.vkeys, 0xFF, sc * sizeof(unsigned long long), h->stream));
-        DLT_RT(h, rt::fill(scr.vwin, 0xFF, sc * sizeof(unsigned long long), h->stream));
-        DLT_LAUNCH(k_ds_bid, G, B, h->stream, h->map, scr, d_pts, n, (const unsigned char *)h->d_dsflag, h->d_vslot, gate);
+        DsScratch scr;
+        if (pre) {
+            scr = *pre;
+        } else {
+            int rs = prepare_scratch(h, n, gate.go != nullptr, &scr);
+            if (rs) return rs;
+            DLT_LAUNCH(k_ds_bid, G, B, h->stream, h->map, scr, d_pts, n, (const unsigned char *)h->d_dsflag, h->d_vslot, gate);
+        }
         DLT_LAUNCH(k_ds_resolve, G, B, h->stream, h->map, scr, d_pts, n, (const unsigned char *)h->d_dsflag, (const int *)h->d_vslot,
                    (const int *)h->d_cellslot, h->d_addflag, gate);
     }
@@ -396,7 +411,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
          !dalloc(h, &h->d_result, (size_t)kResultDoubles) && !dalloc(h, &h->d_ticket, 4) &&
          !dalloc(h, &h->d_far_partial, (size_t)kFarChunk * kFarSlices * kK) && !dalloc(h, &h->d_pw, cap) && !dalloc(h, &h->d_dsflag, cap) &&
          !dalloc(h, &h->d_addflag, cap) && !dalloc(h, &h->d_cellslot, cap) && !dalloc(h, &h->d_vslot, cap) &&
-         !dalloc(h, &h->scratch.vkeys, sc_cap) && !dalloc(h, &h->scratch.vwin, sc_cap) && !dalloc(h, &h->d_iekf, 1);
+         !dalloc(h, &h->scratch.vkeys, 2 * sc_cap) && !dalloc(h, &h->d_iekf, 1);
     if (cfg->shard_count > 1) ok = ok && !dalloc(h, &h->d_flagbuf, cap);
     void *p = nullptr;
     ok = ok && rt::pinned_alloc(&p, sizeof(dlt_iekf_block)) == 0;
@@ -631,9 +646,8 @@ static int enqueue_downsample(dlt_handle h) {
     const int B = 256, G = div_up(n, B);
     ProfScope prof(h, 3);
     DLT_LAUNCH(k_vox_mark, G, B, h->stream, (const float4 *)h->d_undist, n, h->cfg.ds_scan, h->d_sc, h->d_bitmap, h->bitmap_bits, h->d_vidx);
-    DLT_LAUNCH(k_vox_scan1, h->n_scan_blocks, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, (const ScanScalars *)h->d_sc, h->d_wprefix,
-               h->d_blksum);
-    DLT_LAUNCH(k_vox_scan2, 1, 1024, h->stream, h->d_sc, (const unsigned *)h->d_blksum, h->d_blkoff);
+    DLT_LAUNCH(k_vox_scan1, h->n_scan_blocks, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, h->d_sc, h->d_wprefix, h->d_blksum, h->d_blkoff,
+               h->d_ticket + 1);
     DLT_LAUNCH(k_vox_accum, G, B, h->stream, (const float4 *)h->d_undist, n, (const ScanScalars *)h->d_sc, (const unsigned *)h->d_bitmap,
                (const unsigned *)h->d_wprefix, (const unsigned *)h->d_blkoff, (const unsigned *)h->d_vidx, h->acc, h->d_vop);
     DLT_LAUNCH(k_vox_final, G, B, h->stream, h->d_sc, h->acc, h->d_bitmap, (const float4 *)h->d_undist, h->d_down, n);
@@ -1082,11 +1096,13 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
         }
         DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));  // downsample adds, raw adds (far_count is re-armed by the next k_knn8)
+        FuseInsert fi = {1, h->scratch, h->d_cellslot, h->d_vslot};
+        if (int rs = prepare_scratch(h, n_upper, true, &fi.sc)) return rs;
         DLT_LAUNCH(k_incr_classify, div_up(n_upper, 256), 256, h->stream, (const float4 *)h->d_down, 0, P, (const float4 *)h->knn.nbr,
                    (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, la, h->map,
-                   (const int *)h->map.n_live, (const unsigned char *)h->knn.flags, (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key);
+                   (const int *)h->map.n_live, (const unsigned char *)h->knn.flags, (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key, fi);
         InsertGate gate = {&h->d_iekf->b.insert_status, &h->d_sc->n_down};
-        int ri = insert_points(h, h->d_pw, n_upper, true, gate);
+        int ri = insert_points(h, h->d_pw, n_upper, true, gate, &fi.sc);
         if (ri) return ri;
         DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     }
@@ -1285,10 +1301,15 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     }
     Pose P = pose_from(pose24);
     DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
+    FuseInsert fi = {0, h->scratch, h->d_cellslot, h->d_vslot};
+    if (!sharded) {  // unsharded: the classification kernel also claims cells and places the voxel bids
+        if (int rs = prepare_scratch(h, n, false, &fi.sc)) return rs;
+        fi.on = 1;
+    }
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
                (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
                LoopArgs{nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
-               (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key);
+               (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key, fi);
     if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
                                      // (without a match pass every rank already agrees: all points are PointToAdd)
         DLT_LAUNCH(k_incr_pack, div_up(n, 256), 256, h->stream, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag, n, h->d_flagbuf);
@@ -1297,7 +1318,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
         DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
         DLT_LAUNCH(k_incr_unpack, div_up(n, 256), 256, h->stream, (const double *)h->d_flagbuf, n, h->d_dsflag, h->d_addflag, h->d_counters + 6);
     }
-    int rc = insert_points(h, h->d_pw, n, true);
+    int rc = insert_points(h, h->d_pw, n, true, InsertGate{nullptr, nullptr}, fi.on ? &fi.sc : nullptr);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
     rc = map_check_error(h);  // reads the 8 counters back

@@ -192,15 +192,18 @@ DLT_D void voxel_box(float x, float ds, float &mn, float &mx, float &mid) {
     mid = (float)((double)mn + (double)(mx - mn) / 2.0);   // :497
 }
 
-// phase 1b: per ds point, claim a scratch entry for its voxel and bid for it
+// phase 1b: per ds point, claim a scratch entry for its voxel and bid for it; returns the scratch slot
+DLT_D int ds_bid_point(const MapView &m, const DsScratch &sc, float4 p, int i);
+
 __global__ void k_ds_bid(MapView m, DsScratch sc, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
                          int *__restrict__ vslot, InsertGate gate) {
     if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    vslot[i] = -1;
-    if (!ds_flag[i]) return;
-    float4 p = pts[i];
+    vslot[i] = ds_flag[i] ? ds_bid_point(m, sc, pts[i], i) : -1;
+}
+
+DLT_D int ds_bid_point(const MapView &m, const DsScratch &sc, float4 p, int i) {
     float mnx, mxx, mdx, mny, mxy, mdy, mnz, mxz, mdz;
     voxel_box(p.x, m.ds, mnx, mxx, mdx);
     voxel_box(p.y, m.ds, mny, mxy, mdy);
@@ -215,8 +218,17 @@ __global__ void k_ds_bid(MapView m, DsScratch sc, const float4 *__restrict__ pts
     }
     unsigned long long bid = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
     atomicMin(&sc.vwin[h], bid);
-    vslot[i] = (int)h;
+    return (int)h;
 }
+
+// map_incremental on an unsharded map: the classification kernel claims the cell and bids for the voxel of the point it
+// has just classified (no other thread's result is needed for either), which saves two launches per scan
+struct FuseInsert {
+    int on;
+    DsScratch sc;
+    int *cell_slot;
+    int *vslot;
+};
 
 // phase 2: the winning incoming point of each voxel resolves the voxel against the map.
 // Clears the live bits of the points it removes; sets add_flag[i] when it must be added.

@@ -1612,7 +1612,7 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_p
                                 double fs, int ekf_inited, float4 *__restrict__ pw, unsigned char *__restrict__ ds_flag,
                                 unsigned char *__restrict__ add_flag, int *__restrict__ class_counts /* [0] downsample adds, [1] raw adds */,
                                 LoopArgs la, MapView m, const int *__restrict__ live_ptr, const unsigned char *__restrict__ flags,
-                                const int *__restrict__ nn_pos, const unsigned long long *__restrict__ nn_key) {
+                                const int *__restrict__ nn_pos, const unsigned long long *__restrict__ nn_key, FuseInsert fi) {
     __shared__ Pose sP;
     if (!insert_gate(la, n)) return;  // block-uniform
     if (la.ctl) {  // pose after the zeta blend, flg_EKF_inited after the loop
@@ -1677,6 +1677,17 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_p
     if (foreign) ds = 0;
     ds_flag[i] = ds;
     add_flag[i] = add;
+    if (fi.on) {  // k_map_claim + k_ds_bid for this point
+        int cs = -1, vs = -1;
+        if (ds || add) {
+            int cx, cy, cz;
+            cell_of_point(m, wx, wy, wz, cx, cy, cz);
+            cs = map_claim(m, pack_key(cx, cy, cz));
+        }
+        if (ds) vs = ds_bid_point(m, fi.sc, make_float4(wx, wy, wz, pb.w), i);
+        fi.cell_slot[i] = cs;
+        fi.vslot[i] = vs;
+    }
     }
     unsigned bd = __ballot_sync(0xffffffffu, ds != 0), ba = __ballot_sync(0xffffffffu, add != 0);
     if ((threadIdx.x & 31) == 0) {

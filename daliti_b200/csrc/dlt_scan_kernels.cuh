@@ -263,13 +263,56 @@ __global__ void k_vox_mark(const float4 *__restrict__ pts, int n, float leaf, Sc
 constexpr int kScanBlock = 256;
 constexpr int kScanWordsPerBlock = 1024;  // 4 words per thread
 
+// exclusive scan of the block totals by ONE block of NT threads, total -> n_down
+template <int NT>
+DLT_D void vox_scan_block_totals(ScanScalars *sc, const unsigned *__restrict__ blksum, unsigned *__restrict__ blkoff) {
+    __shared__ unsigned warp_tot2[NT / 32];
+    __shared__ unsigned carry_s;
+    const int n_blk = (sc->n_words + kScanWordsPerBlock - 1) / kScanWordsPerBlock;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0u;
+    __syncthreads();
+    for (int base = 0; base < n_blk; base += NT) {  // block-uniform
+        int i = base + threadIdx.x;
+        unsigned mine = (i < n_blk) ? __ldcg(blksum + i) : 0u;
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_tot2[warp] = incl;
+        __syncthreads();
+        unsigned woff = 0, total = 0;
+        for (int k = 0; k < NT / 32; k++) {
+            unsigned t = warp_tot2[k];
+            if (k < warp) woff += t;
+            total += t;
+        }
+        unsigned carry = carry_s;
+        if (i < n_blk) blkoff[i] = carry + woff + incl - mine;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sc->n_down = sc->vox_status ? 0 : (int)carry_s;
+}
+
 // exclusive prefix popcount inside each 1024-word block + per-block totals
+// ... and, by the last block to finish, the exclusive scan of those totals (what used to be a second launch)
 __global__ void __launch_bounds__(kScanBlock)
-    k_vox_scan1(const unsigned *__restrict__ bitmap, const ScanScalars *sc, unsigned *__restrict__ wprefix, unsigned *__restrict__ blksum) {
+    k_vox_scan1(const unsigned *__restrict__ bitmap, ScanScalars *sc, unsigned *__restrict__ wprefix, unsigned *__restrict__ blksum,
+                unsigned *__restrict__ blkoff, unsigned *__restrict__ ticket) {
     __shared__ unsigned warp_tot[kScanBlock / 32];
+    __shared__ int s_last;
     const int n_words = sc->n_words;
     const int w0 = blockIdx.x * kScanWordsPerBlock + threadIdx.x * 4;
-    if (blockIdx.x * kScanWordsPerBlock >= n_words) return;  // block-uniform
+    const int n_blk = (n_words + kScanWordsPerBlock - 1) / kScanWordsPerBlock;
+    if (n_blk == 0) {  // nothing marked (status != 0): n_down = 0 / pass-through is decided downstream
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_down = 0;
+        return;
+    }
+    if (blockIdx.x >= n_blk) return;  // block-uniform
     unsigned c[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) c[k] = (w0 + k < n_words) ? (unsigned)__popc(bitmap[w0 + k]) : 0u;
@@ -297,40 +340,17 @@ __global__ void __launch_bounds__(kScanBlock)
         excl += c[k];
     }
     if (threadIdx.x == 0) blksum[blockIdx.x] = total;
-}
-
-// exclusive scan of the block totals (single block), total -> n_down
-__global__ void __launch_bounds__(1024) k_vox_scan2(ScanScalars *sc, const unsigned *__restrict__ blksum, unsigned *__restrict__ blkoff) {
-    __shared__ unsigned warp_tot[32];
-    __shared__ unsigned carry_s;
-    const int n_blk = (sc->n_words + kScanWordsPerBlock - 1) / kScanWordsPerBlock;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0u;
+    __threadfence();
     __syncthreads();
-    for (int base = 0; base < n_blk; base += 1024) {
-        int i = base + threadIdx.x;
-        unsigned mine = (i < n_blk) ? blksum[i] : 0u;
-        unsigned incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        unsigned woff = 0, total = 0;
-        for (int k = 0; k < 32; k++) {
-            unsigned t = warp_tot[k];
-            if (k < warp) woff += t;
-            total += t;
-        }
-        unsigned carry = carry_s;
-        if (i < n_blk) blkoff[i] = carry + woff + incl - mine;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == (unsigned)n_blk - 1u) ? 1 : 0;
     }
-    if (threadIdx.x == 0) sc->n_down = sc->vox_status ? 0 : (int)carry_s;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0u;
+    vox_scan_block_totals<kScanBlock>(sc, blksum, blkoff);
 }
 
 struct VoxAcc {  // per output voxel: 2^-24 fixed-point sums

@@ -36,10 +36,10 @@ def pose_close(a, b, tol=1e-5):
     return rot_err < tol and pos_err < tol, (rot_err, pos_err)
 
 
-def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal=None, pre_msgs=0, **kw):
+def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal=None, pre_msgs=0, device_loop=2, **kw):
     kind = MAP_REF if oracle.ref_ok else MAP_PORT
     lio = helpers.start_oracle_lio(oracle, seq, None, kind, **kw)
-    lm = LaserMapping(lib, dev=dict(max_scan_points=max_pts, max_map_points=1 << 18), **kw)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=max_pts, max_map_points=1 << 18), device_loop=device_loop, **kw)
     lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
     lm.set_state(helpers.state612(seq.traj, seq.t_start))
     stops = 0
@@ -84,7 +84,8 @@ def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal
     return stops
 
 
-def test_pipeline_first_scan_builds_map(dev, oracle):
+@pytest.mark.parametrize("device_loop", [2, 1, 0])
+def test_pipeline_first_scan_builds_map(dev, oracle, device_loop):
     lib, is_gpu = dev
     if is_gpu:
         seq = helpers.small_sequence(seed=11, half=50.0, beams=32, azimuths=1024, n_boxes=20, speed=2.0, yaw_rate=0.2)
@@ -92,7 +93,7 @@ def test_pipeline_first_scan_builds_map(dev, oracle):
     else:
         seq = helpers.small_sequence(seed=11, half=25.0, beams=16, azimuths=240, n_boxes=8, speed=2.0, yaw_rate=0.2)
         n, cap = 4, 8192
-    stops = run_pair(lib, oracle, seq, n, cap, featptsThreshold=5)
+    stops = run_pair(lib, oracle, seq, n, cap, device_loop=device_loop, featptsThreshold=5)
     assert stops == 0
 
 
@@ -119,7 +120,7 @@ def test_pipeline_degradation_stop_and_thermal(dev, oracle):
     kind = MAP_REF if oracle.ref_ok else MAP_PORT
     # after 100 lidar messages the window threshold becomes featptsThreshold; scans alternate between a
     # reachable and an unreachable threshold by alternating... here: unreachable, so every update stops
-    stops = run_pair(lib, oracle, seq, 5, 32768 if is_gpu else 8192, thermal=thermal, pre_msgs=101, featptsThreshold=1000000)
+    stops = run_pair(lib, oracle, seq, 5, 32768 if is_gpu else 8192, thermal=thermal, pre_msgs=101, device_loop=1, featptsThreshold=1000000)
     assert stops >= 3
 
 
@@ -175,7 +176,8 @@ def test_pipeline_sliding_local_map_box_delete(dev, oracle):
 
 
 @pytest.mark.parametrize("stop", [False, True])
-def test_device_resident_loop_equals_host_loop(dev, stop):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_device_resident_loop_equals_host_loop(dev, stop, mode):
     """dlt_iekf_update (the iteration loop :820-1102 resident on the device, one sync per scan) against the host
     loop over dlt_measure (one round trip per iteration) on the same scans: same control flow, same counts,
     states equal to fp64 round-off (covariance-form gain on the device vs two LU inversions on the host, CUDA vs glibc sin/cos)."""
@@ -184,7 +186,7 @@ def test_device_resident_loop_equals_host_loop(dev, stop):
     map_pts = synth.sample_map(seq.scene, seed=21)
     kw = dict(featptsThreshold=1000000 if stop else 5, max_iteration=4)
     lms = []
-    for device_loop in (1, 0):
+    for device_loop in (mode, 0):  # 1: loop + zeta blend + map insert on the device (one sync); 2: loop on the device, blend / insert host-driven
         lm = LaserMapping(lib, dev=dict(max_scan_points=32768 if is_gpu else 8192, max_map_points=4 * len(map_pts)), device_loop=device_loop, **kw)
         lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
         lm.set_state(helpers.state612(seq.traj, seq.t_start))
