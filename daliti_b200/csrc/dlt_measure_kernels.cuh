@@ -62,8 +62,9 @@ DLT_D bool loop_resolve(const LoopArgs &la, const Pose &P_param, Pose *sP, int &
                 *do_match = dm;
             }
         }
+        if (!go) return false;  // block-uniform: no barrier needed on the way out (this is the no-op launch's whole cost)
         n = *la.n_ptr;
-        if (go && threadIdx.x < 24) reinterpret_cast<double *>(sP)[threadIdx.x] = c.state[threadIdx.x];
+        if (threadIdx.x < 24) reinterpret_cast<double *>(sP)[threadIdx.x] = c.state[threadIdx.x];
     } else {
         if (threadIdx.x < 24) reinterpret_cast<double *>(sP)[threadIdx.x] = reinterpret_cast<const double *>(&P_param)[threadIdx.x];
     }
@@ -472,11 +473,11 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
 // kernel above, which applies the stated order exactly.  A query is finished here when the 3^3 block
 // proves its 5 best exact (the common case on a mapped surface); the rest go to `unres_list`.
 #ifndef DLT_KNN8_BLOCK
-#define DLT_KNN8_BLOCK 128
+#define DLT_KNN8_BLOCK 256
 #endif
 constexpr int kKnn8Block = DLT_KNN8_BLOCK;
 #ifndef DLT_KNN8_MINBLOCKS
-#define DLT_KNN8_MINBLOCKS 12
+#define DLT_KNN8_MINBLOCKS 6
 #endif
 constexpr unsigned long long kKeyInf = (0x7F800000ull << 32) | 0x7FFFFFFFull;
 
@@ -926,7 +927,7 @@ DLT_D void iekf_step_block(IekfDev *dev, const double *__restrict__ result, cons
     __shared__ double C12[12 * N];                    // the first 12 rows of the covariance
     __shared__ double R[kNormalEqDoubles + 2];        // the normal equations of this iteration
     __shared__ double st[36], sprop[36], sother[36];  // state, state_propagat | thermal delta, last_nodegared (non-covariance parts)
-    __shared__ double vec[N], rhs[12], sol[N];
+    __shared__ double vec[N], rhs[12], sol[N], rcpv[12];
     __shared__ int s_i[16];
     __shared__ int s_q[10];
     __shared__ int s_fail, s_piv;
@@ -1086,17 +1087,16 @@ DLT_D void iekf_step_block(IekfDev *dev, const double *__restrict__ result, cons
             return;
         }
         DLT_STAMP(4);
-        if (tid < D) rhs[tid] = 1.0 / W[tid * AW + tid];  // (rhs doubles as the pivots' reciprocals for a moment)
+        if (tid < D) rcpv[tid] = 1.0 / W[tid * AW + tid];
         __syncthreads();
         for (int k = tid; k < N * 12; k += NT) {  // K_1[:, :12] = P'_1 - P'_1[:, :D] Y
             const int i = k / 12, j = k % 12;
             double x = PN[i * N + j];
-            for (int a = 0; a < D; a++) x -= PN[i * N + a] * (W[a * AW + D + j] * rhs[a]);
+            for (int a = 0; a < D; a++) x -= PN[i * N + a] * (W[a * AW + D + j] * rcpv[a]);
             T[k] = x;
             dev->K1c[k] = x;
         }
         for (int k = tid; k < 144; k += NT) dev->HtH12[k] = R[k];
-        __syncthreads();
         if (tid >= 32 && tid < 44) {  // solution = K_1[:, :12] (H^T r - H^T H vec_12) + vec, :1032
             const int a = tid - 32;
             double sacc = 0;

@@ -57,6 +57,8 @@ def main():
             for it in range(4):
                 d = ck[it, 1:9] - ck[it, 0:8]
                 print("  k_iekf_step iter", it, "stage cycles:", d.tolist(), "total", int(ck[it, 8] - ck[it, 0]))
+                print("     gj_warp: entry->", (ck[it, 9] - ck[it, 3]), "steps (pivot, elim):", (ck[it, 11] - ck[it, 10], ck[it, 12] - ck[it, 11]),
+                      (ck[it, 13] - ck[it, 12], ck[it, 14] - ck[it, 13]), "exit->stamp4", ck[it, 4] - ck[it, 15] if ck[it, 15] else None)
     lm.close()
 
 
