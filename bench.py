@@ -292,9 +292,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--seqs-per-gpu", type=int, default=8, help="c5: independent sequences driven concurrently on every GPU (one stream + host thread each)")
-    ap.add_argument("--device-loop", type=int, default=2, choices=[0, 1, 2],
-                    help="1: iteration loop, zeta blend and map insert resident on the device (one sync per scan); 2: loop on the device, "
-                         "blend/insert host-driven; 0: one host round trip per iteration")
+    ap.add_argument("--device-loop", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="-1: the library's default (host loop on one GPU, device-resident loop on a sharded map); 1: iteration loop, zeta blend "
+                         "and map insert resident on the device (one sync per scan); 2: loop on the device, blend/insert host-driven; "
+                         "0: one host round trip per iteration")
     ap.add_argument("--tiles", type=int, default=5, help="c4: the map is tiles x tiles shifted copies of the C2 map")
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans of the same workload timed on the host cores (cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -514,7 +515,8 @@ def main():
             "ms_per_step": t_v / K, "ms_p50": float(np.median(ms_v)), "ms_p99": float(np.percentile(ms_v, 99)),
             "scans_per_s": world * K / (t_v * 1e-3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
-            "config": {"workload": work["name"], "iterations": 4, "iterations_run_mean": iters_mean, "loop": {1: "device-resident loop + zeta blend + map insert (dlt_iekf_update), 1 host sync per scan",
+            "config": {"workload": work["name"], "iterations": 4, "iterations_run_mean": iters_mean, "loop": {-1: "library default: host loop over dlt_measure (single-GPU map), 1 host sync per iteration",
+                                1: "device-resident loop + zeta blend + map insert (dlt_iekf_update), 1 host sync per scan",
                                 2: "device-resident loop (dlt_iekf_update), blend/insert host-driven, 2 host syncs per scan",
                                 0: "host loop over dlt_measure, 1 host sync per iteration"}[args.device_loop],
                        "deleted_total": int(sum(o[13] for o in outs_v)), "degenerate_scans": int(sum(o[14] for o in outs_v)),

@@ -32,11 +32,13 @@ typedef struct dlt_lio_config {
     double extrinT[3];       /* mapping/extrinsic_T              laserMapping.cpp:661              */
     double extrinR[9];       /* mapping/extrinsic_R (row-major)  laserMapping.cpp:662              */
     double degeneracy_eig_threshold; /* new: flag when min eigenvalue of HtH[0:6,0:6] is below     */
-    int device_loop;         /* 2 (default): the iteration loop :820-1102 runs resident on the device
-                                (dlt_iekf_update), zeta blend + map_incremental are driven by the host: two
-                                synchronisations per scan; 1: blend and insert also queued on the device behind
-                                the loop, one synchronisation per scan; 0: one host round trip per iteration
-                                (dlt_measure + host Kalman algebra)                                 */
+    int device_loop;         /* where the iteration loop :820-1102 runs.
+                                0: on the host, one dlt_measure round trip per iteration (Kalman algebra as the
+                                   reference writes it);
+                                2: resident on the device (dlt_iekf_update), zeta blend + map_incremental driven
+                                   by the host: two synchronisations per scan;
+                                1: blend and insert also queued on the device behind the loop: one synchronisation;
+                               -1 (default): 0 on a single-GPU map, 2 on a sharded map (measured)      */
     int reserved;
 } dlt_lio_config;
 

@@ -71,3 +71,14 @@ def test_product_does_not_link_or_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_binding" not in txt and "liboracle" not in txt and '#include "../../oracle' not in txt, f
+
+
+def test_headers_are_plain_c():
+    """the drop-in boundary is a C ABI: both headers must compile as C99 and as C++14 on their own"""
+    import subprocess
+
+    for h in ("daliti_b200.h", "daliti_b200_lio.h"):
+        src = f'#include "{os.path.join(ROOT, "include", h)}"\n'
+        for args in (["gcc", "-x", "c", "-std=c99", "-pedantic"], ["g++", "-x", "c++", "-std=c++14"]):
+            r = subprocess.run(args + ["-fsyntax-only", "-Wall", "-Werror", "-"], input=src, text=True, capture_output=True)
+            assert r.returncode == 0, (h, args[0], r.stderr)

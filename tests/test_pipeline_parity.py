@@ -36,7 +36,7 @@ def pose_close(a, b, tol=1e-5):
     return rot_err < tol and pos_err < tol, (rot_err, pos_err)
 
 
-def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal=None, pre_msgs=0, device_loop=2, **kw):
+def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal=None, pre_msgs=0, device_loop=-1, **kw):
     kind = MAP_REF if oracle.ref_ok else MAP_PORT
     lio = helpers.start_oracle_lio(oracle, seq, None, kind, **kw)
     lm = LaserMapping(lib, dev=dict(max_scan_points=max_pts, max_map_points=1 << 18), device_loop=device_loop, **kw)
@@ -84,7 +84,7 @@ def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal
     return stops
 
 
-@pytest.mark.parametrize("device_loop", [2, 1, 0])
+@pytest.mark.parametrize("device_loop", [-1, 2, 1])
 def test_pipeline_first_scan_builds_map(dev, oracle, device_loop):
     lib, is_gpu = dev
     if is_gpu:

@@ -34,8 +34,8 @@ def main(tag="v5"):
         d = load(name)
         if d:
             rows.append(f"| {label} | {d['ms_p50']:.3f} ms | {d['value'] / 1e6:.0f} M | {d['e2e']['ms_per_step']:.3f} ms / scan | — |")
-    for name, label in ((f"r01_bench_c5_s1_{tag}.json", "C5, 1 sequence on one GPU"), (f"r01_bench_c5_s16_{tag}.json", "C5, 16 concurrent sequences on one GPU"),
-                        ("r01_bench_c5_n2_v4.json", "C5, 2 GPUs x 8 sequences")):
+    for name, label in ((f"r01_bench_c5_s1_{tag}.json", "C5, 1 sequence on one GPU"), (f"r01_bench_c5_s16_{tag}.json", "C5, 16 concurrent sequences on one GPU"), (f"r01_bench_c5_s64_{tag}.json", "C5, 64 concurrent sequences on one GPU"),
+                        ("r01_bench_c5_n2_v4.json", "C5, 2 GPUs x 8 sequences (device-resident loop)")):
         d = load(name)
         if d:
             rows.append(f"| {label} | {d['scans_per_s'] / 1e3:.1f} k scans/s aggregate | {d['value'] / 1e6:.0f} M | {d['e2e']['value'] / 1e6:.0f} M pts/s | — |")
