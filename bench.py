@@ -506,10 +506,14 @@ def main():
         n_raw_mean = float(np.mean([o[0] for o in outs_v]))
         n_down_mean = float(np.mean([o[1] for o in outs_v]))
         iters_mean = float(np.mean([o[2] for o in outs_v]))
-        # per scan: the 48-byte records + IMU poses + the IEKF block prefix (state_propagat, thermal delta, state, last_nodegared,
-        # window) up; the block's in/out + out part with 4 iteration records and the 8 map counters down
-        h2d = n_raw_mean * 48 + 22 * 8 * 22 + (36 + 36 + 1 + 2 * 612) * 8 + 28 * 4
-        d2h = (2 * 612 + 42) * 8 + 24 * 4 + 4 * 1952 + 32
+        # per scan, device loop: the 48-byte records + IMU poses + the IEKF block prefix (state_propagat, thermal delta, state,
+        # last_nodegared, window) up; the block's in/out + out part with 4 iteration records and the 8 map counters down
+        if args.device_loop in (-1, 0):  # host loop: the normal equations come back once per iteration
+            h2d = n_raw_mean * 48 + 22 * 8 * 22
+            d2h = iters_mean * 159 * 8 + 48 + 42 * 8 + 2 * 32
+        else:
+            h2d = n_raw_mean * 48 + 22 * 8 * 22 + (36 + 36 + 1 + 2 * 612) * 8 + 28 * 4
+            d2h = (2 * 612 + 42) * 8 + 24 * 4 + 4 * 1952 + 32
         line = {
             "metric": METRIC, "value": pts_v / (t_v * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_v / K, "ms_p50": float(np.median(ms_v)), "ms_p99": float(np.percentile(ms_v, 99)),
