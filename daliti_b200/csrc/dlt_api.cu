@@ -221,6 +221,16 @@ static int resolve_n_down(dlt_handle h) {
     return DLT_OK;
 }
 
+// ... or take it from a result block that just came back (k_residual leaves it in R[159])
+static int adopt_n_down(dlt_handle h, const double *R) {
+    if (!h->n_down_on_device) return DLT_OK;
+    h->n_down_on_device = false;
+    if (R[159] < 0.0) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    h->n_down = (int)(R[159] + 0.5);
+    h->n_down_hint = h->n_down;
+    return DLT_OK;
+}
+
 static int map_check_error(dlt_handle h) {
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
@@ -875,10 +885,12 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_measure before a downsampled scan is set");
     if (!do_match && !h->have_match) DLT_FAIL(h, DLT_E_STATE, "dlt_measure(do_match=0) before any match pass");
     rt::set_device(h->cfg.device);
-    if (int rn = resolve_n_down(h)) return rn;
+    // right behind dlt_scan_downsample_async feats_down_size is still on the device: the kernels read it there (grids from
+    // an estimate / an upper bound) and it comes back with the result block, so no synchronisation is spent on it
+    const bool dev_n = h->n_down_on_device;
     const int n = h->n_down;
     Pose P = pose_from(pose24);
-    if (n == 0) {
+    if (!dev_n && n == 0) {
         DLT_RT(h, rt::fill(result_dev, 0, kResultDoubles * sizeof(double), h->stream));
         h->have_match = true;
         return DLT_OK;
@@ -887,11 +899,16 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
         h->eig_valid = false;
         if (int rj = eig_join(h)) return rj;
     }
+    LoopArgs la = {nullptr, dev_n ? &h->d_sc->n_down : nullptr, dev_n ? &h->d_sc->vox_status : nullptr, 0, 0, 0ull, 0ull};
+    int n_grid = n;
+    if (dev_n) {
+        n_grid = h->n_down_hint > 0 ? (int)(1.25 * h->n_down_hint) + 1024 : h->n_raw;
+        if (n_grid > h->n_raw) n_grid = h->n_raw;
+    }
     if (do_match) {
         h->nfar_known = false;
         ProfScope prof(h, 0);
-        LoopArgs la0 = {nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull};
-        int rk = launch_knn(h, (const float4 *)h->d_down, n, n, 1, P, la0);
+        int rk = launch_knn(h, (const float4 *)h->d_down, n, n_grid, 1, P, la);
         if (rk) return rk;
         h->have_match = true;
     }
@@ -908,8 +925,8 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     mb.far_count = h->d_counters + 5;
     mb.unres_count = h->d_counters + 8;
     mb.result = result_dev;
-    const int G = div_up(n, kResidBlock);
-    LoopArgs la = {nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull};
+    int G = div_up(dev_n ? h->n_raw : n, kResidBlock);  // surplus blocks return at once
+    if (G < 1) G = 1;
     ProfScope prof(h, 1);
     if (h->cfg.extrinsic_est_en)
         DLT_LAUNCH(k_residual<true>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr, la);
@@ -1154,6 +1171,7 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
     DLT_RT(h, rt::d2h(h->h_result, h->d_result, kFetchDoubles * sizeof(double), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     const double *R = h->h_result;
+    if (int rn = adopt_n_down(h, R)) return rn;
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
     for (int i = 0; i < 12; i++) out->Htr[i] = R[144 + i];
     out->effct_feat_num = (int)(R[156] + 0.5);
@@ -1174,6 +1192,7 @@ int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *ou
     DLT_RT(h, rt::d2h(h->h_result, result_dev, kFetchDoubles * sizeof(double), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     const double *R = h->h_result;
+    if (int rn = adopt_n_down(h, R)) return rn;
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
     for (int i = 0; i < 12; i++) out->Htr[i] = R[144 + i];
     out->effct_feat_num = (int)(R[156] + 0.5);

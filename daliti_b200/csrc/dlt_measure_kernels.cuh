@@ -66,6 +66,7 @@ DLT_D bool loop_resolve(const LoopArgs &la, const Pose &P_param, Pose *sP, int &
         n = *la.n_ptr;
         if (threadIdx.x < 24) reinterpret_cast<double *>(sP)[threadIdx.x] = c.state[threadIdx.x];
     } else {
+        if (la.n_ptr) n = *la.n_ptr;  // host loop right behind dlt_scan_downsample_async: feats_down_size is still on the device
         if (threadIdx.x < 24) reinterpret_cast<double *>(sP)[threadIdx.x] = reinterpret_cast<const double *>(&P_param)[threadIdx.x];
     }
     __syncthreads();
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(kNn1Block)
 }
 
 constexpr int kNormalEqDoubles = 158;                 // HtH[144], Htr[12], effective count, residual sum
-constexpr int kFetchDoubles = kNormalEqDoubles + 1;   // + far_count of the last match pass: one device->host copy per iteration
+constexpr int kFetchDoubles = kNormalEqDoubles + 2;   // + far_count of the last match pass + feats_down_size: one device->host copy per iteration
 constexpr int kEigOffset = 160;                       // eigvals[6], eigvecs[36] (k_eigen6)
 constexpr int kResultDoubles = kEigOffset + 42;
 
@@ -1310,6 +1311,7 @@ __global__ void __launch_bounds__(kResidBlock)
             for (int k = threadIdx.x; k < kNormalEqDoubles; k += kResidBlock) mb.result[k] = 0.0;
             if (threadIdx.x == 0) {
                 mb.result[158] = (double)(*mb.far_count);
+                mb.result[159] = (la.vox_ptr && *la.vox_ptr == 2) ? -1.0 : 0.0;
                 *mb.unres_count = 0;
             }
         }
@@ -1499,6 +1501,7 @@ __global__ void __launch_bounds__(kResidBlock)
     }
     if (threadIdx.x == 0) {
         R[158] = (double)(*mb.far_count);
+        R[159] = (la.vox_ptr && *la.vox_ptr == 2) ? -1.0 : (double)n;  // feats_down_size (-1: VoxelGrid capacity exceeded)
         *mb.ticket = 0u;
         *mb.unres_count = 0;
     }

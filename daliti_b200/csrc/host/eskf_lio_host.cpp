@@ -599,7 +599,9 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     const bool device_loop = loop_mode != 0 && map_built && NUM_MAX_ITERATIONS >= 1 && NUM_MAX_ITERATIONS <= DLT_IEKF_MAX_ITER;
     t0 = wall();
     int feats_down_size = 0;
-    if (device_loop)
+    // (with a map in place nobody needs feats_down_size on the host before the first evaluation of the measurement model
+    // has come back, which brings it along: no synchronisation is spent on the VoxelGrid)
+    if (device_loop || (map_built && !reduce_fn))
         LM_CK(dlt_scan_downsample_async(dev_));
     else
         LM_CK(dlt_scan_downsample(dev_, &feats_down_size));  // :775-778
@@ -622,7 +624,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     out->map_points_before = featsFromMapNum;
 
     int effct_feat_num = 0;
-    if (featsFromMapNum < 5 && device_loop) {  // no update: still report feats_down_size
+    if (featsFromMapNum < 5) {  // no update: still report feats_down_size
         int nd = 0;
         LM_CK(dlt_scan_get_down(dev_, nullptr, 0, &nd));
         out->n_down = nd;
@@ -765,6 +767,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
             effct_feat_num = m.effct_feat_num;
             const double total_residual = m.total_residual;
             rec.n_down = m.n_down;
+            out->n_down = m.n_down;  // (feats_down_size arrives with the first result block)
             rec.effct_feat_num = effct_feat_num;
             rec.total_residual = total_residual;
             rec.res_mean_last = total_residual / effct_feat_num;  // :932 (nan when 0, as in the reference)
