@@ -70,7 +70,7 @@ _SYMBOLS = [
     "dlt_scan_deskew", "dlt_scan_deskew_dev", "dlt_scan_downsample", "dlt_scan_get_undistorted", "dlt_scan_get_down", "dlt_scan_set_down",
     "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
     "dlt_fetch_result", "dlt_degeneracy", "dlt_degeneracy_begin", "dlt_map_incremental", "dlt_set_profiling", "dlt_get_profile", "dlt_launch_count",
-    "dlt_scan_downsample_async", "dlt_iekf_update", "dlt_get_timeline", "dlt_get_iekf_clocks", "dlt_set_shard_reduce", "dlt_result_dev", "dlt_frontend_sample", "dlt_frontend_read",
+    "dlt_scan_downsample_async", "dlt_iekf_update", "dlt_get_timeline", "dlt_get_iekf_clocks", "dlt_set_shard_reduce", "dlt_result_dev", "dlt_frontend_sample", "dlt_frontend_read", "dlt_scan_prefetch",
 ]
 
 

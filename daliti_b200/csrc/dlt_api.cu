@@ -60,6 +60,15 @@ struct dlt_handle_s {
     bool eig_valid = false;       // the eigen block of d_result belongs to its normal equations
     bool sc_clean = true;         // the scan scalars (bounding box, first-point key) are reset
     float4 *d_raw = nullptr, *d_undist = nullptr, *d_down = nullptr;
+    // double-buffered upload (dlt_scan_prefetch): the next scan's records cross PCIe on the copy stream while this one is processed
+    float4 *d_raw_next = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    rt::Event ev_copy;
+    bool have_copy = false;
+    const void *prefetched_ptr = nullptr;
+    int prefetched_n = -1;
+    const void *pf_pending_ptr = nullptr;  // registered by dlt_scan_prefetch, issued behind the current scan's own small uploads
+    int pf_pending_n = -1;
     ImuPoseDev *d_poses = nullptr;
     ScanScalars *d_sc = nullptr;
     unsigned *d_bitmap = nullptr, *d_wprefix = nullptr, *d_blksum = nullptr, *d_blkoff = nullptr, *d_vidx = nullptr;
@@ -355,6 +364,11 @@ int dlt_destroy(dlt_handle h) {
     if (h->loop_exec) cudaGraphExecDestroy(h->loop_exec);
     if (h->loop_graph) cudaGraphDestroy(h->loop_graph);
 #endif
+    if (h->have_copy) {
+        rt::sync(h->copy_stream);
+        rt::event_destroy(h->ev_copy);
+    }
+    rt::stream_destroy(h->copy_stream);
     if (h->have_aux) {
         rt::sync(h->aux_stream);
         rt::event_destroy(h->ev_fork);
@@ -380,6 +394,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->n_sm = rt::sm_count();
     bool ok = rt::stream_create(&h->own_stream) == 0;
     h->stream = h->own_stream;
+    h->have_copy = rt::stream_create(&h->copy_stream) == 0 && rt::event_create_untimed(&h->ev_copy) == 0;
     if (const char *e = std::getenv("DLT_LOOP_GRAPH")) h->use_graph = (e[0] == '1') ? 1 : 0;  // A/B switch for measurements
     h->have_aux = rt::stream_create(&h->aux_stream) == 0 && rt::event_create_untimed(&h->ev_fork) == 0 && rt::event_create_untimed(&h->ev_join) == 0;
 
@@ -625,10 +640,24 @@ static int scan_deskew_impl(dlt_handle h, const void *pts48, bool on_device, int
     h->sc_clean = false;
     if (n_raw == 0) return DLT_OK;
     const float4 *d_in = h->d_raw;
-    if (on_device)
+    if (on_device) {
         d_in = static_cast<const float4 *>(pts48);
-    else
+    } else if (h->pf_pending_ptr == pts48) {  // registered but never issued (no update ran in between): plain upload
+        h->pf_pending_ptr = nullptr;
+        h->pf_pending_n = -1;
         DLT_RT(h, rt::h2d(h->d_raw, pts48, (size_t)n_raw * 48, h->stream));
+    } else if (h->prefetched_ptr == pts48 && h->prefetched_n == n_raw && h->d_raw_next) {
+        // these records were uploaded ahead of time (dlt_scan_prefetch): swap the buffers and order the stream behind the copy
+        float4 *t = h->d_raw;
+        h->d_raw = h->d_raw_next;
+        h->d_raw_next = t;
+        h->prefetched_ptr = nullptr;
+        h->prefetched_n = -1;
+        DLT_RT(h, rt::stream_wait(h->stream, h->ev_copy));
+        d_in = h->d_raw;
+    } else {
+        DLT_RT(h, rt::h2d(h->d_raw, pts48, (size_t)n_raw * 48, h->stream));
+    }
     Pose P = {};
     ProfScope prof(h, 2);
     if (n_pose >= 2) {
@@ -640,6 +669,36 @@ static int scan_deskew_impl(dlt_handle h, const void *pts48, bool on_device, int
     DLT_LAUNCH(k_scan_deskew, div_up(n_raw, kDeskewBlock), kDeskewBlock, h->stream, d_in, n_raw, (const ImuPoseDev *)h->d_poses, n_pose, P,
                n_pose >= 2 ? 1 : 0, h->d_undist, h->d_sc);
     DLT_RT(h, rt::check_launch());
+    return DLT_OK;
+}
+
+// The copy engine serves host->device transfers in issue order, so a 6 MB prefetch issued ahead of the current scan's own small
+// uploads (IMU poses, the IEKF block) would hold them -- and with them the whole update -- back by ~100 us (measured).  The
+// prefetch is therefore only registered here and issued right behind those uploads (issue_prefetch).
+static int issue_prefetch(dlt_handle h) {
+    if (!h->pf_pending_ptr) return DLT_OK;
+    const void *pts48 = h->pf_pending_ptr;
+    const int n_raw = h->pf_pending_n;
+    h->pf_pending_ptr = nullptr;
+    h->pf_pending_n = -1;
+    if (!h->d_raw_next && dalloc(h, &h->d_raw_next, (size_t)h->cap * kRawStride4) != 0)  // (owned through h->allocs: the two buffers swap roles)
+        DLT_FAIL(h, DLT_E_CUDA, "prefetch buffer allocation failed");
+    // d_raw_next is never read by kernels in flight (they read d_raw or the caller's device buffer); a previous, unconsumed
+    // prefetch is simply overwritten, in copy-stream order
+    DLT_RT(h, rt::h2d(h->d_raw_next, pts48, (size_t)n_raw * 48, h->copy_stream));
+    DLT_RT(h, rt::event_record(h->ev_copy, h->copy_stream));
+    h->prefetched_ptr = pts48;
+    h->prefetched_n = n_raw;
+    return DLT_OK;
+}
+
+int dlt_scan_prefetch(dlt_handle h, const void *pts48, int n_raw) {
+    if (!h || n_raw < 0 || (n_raw > 0 && !pts48)) return DLT_E_INVALID;
+    if (n_raw > h->cap) DLT_FAIL(h, DLT_E_CAPACITY, "scan larger than max_scan_points");
+    if (!h->have_copy || n_raw == 0) return DLT_OK;  // nothing to do: dlt_scan_deskew uploads as usual
+    rt::set_device(h->cfg.device);
+    h->pf_pending_ptr = pts48;
+    h->pf_pending_n = n_raw;
     return DLT_OK;
 }
 
@@ -887,6 +946,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     rt::set_device(h->cfg.device);
     // right behind dlt_scan_downsample_async feats_down_size is still on the device: the kernels read it there (grids from
     // an estimate / an upper bound) and it comes back with the result block, so no synchronisation is spent on it
+    if (int rp = issue_prefetch(h)) return rp;  // (this scan's uploads are queued by now)
     const bool dev_n = h->n_down_on_device;
     const int n = h->n_down;
     Pose P = pose_from(pose24);
@@ -1029,6 +1089,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     const size_t up_bytes = offsetof(dlt_iekf_block, blend_state);
     std::memcpy(h->h_iekf, blk, up_bytes);
     DLT_RT(h, rt::h2d(&h->d_iekf->b, h->h_iekf, up_bytes, h->stream));
+    if (int rp = issue_prefetch(h)) return rp;  // (this scan's uploads are queued by now)
 
     // speculative grids: feats_down_size may still be on the device
     int n_grid = h->n_down;

@@ -990,6 +990,12 @@ int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_t
     static_assert(sizeof(ImuSample) == 7 * sizeof(double), "imu7 layout");
     return h->lm->process_scan(pts48, n, lidar_beg_time, reinterpret_cast<const ImuSample *>(imu7), n_imu, thermal, out);
 }
+int dlt_lio_prefetch_scan(dlt_lio h, const void *pts48, int n) {
+    if (!h) return DLT_E_INVALID;
+    int rc = dlt_scan_prefetch(h->lm->dev_, pts48, n);
+    if (rc != 0) h->lm->err = dlt_last_error(h->lm->dev_);
+    return rc;
+}
 int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lidar_beg_time, double observation_end_time, const double *imu7,
                              int n_imu, const dlt_lio_thermal *thermal, dlt_lio_scan_out *out) {
     if (!h || !out || n < 0 || n_imu < 0 || (n > 0 && !pts48_dev) || (n_imu > 0 && !imu7)) return DLT_E_INVALID;

@@ -58,7 +58,7 @@ class LioScanOut(C.Structure):
 _LIO_SYMBOLS = [
     "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
     "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
-    "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_process_cloud", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
+    "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_process_cloud", "dlt_lio_prefetch_scan", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
 ]
 
 
@@ -163,6 +163,16 @@ class LaserMapping:
         self._ck(self.lib.dlt_lio_process_scan(self.h, pp, C.c_int(n), C.c_double(lidar_beg_time), _p(im), C.c_int(im.shape[0]), th,
                                                C.byref(self.out)))
         return self.out
+
+    def prefetch_scan(self, pts48):
+        """start uploading a scan (pinned torch CPU tensor or contiguous float32 numpy array that stays alive and unchanged) ahead of its
+        process_scan call: the copy overlaps whatever the device is doing"""
+        if hasattr(pts48, "data_ptr"):
+            n, pp = int(pts48.shape[0]), C.c_void_p(pts48.data_ptr())
+        else:
+            assert pts48.dtype == np.float32 and pts48.flags["C_CONTIGUOUS"]
+            n, pp = pts48.reshape(-1, 12).shape[0], _p(pts48)
+        self._ck(self.lib.dlt_lio_prefetch_scan(self.h, pp, C.c_int(n)))
 
     def process_scan_dev(self, pts48_dev_ptr: int, n: int, lidar_beg_time, observation_end_time, imu7, thermal: LioThermal | None = None) -> LioScanOut:
         """the scan is already resident in device memory (pointer to n 48-byte records)"""

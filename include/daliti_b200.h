@@ -96,6 +96,10 @@ int dlt_map_knn(dlt_handle h, const float *q_xyz, int nq, float *out_xyzi, float
  * the IMUpose list of the forward pass and the propagated end state; n_imu_pose < 2 copies
  * the points through.  Also the input of dlt_scan_downsample.                                   */
 int dlt_scan_deskew(dlt_handle h, const void *pts48, int n_raw, const double *imu_pose22, int n_imu_pose, const double *pose24);
+/* Optional double buffering: start uploading the NEXT scan's records (pinned HOST memory, untouched until consumed) on the
+ * handle's copy stream now, e.g. from the message callback while the previous update is still running.  A later
+ * dlt_scan_deskew / dlt_lio_process_scan with the same pointer and count uses that copy instead of uploading again.     */
+int dlt_scan_prefetch(dlt_handle h, const void *pts48, int n_raw);
 /* same with the PointXYZINormal records already resident in DEVICE memory (no host->device copy) */
 int dlt_scan_deskew_dev(dlt_handle h, const void *pts48_dev, int n_raw, const double *imu_pose22, int n_imu_pose, const double *pose24);
 /* downSizeFilterSurf.filter(*feats_down)                        laserMapping.cpp:775-776        */

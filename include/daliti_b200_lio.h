@@ -92,6 +92,9 @@ int dlt_lio_get_localmap(dlt_lio h, float *box6);
 /* The per-scan update.  pts48: n PointXYZINormal records; imu7: n_imu rows of t, acc[3], gyr[3]. */
 int dlt_lio_process_scan(dlt_lio h, const void *pts48, int n, double lidar_beg_time, const double *imu7, int n_imu,
                          const dlt_lio_thermal *thermal, dlt_lio_scan_out *out);
+/* feat_points_cbk (:424-446) may hand a scan over as soon as it arrives: its upload then overlaps the update of the previous
+ * scan (dlt_scan_prefetch); the dlt_lio_process_scan call for the same buffer finds the records already on the device.  */
+int dlt_lio_prefetch_scan(dlt_lio h, const void *pts48, int n);
 /* Same with the scan already resident in DEVICE memory (pts48_dev); observation_end_time is then
  * passed explicitly (the host cannot read points.back().normal_z, laserMapping.cpp:546).            */
 int dlt_lio_process_scan_dev(dlt_lio h, const void *pts48_dev, int n, double lidar_beg_time, double observation_end_time,

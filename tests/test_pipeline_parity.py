@@ -229,3 +229,75 @@ def test_device_resident_loop_equals_host_loop(dev, stop, mode):
     assert (n_stop > 0) == stop
     for lm in lms:
         lm.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_handles_are_independent(gpu_lib):
+    """BASELINE config C5: independent sequences on one GPU, one handle + CUDA stream + host thread each.  Driving four
+    sequences concurrently must give exactly the states and maps that driving them one after the other gives."""
+    import threading
+
+    lib = gpu_lib
+    n_seq, n_scans = 4, 5
+    seqs = [helpers.small_sequence(seed=40 + i, half=25.0, beams=16, azimuths=600, n_boxes=8, speed=1.0 + 0.3 * i, yaw_rate=0.1 + 0.05 * i) for i in range(n_seq)]
+    maps = [synth.sample_map(s.scene, seed=40 + i) for i, s in enumerate(seqs)]
+    scans = [[s.scan(k) for k in range(n_scans)] for s in seqs]
+
+    def drive(i, out):
+        seq = seqs[i]
+        lm = LaserMapping(lib, dev=dict(max_scan_points=16384, max_map_points=4 * len(maps[i])), featptsThreshold=5)
+        lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
+        lm.set_state(helpers.state612(seq.traj, seq.t_start))
+        lm.device.map_build(maps[i])
+        res = []
+        for pts, t_beg, imu in scans[i]:
+            lm.on_lidar_msg()
+            o = lm.process_scan(pts, t_beg, imu)
+            res.append((lm.get_state().copy(), o.n_down, o.n_iters, o.added, lm.device.map_valid_count()))
+        out[i] = res
+        lm.close()
+
+    serial, parallel = [None] * n_seq, [None] * n_seq
+    for i in range(n_seq):
+        drive(i, serial)
+    ths = [threading.Thread(target=drive, args=(i, parallel)) for i in range(n_seq)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for i in range(n_seq):
+        assert parallel[i] is not None
+        for (sa, *ra), (sb, *rb) in zip(serial[i], parallel[i]):
+            assert ra == rb, (i, ra, rb)
+            np.testing.assert_array_equal(sa, sb)
+
+
+def test_prefetched_upload_changes_nothing(dev):
+    """dlt_lio_prefetch_scan: uploading scan k+1 on the copy stream while scan k is processed gives bit-identical results;
+    a prefetch that is never consumed (a different buffer is processed) is harmless"""
+    lib, is_gpu = dev
+    seq = helpers.small_sequence(seed=51, half=25.0, beams=16, azimuths=900 if is_gpu else 240, n_boxes=8, speed=2.0, yaw_rate=0.2)
+    map_pts = synth.sample_map(seq.scene, seed=51)
+    scans = [seq.scan(k) for k in range(4)]
+    lms = []
+    for _ in range(2):
+        lm = LaserMapping(lib, dev=dict(max_scan_points=32768 if is_gpu else 8192, max_map_points=4 * len(map_pts)), featptsThreshold=5)
+        lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
+        lm.set_state(helpers.state612(seq.traj, seq.t_start))
+        lm.device.map_build(map_pts)
+        lms.append(lm)
+    bufs = [np.ascontiguousarray(s[0], np.float32) for s in scans]
+    decoy = bufs[0].copy()
+    lms[0].prefetch_scan(bufs[0])
+    for k, (pts, t_beg, imu) in enumerate(scans):
+        for lm in lms:
+            lm.on_lidar_msg()
+        if k + 1 < len(scans):
+            lms[0].prefetch_scan(bufs[k + 1] if k != 1 else decoy)  # (scan 2 is not prefetched: the decoy is, and is never consumed)
+        a = lms[0].process_scan(bufs[k], t_beg, imu)
+        ra = (a.n_raw, a.n_down, a.n_iters, a.added)
+        b = lms[1].process_scan(pts, t_beg, imu)
+        assert ra == (b.n_raw, b.n_down, b.n_iters, b.added), k
+        np.testing.assert_array_equal(lms[0].get_state(), lms[1].get_state())
+    for lm in lms:
+        lm.close()
