@@ -627,6 +627,8 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
                 if mode == "dev":
                     o = lm.process_scan_dev(dev_scans[k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
                 else:
+                    if k + 1 < W + K:
+                        lm.prefetch_scan(pin_scans[k + 1])  # double-buffered upload
                     o = lm.process_scan(pin_scans[k], t_beg, imu)
                 if k >= W:
                     ev[k - W][1].record(stream)
@@ -665,7 +667,7 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
                        "parallelism": f"map sharded {world}-way by 32-cell tiles + halo, NCCL all-reduce (158 doubles) per iteration" if world > 1 else "single GPU, unsharded"},
             "e2e": {"value": float(sum(o[0] for o in outs_e)) / (t_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(np.mean([o[0] for o in outs_e]) * 48 + 22 * 8 * 22),
                     "d2h_bytes_per_step": int(np.mean([o[2] for o in outs_e]) * (158 * 8 + 4) + 48 + 42 * 8), "ms_per_step": t_e / K,
-                    "api": "dlt_lio_process_scan (pinned host buffers) + dlt_lio_set_reduce"},
+                    "api": "dlt_lio_prefetch_scan(next) + dlt_lio_process_scan (pinned host buffers) + dlt_lio_set_reduce"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": None, "cpu_baseline": None,
         }
@@ -726,6 +728,8 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
                         if mode == "dev":
                             o = lm.process_scan_dev(dev_scans[i][k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
                         else:
+                            if k + 1 < W + K:
+                                lm.prefetch_scan(pin_scans[i][k + 1])  # double-buffered upload
                             o = lm.process_scan(pin_scans[i][k], t_beg, imu)
                         if k >= W:
                             pts_total += o.n_raw
@@ -793,7 +797,7 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
                        "timing": "one CUDA event before the workers are released to the last worker's end event (max over sequences and ranks)",
                        "parallelism": "independent sequences, no data-path collective"},
             "e2e": {"value": pts_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(pts_e / (world * K) * 48), "d2h_bytes_per_step": int(S * 18064),
-                    "ms_per_step": ms_e / K, "api": "dlt_lio_process_scan (pinned host buffers), one host thread per sequence"},
+                    "ms_per_step": ms_e / K, "api": "dlt_lio_prefetch_scan(next) + dlt_lio_process_scan (pinned host buffers), one host thread per sequence"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
         }
         emit(line)
