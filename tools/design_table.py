@@ -39,7 +39,7 @@ def main(tag="v5"):
         d = load(name)
         if d:
             rows.append(f"| {label} | {d['scans_per_s'] / 1e3:.1f} k scans/s aggregate | {d['value'] / 1e6:.0f} M | {d['e2e']['value'] / 1e6:.0f} M pts/s | — |")
-    for name, label in (("r01_bench_c2_n2_v4.json", "C2, 2 GPUs (one sequence each)"), ("r01_bench_c2_n8_v4.json", "C2, 8 GPUs (one sequence each)")):
+    for name, label in (("r01_bench_c2_n2_v5.json", "C2, 2 GPUs (one sequence each)"), ("r01_bench_c2_n8_v4.json", "C2, 8 GPUs (one sequence each; measured before the last single-GPU trims)")):
         d = load(name)
         if d:
             rows.append(f"| {label} | {d['ms_p50']:.3f} ms | {d['value'] / 1e6:.0f} M | {d['e2e']['value'] / 1e6:.0f} M pts/s | — |")
