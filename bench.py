@@ -296,6 +296,9 @@ def main():
                     help="-1: the library's default (host loop on one GPU, device-resident loop on a sharded map); 1: iteration loop, zeta blend "
                          "and map insert resident on the device (one sync per scan); 2: loop on the device, blend/insert host-driven; "
                          "0: one host round trip per iteration")
+    ap.add_argument("--shard-exchange", default="peer", choices=["peer", "nccl"],
+                    help="c4: how the partial normal equations / map_incremental decisions are summed over the ranks: inside the kernels "
+                         "over NVLink peer memory (dlt_peer_attach; falls back to nccl when the mailboxes cannot be mapped) or an NCCL all-reduce callback")
     ap.add_argument("--tiles", type=int, default=5, help="c4: the map is tiles x tiles shifted copies of the C2 map")
     ap.add_argument("--cpu-sample", type=int, default=3, help="scans of the same workload timed on the host cores (cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -591,9 +594,16 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
             lm.device.map_add(tile, False)
     t_build = time.perf_counter() - t_build
     live = lm.device.map_valid_count()
+    exchange = "none"
     if world > 1:
-        with torch.cuda.stream(stream):
-            lm.set_allreduce(f"cuda:{local_rank}")
+        if args.shard_exchange == "peer":
+            from daliti_b200.sharded import attach_peers
+
+            exchange = "peer" if attach_peers(lm) else "nccl (peer mailboxes could not be mapped)"
+        if exchange != "peer":
+            exchange = exchange if exchange != "none" else "nccl"
+            with torch.cuda.stream(stream):
+                lm.set_allreduce(f"cuda:{local_rank}")
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
     dev_scans = [torch.from_numpy(np.ascontiguousarray(p)).to(f"cuda:{local_rank}") for p, _, _ in scans]
     pin_scans = [torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p, _, _ in scans]
@@ -664,10 +674,13 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
                        "effct_feat_mean": float(np.mean([o[3] for o in outs_v])),
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
                        "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
-                       "parallelism": f"map sharded {world}-way by 32-cell tiles + halo, NCCL all-reduce (158 doubles) per iteration" if world > 1 else "single GPU, unsharded"},
+                       "parallelism": (f"map sharded {world}-way by 32-cell tiles + halo; 158 doubles summed over the ranks per iteration "
+                                       + ("inside k_residual through NVLink peer mailboxes (CUDA IPC), solve step fused behind it: no collective launch"
+                                          if exchange == "peer" else "by an NCCL all-reduce between k_residual and k_iekf_step")) if world > 1 else "single GPU, unsharded",
+                       "shard_exchange": exchange},
             "e2e": {"value": float(sum(o[0] for o in outs_e)) / (t_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(np.mean([o[0] for o in outs_e]) * 48 + 22 * 8 * 22),
                     "d2h_bytes_per_step": int(np.mean([o[2] for o in outs_e]) * (158 * 8 + 4) + 48 + 42 * 8), "ms_per_step": t_e / K,
-                    "api": "dlt_lio_prefetch_scan(next) + dlt_lio_process_scan (pinned host buffers) + dlt_lio_set_reduce"},
+                    "api": "dlt_lio_prefetch_scan(next) + dlt_lio_process_scan (pinned host buffers) + " + ("dlt_lio_peer_attach" if exchange == "peer" else "dlt_lio_set_reduce")},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": None, "cpu_baseline": None,
         }

@@ -62,6 +62,8 @@ class Measurement:
     n_unresolved: int
 
 
+PEER_BLOB_BYTES = 128  # DLT_PEER_BLOB_BYTES
+
 _ERR = {1: "invalid argument", 2: "no usable CUDA device (there is no CPU path)", 3: "CUDA error", 4: "capacity exceeded", 5: "call-sequence error"}
 
 _SYMBOLS = [
@@ -71,6 +73,7 @@ _SYMBOLS = [
     "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
     "dlt_fetch_result", "dlt_degeneracy", "dlt_degeneracy_begin", "dlt_map_incremental", "dlt_set_profiling", "dlt_get_profile", "dlt_launch_count",
     "dlt_scan_downsample_async", "dlt_iekf_update", "dlt_get_timeline", "dlt_get_iekf_clocks", "dlt_set_shard_reduce", "dlt_result_dev", "dlt_frontend_sample", "dlt_frontend_read", "dlt_scan_prefetch",
+    "dlt_peer_export", "dlt_peer_attach", "dlt_peer_detach",
 ]
 
 
@@ -280,6 +283,21 @@ class ScanToMap:
         return a.value, b.value
 
     PROFILE_GROUPS = ("knn", "residual", "deskew", "voxelgrid", "insert", "far_fallback", "iekf_step", "knn8")
+
+    # ---- sharded map over NVLink peer memory (dlt_peer_*): see daliti_b200.sharded.attach_peers
+    def peer_export(self) -> bytes:
+        blob = (C.c_ubyte * PEER_BLOB_BYTES)()
+        self._ck(self.lib.dlt_peer_export(self.h, blob))
+        return bytes(blob)
+
+    def peer_attach(self, blobs):
+        """blobs: the peer_export() results of all shard_count ranks, in rank order"""
+        raw = b"".join(blobs)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._ck(self.lib.dlt_peer_attach(self.h, buf))
+
+    def peer_detach(self):
+        self._ck(self.lib.dlt_peer_detach(self.h))
 
     def set_profiling(self, on: bool):
         self._ck(self.lib.dlt_set_profiling(self.h, C.c_int(1 if on else 0)))

@@ -98,6 +98,16 @@ struct dlt_handle_s {
     dlt_reduce_fn shard_reduce = nullptr;
     void *shard_reduce_ctx = nullptr;
     double *d_flagbuf = nullptr;
+    // sharded map: exchange through peer mailboxes (dlt_peer_*, dlt_peer.cuh)
+    PeerBox *peer_box = nullptr;       // this rank's mailbox (IPC-exportable allocation)
+    size_t peer_bytes = 0;
+    rt::ShareBlob peer_blob = {};
+    PeerComm *d_peer = nullptr;
+    void *peer_maps[DLT_MAX_PEERS] = {};  // mappings opened by dlt_peer_attach (to be closed)
+    size_t peer_map_bytes[DLT_MAX_PEERS] = {};
+    bool peer_on = false;
+    unsigned long long peer_dec_seq = 0;  // decision exchanges so far (host-counted: every dlt_map_incremental with a match pass)
+    int *h_peer_status = nullptr;         // pinned
     // the iteration loop as a CUDA graph with conditional nodes (built lazily, once: every kernel in it has a fixed grid and
     // takes its sizes from device memory)
 #if !defined(DLT_EMU)
@@ -360,6 +370,10 @@ int dlt_destroy(dlt_handle h) {
     rt::pinned_release(h->h_ints);
     rt::pinned_release(h->h_sc);
     rt::pinned_release(h->h_iekf);
+    dlt_peer_detach(h);
+    if (h->peer_box) rt::shared_release(h->peer_box, h->peer_bytes, &h->peer_blob);
+    rt::release(h->d_peer);
+    rt::pinned_release(h->h_peer_status);
 #if !defined(DLT_EMU)
     if (h->loop_exec) cudaGraphExecDestroy(h->loop_exec);
     if (h->loop_graph) cudaGraphDestroy(h->loop_graph);
@@ -599,7 +613,7 @@ int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *ou
         DLT_RT(h, rt::h2d(h->d_pw, stage.data(), (size_t)c * sizeof(float4), h->stream));
         {
             DLT_RT(h, rt::fill(h->d_counters + 8, 0, sizeof(int), h->stream));  // no residual pass here to re-arm it
-            LoopArgs la = {nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull};
+            LoopArgs la = {nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull, nullptr};
             int rk = launch_knn(h, (const float4 *)h->d_pw, c, c, 0, P, la);
             if (rk) return rk;
         }
@@ -959,7 +973,7 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
         h->eig_valid = false;
         if (int rj = eig_join(h)) return rj;
     }
-    LoopArgs la = {nullptr, dev_n ? &h->d_sc->n_down : nullptr, dev_n ? &h->d_sc->vox_status : nullptr, 0, 0, 0ull, 0ull};
+    LoopArgs la = {nullptr, dev_n ? &h->d_sc->n_down : nullptr, dev_n ? &h->d_sc->vox_status : nullptr, 0, 0, 0ull, 0ull, h->peer_on ? h->d_peer : nullptr};
     int n_grid = n;
     if (dev_n) {
         n_grid = h->n_down_hint > 0 ? (int)(1.25 * h->n_down_hint) + 1024 : h->n_raw;
@@ -1034,7 +1048,7 @@ static bool build_loop_graph(dlt_handle h, const MeasureBufs &mb) {
     if (cudaGraphAddNode(&inode, wbody, nullptr, 0, &ip) != cudaSuccess) return fail();
     cudaGraph_t ibody = ip.conditional.phGraph_out[0];
 
-    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, 1, 1, (unsigned long long)hw, (unsigned long long)hm};
+    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, 1, 1, (unsigned long long)hw, (unsigned long long)hm, nullptr};
     Pose P = {};
     const unsigned long long launches_before = rt::g_launches.load();
     // fixed grids: two full waves of k_knn8 (no stride pass up to 24 * SMs * 16 queries), surplus blocks return at once
@@ -1075,6 +1089,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_iekf_update before a downsampled scan is set");
     if (blk->max_iteration < 1 || blk->max_iteration > DLT_IEKF_MAX_ITER) DLT_FAIL(h, DLT_E_INVALID, "max_iteration out of range");
     rt::set_device(h->cfg.device);
+    if (h->peer_on) reduce = nullptr;  // the sum over ranks happens inside k_residual (peer mailboxes), the solve step stays fused
     const int n_iter = blk->max_iteration;
     // host -> device: everything up to (not including) the out fields
     blk->n_iters = blk->converged = blk->ekf_stop = blk->have_gain = blk->status = 0;
@@ -1114,7 +1129,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     double *res = result_dev ? result_dev : h->d_result;
     mb.result = res;
     // without a reduction over ranks between them the solve step rides in the last block of k_residual
-    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, reduce ? 0 : 1, 0, 0ull, 0ull};
+    LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, reduce ? 0 : 1, 0, 0ull, 0ull, h->peer_on ? h->d_peer : nullptr};
     if (!h->n_down_on_device) {  // the scan was set with a host-known size: publish it where the kernels look
         DLT_RT(h, rt::h2d(&h->d_sc->n_down, &h->n_down, sizeof(int), h->stream));
     }
@@ -1125,7 +1140,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     if (G < 1) G = 1;
     bool graph_run = false;
 #if !defined(DLT_EMU)
-    if (!reduce && res == h->d_result && h->use_graph && !h->prof_on) {
+    if (!reduce && !h->peer_on && res == h->d_result && h->use_graph && !h->prof_on) {
         if (h->loop_graph_state == 0) {
             DLT_RT(h, rt::sync(h->own_stream));
             h->loop_graph_state = build_loop_graph(h, mb) ? 1 : -1;
@@ -1188,8 +1203,10 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     const size_t lo = offsetof(dlt_iekf_block, state);
     const size_t hi = offsetof(dlt_iekf_block, iters) + (size_t)n_iter * sizeof(dlt_iekf_iter);
     DLT_RT(h, rt::d2h((char *)h->h_iekf + lo, (const char *)&h->d_iekf->b + lo, hi - lo, h->stream));
+    if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     std::memcpy((char *)blk + lo, (const char *)h->h_iekf + lo, hi - lo);
+    if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in this update)");
     if (graph_run) {  // kernels the graph actually ran: one residual pass per iteration, two kNN kernels per match pass
         int n_match = 0;
         for (int k = 0; k < blk->n_iters && k < DLT_IEKF_MAX_ITER; k++) n_match += blk->iters[k].did_match ? 1 : 0;
@@ -1230,7 +1247,9 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
     int rc = dlt_measure_dev(h, pose24, do_match, h->d_result);
     if (rc) return rc;
     DLT_RT(h, rt::d2h(h->h_result, h->d_result, kFetchDoubles * sizeof(double), h->stream));
+    if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
+    if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in this evaluation)");
     const double *R = h->h_result;
     if (int rn = adopt_n_down(h, R)) return rn;
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
@@ -1357,7 +1376,8 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     if (!h || !pose24) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental before a scan");
     const bool sharded = h->map.shard_count > 1;
-    if (sharded && !h->shard_reduce) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental on a sharded map needs dlt_set_shard_reduce");
+    if (sharded && !h->shard_reduce && !h->peer_on)
+        DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental on a sharded map needs dlt_peer_attach or dlt_set_shard_reduce");
     rt::set_device(h->cfg.device);
     if (int rn = resolve_n_down(h)) return rn;
     const int n = h->n_down;
@@ -1388,9 +1408,15 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     }
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
                (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
-               LoopArgs{nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
+               LoopArgs{nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull, nullptr}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
                (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key, fi);
-    if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
+    if (sharded && h->have_match && h->peer_on) {  // owners store their decisions straight into every rank's mailbox
+        const unsigned long long seq = ++h->peer_dec_seq;
+        DLT_LAUNCH(k_incr_push, div_up(n, 256), 256, h->stream, h->d_peer, seq, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
+                   (const unsigned char *)h->knn.flags, n, (unsigned char)kFlagForeign);
+        DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
+        DLT_LAUNCH(k_incr_pull, div_up(n, 256), 256, h->stream, h->d_peer, seq, n, h->d_dsflag, h->d_addflag, h->d_counters + 6);
+    } else if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
                                      // (without a match pass every rank already agrees: all points are PointToAdd)
         DLT_LAUNCH(k_incr_pack, div_up(n, 256), 256, h->stream, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag, n, h->d_flagbuf);
         DLT_RT(h, rt::check_launch());
@@ -1401,7 +1427,9 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     int rc = insert_points(h, h->d_pw, n, true, InsertGate{nullptr, nullptr}, fi.on ? &fi.sc : nullptr);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
+    if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
     rc = map_check_error(h);  // reads the 8 counters back
+    if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in map_incremental)");
     if (n_ds) *n_ds = h->h_ints[6];
     if (n_raw) *n_raw = h->h_ints[7];
     return rc;
@@ -1413,6 +1441,103 @@ int dlt_set_shard_reduce(dlt_handle h, dlt_reduce_fn reduce, void *ctx) {
     if (!h) return DLT_E_INVALID;
     h->shard_reduce = reduce;
     h->shard_reduce_ctx = ctx;
+    return DLT_OK;
+}
+
+// ------------------------------------------------------------------ peer mailboxes (sharded map over NVLink peer memory)
+int dlt_peer_export(dlt_handle h, unsigned char *blob) {
+    if (!h || !blob) return DLT_E_INVALID;
+    if (h->cfg.shard_count < 2 || h->cfg.shard_count > DLT_MAX_PEERS) DLT_FAIL(h, DLT_E_STATE, "dlt_peer_export needs 2 <= shard_count <= DLT_MAX_PEERS");
+    rt::set_device(h->cfg.device);
+    if (!h->peer_box) {
+        const size_t dec_cap = ((size_t)h->cfg.max_scan_points + 127) & ~(size_t)127;
+        h->peer_bytes = sizeof(PeerBox) + 2 * dec_cap;
+        void *p = nullptr;
+        if (rt::shared_alloc(&p, h->peer_bytes, &h->peer_blob) != 0) DLT_FAIL(h, DLT_E_CUDA, "peer mailbox allocation failed");
+        h->peer_box = (PeerBox *)p;  // zeroed: sequence numbers start at 1, so early posts of a fast peer are never mistaken
+    }
+    static_assert(sizeof(rt::ShareBlob) == DLT_PEER_BLOB_BYTES, "blob size");
+    std::memcpy(blob, &h->peer_blob, sizeof(h->peer_blob));
+    return DLT_OK;
+}
+
+int dlt_peer_detach(dlt_handle h) {
+    if (!h) return DLT_E_INVALID;
+    if (!h->peer_on) return DLT_OK;
+    rt::set_device(h->cfg.device);
+    rt::sync(h->stream);
+    for (int r = 0; r < DLT_MAX_PEERS; r++) {
+        if (h->peer_maps[r]) rt::shared_close(h->peer_maps[r], h->peer_map_bytes[r]);
+        h->peer_maps[r] = nullptr;
+    }
+    h->peer_on = false;
+    h->peer_dec_seq = ~0ull;  // the mailbox keeps the old sequence numbers: no second attach on this handle
+    return DLT_OK;
+}
+
+int dlt_peer_attach(dlt_handle h, const unsigned char *blobs) {
+    if (!h || !blobs) return DLT_E_INVALID;
+    if (!h->peer_box) DLT_FAIL(h, DLT_E_STATE, "dlt_peer_attach before dlt_peer_export");
+    if (h->peer_on || h->peer_dec_seq == ~0ull) DLT_FAIL(h, DLT_E_STATE, "peers are already attached or were detached (attach once per handle)");
+    rt::set_device(h->cfg.device);
+    h->err.clear();
+    const int W = h->cfg.shard_count, me = h->cfg.shard_rank;
+    PeerComm pc;
+    std::memset(&pc, 0, sizeof(pc));
+    pc.world = W;
+    pc.rank = me;
+    pc.dec_cap = (int)((h->peer_bytes - sizeof(PeerBox)) / 2);
+    bool ok = true;
+    for (int r = 0; r < W && ok; r++) {
+        rt::ShareBlob b;
+        std::memcpy(&b, blobs + (size_t)r * DLT_PEER_BLOB_BYTES, sizeof(b));
+        if (r == me) {
+            if (b.ptr != h->peer_blob.ptr || b.pid != h->peer_blob.pid) {
+                h->err = "blob of this rank is not the one dlt_peer_export produced (blobs must be in rank order)";
+                ok = false;
+            }
+            pc.box[r] = h->peer_box;
+            continue;
+        }
+        if (b.magic != rt::kShareMagic) {
+            h->err = "cannot map a peer's mailbox: not a dlt_peer_export blob";
+            ok = false;
+            break;
+        }
+        if (b.bytes != h->peer_bytes) {
+            h->err = "peer mailbox size differs (max_scan_points must be the same on every rank)";
+            ok = false;
+            break;
+        }
+        void *p = nullptr;
+        bool mapped = false;
+        if (rt::shared_open(&b, h->cfg.device, &p, &mapped) != 0) {
+            h->err = "cannot map a peer's mailbox (CUDA IPC / peer access unavailable between these devices)";
+            ok = false;
+            break;
+        }
+        if (mapped) {
+            h->peer_maps[r] = p;
+            h->peer_map_bytes[r] = (size_t)b.bytes;
+        }
+        pc.box[r] = (PeerBox *)p;
+    }
+    if (ok && !h->d_peer) ok = rt::alloc((void **)&h->d_peer, sizeof(PeerComm)) == 0;
+    if (ok && !h->h_peer_status) ok = rt::pinned_alloc((void **)&h->h_peer_status, 64) == 0;
+    if (ok) {
+        *h->h_peer_status = 0;
+        ok = rt::h2d(h->d_peer, &pc, sizeof(pc), h->stream) == 0 && rt::sync(h->stream) == 0;
+    }
+    if (!ok) {
+        for (int r = 0; r < DLT_MAX_PEERS; r++) {
+            if (h->peer_maps[r]) rt::shared_close(h->peer_maps[r], h->peer_map_bytes[r]);
+            h->peer_maps[r] = nullptr;
+        }
+        if (h->err.empty()) h->err = "dlt_peer_attach failed";
+        return DLT_E_CUDA;
+    }
+    h->peer_dec_seq = 0;
+    h->peer_on = true;
     return DLT_OK;
 }
 

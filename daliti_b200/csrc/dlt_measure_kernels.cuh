@@ -17,6 +17,7 @@
 #include "../../include/daliti_b200.h"
 #include "dlt_common.cuh"
 #include "dlt_map_kernels.cuh"
+#include "dlt_peer.cuh"
 
 namespace dlt {
 
@@ -46,6 +47,9 @@ struct LoopArgs {
     // conditions from the device (cudaGraphSetConditional), so iterations that do not run are never launched.
     int use_cond;
     unsigned long long cond_while, cond_match;
+    // sharded map with attached peers (dlt_peer_attach): the last block of k_residual sums the partial normal equations over
+    // the ranks through the peer mailboxes (dlt_peer.cuh) before the solve step -- no collective launch in between
+    PeerComm *peer;
 };
 // Block-wide: resolve (n, do_match, pose) for this launch; false = nothing to do.  The pose ends
 // up in shared memory either way so that both paths run the same code.
@@ -1504,6 +1508,10 @@ __global__ void __launch_bounds__(kResidBlock)
         R[159] = (la.vox_ptr && *la.vox_ptr == 2) ? -1.0 : (double)n;  // feats_down_size (-1: VoxelGrid capacity exceeded)
         *mb.ticket = 0u;
         *mb.unres_count = 0;
+    }
+    if (la.peer && !peer_allreduce_block(la.peer, R, kNormalEqDoubles)) {  // block-uniform; starts and ends with a barrier
+        if (la.ctl && threadIdx.x == 0) const_cast<IekfDev *>(la.ctl)->b.done = 1;  // a peer never posted: end the loop, the host reports it
+        return;
     }
     if (la.ctl && la.fuse_step) {  // block-uniform: the solve / control step of this iteration, no launch in between
         __syncthreads();           // the block's own global writes to R are visible to it after the barrier

@@ -7,6 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
+#if defined(DLT_EMU)
+#include <fcntl.h>
+#include <sys/mman.h>
+#endif
 
 #include "dlt_common.cuh"
 
@@ -58,6 +63,69 @@ inline int device_count() { return 1; }
 inline int sm_count() { return 4; }
 inline const char *last_error() { return "emu"; }
 inline int check_launch() { return 0; }
+
+// ---- memory shared with peer processes (dlt_peer_*): POSIX shared memory stands in for CUDA IPC
+struct ShareBlob {  // what dlt_peer_export hands out (DLT_PEER_BLOB_BYTES)
+    unsigned long long magic;
+    long long pid;
+    unsigned long long ptr;
+    unsigned long long bytes;
+    int device;
+    int pad;
+    char ipc[64];  // cudaIpcMemHandle_t | shm object name
+    char pad2[24];
+};
+static_assert(sizeof(ShareBlob) == 128, "blob size is part of the ABI");
+constexpr unsigned long long kShareMagic = 0x444C545045455231ull;  // "DLTPEER1"
+inline int shared_alloc(void **p, size_t bytes, ShareBlob *blob) {
+    static std::atomic<int> counter{0};
+    std::memset(blob, 0, sizeof(*blob));
+    std::snprintf(blob->ipc, sizeof(blob->ipc), "/dlt_peer_%ld_%d", (long)getpid(), counter.fetch_add(1));
+    int fd = shm_open(blob->ipc, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return 1;
+    if (ftruncate(fd, (off_t)bytes) != 0) {
+        close(fd);
+        shm_unlink(blob->ipc);
+        return 1;
+    }
+    void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) {
+        shm_unlink(blob->ipc);
+        return 1;
+    }
+    std::memset(m, 0, bytes);
+    *p = m;
+    blob->magic = kShareMagic;
+    blob->pid = (long long)getpid();
+    blob->ptr = (unsigned long long)(uintptr_t)m;
+    blob->bytes = bytes;
+    return 0;
+}
+inline void shared_release(void *p, size_t bytes, const ShareBlob *blob) {
+    if (p) munmap(p, bytes);
+    if (blob->magic == kShareMagic) shm_unlink(blob->ipc);
+}
+// *mapped: the pointer must be handed back to shared_close
+inline int shared_open(const ShareBlob *blob, int /*my_device*/, void **p, bool *mapped) {
+    *mapped = false;
+    if (blob->magic != kShareMagic) return 1;
+    if (blob->pid == (long long)getpid()) {
+        *p = (void *)(uintptr_t)blob->ptr;
+        return 0;
+    }
+    int fd = shm_open(blob->ipc, O_RDWR, 0600);
+    if (fd < 0) return 1;
+    void *m = mmap(nullptr, (size_t)blob->bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return 1;
+    *p = m;
+    *mapped = true;
+    return 0;
+}
+inline void shared_close(void *p, size_t bytes) {
+    if (p) munmap(p, bytes);
+}
 }  // namespace rt
 }  // namespace dlt
 
@@ -120,6 +188,69 @@ inline int sm_count() {
 }
 inline const char *last_error() { return cudaGetErrorString(cudaPeekAtLastError()); }
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? 0 : 1; }
+
+// ---- memory shared with peer processes (dlt_peer_*): CUDA IPC across processes, peer access inside one
+struct ShareBlob {  // what dlt_peer_export hands out (DLT_PEER_BLOB_BYTES)
+    unsigned long long magic;
+    long long pid;
+    unsigned long long ptr;
+    unsigned long long bytes;
+    int device;
+    int pad;
+    char ipc[64];  // cudaIpcMemHandle_t
+    char pad2[24];
+};
+static_assert(sizeof(ShareBlob) == 128, "blob size is part of the ABI");
+static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle fits the blob");
+constexpr unsigned long long kShareMagic = 0x444C545045455231ull;  // "DLTPEER1"
+inline int shared_alloc(void **p, size_t bytes, ShareBlob *blob) {
+    std::memset(blob, 0, sizeof(*blob));
+    if (cudaMalloc(p, bytes) != cudaSuccess) return 1;
+    if (cudaMemset(*p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return 1;
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, *p) != cudaSuccess) {
+        cudaGetLastError();
+        std::memset(&hd, 0, sizeof(hd));  // same-process peers still work through the raw pointer
+    }
+    std::memcpy(blob->ipc, &hd, sizeof(hd));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    blob->magic = kShareMagic;
+    blob->pid = (long long)getpid();
+    blob->ptr = (unsigned long long)(uintptr_t)*p;
+    blob->bytes = bytes;
+    blob->device = dev;
+    return 0;
+}
+inline void shared_release(void *p, size_t, const ShareBlob *) {
+    if (p) cudaFree(p);
+}
+inline int shared_open(const ShareBlob *blob, int my_device, void **p, bool *mapped) {
+    *mapped = false;
+    if (blob->magic != kShareMagic) return 1;
+    if (blob->pid == (long long)getpid()) {  // same process: the allocation is addressable once peer access is on
+        if (blob->device != my_device) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, my_device, blob->device) != cudaSuccess || !can) return 1;
+            cudaError_t e = cudaDeviceEnablePeerAccess(blob->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return 1;
+            cudaGetLastError();
+        }
+        *p = (void *)(uintptr_t)blob->ptr;
+        return 0;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, blob->ipc, sizeof(hd));
+    if (cudaIpcOpenMemHandle(p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    *mapped = true;
+    return 0;
+}
+inline void shared_close(void *p, size_t) {
+    if (p) cudaIpcCloseMemHandle(p);
+}
 }  // namespace rt
 }  // namespace dlt
 

@@ -595,13 +595,13 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     // -1 (default) = by measurement: the host loop for a single-GPU map (same latency as the device loop within noise, fewer
     // launches per scan: +46 % aggregate scans/s when many sequences share a GPU), the device loop for a sharded map (the
     // all-reduce then stays in-stream and the host synchronises twice per scan instead of once per iteration)
-    const int loop_mode = cfg.device_loop >= 0 ? cfg.device_loop : (reduce_fn ? 2 : 0);
+    const int loop_mode = cfg.device_loop >= 0 ? cfg.device_loop : ((reduce_fn || peers) ? 2 : 0);
     const bool device_loop = loop_mode != 0 && map_built && NUM_MAX_ITERATIONS >= 1 && NUM_MAX_ITERATIONS <= DLT_IEKF_MAX_ITER;
     t0 = wall();
     int feats_down_size = 0;
     // (with a map in place nobody needs feats_down_size on the host before the first evaluation of the measurement model
     // has come back, which brings it along: no synchronisation is spent on the VoxelGrid)
-    if (device_loop || (map_built && !reduce_fn))
+    if (device_loop || (map_built && (!reduce_fn || peers)))
         LM_CK(dlt_scan_downsample_async(dev_));
     else
         LM_CK(dlt_scan_downsample(dev_, &feats_down_size));  // :775-778
@@ -666,7 +666,8 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         B.queue_len = (int)effct_q.size();
         for (int i = 0; i < 10; i++) B.effct_queue[i] = i < B.queue_len ? effct_q[i] : 0;
         B.flg_EKF_inited = flg_EKF_inited ? 1 : 0;
-        LM_CK(dlt_iekf_update(dev_, &B, reduce_fn ? &LaserMapping::reduce_trampoline : nullptr, this, reduce_fn ? reduce_buf_dev : nullptr));
+        const bool use_cb = reduce_fn && !peers;  // (with peer mailboxes the sum over the ranks happens inside k_residual)
+        LM_CK(dlt_iekf_update(dev_, &B, use_cb ? &LaserMapping::reduce_trampoline : nullptr, this, use_cb ? reduce_buf_dev : nullptr));
         // mirror the device's bookkeeping back into the host members
         state.from_flat(B.state);
         last_nodegared_state.from_flat(B.last_nodegared);
@@ -717,7 +718,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         } else {
             zeta_blend(effct_feat_num, state_propagat, th);
         }
-        if (B.insert_status == 0 && !EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn)) {  // not armed on the device (sharded map)
+        if (B.insert_status == 0 && !EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn || peers)) {  // not armed on the device (sharded map)
             double pose[24];
             state.pose24(pose);
             LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
@@ -754,7 +755,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
             rec.iter = iterCount;
             rec.did_match = (iterCount == 0 || rematch_en) ? 1 : 0;  // :847
             state.pose24(rec.pose_in);
-            if (reduce_fn) {  // sharded map: partial sums of this rank -> all-reduce -> host
+            if (reduce_fn && !peers) {  // sharded map: partial sums of this rank -> all-reduce -> host
                 LM_CK(dlt_measure_dev(dev_, rec.pose_in, rec.did_match, reduce_buf_dev));
                 if (reduce_fn(reduce_ctx, reduce_buf_dev, 158) != 0) {
                     err = "reduce callback failed";
@@ -870,7 +871,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
 
         // ---- map_incremental(), :1164-1168
         t0 = wall();
-        if (!EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn)) {
+        if (!EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn || peers)) {
             double pose[24];
             state.pose24(pose);
             LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
@@ -1028,6 +1029,24 @@ int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *r
     h->lm->reduce_buf_dev = result_dev;
     // the same sum over the ranks also carries the per-point map_incremental decisions of a sharded map
     return dlt_set_shard_reduce(h->lm->dev_, reduce ? &dlt_host::LaserMapping::reduce_trampoline : nullptr, h->lm);
+}
+int dlt_lio_peer_export(dlt_lio h, unsigned char *blob) {
+    if (!h) return DLT_E_INVALID;
+    int rc = dlt_peer_export(h->lm->dev_, blob);
+    if (rc) h->lm->err = dlt_last_error(h->lm->dev_);
+    return rc;
+}
+int dlt_lio_peer_attach(dlt_lio h, const unsigned char *blobs) {
+    if (!h) return DLT_E_INVALID;
+    int rc = dlt_peer_attach(h->lm->dev_, blobs);
+    if (rc) h->lm->err = dlt_last_error(h->lm->dev_);
+    h->lm->peers = rc == 0;
+    return rc;
+}
+int dlt_lio_peer_detach(dlt_lio h) {
+    if (!h) return DLT_E_INVALID;
+    h->lm->peers = false;
+    return dlt_peer_detach(h->lm->dev_);
 }
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap) {
     if (!h) return DLT_E_INVALID;

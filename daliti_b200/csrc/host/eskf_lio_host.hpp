@@ -173,6 +173,7 @@ class LaserMapping {
     dlt_lio_reduce_fn reduce_fn = nullptr;  // sharded map: sums the partial normal equations over the ranks
     void *reduce_ctx = nullptr;
     double *reduce_buf_dev = nullptr;
+    bool peers = false;  // dlt_lio_peer_attach: the sums over the ranks happen inside the kernels (peer mailboxes), no callback
     ImuProcess imu_;
     StatesGroup state, last_nodegared_state, last_state;
     std::vector<dlt_lio_iter> iters;

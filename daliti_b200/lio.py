@@ -59,6 +59,7 @@ _LIO_SYMBOLS = [
     "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
     "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
     "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_process_cloud", "dlt_lio_prefetch_scan", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
+    "dlt_lio_peer_export", "dlt_lio_peer_attach", "dlt_lio_peer_detach",
 ]
 
 
@@ -230,6 +231,23 @@ class LaserMapping:
 
         self._red_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)(_cb)
         self._ck(self.lib.dlt_lio_set_reduce(self.h, self._red_cb, None, None))
+
+    def peer_export(self) -> bytes:
+        from .binding import PEER_BLOB_BYTES
+
+        blob = (C.c_ubyte * PEER_BLOB_BYTES)()
+        self._ck(self.lib.dlt_lio_peer_export(self.h, blob))
+        return bytes(blob)
+
+    def peer_attach(self, blobs):
+        """Sharded map over NVLink peer memory: blobs = peer_export() of all dev.shard_count ranks in rank order.  Afterwards
+        the sums over the ranks happen inside the kernels (no reduce callback, no collective launch)."""
+        raw = b"".join(blobs)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._ck(self.lib.dlt_lio_peer_attach(self.h, buf))
+
+    def peer_detach(self):
+        self._ck(self.lib.dlt_lio_peer_detach(self.h))
 
     def iters(self):
         n = self.out.n_iters

@@ -37,3 +37,31 @@ def allreduce_measure(handle, pose24, do_match: bool, device: str = "cuda", buf=
             dist.all_reduce(buf[:N_EQ], op=dist.ReduceOp.SUM)
         r = buf[:N_EQ].cpu().numpy()
     return dict(HtH=r[:144].reshape(12, 12).copy(), Htr=r[144:156].copy(), effct_feat_num=int(round(r[156])), total_residual=float(r[157]))
+
+
+def attach_peers(obj):
+    """Collective: exchange the peer-mailbox blobs of all ranks over torch.distributed (any backend -- it is 128 bytes per
+    rank, once) and attach them, so that from here on the sums over the ranks run inside the kernels over NVLink peer
+    memory (dlt_peer_attach) and torch.distributed is no longer on the data path.  obj: ScanToMap or LaserMapping of this
+    rank (shard_rank == dist rank, shard_count == world size).  Returns True when attached on EVERY rank; False (nothing
+    attached anywhere) when some rank could not map a peer -- the caller then stays on the all-reduce callback."""
+    import torch.distributed as dist
+
+    from .binding import DltError
+
+    world = dist.get_world_size()
+    blobs = [None] * world
+    dist.all_gather_object(blobs, obj.peer_export())
+    # every rank first checks that it CAN map its peers before anybody switches over: a half-attached job would wait forever
+    ok = True
+    try:
+        obj.peer_attach(blobs)
+    except DltError:
+        ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if all(oks):
+        return True
+    if ok:
+        obj.peer_detach()
+    return False

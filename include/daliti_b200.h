@@ -240,6 +240,23 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
  * Unresolved far points are classified against this rank's tiles + halo only.                               */
 int dlt_set_shard_reduce(dlt_handle h, dlt_reduce_fn reduce, void *ctx);
 
+/* ---- sharded map: exchange over NVLink peer memory instead of the callbacks above (no reference counterpart) -- */
+/* Every rank owns a mailbox in its HBM; peers store their partial normal equations / map_incremental decisions
+ * straight into it from inside k_residual / k_incr_push and the receiving kernels add them up in rank order
+ * (daliti_b200/csrc/dlt_peer.cuh), so the per-iteration all-reduce costs no launch and no library call.
+ *   1. every rank: dlt_peer_export -> a DLT_PEER_BLOB_BYTES blob (CUDA IPC handle of the mailbox)
+ *   2. the application gathers the blobs of all shard_count ranks in rank order (MPI, torch.distributed, a file ...)
+ *   3. every rank: dlt_peer_attach(blobs).  From then on dlt_iekf_update ignores its reduce callback, dlt_measure /
+ *      dlt_measure_dev return sums over the ranks, and dlt_map_incremental needs no dlt_set_shard_reduce.
+ * Every rank must make the same sequence of these calls (they are collective).  A peer that never shows up makes
+ * the waiting kernel give up after 5 s and the call return DLT_E_STATE; it does not hang the device.
+ * Ranks may be processes (one per GPU) or handles on different devices of one process.  shard_count <= DLT_MAX_PEERS. */
+#define DLT_MAX_PEERS 8
+#define DLT_PEER_BLOB_BYTES 128
+int dlt_peer_export(dlt_handle h, unsigned char *blob /* DLT_PEER_BLOB_BYTES */);
+int dlt_peer_attach(dlt_handle h, const unsigned char *blobs /* shard_count x DLT_PEER_BLOB_BYTES, rank order */);
+int dlt_peer_detach(dlt_handle h);
+
 /* ---- instrumentation (no reference counterpart) ---------------------------------------------- */
 /* Per-kernel-group device time from CUDA events on the launching stream.  Groups: 0 k_knn,
  * 1 k_residual, 2 deskew, 3 VoxelGrid, 4 map insert, 5 exact-neighbour fallback, 6 k_iekf_step, 7 k_knn8 alone (inside group 0).      */

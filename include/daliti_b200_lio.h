@@ -115,6 +115,13 @@ int dlt_lio_process_cloud(dlt_lio h, const void *cloud_data, int n_points, const
  * not one of its own): the owner of a query decides, every rank inserts into its tiles + halo.                     */
 typedef int (*dlt_lio_reduce_fn)(void *ctx, double *result_dev, int n);
 int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *result_dev /* NULL: the handle's own buffer */);
+/* The same sums over NVLink peer memory, from inside the kernels, instead of a callback (dlt_peer_export / dlt_peer_attach
+ * in daliti_b200.h): every rank exports a DLT_PEER_BLOB_BYTES blob, the node gathers the blobs of all dev.shard_count ranks in
+ * rank order and hands them to dlt_lio_peer_attach on every rank.  Afterwards no reduce callback is needed (one that is set
+ * is ignored); the per-iteration sum costs no launch and no host involvement.                                           */
+int dlt_lio_peer_export(dlt_lio h, unsigned char *blob);
+int dlt_lio_peer_attach(dlt_lio h, const unsigned char *blobs);
+int dlt_lio_peer_detach(dlt_lio h); /* back to the callback; a handle attaches at most once */
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap);
 /* IMUpose list of the last scan's forward propagation (22 doubles each)                          */
 int dlt_lio_get_imu_poses(dlt_lio h, double *pose22, int cap);

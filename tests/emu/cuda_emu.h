@@ -81,6 +81,7 @@ static inline void __syncthreads() { emu::block_sync(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_collective(5, mask, 0, 0, 32); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void __threadfence_system() { __sync_synchronize(); }  // (peer mailboxes are shared memory between emulator processes)
 
 namespace emu {
 template <typename T>

@@ -153,17 +153,21 @@ def _tile_owner(xyz, shards, ds=0.5, cell_shift=1, tile_shift=3):
     return ((k & np.uint64(0xFFFFFFFF)) % np.uint64(shards)).astype(np.int64)
 
 
-def _run_lio(lib, rank, world, n_scans=3):
+def _run_lio(lib, rank, world, n_scans=3, peers=False, device_loop=-1, device=0):
     from daliti_b200.lio import LaserMapping
 
     seq = helpers.small_sequence(seed=22, half=30.0, beams=16, azimuths=240, n_boxes=8)
     map_pts = synth.sample_map(seq.scene, seed=22)
-    lm = LaserMapping(lib, dev=dict(max_scan_points=8192, max_map_points=1 << 17, shard_rank=rank, shard_count=world, shard_tile_shift=3),
-                      featptsThreshold=5)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=8192, max_map_points=1 << 17, shard_rank=rank, shard_count=world, shard_tile_shift=3, device=device),
+                      featptsThreshold=5, device_loop=device_loop)
     lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
     lm.set_state(helpers.state612(seq.traj, seq.t_start))
     lm.device.map_build(map_pts)
-    if world > 1:
+    if world > 1 and peers:  # sums over the ranks inside the kernels, through the peer mailboxes; no callback at all
+        from daliti_b200.sharded import attach_peers
+
+        assert attach_peers(lm)
+    elif world > 1:
         lm.set_allreduce("cpu")
     states = []
     for k in range(n_scans):
@@ -178,7 +182,7 @@ def _run_lio(lib, rank, world, n_scans=3):
     return states
 
 
-def _lio_worker_all(rank, world, port, q):
+def _lio_worker_all(rank, world, port, q, peers=False, device_loop=-1, gpu=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -186,24 +190,30 @@ def _lio_worker_all(rank, world, port, q):
 
     from daliti_b200.binding import load_library
 
+    # (gloo only carries the 128-byte mailbox blobs, once; on GPUs the data path is NVLink peer memory)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lib = load_library(os.path.join(ROOT, "tests", "emu", "libdaliti_emu.so"))
-    states = _run_lio(lib, rank, world)
+    lib = load_library() if gpu else load_library(os.path.join(ROOT, "tests", "emu", "libdaliti_emu.so"))
+    states = _run_lio(lib, rank, world, peers=peers, device_loop=device_loop, device=rank if gpu else 0)
     q.put((rank, states))
     dist.destroy_process_group()
 
 
-def test_sharded_per_scan_update_two_processes(emu_lib):
-    """the full per-scan update on a 2-way sharded map -- all-reduce of the normal equations every iteration inside the
-    device-resident loop, replicated 24-state solve, map_incremental with the owners' decisions exchanged -- follows the
+@pytest.mark.parametrize("mode", ["callback", "peers", "peers_host_loop"])
+def test_sharded_per_scan_update_two_processes(emu_lib, mode):
+    """the full per-scan update on a 2-way sharded map -- sum of the normal equations over the ranks every iteration inside
+    the device-resident loop, replicated 24-state solve, map_incremental with the owners' decisions exchanged -- follows the
     unsharded update: effective counts exact, states to fp64 rounding, and the union of the owned tiles holds exactly
-    the unsharded map after every scan."""
+    the unsharded map after every scan.  callback: the sums go through the reduce callback (gloo here, NCCL on GPUs);
+    peers: through the peer mailboxes from inside k_residual / k_incr_push (shared memory between the two emulator
+    processes here, NVLink peer memory on GPUs), with the solve step fused behind the exchange; peers_host_loop: the same
+    with one dlt_measure round trip per iteration."""
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q)) for r in range(2)]
+    port = 31500 + (os.getpid() % 2000) + {"callback": 0, "peers": 1, "peers_host_loop": 2}[mode]
+    peers = mode != "callback"
+    procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, peers, 0 if mode == "peers_host_loop" else -1)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(2))
@@ -211,6 +221,10 @@ def test_sharded_per_scan_update_two_processes(emu_lib):
         p.join(timeout=120)
         assert p.exitcode == 0
     ref = _run_lio(emu_lib, 0, 1)
+    _check_sharded_against_unsharded(got, ref, bitwise_ranks=peers)
+
+
+def _check_sharded_against_unsharded(got, ref, bitwise_ranks):
     for k in range(len(ref)):
         st, eff, n_it, added, pts = ref[k]
         for r in range(2):
@@ -218,6 +232,8 @@ def test_sharded_per_scan_update_two_processes(emu_lib):
             assert n_it_r == n_it and eff_r == eff, (k, r)
             assert added_r == added, (k, r, added_r, added)
             np.testing.assert_allclose(st_r, st, rtol=1e-8, atol=1e-8, err_msg=f"scan {k} rank {r}")
+        if bitwise_ranks:  # the mailboxes are added up in rank order on every rank: the replicated solves see the same bits
+            assert np.array_equal(got[0][k][0], got[1][k][0]), k
         # the sharded run's poses differ from the unsharded ones by the summation order of the partial normal equations
         # (~1e-10), so inserted points may differ in their last float32 bit: match point for point within 1e-5 m
         from scipy.spatial import cKDTree
@@ -228,3 +244,76 @@ def test_sharded_per_scan_update_two_processes(emu_lib):
         assert d.max() < 1e-5, (k, d.max())
         assert len(np.unique(idx)) == len(pts)  # a bijection: no tile is held twice, none is missing
         np.testing.assert_allclose(owned[:, 3], pts[idx, 3], rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["peers", "peers_host_loop"])
+def test_sharded_per_scan_update_two_gpus_peer_memory(gpu_lib, mode):
+    """the same on two B200s, one process per GPU: mailboxes in HBM mapped into the peer process by CUDA IPC, the partial
+    normal equations and the map_incremental decisions stored over NVLink from inside the kernels -- no NCCL, no callback."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + (1 if mode == "peers" else 2)
+    procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, True, 0 if mode == "peers_host_loop" else -1, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = _run_lio(gpu_lib, 0, 1)
+    _check_sharded_against_unsharded(got, ref, bitwise_ranks=True)
+
+
+def test_peer_exchange_times_out_instead_of_hanging(dev):
+    """a rank whose peer never takes part gives up after 5 s and reports it; the device is not left spinning"""
+    import time
+
+    from daliti_b200.binding import DltError
+
+    lib, is_gpu = dev
+    seq, map_pts, pts = scene_scan()
+    down = downsample_body(lib, pts)
+    hs = [ScanToMap(lib, max_scan_points=8192, max_map_points=1 << 17, shard_rank=r, shard_count=2, shard_tile_shift=3) for r in range(2)]
+    blobs = [h.peer_export() for h in hs]
+    for h in hs:
+        h.map_build(map_pts)
+        h.peer_attach(blobs)  # same process: the mailboxes are addressed directly
+    with pytest.raises(DltError, match="attached"):
+        hs[0].peer_attach(blobs)
+    hs[0].scan_set_down(down)
+    t0 = time.time()
+    with pytest.raises(DltError, match="timed out"):
+        hs[0].measure(seq.traj.pose24(0.1), True)  # rank 1 never calls
+    assert 4.0 < time.time() - t0 < 30.0
+    for h in hs:
+        h.close()
+
+
+def test_peer_attach_argument_errors(dev):
+    from daliti_b200.binding import DltError
+
+    lib, is_gpu = dev
+    one = ScanToMap(lib, max_scan_points=4096, max_map_points=4096)
+    with pytest.raises(DltError):
+        one.peer_export()  # not a sharded handle
+    one.close()
+    a = ScanToMap(lib, max_scan_points=4096, max_map_points=4096, shard_rank=0, shard_count=2, shard_tile_shift=3)
+    b = ScanToMap(lib, max_scan_points=8192, max_map_points=4096, shard_rank=1, shard_count=2, shard_tile_shift=3)
+    with pytest.raises(DltError, match="before dlt_peer_export"):
+        a.peer_attach([bytes(128), bytes(128)])
+    ba, bb = a.peer_export(), b.peer_export()
+    with pytest.raises(DltError, match="rank order"):
+        a.peer_attach([bb, ba])
+    with pytest.raises(DltError, match="size differs"):
+        a.peer_attach([ba, bb])  # max_scan_points differ
+    with pytest.raises(DltError, match="cannot map"):
+        a.peer_attach([ba, bytes(128)])
+    a.close()
+    b.close()
