@@ -198,6 +198,24 @@ def _lio_worker_all(rank, world, port, q, peers=False, device_loop=-1, gpu=False
     dist.destroy_process_group()
 
 
+def test_sharded_per_scan_update_four_processes_peers(emu_lib):
+    """four ranks on the peer mailboxes: every rank posts to three peers and adds four slots in rank order"""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_lio_worker_all, args=(r, 4, port, q, True, -1)) for r in range(4)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(4))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = _run_lio(emu_lib, 0, 1)
+    _check_sharded_against_unsharded(got, ref, bitwise_ranks=True)
+
+
 @pytest.mark.parametrize("mode", ["callback", "peers", "peers_host_loop"])
 def test_sharded_per_scan_update_two_processes(emu_lib, mode):
     """the full per-scan update on a 2-way sharded map -- sum of the normal equations over the ranks every iteration inside
@@ -227,18 +245,19 @@ def test_sharded_per_scan_update_two_processes(emu_lib, mode):
 def _check_sharded_against_unsharded(got, ref, bitwise_ranks):
     for k in range(len(ref)):
         st, eff, n_it, added, pts = ref[k]
-        for r in range(2):
+        for r in range(len(got)):
             st_r, eff_r, n_it_r, added_r, _ = got[r][k]
             assert n_it_r == n_it and eff_r == eff, (k, r)
             assert added_r == added, (k, r, added_r, added)
             np.testing.assert_allclose(st_r, st, rtol=1e-8, atol=1e-8, err_msg=f"scan {k} rank {r}")
         if bitwise_ranks:  # the mailboxes are added up in rank order on every rank: the replicated solves see the same bits
-            assert np.array_equal(got[0][k][0], got[1][k][0]), k
+            for r in range(1, len(got)):
+                assert np.array_equal(got[0][k][0], got[r][k][0]), (k, r)
         # the sharded run's poses differ from the unsharded ones by the summation order of the partial normal equations
         # (~1e-10), so inserted points may differ in their last float32 bit: match point for point within 1e-5 m
         from scipy.spatial import cKDTree
 
-        owned = np.concatenate([got[0][k][4], got[1][k][4]], 0)
+        owned = np.concatenate([got[r][k][4] for r in range(len(got))], 0)
         assert len(owned) == len(pts), (k, len(owned), len(pts))
         d, idx = cKDTree(pts[:, :3]).query(owned[:, :3])
         assert d.max() < 1e-5, (k, d.max())

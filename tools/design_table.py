@@ -30,10 +30,13 @@ def main(tag="v5"):
         if key == "c3":
             cpu = f"— ({d['config']['deleted_total']} points box-deleted, {d['config']['degenerate_scans']} / {d['steps']} scans flagged degenerate)"
         rows.append(f"| {label} | {d['ms_p50']:.3f} ms | {d['value'] / 1e6:.0f} M | {e2e} | {cpu} |")
-    for name, label in (("r01_bench_c4_n2_v4.json", "C4, 2 GPUs (sharded, NCCL all-reduce inside the device loop)"),):
+    for name, label in (("r01_bench_c4_n2_peer_v6.json", "C4, 2 GPUs (sharded, sums inside `k_residual` over NVLink peer mailboxes)"),
+                        ("r01_bench_c4_n2_nccl_v6.json", "C4, 2 GPUs (sharded, NCCL all-reduce between `k_residual` and `k_iekf_step`; same run)"),
+                        ("r01_bench_c4_n4_peer_v6.json", "C4, 4 GPUs (sharded, peer mailboxes)")):
         d = load(name)
         if d:
-            rows.append(f"| {label} | {d['ms_p50']:.3f} ms | {d['value'] / 1e6:.0f} M | {d['e2e']['ms_per_step']:.3f} ms / scan | — |")
+            p50 = f"{d['ms_p50']:.3f} ms" + (f" (mean {d['ms_per_step']:.3f})" if d["ms_per_step"] > 1.1 * d["ms_p50"] else "")
+            rows.append(f"| {label} | {p50} | {d['value'] / 1e6:.0f} M | {d['e2e']['ms_per_step']:.3f} ms / scan | — |")
     for name, label in ((f"r01_bench_c5_s1_{tag}.json", "C5, 1 sequence on one GPU"), (f"r01_bench_c5_s16_{tag}.json", "C5, 16 concurrent sequences on one GPU"), (f"r01_bench_c5_s64_{tag}.json", "C5, 64 concurrent sequences on one GPU"),
                         ("r01_bench_c5_n2_v4.json", "C5, 2 GPUs x 8 sequences (device-resident loop)")):
         d = load(name)
