@@ -117,3 +117,4 @@ def test_map_incremental_far_points_nearest_only(dev, oracle):
     map_pts = synth.sample_map(seq.scene, seed=3, region=(-8.0, 8.0, -8.0, 8.0))
     run_sequence(lib, oracle, seq, map_pts, 3, max_pts=32768 if is_gpu else 8192, read_nearest=False, featptsThreshold=5)
 
+
