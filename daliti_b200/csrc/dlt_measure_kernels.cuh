@@ -485,6 +485,16 @@ constexpr int kKnn8Block = DLT_KNN8_BLOCK;
 #define DLT_KNN8_MINBLOCKS 6
 #endif
 constexpr unsigned long long kKeyInf = (0x7F800000ull << 32) | 0x7FFFFFFFull;
+// Opt-in variant (default off: the committed profiles and bench lines are of the build without it; A/B with
+// tools/knn_variants.py).  A query is only finished here when d2[4] < thr = (cov - slack)^2 * 0.99999, cov = distance to the
+// faces of the 3^3 block.  So a candidate with d2 >= thr can never be one of the five winners of a FINISHED query, nor tie
+// with its fifth: it need not be kept, and a cell whose box distance is >= thr need not be probed at all.  Queries this
+// leaves without five candidates go to k_knn exactly as before (k_knn searches from scratch).  Result-identical by
+// construction; the emulator suite passes with it on.  On a surface it drops about half of the sorted inserts (the sphere
+// of radius cov against the 3 m block) and the corner / edge cells of queries that sit off-centre in their cell.
+#ifndef DLT_KNN8_PRUNE
+#define DLT_KNN8_PRUNE 0
+#endif
 
 DLT_D unsigned long long group8_min_u64(unsigned long long k) {
 #pragma unroll
@@ -517,11 +527,14 @@ DLT_D void topk_insert_key(unsigned long long (&b)[kK], unsigned long long k, un
 }
 // one staged bucket line: lane `sub` of the group holds 16 bytes of bucket bb (sub 0 = header)
 DLT_D void knn8_consume(const float4 v, int &bb, int lane, int sub, float qx, float qy, float qz, unsigned long long (&best)[kK],
-                        unsigned &dropped) {
+                        unsigned &dropped, float thr) {
     const int hdr_next = __shfl_sync(0xffffffffu, __float_as_int(v.z), lane & ~7);
     const unsigned hdr_mask = __shfl_sync(0xffffffffu, __float_as_uint(v.w), lane & ~7);
     if (bb >= 0 && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u)) {
         const float d2 = calc_dist(qx, qy, qz, v.x, v.y, v.z);
+#if DLT_KNN8_PRUNE
+        if (d2 < thr)
+#endif
         topk_insert_key(best, ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(unsigned)(bb * 8 + sub), dropped);
     }
     bb = (bb >= 0) ? hdr_next : -1;
@@ -559,11 +572,36 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
 #pragma unroll
     for (int t = 0; t < kK; t++) best[t] = kKeyInf;
     unsigned dropped = 0x7F800000u;
+    float thr = INFINITY;
+#if DLT_KNN8_PRUNE
+    const float slack_p = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
+    {  // the same expressions as the `resolved` test below
+        float cov = INFINITY;
+        cov = fminf(cov, qx - (float)(cx - 1) * cell_edge);
+        cov = fminf(cov, (float)(cx + 2) * cell_edge - qx);
+        cov = fminf(cov, qy - (float)(cy - 1) * cell_edge);
+        cov = fminf(cov, (float)(cy + 2) * cell_edge - qy);
+        cov = fminf(cov, qz - (float)(cz - 1) * cell_edge);
+        cov = fminf(cov, (float)(cz + 2) * cell_edge - qz);
+        cov -= slack_p;
+        thr = (cov > 0.f) ? cov * cov * 0.99999f : 0.f;
+    }
+#endif
 
     for (int r = 0; r < 4; r++) {
         const int ci = r * 8 + sub;
         int b = -1;
+#if DLT_KNN8_PRUNE
+        if (work && ci < 27) {
+            const int ox = (ci % 3) - 1, oy = ((ci / 3) % 3) - 1, oz = (ci / 9) - 1;
+            const float gx = axis_gap(qx, cx + ox, cell_edge, slack_p), gy = axis_gap(qy, cy + oy, cell_edge, slack_p),
+                        gz = axis_gap(qz, cz + oz, cell_edge, slack_p);
+            const float bd = gx * gx + gy * gy + gz * gz;  // every point of the cell is at least this far (conservatively)
+            if (!(bd * 0.99999f >= thr)) b = map_find(m, pack_key(cx + ox, cy + oy, cz + oz));
+        }
+#else
         if (work && ci < 27) b = map_find(m, pack_key(cx + (ci % 3) - 1, cy + ((ci / 3) % 3) - 1, cz + (ci / 9) - 1));
+#endif
         unsigned gb = (__ballot_sync(FULL, b >= 0) >> (grp * 8)) & 0xFFu;  // this group's found cells
         while (__any_sync(FULL, gb != 0u)) {                                // warp-uniform
             const int s0 = gb ? (__ffs((int)gb) - 1) : -1;
@@ -578,8 +616,8 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (bb0 >= 0) v0 = reinterpret_cast<const float4 *>(&m.buckets[bb0])[sub];  // 8 lanes x 16 B = one line
                 if (bb1 >= 0) v1 = reinterpret_cast<const float4 *>(&m.buckets[bb1])[sub];
-                knn8_consume(v0, bb0, lane, sub, qx, qy, qz, best, dropped);
-                knn8_consume(v1, bb1, lane, sub, qx, qy, qz, best, dropped);
+                knn8_consume(v0, bb0, lane, sub, qx, qy, qz, best, dropped, thr);
+                knn8_consume(v1, bb1, lane, sub, qx, qy, qz, best, dropped, thr);
             }
         }
     }

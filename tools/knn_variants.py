@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Times k_knn / k_residual of several builds of the library (gpurun_scratch/*.so) on the C2 workload.
+"""Times k_knn / k_residual of several builds of the library (gpurun_scratch/*.so; `make -C daliti_b200/csrc variants` builds the
+opt-in ones, e.g. DLT_KNN8_PRUNE) on the C2 workload.
 Development tool for choosing launch bounds / load batching; not a bench value."""
 import glob
 import os
