@@ -141,8 +141,51 @@ void StatesGroup::from_flat(const double *f) {
 }
 
 // ------------------------------------------------------------------ dense helpers
+// The two 24 x 24 systems of the Kalman update sit on the critical path of the host loop (the GPU idles while they are
+// solved), so the sizes the update uses get a fixed-size instance: compile-time bounds, a stack work area, and -- on
+// x86-64 -- an AVX2 clone picked at load time.  Same operations in the same order as the generic routine (no FMA: the
+// clone enables AVX2 only), so the results are bit-identical; 8 -> 2.6 us per solve on the build machine.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(DLT_NO_TARGET_CLONES)
+#define DLT_HOST_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define DLT_HOST_CLONES
+#endif
+
+// Gauss-Jordan on [A | I] with partial pivoting
+template <int N>
+__attribute__((always_inline)) static inline bool invert_fixed(const double *A, double *out) {
+    constexpr int W = 2 * N;
+    alignas(32) double w[N][W];
+    for (int i = 0; i < N; i++) {
+        for (int j = 0; j < N; j++) {
+            w[i][j] = A[i * N + j];
+            w[i][N + j] = (i == j) ? 1.0 : 0.0;
+        }
+    }
+    for (int c = 0; c < N; c++) {
+        int p = c;
+        for (int r = c + 1; r < N; r++)
+            if (std::fabs(w[r][c]) > std::fabs(w[p][c])) p = r;
+        if (w[p][c] == 0.0) return false;
+        if (p != c)
+            for (int j = 0; j < W; j++) std::swap(w[p][j], w[c][j]);
+        const double inv = 1.0 / w[c][c];
+        for (int j = 0; j < W; j++) w[c][j] *= inv;
+        for (int r = 0; r < N; r++) {
+            if (r == c) continue;
+            const double f = w[r][c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < W; j++) w[r][j] -= f * w[c][j];
+        }
+    }
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) out[i * N + j] = w[i][N + j];
+    return true;
+}
+DLT_HOST_CLONES static bool invert24(const double *A, double *out) { return invert_fixed<24>(A, out); }
+
 bool invert(const double *A, int n, double *out) {
-    // Gauss-Jordan on [A | I] with partial pivoting
+    if (n == 24) return invert24(A, out);
     std::vector<double> w((size_t)n * 2 * n);
     const int W = 2 * n;
     for (int i = 0; i < n; i++) {
@@ -173,7 +216,44 @@ bool invert(const double *A, int n, double *out) {
 }
 
 // X (n x m, row-major) = first m columns of A^-1, by LU with partial pivoting on [A | I[:, :m]]
+template <int N, int M>
+__attribute__((always_inline)) static inline bool solve_first_columns_fixed(const double *A, double *X) {
+    constexpr int W = N + M;
+    alignas(32) double w[N][W];
+    for (int i = 0; i < N; i++) {
+        for (int j = 0; j < N; j++) w[i][j] = A[i * N + j];
+        for (int j = 0; j < M; j++) w[i][N + j] = (i == j) ? 1.0 : 0.0;
+    }
+    for (int c = 0; c < N; c++) {
+        int p = c;
+        for (int r = c + 1; r < N; r++)
+            if (std::fabs(w[r][c]) > std::fabs(w[p][c])) p = r;
+        if (w[p][c] == 0.0) return false;
+        if (p != c)
+            for (int j = c; j < W; j++) std::swap(w[p][j], w[c][j]);
+        const double piv = w[c][c];
+        for (int r = c + 1; r < N; r++) {
+            const double f = w[r][c] / piv;
+            if (f == 0.0) continue;
+            for (int j = c + 1; j < W; j++) w[r][j] -= f * w[c][j];
+        }
+    }
+    for (int c = N - 1; c >= 0; c--) {  // all M right-hand sides side by side: per column the same k order as below
+        const double piv = w[c][c];
+        double s[M];
+        for (int j = 0; j < M; j++) s[j] = w[c][N + j];
+        for (int k = c + 1; k < N; k++) {
+            const double a = w[c][k];
+            for (int j = 0; j < M; j++) s[j] -= a * X[k * M + j];
+        }
+        for (int j = 0; j < M; j++) X[c * M + j] = s[j] / piv;
+    }
+    return true;
+}
+DLT_HOST_CLONES static bool solve_first_columns_24_12(const double *A, double *X) { return solve_first_columns_fixed<24, 12>(A, X); }
+
 bool solve_first_columns(const double *A, int n, int m, double *X) {
+    if (n == 24 && m == 12) return solve_first_columns_24_12(A, X);
     const int W = n + m;
     std::vector<double> w((size_t)n * W);
     for (int i = 0; i < n; i++) {
@@ -839,7 +919,14 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
                 rematch_num++;
             }
             if (rematch_num >= 2 || (iterCount == NUM_MAX_ITERATIONS - 1)) {  // :1078-1094
-                if (flg_EKF_inited && have_gain) {
+                // The reference's covariance update (:1084-1085) is DEAD: the zeta blend that always follows (:1119 / :1127) builds
+                // the new state with StatesGroup::operator+, which returns `this->cov` of last_state (common_lib.h:126, 142), and
+                // nothing reads state.cov in between.  It used to cost ~5 us of host time on the critical path (the GPU idle
+                // behind it); -DDLT_HOST_DEAD_COV_UPDATE=1 compiles it back in.  (k_iekf_step still evaluates it on the device.)
+#ifndef DLT_HOST_DEAD_COV_UPDATE
+#define DLT_HOST_DEAD_COV_UPDATE 0
+#endif
+                if (DLT_HOST_DEAD_COV_UPDATE && flg_EKF_inited && have_gain) {
                     // G[:, :12] = K H = K_1[:, :12] H^T H;  cov = (I - G) cov      :1084-1085
                     double G[kDim * 12], ncov[kDim * kDim];
                     for (int i = 0; i < kDim; i++)
