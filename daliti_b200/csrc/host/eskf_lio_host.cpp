@@ -346,7 +346,86 @@ void ImuProcess::IMU_Initial(const std::vector<ImuSample> &imu, StatesGroup &st,
     last_imu_ = imu.back();
 }
 
-void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_time, double pcl_end_time, StatesGroup &st, bool EKF_stop_flg) {
+// One IMU step of cov = F cov F^T + Q, IMU_Processing.hpp:262-288.  F = I + six 3x3 blocks, Q = five 3x3 diagonal blocks
+// (:270-286): the caller's F / Q buffers keep the fixed structure, only the block values are rewritten here.
+void ImuProcess::PropagateCovStep(const CovStep &step, StatesGroup &st, double *__restrict__ F, double *__restrict__ Q, double *__restrict__ FP) const {
+    const Vec3 &angvel_avr = step.angvel_avr, &acc_avr = step.acc_avr;
+    const Mat3 &R_imu = step.R_imu;
+    const double dt = step.dt;
+    set_block3(F, 0, 0, so3_exp_rate(angvel_avr, -dt));
+    set_block3(F, 0, 15, Mat3::identity() * (-dt));
+    set_block3(F, 3, 12, Mat3::identity() * dt);
+    set_block3(F, 12, 0, (R_imu * -1.0) * Mat3::hat(acc_avr) * dt);
+    set_block3(F, 12, 18, R_imu * (-dt));
+    set_block3(F, 12, 21, Mat3::identity() * dt);
+    Mat3 Ca, Cg;
+    Ca.a[0] = cov_acc.x;
+    Ca.a[4] = cov_acc.y;
+    Ca.a[8] = cov_acc.z;
+    Cg.a[0] = cov_gyr.x;
+    Cg.a[4] = cov_gyr.y;
+    Cg.a[8] = cov_gyr.z;
+    Q[0 * kDim + 0] = cov_gyr.x * dt * dt * 10000;
+    Q[1 * kDim + 1] = cov_gyr.y * dt * dt * 10000;
+    Q[2 * kDim + 2] = cov_gyr.z * dt * dt * 10000;
+    set_block3(Q, 3, 3, R_imu * Cg * R_imu.t() * dt * dt * 10000);
+    set_block3(Q, 12, 12, R_imu * Ca * R_imu.t() * dt * dt * 10000);
+    for (int a = 0; a < 3; a++) {
+        Q[(15 + a) * kDim + 15 + a] = 0.0001 * dt * dt;
+        Q[(18 + a) * kDim + 18 + a] = 0.0001 * dt * dt;
+    }
+    // cov = F cov F^T + Q with the block structure written out (terms in ascending column order of F, i.e. the
+    // order a dense product would add the non-zeros in).  Rows / columns 0-5 and 12-14 are the only non-identity ones.
+    {
+        const double *E = &F[0];            // F[0:3, 0:3]   = Exp(w, -dt)
+        const double *A = &F[12 * kDim];    // F[12:15, 0:3] = -R a^ dt   (row stride kDim)
+        const double *B = &F[12 * kDim + 18];  // F[12:15, 18:21] = -R dt
+        const double *P = st.cov;
+        std::memcpy(FP, P, sizeof(double) * kDim * kDim);
+        for (int r = 0; r < 3; r++) {
+            double *o0 = &FP[r * kDim], *o3 = &FP[(3 + r) * kDim], *o12 = &FP[(12 + r) * kDim];
+            const double e0 = E[r * kDim], e1 = E[r * kDim + 1], e2 = E[r * kDim + 2];
+            const double a0 = A[r * kDim], a1 = A[r * kDim + 1], a2 = A[r * kDim + 2];
+            const double b0 = B[r * kDim], b1 = B[r * kDim + 1], b2 = B[r * kDim + 2];
+            for (int j = 0; j < kDim; j++) {
+                o0[j] = ((e0 * P[j] + e1 * P[kDim + j]) + e2 * P[2 * kDim + j]) + (-dt) * P[(15 + r) * kDim + j];
+                o3[j] = P[(3 + r) * kDim + j] + dt * P[(12 + r) * kDim + j];
+                o12[j] = ((((((a0 * P[j] + a1 * P[kDim + j]) + a2 * P[2 * kDim + j]) + P[(12 + r) * kDim + j]) + b0 * P[18 * kDim + j]) +
+                           b1 * P[19 * kDim + j]) + b2 * P[20 * kDim + j]) + dt * P[(21 + r) * kDim + j];
+            }
+        }
+        for (int i = 0; i < kDim; i++) {
+            const double *X = &FP[i * kDim];
+            double *o = &st.cov[i * kDim];
+            double c0[3], c3[3], c12[3];
+            for (int c = 0; c < 3; c++) {
+                c0[c] = ((E[c * kDim] * X[0] + E[c * kDim + 1] * X[1]) + E[c * kDim + 2] * X[2]) + (-dt) * X[15 + c];
+                c3[c] = X[3 + c] + dt * X[12 + c];
+                c12[c] = ((((((A[c * kDim] * X[0] + A[c * kDim + 1] * X[1]) + A[c * kDim + 2] * X[2]) + X[12 + c]) + B[c * kDim] * X[18]) +
+                           B[c * kDim + 1] * X[19]) + B[c * kDim + 2] * X[20]) + dt * X[21 + c];
+            }
+            for (int j = 0; j < kDim; j++) o[j] = X[j] + Q[i * kDim + j];
+            for (int c = 0; c < 3; c++) {
+                o[c] = c0[c] + Q[i * kDim + c];
+                o[3 + c] = c3[c] + Q[i * kDim + 3 + c];
+                o[12 + c] = c12[c] + Q[i * kDim + 12 + c];
+            }
+        }
+    }
+}
+
+void ImuProcess::FinishCovariance(StatesGroup &st) {
+    if (pending_cov_.empty()) return;
+    double F[kDim * kDim], Q[kDim * kDim], FP[kDim * kDim];
+    std::memset(F, 0, sizeof(F));
+    std::memset(Q, 0, sizeof(Q));
+    for (int i = 0; i < kDim; i++) F[i * kDim + i] = 1.0;
+    for (const CovStep &cs : pending_cov_) PropagateCovStep(cs, st, F, Q, FP);
+    pending_cov_.clear();
+}
+
+void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_time, double pcl_end_time, StatesGroup &st, bool EKF_stop_flg,
+                           bool defer_cov) {
     std::vector<ImuSample> v;
     v.reserve(imu.size() + 1);
     v.push_back(last_imu_);  // IMU_Processing.hpp:207-208
@@ -379,67 +458,17 @@ void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_tim
         acc_avr = (Vec3(head.acc) + Vec3(tail.acc)) * 0.5 * G_m_s2 / mean_acc.norm() - st.bias_a;  // :248
         dt = (head.t < last_observation_end_time_) ? tail.t - last_observation_end_time_ : tail.t - head.t;
 
-        // covariance propagation, :262-288
         const Mat3 Exp_f = so3_exp_rate(angvel_avr, dt);
-        set_block3(F, 0, 0, so3_exp_rate(angvel_avr, -dt));
-        set_block3(F, 0, 15, Mat3::identity() * (-dt));
-        set_block3(F, 3, 12, Mat3::identity() * dt);
-        set_block3(F, 12, 0, (R_imu * -1.0) * Mat3::hat(acc_avr) * dt);
-        set_block3(F, 12, 18, R_imu * (-dt));
-        set_block3(F, 12, 21, Mat3::identity() * dt);
-        Mat3 Ca, Cg;
-        Ca.a[0] = cov_acc.x;
-        Ca.a[4] = cov_acc.y;
-        Ca.a[8] = cov_acc.z;
-        Cg.a[0] = cov_gyr.x;
-        Cg.a[4] = cov_gyr.y;
-        Cg.a[8] = cov_gyr.z;
-        Q[0 * kDim + 0] = cov_gyr.x * dt * dt * 10000;
-        Q[1 * kDim + 1] = cov_gyr.y * dt * dt * 10000;
-        Q[2 * kDim + 2] = cov_gyr.z * dt * dt * 10000;
-        set_block3(Q, 3, 3, R_imu * Cg * R_imu.t() * dt * dt * 10000);
-        set_block3(Q, 12, 12, R_imu * Ca * R_imu.t() * dt * dt * 10000);
-        for (int a = 0; a < 3; a++) {
-            Q[(15 + a) * kDim + 15 + a] = 0.0001 * dt * dt;
-            Q[(18 + a) * kDim + 18 + a] = 0.0001 * dt * dt;
-        }
-        // cov = F cov F^T + Q with the block structure written out (terms in ascending column order of F, i.e. the
-        // order a dense product would add the non-zeros in).  Rows / columns 0-5 and 12-14 are the only non-identity ones.
-        {
-            const double *E = &F[0];            // F[0:3, 0:3]   = Exp(w, -dt)
-            const double *A = &F[12 * kDim];    // F[12:15, 0:3] = -R a^ dt   (row stride kDim)
-            const double *B = &F[12 * kDim + 18];  // F[12:15, 18:21] = -R dt
-            const double *P = st.cov;
-            std::memcpy(FP, P, sizeof(FP));
-            for (int r = 0; r < 3; r++) {
-                double *o0 = &FP[r * kDim], *o3 = &FP[(3 + r) * kDim], *o12 = &FP[(12 + r) * kDim];
-                const double e0 = E[r * kDim], e1 = E[r * kDim + 1], e2 = E[r * kDim + 2];
-                const double a0 = A[r * kDim], a1 = A[r * kDim + 1], a2 = A[r * kDim + 2];
-                const double b0 = B[r * kDim], b1 = B[r * kDim + 1], b2 = B[r * kDim + 2];
-                for (int j = 0; j < kDim; j++) {
-                    o0[j] = ((e0 * P[j] + e1 * P[kDim + j]) + e2 * P[2 * kDim + j]) + (-dt) * P[(15 + r) * kDim + j];
-                    o3[j] = P[(3 + r) * kDim + j] + dt * P[(12 + r) * kDim + j];
-                    o12[j] = ((((((a0 * P[j] + a1 * P[kDim + j]) + a2 * P[2 * kDim + j]) + P[(12 + r) * kDim + j]) + b0 * P[18 * kDim + j]) +
-                               b1 * P[19 * kDim + j]) + b2 * P[20 * kDim + j]) + dt * P[(21 + r) * kDim + j];
-                }
-            }
-            for (int i = 0; i < kDim; i++) {
-                const double *X = &FP[i * kDim];
-                double *o = &st.cov[i * kDim];
-                double c0[3], c3[3], c12[3];
-                for (int c = 0; c < 3; c++) {
-                    c0[c] = ((E[c * kDim] * X[0] + E[c * kDim + 1] * X[1]) + E[c * kDim + 2] * X[2]) + (-dt) * X[15 + c];
-                    c3[c] = X[3 + c] + dt * X[12 + c];
-                    c12[c] = ((((((A[c * kDim] * X[0] + A[c * kDim + 1] * X[1]) + A[c * kDim + 2] * X[2]) + X[12 + c]) + B[c * kDim] * X[18]) +
-                               B[c * kDim + 1] * X[19]) + B[c * kDim + 2] * X[20]) + dt * X[21 + c];
-                }
-                for (int j = 0; j < kDim; j++) o[j] = X[j] + Q[i * kDim + j];
-                for (int c = 0; c < 3; c++) {
-                    o[c] = c0[c] + Q[i * kDim + c];
-                    o[3 + c] = c3[c] + Q[i * kDim + 3 + c];
-                    o[12 + c] = c12[c] + Q[i * kDim + 12 + c];
-                }
-            }
+        {  // covariance propagation, :262-288 (now, or recorded for FinishCovariance)
+            CovStep cs;
+            cs.angvel_avr = angvel_avr;
+            cs.acc_avr = acc_avr;
+            cs.R_imu = R_imu;
+            cs.dt = dt;
+            if (defer_cov)
+                pending_cov_.push_back(cs);
+            else
+                PropagateCovStep(cs, st, F, Q, FP);
         }
 
         R_imu = R_imu * Exp_f;                                      // :291
@@ -467,7 +496,7 @@ void ImuProcess::Propagate(const std::vector<ImuSample> &imu, double pcl_beg_tim
 }
 
 bool ImuProcess::Process(const std::vector<ImuSample> &imu, double lidar_beg_time, double observation_end_time, StatesGroup &st,
-                         bool EKF_stop_flg) {
+                         bool EKF_stop_flg, bool defer_cov) {
     if (imu.empty()) return false;  // :378-382
     if (imu_need_init_) {
         IMU_Initial(imu, st, init_iter_num);
@@ -485,7 +514,8 @@ bool ImuProcess::Process(const std::vector<ImuSample> &imu, double lidar_beg_tim
     st.bias_g = Vec3(5.3e-05, 5.3e-05, 5.3e-05);
     st.R_L_I = Lidar_R_wrt_IMU;
     st.T_L_I = Lidar_T_wrt_IMU;
-    Propagate(imu, lidar_beg_time, observation_end_time, st, EKF_stop_flg);
+    FinishCovariance(st);  // (a caller that deferred and never finished: keep the sequence of updates intact)
+    Propagate(imu, lidar_beg_time, observation_end_time, st, EKF_stop_flg, defer_cov);
     last_imu_ = imu.back();  // :422
     return true;
 }
@@ -635,7 +665,14 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
     // ---- p_imu->Process(Measures, state, feats_undistort, EKF_stop_flg)   :750
     double t0 = wall();
     std::vector<ImuSample> imu_v(imu, imu + n_imu);
-    bool undistorted = imu_.Process(imu_v, lidar_beg_time, observation_end_time, state, EKF_stop_flg);
+    // the deskew kernel only waits for the IMU poses: the covariance propagation of the same IMU steps (~15 us) runs below,
+    // once the scan's first kernels are in flight (finish_cov), instead of in front of them
+    bool undistorted = imu_.Process(imu_v, lidar_beg_time, observation_end_time, state, EKF_stop_flg, /*defer_cov=*/true);
+    struct FinishCov {  // ... and on every way out of this function
+        ImuProcess &imu;
+        StatesGroup &st;
+        ~FinishCov() { imu.FinishCovariance(st); }
+    } finish_cov_guard{imu_, state};
     int n_raw = 0;
     if (undistorted && n > 0) {
         double pose[24];
@@ -687,6 +724,8 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         LM_CK(dlt_scan_downsample(dev_, &feats_down_size));  // :775-778
     out->t_voxel = wall() - t0;
     out->n_down = feats_down_size;
+    imu_.FinishCovariance(state);  // deskew + VoxelGrid are running: now the covariance propagation (state.cov is read from here on)
+    std::memcpy(state_propagat.cov, state.cov, sizeof(state.cov));
 
     if (!map_built) {  // ikdtree.Root_Node == nullptr, :780-793
         if (feats_down_size > 5) {

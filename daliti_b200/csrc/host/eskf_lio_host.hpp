@@ -131,7 +131,12 @@ class ImuProcess {
     void Reset();                                           // IMU_Processing.hpp:117-141
     void set_extrinsic(const Vec3 &t, const Mat3 &r);       // :155-159
     // Process, :373-427.  Returns true when the scan is to be undistorted (IMUpose / state updated).
-    bool Process(const std::vector<ImuSample> &imu, double lidar_beg_time, double observation_end_time, StatesGroup &state, bool EKF_stop_flg);
+    // defer_cov: only the poses are integrated now (that is all the deskew kernel waits for); the covariance propagation of
+    // the same IMU steps (:262-288) is recorded and runs in FinishCovariance, which the caller invokes once the scan's first
+    // kernels are in flight and before anything reads state.cov.  Same operations on the same numbers either way.
+    bool Process(const std::vector<ImuSample> &imu, double lidar_beg_time, double observation_end_time, StatesGroup &state, bool EKF_stop_flg,
+                 bool defer_cov = false);
+    void FinishCovariance(StatesGroup &state);
     void force_ready(const Vec3 &mean_acc, const ImuSample &last);
     bool need_init() const { return imu_need_init_; }
     std::vector<Pose6D> IMUpose;
@@ -139,7 +144,14 @@ class ImuProcess {
    private:
     void IMU_Initial(const std::vector<ImuSample> &imu, StatesGroup &state, int &N);  // :161-202
     void Propagate(const std::vector<ImuSample> &imu, double pcl_beg_time, double pcl_end_time, StatesGroup &state,
-                   bool EKF_stop_flg);                                                  // :204-330
+                   bool EKF_stop_flg, bool defer_cov);                                  // :204-330
+    struct CovStep {  // what one IMU step's F and Q are made of (:270-286)
+        Vec3 angvel_avr, acc_avr;
+        Mat3 R_imu;
+        double dt;
+    };
+    void PropagateCovStep(const CovStep &s, StatesGroup &state, double *__restrict__ F, double *__restrict__ Q, double *__restrict__ FP) const;
+    std::vector<CovStep> pending_cov_;
     bool b_first_frame_ = true, imu_need_init_ = true;
     int init_iter_num = 1;
     Vec3 mean_acc{0, 0, -1.0}, mean_gyr;
