@@ -680,6 +680,7 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
                        "shard_exchange": exchange},
             "e2e": {"value": float(sum(o[0] for o in outs_e)) / (t_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(np.mean([o[0] for o in outs_e]) * 48 + 22 * 8 * 22),
                     "d2h_bytes_per_step": int(np.mean([o[2] for o in outs_e]) * (158 * 8 + 4) + 48 + 42 * 8), "ms_per_step": t_e / K,
+                    "ms_p50": float(np.median(ms_e)), "ms_p99": float(np.percentile(ms_e, 99)),
                     "api": "dlt_lio_prefetch_scan(next) + dlt_lio_process_scan (pinned host buffers) + " + ("dlt_lio_peer_attach" if exchange == "peer" else "dlt_lio_set_reduce")},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": None, "cpu_baseline": None,
