@@ -105,6 +105,10 @@ struct dlt_handle_s {
     PeerComm *d_peer = nullptr;
     void *peer_maps[DLT_MAX_PEERS] = {};  // mappings opened by dlt_peer_attach (to be closed)
     size_t peer_map_bytes[DLT_MAX_PEERS] = {};
+    // opt-in (DLT_ZEROCOPY=1): dlt_measure's result block is stored by k_residual straight into pinned host memory and the
+    // host spins on a flag there instead of issuing a device->host copy and synchronising the stream
+    bool zerocopy = false;
+    unsigned long long zc_seq = 0;
     bool peer_on = false;
     unsigned long long peer_dec_seq = 0;  // decision exchanges so far (host-counted: every dlt_map_incremental with a match pass)
     int *h_peer_status = nullptr;         // pinned
@@ -410,6 +414,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->stream = h->own_stream;
     h->have_copy = rt::stream_create(&h->copy_stream) == 0 && rt::event_create_untimed(&h->ev_copy) == 0;
     if (const char *e = std::getenv("DLT_LOOP_GRAPH")) h->use_graph = (e[0] == '1') ? 1 : 0;  // A/B switch for measurements
+    if (const char *e = std::getenv("DLT_ZEROCOPY")) h->zerocopy = (e[0] == '1');            // A/B switch for measurements
     h->have_aux = rt::stream_create(&h->aux_stream) == 0 && rt::event_create_untimed(&h->ev_fork) == 0 && rt::event_create_untimed(&h->ev_join) == 0;
 
     // search cell edge = ds_map * 2^shift with 3 edges covering sqrt(max_sq_dist)
@@ -953,7 +958,8 @@ int dlt_frontend_read(dlt_handle h, void *pts48, int n) {
 }
 
 // ------------------------------------------------------------------ measurement model
-int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev) {
+static int measure_dev_impl(dlt_handle h, const double *pose24, int do_match, double *result_dev, bool zc, bool *launched) {
+    if (launched) *launched = false;
     if (!h || !pose24 || !result_dev) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_measure before a downsampled scan is set");
     if (!do_match && !h->have_match) DLT_FAIL(h, DLT_E_STATE, "dlt_measure(do_match=0) before any match pass");
@@ -999,6 +1005,14 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     mb.far_count = h->d_counters + 5;
     mb.unres_count = h->d_counters + 8;
     mb.result = result_dev;
+    mb.zc_result = nullptr;
+    mb.zc_flag = nullptr;
+    mb.zc_seq = 0;
+    if (zc) {  // (pinned allocations are addressable from the device under unified addressing)
+        mb.zc_result = h->h_result;
+        mb.zc_flag = reinterpret_cast<unsigned long long *>(h->h_ints + 32);
+        mb.zc_seq = ++h->zc_seq;
+    }
     int G = div_up(dev_n ? h->n_raw : n, kResidBlock);  // surplus blocks return at once
     if (G < 1) G = 1;
     ProfScope prof(h, 1);
@@ -1007,7 +1021,12 @@ int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *re
     else
         DLT_LAUNCH(k_residual<false>, G, kResidBlock, h->stream, mb, n, do_match ? 1 : 0, P, h->cfg.plane_thr, la);
     DLT_RT(h, rt::check_launch());
+    if (launched) *launched = true;
     return DLT_OK;
+}
+
+int dlt_measure_dev(dlt_handle h, const double *pose24, int do_match, double *result_dev) {
+    return measure_dev_impl(h, pose24, do_match, result_dev, false, nullptr);
 }
 
 // ------------------------------------------------------------------ the iteration loop on the device
@@ -1128,6 +1147,9 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     mb.unres_count = h->d_counters + 8;
     double *res = result_dev ? result_dev : h->d_result;
     mb.result = res;
+    mb.zc_result = nullptr;
+    mb.zc_flag = nullptr;
+    mb.zc_seq = 0;
     // without a reduction over ranks between them the solve step rides in the last block of k_residual
     LoopArgs la = {h->d_iekf, &h->d_sc->n_down, &h->d_sc->vox_status, reduce ? 0 : 1, 0, 0ull, 0ull, h->peer_on ? h->d_peer : nullptr};
     if (!h->n_down_on_device) {  // the scan was set with a host-known size: publish it where the kernels look
@@ -1244,11 +1266,29 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
 
 int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_out *out) {
     if (!h || !out) return DLT_E_INVALID;
-    int rc = dlt_measure_dev(h, pose24, do_match, h->d_result);
+    const bool zc = h->zerocopy && !h->peer_on && !h->prof_on;
+    bool launched = false;
+    int rc = measure_dev_impl(h, pose24, do_match, h->d_result, zc, &launched);
     if (rc) return rc;
-    DLT_RT(h, rt::d2h(h->h_result, h->d_result, kFetchDoubles * sizeof(double), h->stream));
-    if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
-    DLT_RT(h, rt::sync(h->stream));
+    if (zc && launched) {  // k_residual's last block stores the block into h_result and then this launch's number into the flag
+        const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(h->h_ints + 32);
+        const unsigned long long want = h->zc_seq;
+        for (unsigned spins = 1; *flag != want; spins++) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0xFFFu) == 0u) {  // a kernel that died never raises the flag: ask the stream now and then
+                const int q = rt::stream_query(h->stream);
+                if (q == 2) DLT_FAIL(h, DLT_E_CUDA, std::string("stream error while waiting for the result block: ") + rt::last_error());
+                if (q == 0 && *flag != want) DLT_FAIL(h, DLT_E_CUDA, "the stream drained without the result flag");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+        DLT_RT(h, rt::d2h(h->h_result, h->d_result, kFetchDoubles * sizeof(double), h->stream));
+        if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+    }
     if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in this evaluation)");
     const double *R = h->h_result;
     if (int rn = adopt_n_down(h, R)) return rn;

@@ -1335,7 +1335,18 @@ struct MeasureBufs {
     const int *far_count;     // unresolved queries of the last match pass
     int *unres_count;         // k_knn8 -> k_knn hand-over counter, re-armed here for the next match pass
     double *result;           // kResultDoubles
+    // opt-in (DLT_ZEROCOPY=1): the last block also stores the kFetchDoubles result block straight into pinned HOST memory and
+    // then the launch's sequence number into a host flag the caller spins on -- no device->host copy, no stream synchronisation
+    double *zc_result;
+    unsigned long long *zc_flag;
+    unsigned long long zc_seq;
 };
+DLT_D void zc_publish(const MeasureBufs &mb, const double *R) {  // whole block; R complete and visible to the block
+    for (int k = threadIdx.x; k < kFetchDoubles; k += blockDim.x) mb.zc_result[k] = R[k];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile unsigned long long *)mb.zc_flag = mb.zc_seq;
+}
 
 template <bool EXT>
 __global__ void __launch_bounds__(kResidBlock)
@@ -1355,6 +1366,10 @@ __global__ void __launch_bounds__(kResidBlock)
                 mb.result[158] = (double)(*mb.far_count);
                 mb.result[159] = (la.vox_ptr && *la.vox_ptr == 2) ? -1.0 : 0.0;
                 *mb.unres_count = 0;
+            }
+            if (mb.zc_result) {  // block-uniform
+                __syncthreads();
+                zc_publish(mb, mb.result);
             }
         }
         return;
@@ -1550,6 +1565,10 @@ __global__ void __launch_bounds__(kResidBlock)
     if (la.peer && !peer_allreduce_block(la.peer, R, kNormalEqDoubles)) {  // block-uniform; starts and ends with a barrier
         if (la.ctl && threadIdx.x == 0) const_cast<IekfDev *>(la.ctl)->b.done = 1;  // a peer never posted: end the loop, the host reports it
         return;
+    }
+    if (mb.zc_result) {  // block-uniform
+        __syncthreads();  // thread 0's R[158], R[159] and (with peers) the summed block are visible to all threads
+        zc_publish(mb, R);
     }
     if (la.ctl && la.fuse_step) {  // block-uniform: the solve / control step of this iteration, no launch in between
         __syncthreads();           // the block's own global writes to R are visible to it after the barrier

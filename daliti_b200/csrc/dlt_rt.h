@@ -53,6 +53,7 @@ inline int fill(void *d, int byte, size_t n, cudaStream_t) {
     return 0;
 }
 inline int sync(cudaStream_t) { return 0; }
+inline int stream_query(cudaStream_t) { return 0; }  // 0 idle, 1 still busy, 2 error
 inline int stream_create(cudaStream_t *s) {
     *s = nullptr;
     return 0;
@@ -170,6 +171,10 @@ inline int d2d(void *d, const void *s, size_t n, cudaStream_t st) {
 }
 inline int fill(void *d, int byte, size_t n, cudaStream_t st) { return cudaMemsetAsync(d, byte, n, st) == cudaSuccess ? 0 : 1; }
 inline int sync(cudaStream_t st) { return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1; }
+inline int stream_query(cudaStream_t st) {  // 0 idle, 1 still busy, 2 error
+    cudaError_t e = cudaStreamQuery(st);
+    return e == cudaSuccess ? 0 : (e == cudaErrorNotReady ? 1 : 2);
+}
 inline int stream_create(cudaStream_t *s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess ? 0 : 1; }
 inline void stream_destroy(cudaStream_t s) {
     if (s) cudaStreamDestroy(s);

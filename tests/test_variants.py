@@ -58,3 +58,45 @@ def test_knn8_prune_variant_is_result_identical(emu_lib, tmp_path):
             np.testing.assert_array_equal(x, y)  # neighbours (coordinates, d2), counts, point_selected_surf
         assert a[4] == b[4]
         assert set(map(tuple, a[5].tolist())) == set(map(tuple, b[5].tolist()))
+
+
+def _replay(lib, n_scans=3):
+    from daliti_b200.lio import LaserMapping
+
+    seq = helpers.small_sequence(seed=41, half=30.0, beams=16, azimuths=240, n_boxes=8)
+    map_pts = synth.sample_map(seq.scene, seed=41)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=8192, max_map_points=1 << 17), featptsThreshold=5, device_loop=0)
+    lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
+    lm.set_state(helpers.state612(seq.traj, seq.t_start))
+    lm.device.map_build(map_pts)
+    out = []
+    for k in range(n_scans):
+        pts, t_beg, imu = seq.scan(k)
+        lm.on_lidar_msg()
+        o = lm.process_scan(pts, t_beg, imu)
+        out.append((lm.get_state().copy(), o.n_iters, o.added, [np.array(it.HtH) for it in lm.iters()]))
+    lm.close()
+    return out
+
+
+def test_zerocopy_result_path_is_result_identical(emu_lib, monkeypatch):
+    """DLT_ZEROCOPY=1: k_residual's last block stores the result block into pinned host memory and raises a flag the host
+    spins on, instead of a device->host copy + stream synchronisation per iteration (host loop).  Same numbers."""
+    a = _replay(emu_lib)
+    monkeypatch.setenv("DLT_ZEROCOPY", "1")
+    b = _replay(emu_lib)
+    for (sa, ia, aa, ha), (sb, ib, ab, hb) in zip(a, b):
+        assert (ia, aa) == (ib, ab)
+        np.testing.assert_array_equal(sa, sb)
+        for x, y in zip(ha, hb):
+            np.testing.assert_array_equal(x, y)
+    # the empty scan takes the same road
+    dm = ScanToMap(emu_lib, max_scan_points=1024, max_map_points=4096)
+    dm.map_build(np.array([[0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1], [0, 0, 1, 1], [1, 1, 0, 1], [1, 1, 1, 1]], np.float32))
+    dm.scan_deskew(np.zeros((0, 12), np.float32))
+    assert dm.scan_downsample() == 0
+    pose = np.zeros(24)
+    pose[[0, 4, 8, 12, 16, 20]] = 1.0
+    m = dm.measure(pose, True)
+    assert m.effct_feat_num == 0 and not m.HtH.any()
+    dm.close()
