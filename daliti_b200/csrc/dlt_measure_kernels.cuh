@@ -1337,9 +1337,9 @@ struct MeasureBufs {
     double *result;           // kResultDoubles
     // opt-in (DLT_ZEROCOPY=1): the last block also stores the kFetchDoubles result block straight into pinned HOST memory and
     // then the launch's sequence number into a host flag the caller spins on -- no device->host copy, no stream synchronisation
-    double *zc_result;
-    unsigned long long *zc_flag;
-    unsigned long long zc_seq;
+    double *zc_result = nullptr;
+    unsigned long long *zc_flag = nullptr;
+    unsigned long long zc_seq = 0;
 };
 DLT_D void zc_publish(const MeasureBufs &mb, const double *R) {  // whole block; R complete and visible to the block
     for (int k = threadIdx.x; k < kFetchDoubles; k += blockDim.x) mb.zc_result[k] = R[k];
