@@ -110,7 +110,7 @@ struct dlt_handle_s {
     bool zerocopy = false;
     unsigned long long zc_seq = 0;
     bool peer_on = false;
-    unsigned long long peer_dec_seq = 0;  // decision exchanges so far (host-counted: every dlt_map_incremental with a match pass)
+    bool peer_detached = false;
     int *h_peer_status = nullptr;         // pinned
     // the iteration loop as a CUDA graph with conditional nodes (built lazily, once: every kernel in it has a fixed grid and
     // takes its sizes from device memory)
@@ -1116,7 +1116,9 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     blk->iter = blk->rematch_num = blk->rematch_en = blk->done = 0;
     blk->insert_status = 0;
     // the device-side finish needs an unsharded map (a sharded map_incremental exchanges the per-point decisions first)
-    const bool finish = blk->finish && h->map.shard_count <= 1;
+    // ... or peer mailboxes, through which the kernels exchange them themselves
+    const bool finish = blk->finish && (h->map.shard_count <= 1 || h->peer_on);
+    const bool sharded_finish = finish && h->map.shard_count > 1;
     blk->finish = finish ? 1 : 0;
     const bool far_q = finish && h->far_hint > 0;
     blk->far_enqueued = far_q ? 1 : 0;
@@ -1211,13 +1213,24 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
         }
         DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));  // downsample adds, raw adds (far_count is re-armed by the next k_knn8)
-        FuseInsert fi = {1, h->scratch, h->d_cellslot, h->d_vslot};
-        if (int rs = prepare_scratch(h, n_upper, true, &fi.sc)) return rs;
+        // unsharded: the classification kernel also claims cells and places the voxel bids.  Sharded: the owners' decisions are
+        // exchanged first (k_incr_push / k_incr_pull through the peer mailboxes, gated like everything here), then every rank
+        // inserts what falls into its tiles + halo
+        FuseInsert fi = {sharded_finish ? 0 : 1, h->scratch, h->d_cellslot, h->d_vslot};
+        if (!sharded_finish)
+            if (int rs = prepare_scratch(h, n_upper, true, &fi.sc)) return rs;
         DLT_LAUNCH(k_incr_classify, div_up(n_upper, 256), 256, h->stream, (const float4 *)h->d_down, 0, P, (const float4 *)h->knn.nbr,
                    (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, la, h->map,
                    (const int *)h->map.n_live, (const unsigned char *)h->knn.flags, (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key, fi);
         InsertGate gate = {&h->d_iekf->b.insert_status, &h->d_sc->n_down};
-        int ri = insert_points(h, h->d_pw, n_upper, true, gate, &fi.sc);
+        if (sharded_finish) {
+            const int Gx = div_up(n_upper, 256);
+            DLT_LAUNCH(k_incr_push, Gx, 256, h->stream, h->d_peer, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
+                       (const unsigned char *)h->knn.flags, 0, (unsigned char)kFlagForeign, (const int *)gate.go, (const int *)gate.n_ptr);
+            DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
+            DLT_LAUNCH(k_incr_pull, Gx, 256, h->stream, h->d_peer, 0, h->d_dsflag, h->d_addflag, h->d_counters + 6, (const int *)gate.go, (const int *)gate.n_ptr);
+        }
+        int ri = insert_points(h, h->d_pw, n_upper, true, gate, sharded_finish ? nullptr : &fi.sc);
         if (ri) return ri;
         DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     }
@@ -1451,11 +1464,11 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
                LoopArgs{nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull, nullptr}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
                (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key, fi);
     if (sharded && h->have_match && h->peer_on) {  // owners store their decisions straight into every rank's mailbox
-        const unsigned long long seq = ++h->peer_dec_seq;
-        DLT_LAUNCH(k_incr_push, div_up(n, 256), 256, h->stream, h->d_peer, seq, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
-                   (const unsigned char *)h->knn.flags, n, (unsigned char)kFlagForeign);
+        DLT_LAUNCH(k_incr_push, div_up(n, 256), 256, h->stream, h->d_peer, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
+                   (const unsigned char *)h->knn.flags, n, (unsigned char)kFlagForeign, (const int *)nullptr, (const int *)nullptr);
         DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
-        DLT_LAUNCH(k_incr_pull, div_up(n, 256), 256, h->stream, h->d_peer, seq, n, h->d_dsflag, h->d_addflag, h->d_counters + 6);
+        DLT_LAUNCH(k_incr_pull, div_up(n, 256), 256, h->stream, h->d_peer, n, h->d_dsflag, h->d_addflag, h->d_counters + 6, (const int *)nullptr,
+                   (const int *)nullptr);
     } else if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
                                      // (without a match pass every rank already agrees: all points are PointToAdd)
         DLT_LAUNCH(k_incr_pack, div_up(n, 256), 256, h->stream, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag, n, h->d_flagbuf);
@@ -1511,14 +1524,14 @@ int dlt_peer_detach(dlt_handle h) {
         h->peer_maps[r] = nullptr;
     }
     h->peer_on = false;
-    h->peer_dec_seq = ~0ull;  // the mailbox keeps the old sequence numbers: no second attach on this handle
+    h->peer_detached = true;  // the mailbox keeps the old sequence numbers: no second attach on this handle
     return DLT_OK;
 }
 
 int dlt_peer_attach(dlt_handle h, const unsigned char *blobs) {
     if (!h || !blobs) return DLT_E_INVALID;
     if (!h->peer_box) DLT_FAIL(h, DLT_E_STATE, "dlt_peer_attach before dlt_peer_export");
-    if (h->peer_on || h->peer_dec_seq == ~0ull) DLT_FAIL(h, DLT_E_STATE, "peers are already attached or were detached (attach once per handle)");
+    if (h->peer_on || h->peer_detached) DLT_FAIL(h, DLT_E_STATE, "peers are already attached or were detached (attach once per handle)");
     rt::set_device(h->cfg.device);
     h->err.clear();
     const int W = h->cfg.shard_count, me = h->cfg.shard_rank;
@@ -1576,7 +1589,6 @@ int dlt_peer_attach(dlt_handle h, const unsigned char *blobs) {
         if (h->err.empty()) h->err = "dlt_peer_attach failed";
         return DLT_E_CUDA;
     }
-    h->peer_dec_seq = 0;
     h->peer_on = true;
     return DLT_OK;
 }

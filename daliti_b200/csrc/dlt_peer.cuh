@@ -39,8 +39,8 @@ struct PeerComm {  // device-resident, one per attached handle
     int dec_cap;
     int status;                  // sticky: 1 = timed out waiting for a peer
     unsigned long long eq_seq;   // exchanges of normal equations completed so far (device-owned: no-op launches do not exchange)
-    unsigned dec_ticket;
-    unsigned pad;
+    unsigned long long dec_seq;  // exchanges of map_incremental decisions completed so far (device-owned: gated launches do not exchange)
+    unsigned dec_ticket, pull_ticket;
     PeerBox *box[kPeerMax];      // every rank's mailbox as mapped in this process; box[rank] is this rank's own
 };
 
@@ -110,9 +110,14 @@ DLT_D bool peer_allreduce_block(PeerComm *pc, double *R, int n) {
 // map_incremental on a sharded map: the owner of a query point decides (laserMapping.cpp:588-625 needs the point's
 // neighbours, which only the owner holds) and stores the decision code (0 drop, 1 PointToAdd, 2 PointNoNeedDownsample)
 // into dec[parity][i] of EVERY rank's mailbox, its own included; the last block to finish publishes the sequence number.
-__global__ void k_incr_push(PeerComm *pc, unsigned long long seq, const unsigned char *__restrict__ ds_flag, const unsigned char *__restrict__ add_flag,
-                            const unsigned char *__restrict__ flags, int n, unsigned char foreign_bit) {
+// gate_go / gate_n (optional): behind the device-resident loop the exchange only runs when the loop armed the insert
+// (*gate_go == 1, the same on every rank), with feats_down_size read from the device.
+__global__ void k_incr_push(PeerComm *pc, const unsigned char *__restrict__ ds_flag, const unsigned char *__restrict__ add_flag,
+                            const unsigned char *__restrict__ flags, int n, unsigned char foreign_bit, const int *gate_go, const int *gate_n) {
     __shared__ int s_last;
+    if (gate_go && *gate_go != 1) return;  // block-uniform
+    if (gate_n) n = *gate_n;
+    const unsigned long long seq = pc->dec_seq + 1ull;  // (only the LAST block of k_incr_pull advances dec_seq, in stream order behind this kernel)
     const int W = pc->world, me = pc->rank, par = (int)(seq & 1ull);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && !(flags[i] & foreign_bit)) {
@@ -129,9 +134,12 @@ __global__ void k_incr_push(PeerComm *pc, unsigned long long seq, const unsigned
     if (threadIdx.x == 0) pc->dec_ticket = 0u;
 }
 // ... and every rank, once all owners have published, reads all n decisions from its own mailbox.
-__global__ void k_incr_pull(PeerComm *pc, unsigned long long seq, int n, unsigned char *__restrict__ ds_flag, unsigned char *__restrict__ add_flag,
-                            int *__restrict__ class_counts) {
+__global__ void k_incr_pull(PeerComm *pc, int n, unsigned char *__restrict__ ds_flag, unsigned char *__restrict__ add_flag,
+                            int *__restrict__ class_counts, const int *gate_go, const int *gate_n) {
     __shared__ int s_timeout;
+    if (gate_go && *gate_go != 1) return;  // block-uniform
+    if (gate_n) n = *gate_n;
+    const unsigned long long seq = pc->dec_seq + 1ull;  // read before this block's ticket: the last ticket holder writes it
     const int W = pc->world, me = pc->rank, par = (int)(seq & 1ull);
     if (threadIdx.x == 0) s_timeout = 0;
     __syncthreads();
@@ -150,6 +158,11 @@ __global__ void k_incr_pull(PeerComm *pc, unsigned long long seq, int n, unsigne
     if ((threadIdx.x & 31) == 0) {
         if (bd) atomicAdd(&class_counts[0], __popc(bd));
         if (ba) atomicAdd(&class_counts[1], __popc(ba));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&pc->pull_ticket, 1u) == gridDim.x - 1u) {  // every block has read dec_seq by now
+        pc->pull_ticket = 0u;
+        pc->dec_seq = seq;
     }
 }
 

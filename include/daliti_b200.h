@@ -194,7 +194,7 @@ typedef struct dlt_iekf_block {
     int max_iteration;                  /* NUM_MAX_ITERATIONS (<= DLT_IEKF_MAX_ITER)             */
     int finish;                         /* 1: also run the zeta blend (:1105-1131) and map_incremental (:1164-1168)
                                            on the device behind the loop, before the one synchronisation; cleared
-                                           on return when that was not possible (sharded map)                */
+                                           on return when that was not possible (sharded map without attached peers) */
     int blend_mode;                     /* which branch of :1107 applies: 1 = LiDAR/IMU blend, 2 = thermal  */
     double last_state[36];              /* last_state, :1131 (finish only)                        */
     double l2l_state[36];               /* odomToStateGruop(g_tis_odom_delta_lframe2lframe), :1125 */

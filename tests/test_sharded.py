@@ -216,7 +216,7 @@ def test_sharded_per_scan_update_four_processes_peers(emu_lib):
     _check_sharded_against_unsharded(got, ref, bitwise_ranks=True)
 
 
-@pytest.mark.parametrize("mode", ["callback", "peers", "peers_host_loop"])
+@pytest.mark.parametrize("mode", ["callback", "peers", "peers_host_loop", "peers_device_finish"])
 def test_sharded_per_scan_update_two_processes(emu_lib, mode):
     """the full per-scan update on a 2-way sharded map -- sum of the normal equations over the ranks every iteration inside
     the device-resident loop, replicated 24-state solve, map_incremental with the owners' decisions exchanged -- follows the
@@ -224,14 +224,16 @@ def test_sharded_per_scan_update_two_processes(emu_lib, mode):
     the unsharded map after every scan.  callback: the sums go through the reduce callback (gloo here, NCCL on GPUs);
     peers: through the peer mailboxes from inside k_residual / k_incr_push (shared memory between the two emulator
     processes here, NVLink peer memory on GPUs), with the solve step fused behind the exchange; peers_host_loop: the same
-    with one dlt_measure round trip per iteration."""
+    with one dlt_measure round trip per iteration; peers_device_finish: device_loop = 1 -- zeta blend and map_incremental
+    (classification, k_incr_push / k_incr_pull, insert) queued on the device behind the loop, one synchronisation per scan."""
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000) + {"callback": 0, "peers": 1, "peers_host_loop": 2}[mode]
+    port = 31500 + (os.getpid() % 2000) + {"callback": 0, "peers": 1, "peers_host_loop": 2, "peers_device_finish": 3}[mode]
     peers = mode != "callback"
-    procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, peers, 0 if mode == "peers_host_loop" else -1)) for r in range(2)]
+    loop = {"peers_host_loop": 0, "peers_device_finish": 1}.get(mode, -1)
+    procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, peers, loop)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(2))
