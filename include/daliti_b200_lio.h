@@ -37,7 +37,8 @@ typedef struct dlt_lio_config {
                                    reference writes it);
                                 2: resident on the device (dlt_iekf_update), zeta blend + map_incremental driven
                                    by the host: two synchronisations per scan;
-                                1: blend and insert also queued on the device behind the loop: one synchronisation;
+                                1: blend and insert also queued on the device behind the loop: one synchronisation
+                                   (on a sharded map this needs attached peers, dlt_lio_peer_attach; otherwise it acts as 2);
                                -1 (default): 0 on a single-GPU map, 2 on a sharded map (measured)      */
     int reserved;
 } dlt_lio_config;
