@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the per-scan update latency between configurations of the host loop (device_loop = 0 host loop, 2 device loop +
-host-driven blend/insert, 1 device loop + device-side finish) on the C2 workload: p50 of per-scan CUDA-event times with
+host-driven blend/insert, 1 device loop + device-side finish, 0z host loop with the zero-copy result block) on the C2 workload: p50 of per-scan CUDA-event times with
 the L2 flushed between scans, and the host wall clock.  Development tool."""
 import os
 import sys
@@ -24,11 +24,13 @@ def main():
     devs = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p, _, _ in scans]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
     stream = torch.cuda.Stream()
-    modes = [a for a in sys.argv[1:]] or ["0", "2", "1", "1g"]  # "1g" / "2g": device loop as a CUDA graph with conditional nodes
+    # "1g" / "2g": device loop as a CUDA graph with conditional nodes; "0z": host loop with the zero-copy result block (DLT_ZEROCOPY)
+    modes = [a for a in sys.argv[1:]] or ["0", "0z", "2", "1", "1g"]
     for rep in range(2):
         for mtag in modes:
             mode = int(mtag[0])
             os.environ["DLT_LOOP_GRAPH"] = "1" if mtag.endswith("g") else "0"
+            os.environ["DLT_ZEROCOPY"] = "1" if mtag.endswith("z") else "0"
             lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30,
                               device_loop=mode)
             lm.device.set_stream(stream.cuda_stream)
