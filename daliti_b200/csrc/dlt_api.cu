@@ -59,6 +59,8 @@ struct dlt_handle_s {
     int h_last_nfar = 0;
     bool eig_valid = false;       // the eigen block of d_result belongs to its normal equations
     bool sc_clean = true;         // the scan scalars (bounding box, first-point key) are reset
+    bool vox_retry = false;       // a scan is being re-evaluated after the VoxelGrid bitmap was grown
+    bool map_dead = false;        // the bucket pool / table overflowed: refuse everything but dlt_map_build
     float4 *d_raw = nullptr, *d_undist = nullptr, *d_down = nullptr;
     // double-buffered upload (dlt_scan_prefetch): the next scan's records cross PCIe on the copy stream while this one is processed
     float4 *d_raw_next = nullptr;
@@ -105,9 +107,9 @@ struct dlt_handle_s {
     PeerComm *d_peer = nullptr;
     void *peer_maps[DLT_MAX_PEERS] = {};  // mappings opened by dlt_peer_attach (to be closed)
     size_t peer_map_bytes[DLT_MAX_PEERS] = {};
-    // opt-in (DLT_ZEROCOPY=1): dlt_measure's result block is stored by k_residual straight into pinned host memory and the
+    // (DLT_ZEROCOPY=0 opts out): dlt_measure's result block is stored by k_residual straight into pinned host memory and the
     // host spins on a flag there instead of issuing a device->host copy and synchronising the stream
-    bool zerocopy = false;
+    bool zerocopy = true;  // measured on B200 (round 2): -22 us per C2 scan against the copy + stream synchronisation; DLT_ZEROCOPY=0 switches it off
     unsigned long long zc_seq = 0;
     bool peer_on = false;
     bool peer_detached = false;
@@ -198,6 +200,7 @@ static Pose pose_from(const double *p) {
 
 static int map_reset(dlt_handle h) {
     h->counters_fresh = false;
+    h->map_dead = false;
     DLT_RT(h, rt::fill(h->map.table, 0xFF, h->table_cap * sizeof(Slot), h->stream));
     DLT_RT(h, rt::fill(h->d_counters, 0, 16 * sizeof(int), h->stream));
     return DLT_OK;
@@ -238,7 +241,10 @@ static int resolve_n_down(dlt_handle h) {
     DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     h->n_down_on_device = false;
-    if (h->h_sc->vox_status == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    if (h->h_sc->vox_status == 2) {  // the bitmap was too small for this scan's bounding box: grow it and run the VoxelGrid again
+        int nd = 0;
+        return dlt_scan_downsample(h, &nd);
+    }
     h->n_down = h->h_sc->n_down;
     h->n_down_hint = h->n_down;
     return DLT_OK;
@@ -248,9 +254,22 @@ static int resolve_n_down(dlt_handle h) {
 static int adopt_n_down(dlt_handle h, const double *R) {
     if (!h->n_down_on_device) return DLT_OK;
     h->n_down_on_device = false;
-    if (R[159] < 0.0) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    if (R[159] < 0.0) return -1;  // the occupancy bitmap was too small for this scan: the caller grows it and runs again
     h->n_down = (int)(R[159] + 0.5);
     h->n_down_hint = h->n_down;
+    return DLT_OK;
+}
+
+// The device counter keeps growing after the bucket pool is exhausted (map_claim / map_append add first, then flag the
+// error), so every host-side use of it as a loop bound is clamped to the pool size.
+static inline int clamped_buckets(dlt_handle h) {
+    const int nb = h->h_ints[0];
+    return nb < 0 ? 0 : (nb > h->map.bucket_cap ? h->map.bucket_cap : nb);
+}
+// Once the pool or the table overflowed the map no longer mirrors the reference tree: every later mutation / update is
+// refused until dlt_map_build starts a new map.
+static int map_refuse_if_dead(dlt_handle h) {
+    if (h->map_dead) DLT_FAIL(h, DLT_E_CAPACITY, "the map overflowed earlier (max_map_points): rebuild it with dlt_map_build");
     return DLT_OK;
 }
 
@@ -258,6 +277,7 @@ static int map_check_error(dlt_handle h) {
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     h->counters_fresh = true;
+    if (h->h_ints[2] != 0) h->map_dead = true;
     if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
     if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
     return DLT_OK;
@@ -327,7 +347,7 @@ static int run_far(dlt_handle h, int *n_far_out) {
     }
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
-    int nfar = h->h_ints[5], n_buckets = h->h_ints[0];
+    int nfar = h->h_ints[5], n_buckets = clamped_buckets(h);
     if (n_far_out) *n_far_out = nfar;
     if (nfar <= 0) return DLT_OK;
     ProfScope prof(h, 5);
@@ -404,6 +424,9 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     if (cfg->ds_scan <= 0.f || cfg->ds_map <= 0.f || cfg->max_scan_points <= 0 || cfg->max_map_points <= 0 || cfg->shard_count < 1 ||
         cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count)
         return DLT_E_INVALID;
+    // shard_keeps_cell tests the 8 corners of the +-kShardHalo cube: sufficient only while that 9-cell span touches at most two
+    // tiles per axis, i.e. a tile edge of at least 8 cells
+    if (cfg->shard_count > 1 && cfg->shard_tile_shift != 0 && cfg->shard_tile_shift < 3) return DLT_E_INVALID;
     if (rt::device_count() <= cfg->device) return DLT_E_NO_DEVICE;  // no CPU path: fail loudly
     if (rt::set_device(cfg->device) != 0) return DLT_E_NO_DEVICE;
     dlt_handle h = new dlt_handle_s();
@@ -534,18 +557,20 @@ int dlt_map_build_from_scan(dlt_handle h, const double *pose24) {
 int dlt_map_add(dlt_handle h, const float *xyzi, int n, int downsample_on) {
     if (!h || (n > 0 && !xyzi) || n < 0) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
+    if (int rd = map_refuse_if_dead(h)) return rd;
     h->have_match = false;
     return add_host_points(h, xyzi, n, downsample_on);
 }
 
 int dlt_map_delete_boxes(dlt_handle h, const float *boxes6, int nb, int *deleted) {
     if (!h || nb < 0 || (nb > 0 && !boxes6)) return DLT_E_INVALID;
+    if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
     h->counters_fresh = false;
     DLT_RT(h, rt::fill(h->d_counters + 3, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
-    int n_buckets = h->h_ints[0];
+    int n_buckets = clamped_buckets(h);
     for (int off = 0; off < nb && n_buckets > 0; off += 8) {
         BoxSet bs;
         bs.n = nb - off < 8 ? nb - off : 8;
@@ -583,7 +608,7 @@ int dlt_map_export(dlt_handle h, float *xyzi, int cap, int *n) {
     DLT_RT(h, rt::fill(h->d_counters + 4, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
-    int n_buckets = h->h_ints[0], live = h->h_ints[1];
+    int n_buckets = clamped_buckets(h), live = h->h_ints[1];
     *n = live;
     if (cap == 0 || live == 0 || n_buckets == 0) return DLT_OK;
     float4 *d_out = nullptr;
@@ -728,11 +753,50 @@ int dlt_scan_deskew_dev(dlt_handle h, const void *pts48_dev, int n_raw, const do
     return scan_deskew_impl(h, pts48_dev, true, n_raw, imu_pose22, n_pose, pose24);
 }
 
+// pcl::VoxelGrid accepts any bounding box whose voxel-index space fits an int (beyond that it passes the cloud through,
+// vox_status 1); the occupancy bitmap starts at voxel_bitmap_bits and is grown to what a scan needs (one far outlier
+// point, or a small leaf at long range) instead of failing the scan.
+static int grow_bitmap(dlt_handle h, long long cells) {
+    if (cells <= h->bitmap_bits) return DLT_OK;
+    if (cells > 2147483647ll) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid index space beyond PCL's own limit");
+    long long bits = h->bitmap_bits;
+    while (bits < cells) bits <<= 1;
+    const size_t words = (size_t)((bits + 31) / 32);
+    const int n_blocks = div_up((long long)words, kScanWordsPerBlock);
+    DLT_RT(h, rt::sync(h->stream));
+    unsigned *nb = nullptr, *nw = nullptr, *ns = nullptr, *no = nullptr;
+    void *v[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (rt::alloc(&v[0], words * 4) || rt::alloc(&v[1], words * 4) || rt::alloc(&v[2], (size_t)n_blocks * 4) || rt::alloc(&v[3], (size_t)n_blocks * 4)) {
+        for (void *q : v) rt::release(q);
+        DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bitmap cannot grow to this scan's bounding box (out of device memory)");
+    }
+    nb = (unsigned *)v[0], nw = (unsigned *)v[1], ns = (unsigned *)v[2], no = (unsigned *)v[3];
+    for (void *old : {(void *)h->d_bitmap, (void *)h->d_wprefix, (void *)h->d_blksum, (void *)h->d_blkoff}) {
+        for (size_t k = 0; k < h->allocs.size(); k++)
+            if (h->allocs[k] == old) {
+                h->allocs.erase(h->allocs.begin() + (long)k);
+                break;
+            }
+        rt::release(old);
+    }
+    for (void *q : v) h->allocs.push_back(q);
+    h->d_bitmap = nb;
+    h->d_wprefix = nw;
+    h->d_blksum = ns;
+    h->d_blkoff = no;
+    h->bitmap_bits = bits;
+    h->n_scan_blocks = n_blocks;
+    DLT_RT(h, rt::fill(h->d_bitmap, 0, words * 4, h->stream));
+    return DLT_OK;
+}
+
 // the five VoxelGrid kernels, enqueued
 static int enqueue_downsample(dlt_handle h) {
     const int n = h->n_raw;
     const int B = 256, G = div_up(n, B);
     ProfScope prof(h, 3);
+    // k_vox_final of an earlier downsample of this very scan reset the bounding box: recompute it from the undistorted points
+    if (h->sc_clean) DLT_LAUNCH(k_scan_bbox, G, B, h->stream, (const float4 *)h->d_undist, n, h->d_sc);
     DLT_LAUNCH(k_vox_mark, G, B, h->stream, (const float4 *)h->d_undist, n, h->cfg.ds_scan, h->d_sc, h->d_bitmap, h->bitmap_bits, h->d_vidx);
     DLT_LAUNCH(k_vox_scan1, h->n_scan_blocks, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, h->d_sc, h->d_wprefix, h->d_blksum, h->d_blkoff,
                h->d_ticket + 1);
@@ -756,11 +820,15 @@ int dlt_scan_downsample(dlt_handle h, int *n_down) {
         h->have_down = true;
         return DLT_OK;
     }
-    enqueue_downsample(h);
-    DLT_RT(h, rt::check_launch());
-    DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
-    DLT_RT(h, rt::sync(h->stream));
-    if (h->h_sc->vox_status == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    for (int attempt = 0;; attempt++) {
+        enqueue_downsample(h);
+        DLT_RT(h, rt::check_launch());
+        DLT_RT(h, rt::d2h(h->h_sc, h->d_sc, sizeof(ScanScalars), h->stream));
+        DLT_RT(h, rt::sync(h->stream));
+        if (h->h_sc->vox_status != 2) break;
+        if (attempt > 0) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds the occupancy bitmap");
+        if (int rg = grow_bitmap(h, h->h_sc->vox_cells)) return rg;
+    }
     h->n_down = h->h_sc->n_down;
     h->n_down_hint = h->n_down;
     *n_down = h->n_down;
@@ -963,6 +1031,7 @@ static int measure_dev_impl(dlt_handle h, const double *pose24, int do_match, do
     if (!h || !pose24 || !result_dev) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_measure before a downsampled scan is set");
     if (!do_match && !h->have_match) DLT_FAIL(h, DLT_E_STATE, "dlt_measure(do_match=0) before any match pass");
+    if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
     // right behind dlt_scan_downsample_async feats_down_size is still on the device: the kernels read it there (grids from
     // an estimate / an upper bound) and it comes back with the result block, so no synchronisation is spent on it
@@ -1107,6 +1176,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     if (!h || !blk) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_iekf_update before a downsampled scan is set");
     if (blk->max_iteration < 1 || blk->max_iteration > DLT_IEKF_MAX_ITER) DLT_FAIL(h, DLT_E_INVALID, "max_iteration out of range");
+    if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
     if (h->peer_on) reduce = nullptr;  // the sum over ranks happens inside k_residual (peer mailboxes), the solve step stays fused
     const int n_iter = blk->max_iteration;
@@ -1240,6 +1310,14 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     DLT_RT(h, rt::d2h((char *)h->h_iekf + lo, (const char *)&h->d_iekf->b + lo, hi - lo, h->stream));
     if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
+    if (h->h_iekf->reserved1 == 2 && !h->vox_retry) {  // the occupancy bitmap was too small for this scan: grow it, run the
+        int nd = 0;                                   // VoxelGrid again and repeat the update from the caller's untouched block
+        if (int rg = dlt_scan_downsample(h, &nd)) return rg;
+        h->vox_retry = true;
+        const int r2 = dlt_iekf_update(h, blk, reduce, reduce_ctx, result_dev);
+        h->vox_retry = false;
+        return r2;
+    }
     std::memcpy((char *)blk + lo, (const char *)h->h_iekf + lo, hi - lo);
     if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in this update)");
     if (graph_run) {  // kernels the graph actually ran: one residual pass per iteration, two kNN kernels per match pass
@@ -1262,6 +1340,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
             blk->n_added_ds = h->h_ints[6];
             blk->n_added_raw = h->h_ints[7];
             for (int i = 0; i < 5; i++) blk->map_counters[i] = h->h_ints[i];
+            if (h->h_ints[2] != 0) h->map_dead = true;
             if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
             if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
         } else {
@@ -1272,7 +1351,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     h->h_last_nfar = blk->n_unresolved;
     h->far_hint = blk->n_unresolved;
     h->nfar_known = blk->n_iters > 0;
-    if (blk->reserved1 == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds voxel_bitmap_bits");
+    if (blk->reserved1 == 2) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds the occupancy bitmap");
     if (blk->status == 1) DLT_FAIL(h, DLT_E_STATE, "H^T H + (P/R)^-1 is singular");
     return DLT_OK;
 }
@@ -1304,7 +1383,16 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
     }
     if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in this evaluation)");
     const double *R = h->h_result;
-    if (int rn = adopt_n_down(h, R)) return rn;
+    if (int rn = adopt_n_down(h, R)) {
+        if (rn > 0) return rn;
+        if (h->vox_retry) DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid bounding box exceeds the occupancy bitmap");
+        int nd = 0;
+        if (int rg = dlt_scan_downsample(h, &nd)) return rg;  // grows the bitmap, runs the VoxelGrid again (synchronously)
+        h->vox_retry = true;
+        const int r2 = dlt_measure(h, pose24, do_match, out);
+        h->vox_retry = false;
+        return r2;
+    }
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
     for (int i = 0; i < 12; i++) out->Htr[i] = R[144 + i];
     out->effct_feat_num = (int)(R[156] + 0.5);
@@ -1325,7 +1413,12 @@ int dlt_fetch_result(dlt_handle h, const double *result_dev, dlt_measure_out *ou
     DLT_RT(h, rt::d2h(h->h_result, result_dev, kFetchDoubles * sizeof(double), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     const double *R = h->h_result;
-    if (int rn = adopt_n_down(h, R)) return rn;
+    if (int rn = adopt_n_down(h, R)) {
+        if (rn > 0) return rn;
+        int nd = 0;  // grow the bitmap for the scans to come; this evaluation (already reduced over the ranks) cannot be redone here
+        if (int rg = dlt_scan_downsample(h, &nd)) return rg;
+        DLT_FAIL(h, DLT_E_CAPACITY, "VoxelGrid occupancy bitmap was too small for this scan and has been grown: evaluate the scan again");
+    }
     for (int i = 0; i < 144; i++) out->HtH[i] = R[i];
     for (int i = 0; i < 12; i++) out->Htr[i] = R[144 + i];
     out->effct_feat_num = (int)(R[156] + 0.5);
@@ -1431,6 +1524,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     const bool sharded = h->map.shard_count > 1;
     if (sharded && !h->shard_reduce && !h->peer_on)
         DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental on a sharded map needs dlt_peer_attach or dlt_set_shard_reduce");
+    if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
     if (int rn = resolve_n_down(h)) return rn;
     const int n = h->n_down;

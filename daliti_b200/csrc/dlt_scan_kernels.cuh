@@ -34,6 +34,7 @@ struct ScanScalars {        // device-side scalars of the current scan
     int vox_status;  // 0 ok, 1 leaf too small (PCL passes the cloud through), 2 bitmap capacity exceeded
     int n_words;
     int pad;
+    long long vox_cells;  // size of PCL's voxel-index space for this scan's bounding box (what the bitmap has to cover)
 };
 
 DLT_HD unsigned float_to_ordered(float f) {
@@ -66,6 +67,7 @@ __global__ void k_scan_reset(ScanScalars *sc) {
         sc->n_down = 0;
         sc->vox_status = 0;
         sc->n_words = 0;
+        sc->vox_cells = 0;
     }
 }
 
@@ -252,6 +254,7 @@ __global__ void k_vox_mark(const float4 *__restrict__ pts, int n, float leaf, Sc
     if (i == 0) {
         sc->vox_status = status;
         sc->n_words = status ? 0 : (int)((g.cells + 31) >> 5);
+        sc->vox_cells = g.cells;
     }
     if (i >= n || status) return;
     float4 p = pts[i];

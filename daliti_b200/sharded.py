@@ -32,7 +32,14 @@ def allreduce_measure(handle, pose24, do_match: bool, device: str = "cuda", buf=
     else:
         if buf is None:
             buf = torch.zeros(256, dtype=torch.float64, device=device)
+        # the handle launches on its own non-blocking stream unless told otherwise: put k_residual on the stream NCCL and the
+        # read-back below are ordered on, or the all-reduce could read the buffer before the partial sums are written
+        cur = torch.cuda.current_stream().cuda_stream
+        if cur:
+            handle.set_stream(cur)
         handle.measure_dev(pose24, do_match, buf.data_ptr())
+        if not cur:  # torch's legacy default stream has no handle to adopt: wait for the handle's own stream instead
+            handle.sync()
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(buf[:N_EQ], op=dist.ReduceOp.SUM)
         r = buf[:N_EQ].cpu().numpy()
