@@ -15,6 +15,7 @@
 #include "dlt_frontend_kernels.cuh"
 #include "dlt_map_kernels.cuh"
 #include "dlt_measure_kernels.cuh"
+#include "dlt_loop_kernels.cuh"
 #include "dlt_rt.h"
 #include "dlt_scan_kernels.cuh"
 
@@ -123,6 +124,11 @@ struct dlt_handle_s {
     int loop_graph_state = 0;  // 0 not tried, 1 ready, -1 unavailable (stream launches are used instead)
     int use_graph = 0;  // measured slower than stream launches with early-exit kernels: opt-in via DLT_LOOP_GRAPH=1
     int far_hint = 1;                  // unresolved queries of the previous scan: queue the exact-neighbour fallback behind the loop?
+    // fused loop kernels (dlt_loop_kernels.cuh): one launch per iteration, or -- cooperative launch -- one per scan
+    int loop_fused = 1;                // DLT_LOOP_FUSED=0: the classic three kernels per iteration
+    int loop_coop = 1;                 // DLT_LOOP_COOP=0: k_iekf_iter launches instead of the persistent k_iekf_loop
+    int loop_blocks = 0;               // grid of the loop kernels (0 = not sized yet); DLT_LOOP_BLOCKS caps it (several sequences per GPU)
+    GridBar *d_bar = nullptr;
     // front end (dlt_frontend_sample): sensor cloud staging, grown on demand
     unsigned char *d_sensor = nullptr;
     size_t sensor_cap = 0;
@@ -339,6 +345,34 @@ static int add_host_points(dlt_handle h, const float *xyzi, int n, int downsampl
     return map_check_error(h);
 }
 
+// grid of the fused loop kernels: what is co-resident on the device (a cooperative launch needs exactly that bound), or
+// DLT_LOOP_BLOCKS when several sequences are meant to share the GPU
+static int size_loop_grid(dlt_handle h) {
+    if (h->loop_blocks > 0) return DLT_OK;
+    int per_sm = 2;
+#if !defined(DLT_EMU)
+    int a = 0, b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_iekf_loop<false>, kLoopBlock, 0) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_iekf_loop<true>, kLoopBlock, 0) != cudaSuccess || a < 1 || b < 1) {
+        cudaGetLastError();
+        h->loop_coop = 0;
+    } else {
+        per_sm = h->cfg.extrinsic_est_en ? b : a;
+    }
+    int coop = 0, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) h->loop_coop = 0;
+#endif
+    int g = per_sm * h->n_sm;
+    if (const char *e = std::getenv("DLT_LOOP_BLOCKS")) {
+        const int cap = std::atoi(e);
+        if (cap > 0 && cap < g) g = cap;
+    }
+    if (g < 1) g = 1;
+    h->loop_blocks = g;
+    return DLT_OK;
+}
+
 // exact neighbours for the queries the ring search could not resolve
 static int run_far(dlt_handle h, int *n_far_out) {
     if (h->nfar_known && h->h_last_nfar == 0) {
@@ -438,6 +472,8 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->have_copy = rt::stream_create(&h->copy_stream) == 0 && rt::event_create_untimed(&h->ev_copy) == 0;
     if (const char *e = std::getenv("DLT_LOOP_GRAPH")) h->use_graph = (e[0] == '1') ? 1 : 0;  // A/B switch for measurements
     if (const char *e = std::getenv("DLT_ZEROCOPY")) h->zerocopy = (e[0] == '1');            // A/B switch for measurements
+    if (const char *e = std::getenv("DLT_LOOP_FUSED")) h->loop_fused = (e[0] == '1');
+    if (const char *e = std::getenv("DLT_LOOP_COOP")) h->loop_coop = (e[0] == '1');
     h->have_aux = rt::stream_create(&h->aux_stream) == 0 && rt::event_create_untimed(&h->ev_fork) == 0 && rt::event_create_untimed(&h->ev_join) == 0;
 
     // search cell edge = ds_map * 2^shift with 3 edges covering sqrt(max_sq_dist)
@@ -459,7 +495,8 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     const size_t words = (size_t)((h->bitmap_bits + 31) / 32);
     h->n_scan_blocks = div_up((long long)words, kScanWordsPerBlock);
     const size_t cap = (size_t)h->cap;
-    const int blocks_max = div_up((long long)cap, kResidBlock);
+    int blocks_max = div_up((long long)cap, kResidBlock);
+    if (blocks_max < 16 * h->n_sm) blocks_max = 16 * h->n_sm;  // the fused loop kernels write one partial per block of their grid
     size_t sc_cap = 1;
     while (sc_cap < 4 * cap) sc_cap <<= 1;
     h->scratch.mask = (unsigned)(sc_cap - 1);
@@ -478,7 +515,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
          !dalloc(h, &h->d_result, (size_t)kResultDoubles) && !dalloc(h, &h->d_ticket, 4) &&
          !dalloc(h, &h->d_far_partial, (size_t)kFarChunk * kFarSlices * kK) && !dalloc(h, &h->d_pw, cap) && !dalloc(h, &h->d_dsflag, cap) &&
          !dalloc(h, &h->d_addflag, cap) && !dalloc(h, &h->d_cellslot, cap) && !dalloc(h, &h->d_vslot, cap) &&
-         !dalloc(h, &h->scratch.vkeys, 2 * sc_cap) && !dalloc(h, &h->d_iekf, 1);
+         !dalloc(h, &h->scratch.vkeys, 2 * sc_cap) && !dalloc(h, &h->d_iekf, 1) && !dalloc(h, &h->d_bar, 1);
     if (cfg->shard_count > 1) ok = ok && !dalloc(h, &h->d_flagbuf, cap);
     void *p = nullptr;
     ok = ok && rt::pinned_alloc(&p, sizeof(dlt_iekf_block)) == 0;
@@ -503,7 +540,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
              rt::fill(h->acc.sy, 0, cap * 8, h->stream) == 0 && rt::fill(h->acc.sz, 0, cap * 8, h->stream) == 0 &&
              rt::fill(h->acc.si, 0, cap * 8, h->stream) == 0 && rt::fill(h->acc.cnt, 0, cap * 4, h->stream) == 0 &&
              rt::fill(h->d_ticket, 0, 16, h->stream) == 0 && rt::fill(h->d_sel, 0, cap, h->stream) == 0 &&
-             rt::fill(h->d_result, 0, kResultDoubles * sizeof(double), h->stream) == 0;
+             rt::fill(h->d_result, 0, kResultDoubles * sizeof(double), h->stream) == 0 && rt::fill(h->d_bar, 0, sizeof(GridBar), h->stream) == 0;
     DLT_LAUNCH(k_scan_reset, 1, 32, h->stream, h->d_sc);
     if (!z || map_reset(h) != DLT_OK || rt::sync(h->stream) != 0) {
         dlt_destroy(h);
@@ -1249,7 +1286,53 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
         }
     }
 #endif
-    for (int it = 0; it < n_iter && !graph_run; it++) {
+    // ---- fused loop kernels: match pass + residual pass + solve of an iteration in one launch, or the whole loop in one
+    //      cooperative launch with the eigen-decomposition inside (dlt_loop_kernels.cuh).  Not with a reduce callback (the
+    //      library collective has to run between the residual pass and the solve) and not while per-kernel profiling is on.
+    bool fused_run = false, eig_in_kernel = false;
+    if (!graph_run && !reduce && res == h->d_result && h->loop_fused && !h->prof_on) {
+        if (int rs = size_loop_grid(h)) return rs;
+        LoopK lk;
+        lk.m = h->map;
+        lk.down = h->d_down;
+        lk.knn = h->knn;
+        lk.mb = mb;
+        lk.dev = h->d_iekf;
+        lk.n_ptr = &h->d_sc->n_down;
+        lk.vox_ptr = &h->d_sc->vox_status;
+        lk.max_sq_dist = h->cfg.max_sq_dist;
+        lk.plane_thr = h->cfg.plane_thr;
+        lk.peer = h->peer_on ? h->d_peer : nullptr;
+        lk.bar = h->d_bar;
+        lk.eig_out = h->d_result + kEigOffset;
+        lk.max_iter = n_iter;
+        // far_count, the add counters, the hand-over counter and the nearest-point counters in one memset (d_counters[5..10])
+        DLT_RT(h, rt::fill(h->d_counters + 5, 0, 6 * sizeof(int), h->stream));
+        const bool ext = h->cfg.extrinsic_est_en != 0;
+#if !defined(DLT_EMU)
+        if (h->loop_coop) {
+            void *args[] = {(void *)&lk};
+            const void *fn = ext ? (const void *)k_iekf_loop<true> : (const void *)k_iekf_loop<false>;
+            if (cudaLaunchCooperativeKernel(fn, dim3(h->loop_blocks), dim3(kLoopBlock), args, 0, h->stream) == cudaSuccess) {
+                ++rt::g_launches;
+                fused_run = eig_in_kernel = true;
+            } else {
+                cudaGetLastError();
+                h->loop_coop = 0;  // (e.g. a device without cooperative launch): one launch per iteration from here on
+            }
+        }
+#endif
+        if (!fused_run) {
+            for (int it = 0; it < n_iter; it++) {
+                if (ext)
+                    DLT_LAUNCH(k_iekf_iter<true>, h->loop_blocks, kLoopBlock, h->stream, lk);
+                else
+                    DLT_LAUNCH(k_iekf_iter<false>, h->loop_blocks, kLoopBlock, h->stream, lk);
+            }
+            fused_run = true;
+        }
+    }
+    for (int it = 0; it < n_iter && !graph_run && !fused_run; it++) {
         {
             ProfScope prof(h, 0);
             int rk = launch_knn(h, (const float4 *)h->d_down, 0, n_grid, 1, P, la);
@@ -1274,7 +1357,13 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     // degeneracy output: fork the eigen-decomposition of the last normal equations onto the side stream now, so that
     // it runs while the host waits for / digests the block below
     h->have_match = true;
-    if (int re = dlt_degeneracy_begin(h)) return re;
+    if (eig_in_kernel) {  // k_iekf_loop left the decomposition of the last iteration's pose block next to the normal equations
+        DLT_RT(h, rt::d2h(h->h_result + kEigOffset, h->d_result + kEigOffset, 42 * sizeof(double), h->stream));
+        h->eig_valid = true;
+        h->eig_pending = false;
+    } else if (int re = dlt_degeneracy_begin(h)) {
+        return re;
+    }
     if (finish) {  // ---- map_incremental (:582-630, 1164-1168) behind the loop, armed by the last k_iekf_step
         IekfDev *ctl = h->d_iekf;
         if (far_q) {
@@ -1282,7 +1371,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
             DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 2 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
         }
-        DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));  // downsample adds, raw adds (far_count is re-armed by the next k_knn8)
+        if (!fused_run) DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));  // downsample adds, raw adds (far_count is re-armed by the next k_knn8)
         // unsharded: the classification kernel also claims cells and places the voxel bids.  Sharded: the owners' decisions are
         // exchanged first (k_incr_push / k_incr_pull through the peer mailboxes, gated like everything here), then every rank
         // inserts what falls into its tiles + halo

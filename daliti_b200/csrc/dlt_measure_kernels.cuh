@@ -542,7 +542,7 @@ DLT_D void knn8_consume(const float4 v, int &bb, int lane, int sub, float qx, fl
 
 // the four queries q0 .. q0+3 of one warp
 DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n, int body_frame, const Pose &P, float max_sq_dist, const KnnOut &out,
-                      int *__restrict__ unres_list, int *__restrict__ unres_count, int q0, int lane) {
+                      int *unres_list, int *unres_count, int q0, int lane, int unres_cap = 0x7FFFFFFF) {
     const unsigned FULL = 0xffffffffu;
     const int grp = lane >> 3, sub = lane & 7;
     const int qi = q0 + grp;
@@ -657,7 +657,10 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
     cov -= slack;
     const bool resolved = (nb == kK) && !tie && cov > 0.f && d5 < cov * cov * 0.99999f;
     if (!resolved) {
-        if (sub == 0) unres_list[atomicAdd(unres_count, 1)] = qi;
+        if (sub == 0) {
+            const int pos = atomicAdd(unres_count, 1);
+            if (pos < unres_cap) unres_list[pos] = qi;  // (the fused loop kernels size their block-local list to the chunk: never full)
+        }
         return;
     }
     if (sub < kK) {
@@ -1348,166 +1351,128 @@ DLT_D void zc_publish(const MeasureBufs &mb, const double *R) {  // whole block;
     if (threadIdx.x == 0) *(volatile unsigned long long *)mb.zc_flag = mb.zc_seq;
 }
 
+// One point of the residual pass: plane (fitted on a match iteration, cached otherwise), residual + gates, Jacobian row.
+// Returns `effective`; row / meas / absr are only meaningful then.  Writes plane / coeff / sel / eff of the point.
 template <bool EXT>
-__global__ void __launch_bounds__(kResidBlock)
-    k_residual(MeasureBufs mb, int n, int do_match, Pose P_param, float plane_thr, LoopArgs la) {
-    using NE = NormalEq<EXT>;
-    constexpr int D = NE::D, NR = NE::NR;
-    __shared__ double s_part[kResidBlock / 32][NR];
-    __shared__ int s_last;
-    __shared__ Pose sP;
-    if (!loop_resolve(la, P_param, &sP, n, &do_match)) return;  // block-uniform
-    // the grid may be larger than needed (sized before the host knows n): only the first n_blocks blocks work
-    const unsigned n_blocks = (unsigned)((n + kResidBlock - 1) / kResidBlock);
-    if (n_blocks == 0u) {  // empty scan: the normal equations are zero
-        if (blockIdx.x == 0) {
-            for (int k = threadIdx.x; k < kNormalEqDoubles; k += kResidBlock) mb.result[k] = 0.0;
-            if (threadIdx.x == 0) {
-                mb.result[158] = (double)(*mb.far_count);
-                mb.result[159] = (la.vox_ptr && *la.vox_ptr == 2) ? -1.0 : 0.0;
-                *mb.unres_count = 0;
-            }
-            if (mb.zc_result) {  // block-uniform
-                __syncthreads();
-                zc_publish(mb, mb.result);
-            }
-        }
-        return;
-    }
-    if (blockIdx.x >= n_blocks) return;
-    const Pose &P = sP;
-    const int i = blockIdx.x * kResidBlock + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    double row[D];
-    double meas = 0.0, absr = 0.0;
+DLT_D bool residual_point(const MeasureBufs &mb, int i, int do_match, const Pose &P, float plane_thr, double (&row)[NormalEq<EXT>::D], double &meas,
+                          double &absr) {
+    constexpr int D = NormalEq<EXT>::D;
     bool effective = false;
-#pragma unroll
-    for (int d = 0; d < D; d++) row[d] = 0.0;
-
-    if (i < n) {
-        float4 pb = mb.down[i];
-        float wx, wy, wz;
-        body_to_world(P, pb.x, pb.y, pb.z, wx, wy, wz);
-        bool sel;
-        float4 pl;
-        if (do_match) {  // :847-863
-            sel = (mb.flags[i] & kFlagMatched) != 0;
-            pl = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (sel) {
-                float px[5], py[5], pz[5];
-#pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    float4 e = mb.nbr[(size_t)i * kK + j];
-                    px[j] = e.x;
-                    py[j] = e.y;
-                    pz[j] = e.z;
-                }
-                float pabcd[4];
-                sel = esti_plane(pabcd, px, py, pz, plane_thr);
-                pl = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
-            }
-            mb.plane[i] = pl;
-        } else {
-            sel = mb.sel[i] != 0;
-            pl = mb.plane[i];
-        }
-        bool sel_out = false;
+    float4 pb = mb.down[i];
+    float wx, wy, wz;
+    body_to_world(P, pb.x, pb.y, pb.z, wx, wy, wz);
+    bool sel;
+    float4 pl;
+    if (do_match) {  // :847-863
+        sel = (mb.flags[i] & kFlagMatched) != 0;
+        pl = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sel) {
-            float pd2 = pl.x * wx + pl.y * wy;  // :866
-            pd2 = pd2 + pl.z * wz;
-            pd2 = pd2 + pl.w;
-            double bn = sqrt(((double)pb.x * (double)pb.x + (double)pb.y * (double)pb.y) + (double)pb.z * (double)pb.z);
-            float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(bn));  // :868
-            if ((double)s > 0.9) {                                         // :870
-                sel_out = true;
-                mb.coeff[i] = make_float4(pl.x, pl.y, pl.z, pd2);
-                absr = (double)fabsf(pd2);  // res_last, :879
-                if (absr <= 2.0) {           // :889
-                    effective = true;
-                    // Jacobian row, :948-977
-                    double tx, ty, tz, Cx, Cy, Cz;
-                    mat3_vec(P.R_L_I, (double)pb.x, (double)pb.y, (double)pb.z, tx, ty, tz);
-                    tx += P.T_L_I[0];
-                    ty += P.T_L_I[1];
-                    tz += P.T_L_I[2];
-                    mat3T_vec(P.rot_end, (double)pl.x, (double)pl.y, (double)pl.z, Cx, Cy, Cz);
-                    row[0] = ty * Cz - tz * Cy;  // [point_this]x * C
-                    row[1] = tz * Cx - tx * Cz;
-                    row[2] = tx * Cy - ty * Cx;
-                    row[3] = (double)pl.x;
-                    row[4] = (double)pl.y;
-                    row[5] = (double)pl.z;
-                    if (EXT) {
-                        double ux, uy, uz;  // R_L_I^T * C
-                        mat3T_vec(P.R_L_I, Cx, Cy, Cz, ux, uy, uz);
-                        double bx = (double)pb.x, by = (double)pb.y, bz = (double)pb.z;
-                        row[D - 6] = by * uz - bz * uy;  // [point_this_be]x * R_L_I^T * C
-                        row[D - 5] = bz * ux - bx * uz;
-                        row[D - 4] = bx * uy - by * ux;
-                        row[D - 3] = Cx;
-                        row[D - 2] = Cy;
-                        row[D - 1] = Cz;
-                    }
-                    meas = -(double)pd2;  // :977
-                }
+            float px[5], py[5], pz[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                float4 e = mb.nbr[(size_t)i * kK + j];
+                px[j] = e.x;
+                py[j] = e.y;
+                pz[j] = e.z;
             }
+            float pabcd[4];
+            sel = esti_plane(pabcd, px, py, pz, plane_thr);
+            pl = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
         }
-        mb.sel[i] = sel_out ? 1 : 0;
-        mb.eff[i] = effective ? 1 : 0;
+        mb.plane[i] = pl;
+    } else {
+        sel = mb.sel[i] != 0;
+        pl = mb.plane[i];
     }
-
-    // ---- warp shuffle reduction of the NR accumulators, then shared memory across warps
-    {
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < D; a++) {
-#pragma unroll
-            for (int b = a; b < D; b++) {
-                double v = effective ? row[a] * row[b] : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) s_part[warp][k] = v;
-                k++;
+    bool sel_out = false;
+    if (sel) {
+        float pd2 = pl.x * wx + pl.y * wy;  // :866
+        pd2 = pd2 + pl.z * wz;
+        pd2 = pd2 + pl.w;
+        double bn = sqrt(((double)pb.x * (double)pb.x + (double)pb.y * (double)pb.y) + (double)pb.z * (double)pb.z);
+        float s = (float)(1 - 0.9 * (double)fabsf(pd2) / sqrt(bn));  // :868
+        if ((double)s > 0.9) {                                         // :870
+            sel_out = true;
+            mb.coeff[i] = make_float4(pl.x, pl.y, pl.z, pd2);
+            absr = (double)fabsf(pd2);  // res_last, :879
+            if (absr <= 2.0) {           // :889
+                effective = true;
+                // Jacobian row, :948-977
+                double tx, ty, tz, Cx, Cy, Cz;
+                mat3_vec(P.R_L_I, (double)pb.x, (double)pb.y, (double)pb.z, tx, ty, tz);
+                tx += P.T_L_I[0];
+                ty += P.T_L_I[1];
+                tz += P.T_L_I[2];
+                mat3T_vec(P.rot_end, (double)pl.x, (double)pl.y, (double)pl.z, Cx, Cy, Cz);
+                row[0] = ty * Cz - tz * Cy;  // [point_this]x * C
+                row[1] = tz * Cx - tx * Cz;
+                row[2] = tx * Cy - ty * Cx;
+                row[3] = (double)pl.x;
+                row[4] = (double)pl.y;
+                row[5] = (double)pl.z;
+                if (EXT) {
+                    double ux, uy, uz;  // R_L_I^T * C
+                    mat3T_vec(P.R_L_I, Cx, Cy, Cz, ux, uy, uz);
+                    double bx = (double)pb.x, by = (double)pb.y, bz = (double)pb.z;
+                    row[D - 6] = by * uz - bz * uy;  // [point_this_be]x * R_L_I^T * C
+                    row[D - 5] = bz * ux - bx * uz;
+                    row[D - 4] = bx * uy - by * ux;
+                    row[D - 3] = Cx;
+                    row[D - 2] = Cy;
+                    row[D - 1] = Cz;
+                }
+                meas = -(double)pd2;  // :977
             }
         }
+    }
+    mb.sel[i] = sel_out ? 1 : 0;
+    mb.eff[i] = effective ? 1 : 0;
+    return effective;
+}
+
+// warp shuffle reduction of the NR accumulators of one warp's 32 points into dst[0..NR) (lane 0 stores or adds)
+template <bool EXT, bool ACCUM>
+DLT_D void residual_warp_reduce(const double (&row)[NormalEq<EXT>::D], double meas, double absr, bool effective, double *dst, int lane) {
+    constexpr int D = NormalEq<EXT>::D;
+    int k = 0;
 #pragma unroll
-        for (int a = 0; a < D; a++) {
-            double v = effective ? row[a] * meas : 0.0;
+    for (int a = 0; a < D; a++) {
+#pragma unroll
+        for (int b = a; b < D; b++) {
+            double v = effective ? row[a] * row[b] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_part[warp][k] = v;
+            if (lane == 0) dst[k] = ACCUM ? dst[k] + v : v;
             k++;
         }
-        double c = effective ? 1.0 : 0.0, r = effective ? absr : 0.0;
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            c += __shfl_xor_sync(0xffffffffu, c, o);
-            r += __shfl_xor_sync(0xffffffffu, r, o);
-        }
-        if (lane == 0) {
-            s_part[warp][k] = c;
-            s_part[warp][k + 1] = r;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < NR) {
-        double v = 0.0;
+    for (int a = 0; a < D; a++) {
+        double v = effective ? row[a] * meas : 0.0;
 #pragma unroll
-        for (int w = 0; w < kResidBlock / 32; w++) v += s_part[w][threadIdx.x];
-        mb.partials[(size_t)blockIdx.x * NR + threadIdx.x] = v;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) dst[k] = ACCUM ? dst[k] + v : v;
+        k++;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(mb.ticket, 1u);
-        s_last = (t == n_blocks - 1u) ? 1 : 0;
+    double c = effective ? 1.0 : 0.0, r = effective ? absr : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
     }
-    __syncthreads();
-    if (!s_last) return;
-    // ---- last block: fixed-order sum over blocks (deterministic): 8 interleaved slices per value (one per warp),
-    //      each summed in block order with 16 loads in flight, then combined in slice order
-    __threadfence();
+    if (lane == 0) {
+        dst[k] = ACCUM ? dst[k] + c : c;
+        dst[k + 1] = ACCUM ? dst[k + 1] + r : r;
+    }
+}
+
+// Last block of a residual pass (256 threads): fixed-order sum over the per-block partials (deterministic): 8 interleaved
+// slices per value (one per warp), each summed in block order with 16 loads in flight, then combined in slice order;
+// unpacked into the 12 x 12 result block R together with the scalars that ride along (far_count, feats_down_size).
+template <bool EXT>
+DLT_D void residual_final_reduce(const MeasureBufs &mb, unsigned n_parts, int n, const LoopArgs &la) {
+    using NE = NormalEq<EXT>;
+    constexpr int D = NE::D, NR = NE::NR;
     constexpr unsigned S = kResidBlock / 32;
     __shared__ double s_sum[S][32];
     __shared__ double s_fin[NR];
@@ -1516,10 +1481,10 @@ __global__ void __launch_bounds__(kResidBlock)
         double acc = 0.0;
         if (v < NR) {
             const double *vp = mb.partials;
-            for (unsigned b = sl; b < n_blocks; b += S * 16) {  // (adding 0.0 for the padding is exact)
+            for (unsigned b = sl; b < n_parts; b += S * 16) {  // (adding 0.0 for the padding is exact)
                 double t[16];
 #pragma unroll
-                for (unsigned u = 0; u < 16; u++) t[u] = (b + S * u < n_blocks) ? __ldcg(vp + (size_t)(b + S * u) * NR + v) : 0.0;
+                for (unsigned u = 0; u < 16; u++) t[u] = (b + S * u < n_parts) ? __ldcg(vp + (size_t)(b + S * u) * NR + v) : 0.0;
 #pragma unroll
                 for (unsigned u = 0; u < 16; u++) acc += t[u];
             }
@@ -1557,11 +1522,71 @@ __global__ void __launch_bounds__(kResidBlock)
         }
     }
     if (threadIdx.x == 0) {
-        R[158] = (double)(*mb.far_count);
+        R[158] = (double)(*(volatile const int *)mb.far_count);
         R[159] = (la.vox_ptr && *la.vox_ptr == 2) ? -1.0 : (double)n;  // feats_down_size (-1: VoxelGrid capacity exceeded)
         *mb.ticket = 0u;
         *mb.unres_count = 0;
     }
+}
+
+template <bool EXT>
+__global__ void __launch_bounds__(kResidBlock)
+    k_residual(MeasureBufs mb, int n, int do_match, Pose P_param, float plane_thr, LoopArgs la) {
+    using NE = NormalEq<EXT>;
+    constexpr int D = NE::D, NR = NE::NR;
+    __shared__ double s_part[kResidBlock / 32][NR];
+    __shared__ int s_last;
+    __shared__ Pose sP;
+    if (!loop_resolve(la, P_param, &sP, n, &do_match)) return;  // block-uniform
+    // the grid may be larger than needed (sized before the host knows n): only the first n_blocks blocks work
+    const unsigned n_blocks = (unsigned)((n + kResidBlock - 1) / kResidBlock);
+    if (n_blocks == 0u) {  // empty scan: the normal equations are zero
+        if (blockIdx.x == 0) {
+            for (int k = threadIdx.x; k < kNormalEqDoubles; k += kResidBlock) mb.result[k] = 0.0;
+            if (threadIdx.x == 0) {
+                mb.result[158] = (double)(*mb.far_count);
+                mb.result[159] = (la.vox_ptr && *la.vox_ptr == 2) ? -1.0 : 0.0;
+                *mb.unres_count = 0;
+            }
+            if (mb.zc_result) {  // block-uniform
+                __syncthreads();
+                zc_publish(mb, mb.result);
+            }
+        }
+        return;
+    }
+    if (blockIdx.x >= n_blocks) return;
+    const Pose &P = sP;
+    const int i = blockIdx.x * kResidBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    double row[D];
+    double meas = 0.0, absr = 0.0;
+    bool effective = false;
+#pragma unroll
+    for (int d = 0; d < D; d++) row[d] = 0.0;
+    if (i < n) effective = residual_point<EXT>(mb, i, do_match, P, plane_thr, row, meas, absr);
+
+    // ---- warp shuffle reduction of the NR accumulators, then shared memory across warps
+    residual_warp_reduce<EXT, false>(row, meas, absr, effective, s_part[warp], lane);
+    __syncthreads();
+    if (threadIdx.x < NR) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kResidBlock / 32; w++) v += s_part[w][threadIdx.x];
+        mb.partials[(size_t)blockIdx.x * NR + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(mb.ticket, 1u);
+        s_last = (t == n_blocks - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    residual_final_reduce<EXT>(mb, n_blocks, n, la);
+    double *R = mb.result;
     if (la.peer && !peer_allreduce_block(la.peer, R, kNormalEqDoubles)) {  // block-uniform; starts and ends with a barrier
         if (la.ctl && threadIdx.x == 0) const_cast<IekfDev *>(la.ctl)->b.done = 1;  // a peer never posted: end the loop, the host reports it
         return;
@@ -1587,12 +1612,11 @@ __global__ void __launch_bounds__(kResidBlock)
 // the 15 index pairs of a sweep are visited in 5 rounds of 3 disjoint pairs (round-robin
 // tournament); lanes 0-2 compute the three rotations of a round, then 18 lanes apply them to
 // the columns / rows of A and the columns of V.  Ascending eigenvalues, eigenvectors in columns.
-__global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result, double *__restrict__ eig_out /* eigvals[6], eigvecs[36] */) {
+DLT_D void eigen6_warp(const double *__restrict__ result, double *__restrict__ eig_out /* eigvals[6], eigvecs[36] */, int lane) {
     __shared__ double A[36], V[36], cs[3][2];
     __shared__ int pq[3][2];
-    const int lane = threadIdx.x;
     for (int i = lane; i < 36; i += 32) {
-        A[i] = result[(i / 6) * 12 + (i % 6)];
+        A[i] = __ldcg(result + (i / 6) * 12 + (i % 6));  // (inside the persistent loop kernel another block wrote it)
         V[i] = (i % 7 == 0) ? 1.0 : 0.0;
     }
     __syncwarp();
@@ -1672,6 +1696,7 @@ __global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result
         }
     }
 }
+__global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result, double *__restrict__ eig_out) { eigen6_warp(result, eig_out, threadIdx.x); }
 
 // ------------------------------------------------------------------ map_incremental classification
 // laserMapping.cpp:582-630: decide per downsampled point whether it is added raw

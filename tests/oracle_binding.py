@@ -266,6 +266,9 @@ class OracleLio:
         self.o.lib.orc_lio_get_localmap(C.c_void_p(self.h), _p(b))
         return b
 
+    def imu_ready(self) -> bool:
+        return bool(self.o.lib.orc_lio_imu_ready(C.c_void_p(self.h)))
+
 
 class Oracle:
     def __init__(self, lib, ref_ok):

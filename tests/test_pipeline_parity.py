@@ -4,7 +4,12 @@ the same raw scans + IMU: deskew -> VoxelGrid -> IEKF iterations -> zeta blend -
 
 Chained end to end the two paths are not bit-identical (CUDA vs glibc sin/cos in the deskew, and
 the order-independent fixed-point VoxelGrid centroids differ from PCL's float sums in the last
-bit), so poses are compared at the north-star tolerance (1e-5 relative), counts within 1%."""
+bit).  The bounds below come from the measured series profiles/r02_parity_series_mid.json
+(tools/parity_series.py, 100 chained scans of 32 x 1024 on a B200): for the first 22 scans every count
+(feats_down_size, effct_feat_num, added points) is EQUAL and the pose differs by < 4e-8; then one plane-fit
+gate flips on one of ~12 k points (effct differs by 1) and the chains separate to 5e-7 .. 1.3e-5 (max over
+the 100 scans), with feats_down_size never more than 1 apart, effct_feat_num <= 19 (0.16 %) and <= 5 of
+12.7 k voxels per scan differing.  Re-synced per scan (identical inputs) the pose stays below 8e-7."""
 import numpy as np
 import pytest
 
@@ -53,21 +58,20 @@ def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal
         th_o = th_d = None
         if thermal is not None:
             th_o, th_d = thermal(k)
-        # identical inputs hold for the first updates only; afterwards the two chains carry their own maps
-        # and states (one differently-won voxel changes later neighbour sets), so the bound is loosened
-        chain_tol = 1e-5 if k <= 2 else 2e-4
+        # north-star tolerance; measured over these short chains: < 4e-8 until a gate flips, < 1e-5 for 40 scans after one does
+        chain_tol = 1e-5
         so = lio.process_scan(pts, t_beg, imu, th_o)
         sd = lm.process_scan(pts, t_beg, imu, th_d)
         assert (sd.had_points, sd.built_map, sd.did_update) == (so.had_points, so.built_map, so.did_update), k
         assert sd.n_raw == so.n_raw
-        assert abs(sd.n_down - so.n_down) <= max(2, so.n_down // 200), (sd.n_down, so.n_down)
+        assert abs(sd.n_down - so.n_down) <= 1, (sd.n_down, so.n_down)  # (measured: never more than 1 apart in 100 chained scans)
         ok, e = pose_close(np.array(sd.state_prop), np.array(so.state_prop), 1e-9 if k == 0 else chain_tol)
         assert ok, ("state_propagat", k, e)
         if so.did_update:
             assert sd.n_iters == so.n_iters, (k, sd.n_iters, so.n_iters)
             for a, b in zip(lm.iters(), lio.iters()):
                 assert (a.did_match, a.ekf_stop, a.converged) == (b.did_match, b.ekf_stop, b.converged), (k, a.iter)
-                assert abs(a.effct_feat_num - b.effct_feat_num) <= max(3, b.effct_feat_num // 100), (k, a.iter, a.effct_feat_num, b.effct_feat_num)
+                assert abs(a.effct_feat_num - b.effct_feat_num) <= 3 + b.effct_feat_num // 2000, (k, a.iter, a.effct_feat_num, b.effct_feat_num)
                 ok, e = pose_close(np.array(a.state_out), np.array(b.state_out), chain_tol)
                 assert ok, ("iteration state", k, a.iter, e)
             assert sd.ekf_stop == so.ekf_stop
@@ -78,7 +82,7 @@ def run_pair(lib, oracle, seq, n_scans, max_pts, first_scan_builds=True, thermal
         np.testing.assert_allclose(s_d[24:36], s_o[24:36], rtol=10 * chain_tol, atol=chain_tol)     # vel, biases, gravity
         np.testing.assert_allclose(s_d[36:], s_o[36:], rtol=1e-6, atol=1e-9)         # covariance
         n_d, n_o = lm.device.map_valid_count(), lio.map().validnum()
-        assert abs(n_d - n_o) <= max(4, n_o // 100), (k, n_d, n_o)
+        assert abs(n_d - n_o) <= 4 + n_o // 5000, (k, n_d, n_o)
         assert lm.flags()["ekf_stop"] == lio.flags()["ekf_stop"]
     lm.close()
     return stops
@@ -95,6 +99,50 @@ def test_pipeline_first_scan_builds_map(dev, oracle, device_loop):
         n, cap = 4, 8192
     stops = run_pair(lib, oracle, seq, n, cap, device_loop=device_loop, featptsThreshold=5)
     assert stops == 0
+
+
+def test_pipeline_imu_initial(dev, oracle):
+    """ImuProcess::IMU_Initial (IMU_Processing.hpp:161-202, 385-405) instead of force_imu_ready: the first MAX_INI_COUNT = 100
+    IMU samples (five 20-sample scans) only feed the running mean / covariance and set gravity, bias_g and the extrinsics;
+    no scan is processed until then (laserMapping.cpp:755-759).  Afterwards the first processed scan builds the map and the
+    following ones update against it -- all from the default StatesGroup, exactly as the node starts."""
+    lib, is_gpu = dev
+    seq = helpers.small_sequence(seed=15, half=25.0, beams=16, azimuths=900 if is_gpu else 240, n_boxes=8, speed=1.0, yaw_rate=0.1)
+    kind = MAP_REF if oracle.ref_ok else MAP_PORT
+    import oracle_binding as ob
+
+    kw = dict(featptsThreshold=5)
+    lio = oracle.new_lio(ob.default_lio_config(**kw), kind)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=32768 if is_gpu else 8192, max_map_points=1 << 18), **kw)
+    assert not lio.imu_ready() and lm.flags()["imu_ready"] == 0
+    ready_at, built_at, updates = None, None, 0
+    for k in range(10):
+        pts, t_beg, imu = seq.scan(k)
+        assert len(imu) >= 19
+        lio.on_lidar_msg()
+        lm.on_lidar_msg()
+        so = lio.process_scan(pts, t_beg, imu)
+        sd = lm.process_scan(pts, t_beg, imu)
+        assert (sd.had_points, sd.built_map, sd.did_update, sd.n_raw) == (so.had_points, so.built_map, so.did_update, so.n_raw), k
+        assert bool(lm.flags()["imu_ready"]) == lio.imu_ready(), k
+        if ready_at is None and lio.imu_ready():
+            ready_at = k
+        if so.built_map:
+            built_at = k
+        s_d, s_o = lm.get_state(), lio.get_state()
+        if not so.had_points:  # initialising: gravity, bias_g, extrinsics come from the running means -- plain fp64 host arithmetic on both sides
+            np.testing.assert_allclose(s_d[:36], s_o[:36], rtol=0, atol=1e-13)
+            np.testing.assert_array_equal(s_d[36:], s_o[36:])
+        else:
+            ok, e = pose_close(s_d, s_o, 1e-5)
+            assert ok, (k, e)
+            np.testing.assert_allclose(s_d[24:36], s_o[24:36], rtol=1e-4, atol=1e-5)
+        if so.did_update:
+            updates += 1
+            assert sd.n_iters == so.n_iters and sd.ekf_stop == so.ekf_stop, k
+    # 100 samples at 20 per scan: scans 0-4 initialise, scan 5 is the first one processed (builds the map), 6.. update
+    assert ready_at is not None and built_at == ready_at + 1 and updates >= 3, (ready_at, built_at, updates)
+    lm.close()
 
 
 def test_pipeline_degradation_stop_and_thermal(dev, oracle):
@@ -164,12 +212,12 @@ def test_pipeline_sliding_local_map_box_delete(dev, oracle):
         lm.on_lidar_msg()
         so = lio.process_scan(pts, t_beg, imu)
         sd = lm.process_scan(pts, t_beg, imu)
-        assert abs(sd.deleted - so.deleted) <= max(3, so.deleted // 50), (k, sd.deleted, so.deleted)
+        assert abs(sd.deleted - so.deleted) <= 2 + so.deleted // 2000, (k, sd.deleted, so.deleted)
         deleted_total += so.deleted
         np.testing.assert_array_equal(lm.localmap(), lio.localmap())
         n_d, n_o = lm.device.map_valid_count(), lio.map().validnum()
-        assert abs(n_d - n_o) <= max(4, n_o // 100), (k, n_d, n_o)
-        ok, e = pose_close(lm.get_state(), lio.get_state(), 2e-4)
+        assert abs(n_d - n_o) <= 4 + n_o // 5000, (k, n_d, n_o)
+        ok, e = pose_close(lm.get_state(), lio.get_state(), 1e-5)
         assert ok, (k, e)
     assert deleted_total > 0
     lm.close()
@@ -219,10 +267,11 @@ def test_device_resident_loop_equals_host_loop(dev, stop, mode):
             hs = max(1.0, np.abs(np.array(rb.HtH)).max())
             np.testing.assert_allclose(np.array(ra.HtH), np.array(rb.HtH), rtol=1e-7, atol=1e-8 * hs)
             np.testing.assert_allclose(np.array(ra.Htr), np.array(rb.Htr), rtol=1e-7, atol=1e-8 * hs)
-            np.testing.assert_allclose(np.array(ra.pose_in), np.array(rb.pose_in), rtol=0, atol=2e-8)
-            np.testing.assert_allclose(np.array(ra.solution), np.array(rb.solution), rtol=1e-5, atol=2e-8)
-            np.testing.assert_allclose(np.array(ra.state_out), np.array(rb.state_out), rtol=0, atol=2e-8)
-        np.testing.assert_allclose(lms[0].get_state(), lms[1].get_state(), rtol=1e-6, atol=2e-8)
+            # (5e-8: the fused loop kernels also sum the normal equations in another order than k_residual does)
+            np.testing.assert_allclose(np.array(ra.pose_in), np.array(rb.pose_in), rtol=0, atol=5e-8)
+            np.testing.assert_allclose(np.array(ra.solution), np.array(rb.solution), rtol=1e-5, atol=5e-8)
+            np.testing.assert_allclose(np.array(ra.state_out), np.array(rb.state_out), rtol=0, atol=5e-8)
+        np.testing.assert_allclose(lms[0].get_state(), lms[1].get_state(), rtol=1e-6, atol=5e-8)
         np.testing.assert_allclose(np.array(a.eigvals), np.array(b.eigvals), rtol=1e-6, atol=1e-6)
         assert lms[0].flags() == lms[1].flags()
         assert lms[0].device.map_valid_count() == lms[1].device.map_valid_count()
