@@ -70,7 +70,7 @@ def build_workload(rank: int, n_scans: int, workload: str):
     try:
         from concurrent.futures import ProcessPoolExecutor
 
-        workers = max(1, min(8, (os.cpu_count() or 2) - 1, n_scans))
+        workers = max(1, min(16, len(os.sched_getaffinity(0)) - 1, n_scans))
         if workers > 1:
             with ProcessPoolExecutor(workers) as ex:
                 scans = list(ex.map(_gen_scan, [(seq, k) for k in range(n_scans)]))
@@ -217,6 +217,35 @@ def run_cpu(work, n_steps, n_warm, threads_list):
         return _run_cpu(work, n_steps, n_warm, threads_list)
 
 
+def run_cpu_concurrent(works, n_steps, n_warm, threads_each):
+    """N independent CPU pipelines at once (the reference arm's counterpart of N GPUs running one sequence each): one Python
+    thread per pipeline (ctypes releases the GIL inside the oracle), threads_each OpenMP threads in each.  Aggregate = total
+    points / wall time of the slowest pipeline."""
+    import threading
+
+    res = [None] * len(works)
+
+    def one(i):
+        res[i] = _run_cpu(works[i], n_steps, n_warm, [threads_each])
+
+    with _QuietStdout():
+        ths = [threading.Thread(target=one, args=(i,)) for i in range(len(works))]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        wall = time.perf_counter() - t0
+    if any(r is None for r in res):
+        raise RuntimeError("a CPU pipeline failed")
+    tot_pts = sum(r["points_per_s"] * r["ms_per_step"] * 1e-3 * r["steps"] for r in res)
+    slowest = max(r["ms_per_step"] * r["steps"] * 1e-3 for r in res)
+    best = dict(res[0])
+    best.update(points_per_s=tot_pts / slowest, ms_per_step=max(r["ms_per_step"] for r in res), ms_p50=float(np.median([r["ms_p50"] for r in res])),
+                pipelines=len(works), wall_s=wall)
+    return best
+
+
 def _run_cpu(work, n_steps, n_warm, threads_list):
     """the reference's CPU path: unmodified ikd-Tree (oracle/_ref) under the restated loop (oracle/oracle.cpp)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -259,6 +288,30 @@ def _run_cpu(work, n_steps, n_warm, threads_list):
     return best
 
 
+def run_parity(work, n_scans, threads, local_rank=0):
+    """The device path against the oracle on the benchmark's own scans and map (tests/parity_tools.py; test infrastructure):
+    identical inputs (the oracle's feats_down / poses / map through dlt_measure) and the whole pipeline re-synced per scan."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from daliti_b200.binding import load_library
+    from parity_tools import ParityRun
+
+    with _QuietStdout():
+        run = ParityRun(load_library(), ob.load(), work["seq"], work["map_pts"], lm_kwargs=work["lm_kwargs"], threads=threads, device=local_rank,
+                        featptsThreshold=30)
+        for k in range(n_scans):
+            run.step(k, work["scans"][k])
+        rec = run.summary()
+        run.close()
+    rec["ok"] = bool(rec["knn_sets_equal"] and rec["selected_equal"] and rec["effct_equal"] and rec["add_lists_equal"] and rec["map_contents_equal"]
+                     and rec["n_iters_equal"] and rec["max_pose_rel_err"] < 1e-5 and rec["max_HtH_rel_err"] < 1e-10)
+    rec["tolerances"] = {"pose_rel": 1e-5, "HtH_rel": 1e-10, "neighbour_sets / selections / counts / map contents": "exact"}
+    rec["what"] = ("identical inputs: oracle feats_down + per-iteration pose + map-before through dlt_measure (knn_sets_equal, selected_equal, effct_equal, "
+                   "max_HtH_rel_err, add_lists_equal, map_contents_equal); pipeline: dlt_lio_process_scan from the oracle's state and map, one scan at "
+                   "a time (max_pose_rel_err, voxels_differing, pipeline_*)")
+    return rec
+
+
 # ------------------------------------------------------------------------------------------ main
 _REAL_STDOUT = None
 
@@ -283,25 +336,57 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, txt)
 
 
+REPLAY_SCANS = 100  # BASELINE.json configs[1] is a 100-scan replay: latency percentiles are taken over that many scans
+
+
+def base_config(work):
+    """the `config` object: the same keys and values in both arms (everything run-specific goes to `detail`)"""
+    return {"workload": work["name"], "iterations": 4, "map_points": int(len(work["map_pts"]))}
+
+
+def pin_rank(local_rank, world):
+    """One block of host cores per rank: N replicas that spin on their own result flags must not share cores (r1: 0.92 weak
+    scaling at N = 8 with zero communication was host contention).  Returns the cores or None."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(1, world)
+        if world <= 1 or per < 1:
+            return None
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=5).stdout.strip() or None
+    except Exception:
+        return None
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--seqs-per-gpu", type=int, default=8, help="c5: independent sequences driven concurrently on every GPU (one stream + host thread each)")
     ap.add_argument("--device-loop", type=int, default=-1, choices=[-1, 0, 1, 2],
-                    help="-1: the library's default (host loop on one GPU, device-resident loop on a sharded map); 1: iteration loop, zeta blend "
-                         "and map insert resident on the device (one sync per scan); 2: loop on the device, blend/insert host-driven; "
-                         "0: one host round trip per iteration")
+                    help="-1: the library's default (host loop); 1: iteration loop, zeta blend and map insert resident on the device (one sync "
+                         "per scan); 2: loop on the device, blend/insert host-driven; 0: one host round trip per iteration")
     ap.add_argument("--shard-exchange", default="peer", choices=["peer", "nccl"],
                     help="c4: how the partial normal equations / map_incremental decisions are summed over the ranks: inside the kernels "
                          "over NVLink peer memory (dlt_peer_attach; falls back to nccl when the mailboxes cannot be mapped) or an NCCL all-reduce callback")
     ap.add_argument("--tiles", type=int, default=5, help="c4: the map is tiles x tiles shifted copies of the C2 map")
-    ap.add_argument("--cpu-sample", type=int, default=3, help="scans of the same workload timed on the host cores (cpu_baseline)")
+    ap.add_argument("--cpu-sample", type=int, default=3, help="scans of the same workload timed on the host cores (cpu_baseline) and checked for parity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the sharded-map (C4) leg that rides along with the replica measurement")
+    ap.add_argument("--c4-steps", type=int, default=40)
+    ap.add_argument("--no-replay", action="store_true", help="N = 1: skip the 100-scan replay that the latency percentiles are taken from")
     args = ap.parse_args()
     K, W = args.steps, max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -311,20 +396,28 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        work = build_workload(0, K + W, args.workload)
-        ncpu = os.cpu_count() or 1
+        n_pipe = max(1, args.gpus)  # one CPU pipeline per GPU of our arm: the same weak-scaling job on the host cores
+        works = [build_workload(i, K + W, args.workload) for i in range(n_pipe)]
+        work = works[0]
+        ncpu = len(os.sched_getaffinity(0))
         cand = sorted({1, 4, min(ncpu, 16)})
         # pick the thread count on two scans, then time K steps with it
         probe = {t: run_cpu(dict(work, scans=work["scans"][:3]), 2, 1, [t])["points_per_s"] for t in cand}
         thr = max(probe, key=probe.get)
-        r = run_cpu(work, K, W, [thr])
+        if n_pipe == 1:
+            r = run_cpu(work, K, W, [thr])
+        else:
+            thr = max(1, min(thr, ncpu // n_pipe))
+            r = run_cpu_concurrent(works, K, W, thr)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["points_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"], "warmup": W,
             "ms_per_step": r["ms_per_step"], "ms_p50": r["ms_p50"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
-            "config": {"workload": work["name"], "iterations": 4, "threads_probe_points_per_s": {str(k): v for k, v in probe.items()}},
-            "cpu_baseline": {"value": r["points_per_s"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
-                             "sample": f"{r['steps']} scans of the workload after {W} warm-up scans; as-shipped is 1 thread (both OpenMP pragmas commented out, laserMapping.cpp:827-828,946-947)",
+            "config": base_config(work),
+            "detail": {"threads_probe_points_per_s": {str(k): v for k, v in probe.items()}, "pipelines": n_pipe, "threads_per_pipeline": thr, "host_cores": ncpu,
+                       "note": "N > 1: N independent CPU pipelines run concurrently on the box's host cores (one per GPU of the other arm)"},
+            "cpu_baseline": {"value": r["points_per_s"], "unit": UNIT, "cores": thr * n_pipe, "kind": r["kind"],
+                             "sample": f"{r['steps']} scans of the workload after {W} warm-up scans, {n_pipe} pipeline(s) x {thr} thread(s); as-shipped is 1 thread (both OpenMP pragmas commented out, laserMapping.cpp:827-828,946-947)",
                              "stage_ms": r["stage_ms"], "map_build_s": r["map_build_s"]},
             "e2e": {"value": r["points_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
@@ -352,11 +445,23 @@ def main():
     from daliti_b200.lio import LaserMapping
 
     if args.workload == "c4":
-        return main_c4(args, K, W, rank, local_rank, world, dist)
+        line = measure_c4(args, K, W, rank, local_rank, world, dist)
+        if rank == 0:
+            emit(line)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     if args.workload == "c5":
         return main_c5(args, K, W, rank, local_rank, world, dist)
 
-    work = build_workload(rank, K + W, args.workload)
+    replay = 0 if (args.no_replay or world > 1 or args.workload != "c2" or K >= REPLAY_SCANS) else REPLAY_SCANS
+    work = build_workload(rank, max(K, replay) + W, args.workload)
+    k4 = max(10, min(args.c4_steps, K))
+    work_c4 = None
+    if world > 1 and not args.no_c4:  # the sharded-map leg: every rank cooperates on the SAME scans (rank 0's)
+        work_c4 = work if (rank == 0 and args.workload == "c2" and len(work["scans"]) >= k4 + W) else build_workload(0, k4 + W, "c2")
+    pinned_cores = pin_rank(local_rank, world)
     seq, scans = work["seq"], work["scans"]
     n_map = len(work["map_pts"])
     stream = torch.cuda.Stream(device=local_rank)
@@ -385,7 +490,7 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    def run(mode, flush):
+    def run(mode, flush, K=K):
         """W warm-up scans, then K timed scans.  Returns per-step ms (CUDA events on the launching stream), outputs."""
         lmx = reset()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -429,13 +534,23 @@ def main():
     lm_s, ms_s, _, outs_s, _ = run("host", flush=True)       # serial: upload, then update, inside every step
     lm_s.close()
     lm_e, ms_e, host_e, outs_e, _ = run("host_pf", flush=True)  # the upload of scan k+1 overlaps the update of scan k
+    lm_e.close()
+    replay_rec = None
+    if replay:  # latency percentiles over a 100-scan replay (the K timed steps above give `value`)
+        lm_r, ms_r, _, outs_r, _ = run("dev", flush=True, K=replay)
+        lm_r.close()
+        lm_r, ms_rs, _, _, _ = run("host", flush=True, K=replay)
+        lm_r.close()
+        replay_rec = {"scans": replay, "ms_p50": float(np.median(ms_r)), "ms_p90": float(np.percentile(ms_r, 90)), "ms_p99": float(np.percentile(ms_r, 99)),
+                      "ms_max": float(ms_r.max()), "ms_mean": float(ms_r.mean()), "serial_e2e_ms_p50": float(np.median(ms_rs)),
+                      "serial_e2e_ms_p99": float(np.percentile(ms_rs, 99)), "iterations_run_mean": float(np.mean([o[2] for o in outs_r])),
+                      "note": "device-resident scans, L2 flushed between scans, per-scan CUDA events; serial_e2e: dlt_lio_process_scan from pinned host buffers (upload, then update)"}
 
     # ---- per-kernel device time (separate short pass with event pairs around each kernel group)
     prof = None
     roof = None
     try:
         n_prof, nd_sum, nraw_sum, match_passes, iters_sum = 0, 0, 0, 0, 0
-        lm_e.close()
         lm_p = reset(device_loop=0)  # one real launch per event pair (the device-resident loop also enqueues no-op launches)
         lm_p.device.set_profiling(True)
         with torch.cuda.stream(stream):
@@ -464,21 +579,40 @@ def main():
         k8_ms, k8_n = prof["knn8"]       # k_knn8 alone
         res_ms, res_n = prof["residual"]
         nd_mean = nd_sum / max(1, n_prof)
+        nraw_mean = nraw_sum / max(1, n_prof)
         # algorithmic bytes per launch: kNN pass  N*(16 + 5*16 + 5*4), residual pass N*(16+16) + 92*8
         knn_bytes = nd_mean * (16 + 5 * 16 + 5 * 4)
         res_bytes = nd_mean * 32 + 92 * 8
         dom = "k_knn8" if k8_ms >= res_ms else "k_residual"
         d_ms, d_n, d_bytes = (k8_ms, k8_n, knn_bytes) if dom == "k_knn8" else (res_ms, res_n, res_bytes)
         achieved = d_bytes / (1e-3 * d_ms / max(1, d_n)) / 1e9 if d_ms > 0 else 0.0
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_commit, inst_per_launch = None, None, None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram__bytes_read+write per launch from the committed --set full capture
         if os.path.exists(tp):
             tj = json.load(open(tp))
             if dom in tj:
                 traffic, traffic_src = tj[dom].get("dram_bytes_per_launch"), tj[dom].get("source")
+                traffic_commit, inst_per_launch = tj[dom].get("commit"), tj[dom].get("warp_instructions_per_launch")
+        launch_us = 1e3 * d_ms / max(1, d_n)
+        # whole-step figure (SURVEY.md 8d formula for B_scan) against the same peak
+        mp_scan, it_scan = match_passes / max(1, n_prof), iters_sum / max(1, n_prof)
+        b_scan = nraw_mean * 48 + nraw_mean * 16 + nd_mean * 16 + mp_scan * nd_mean * 116 + it_scan * nd_mean * 32 + it_scan * 92 * 8
+        step_ms = float(ms_v.mean())
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6  # warp instructions / s: 4 schedulers per SM, one instruction per cycle each
+        issue = None
+        if inst_per_launch:
+            ia = inst_per_launch / (launch_us * 1e-6)
+            issue = {"bound": "issue", "kernel": dom, "achieved": ia / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s", "frac": ia / issue_peak,
+                     "warp_instructions_per_launch": inst_per_launch, "from_committed_profile": True, "profile_commit": traffic_commit,
+                     "note": "instruction count from the committed ncu --set full capture, launch time measured in this run"}
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_us": 1e3 * d_ms / max(1, d_n), "algorithmic_bytes_per_launch": d_bytes,
+                "traffic_source": traffic_src, "traffic_from_committed_profile": traffic is not None, "traffic_profile_commit": traffic_commit,
+                "peak_source": peak_src, "avg_launch_us": launch_us, "algorithmic_bytes_per_launch": d_bytes,
                 "note": "single-scan working set is L2-resident and the kernel is issue/latency-bound (SURVEY.md 8d); the fraction is reported, not a target at this size",
+                "issue": issue,
+                "step": {"bound": "hbm", "achieved": b_scan / (step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": b_scan / (step_ms * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_scan": b_scan, "ms_per_scan": step_ms, "match_passes_per_scan": mp_scan, "iterations_per_scan": it_scan},
                 "kernel_ms_per_scan": {k: round(v[0] / max(1, n_prof), 4) for k, v in prof.items() if v[1]},
                 "kernel_launch_groups_per_scan": {k: round(v[1] / max(1, n_prof), 2) for k, v in prof.items() if v[1]}}
     except Exception as e:  # profiling is auxiliary: never lose the headline number over it
@@ -497,10 +631,10 @@ def main():
         pts_v, pts_e, launches = float(tot[0]), float(tot[1]), int(tot[5])
         t_v, t_w, t_e, t_s = float(mx[2]), float(mx[3]), float(mx[4]), float(mx[6])
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
-            ncpu = os.cpu_count() or 1
+            ncpu = len(os.sched_getaffinity(0))
             cwork = dict(work, scans=scans[: 1 + args.cpu_sample])
             cpu_r = run_cpu(cwork, args.cpu_sample, 1, sorted({1, min(4, ncpu)}))
             cpu = {"value": cpu_r["points_per_s"], "unit": UNIT, "cores": cpu_r["threads"], "kind": cpu_r["kind"],
@@ -508,6 +642,26 @@ def main():
                    "ms_per_scan": cpu_r["ms_per_step"], "stage_ms": cpu_r["stage_ms"], "map_build_s": cpu_r["map_build_s"]}
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        try:
+            parity = run_parity(work, max(1, args.cpu_sample), min(8, len(os.sched_getaffinity(0))), local_rank)
+        except Exception as e:
+            parity = {"ok": False, "error": repr(e)}
+
+    # ---- N > 1: the sharded-map configuration (C4) rides along, so that the scaling record holds a partitioned curve too
+    c4 = None
+    if world > 1 and not args.no_c4:
+        try:
+            c4_line = measure_c4(args, k4, W, rank, local_rank, world, dist, work=work_c4)
+            if rank == 0:
+                c4 = {"ms_p50": c4_line["ms_p50"], "ms_per_step": c4_line["ms_per_step"], "ms_p99": c4_line["ms_p99"], "points_per_s": c4_line["value"],
+                      "scans_per_s": c4_line["scans_per_s"], "steps": c4_line["steps"], "nranks": world, "scaling": "strong",
+                      "exchange": c4_line["config"]["shard_exchange"], "loop": c4_line["config"]["loop"], "map_points": c4_line["config"]["map_points"],
+                      "live_points_incl_halos": c4_line["config"]["live_points_incl_halos"], "map_build_s": c4_line["config"]["map_build_s"],
+                      "e2e": c4_line["e2e"], "gpu_launches": c4_line["gpu_launches"], "workload": c4_line["config"]["workload"],
+                      "unsharded_replica_ms_p50_same_run": float(np.median(ms_v)),
+                      "sharded_over_unsharded_p50": c4_line["ms_p50"] / float(np.median(ms_v))}
+        except Exception as e:
+            c4 = {"error": repr(e)}
 
     if rank == 0:
         n_raw_mean = float(np.mean([o[0] for o in outs_v]))
@@ -517,7 +671,7 @@ def main():
         # last_nodegared, window) up; the block's in/out + out part with 4 iteration records and the 8 map counters down
         if args.device_loop in (-1, 0):  # host loop: the normal equations come back once per iteration
             h2d = n_raw_mean * 48 + 22 * 8 * 22
-            d2h = iters_mean * 159 * 8 + 48 + 42 * 8 + 2 * 32
+            d2h = iters_mean * 160 * 8 + 48 + 42 * 8 + 2 * 32
         else:
             h2d = n_raw_mean * 48 + 22 * 8 * 22 + (36 + 36 + 1 + 2 * 612) * 8 + 28 * 4
             d2h = (2 * 612 + 42) * 8 + 24 * 4 + 4 * 1952 + 32
@@ -526,19 +680,23 @@ def main():
             "ms_per_step": t_v / K, "ms_p50": float(np.median(ms_v)), "ms_p99": float(np.percentile(ms_v, 99)),
             "scans_per_s": world * K / (t_v * 1e-3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
-            "config": {"workload": work["name"], "iterations": 4, "iterations_run_mean": iters_mean, "loop": {-1: "library default: host loop over dlt_measure (single-GPU map), 1 host sync per iteration",
-                                1: "device-resident loop + zeta blend + map insert (dlt_iekf_update), 1 host sync per scan",
+            "config": base_config(work),
+            "detail": {"iterations_run_mean": iters_mean,
+                       "loop": {-1: "library default: host loop over dlt_measure, result block written straight into pinned host memory (no copy, no stream sync per iteration)",
+                                1: "device-resident loop + zeta blend + map insert (dlt_iekf_update, one fused launch per iteration), 1 host sync per scan",
                                 2: "device-resident loop (dlt_iekf_update), blend/insert host-driven, 2 host syncs per scan",
-                                0: "host loop over dlt_measure, 1 host sync per iteration"}[args.device_loop],
+                                0: "host loop over dlt_measure"}[args.device_loop],
                        "deleted_total": int(sum(o[13] for o in outs_v)), "degenerate_scans": int(sum(o[14] for o in outs_v)),
-                       "n_raw_mean": n_raw_mean, "n_down_mean": n_down_mean, "map_points": n_map, "effct_feat_mean": float(np.mean([o[6] for o in outs_v])),
+                       "n_raw_mean": n_raw_mean, "n_down_mean": n_down_mean, "effct_feat_mean": float(np.mean([o[6] for o in outs_v])),
                        "ekf_stops": int(sum(o[3] for o in outs_v)), "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
                        "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                        "parallelism": "1 sequence per GPU, no data-path collective" if world > 1 else "single GPU",
+                       "host_cores_of_this_rank": pinned_cores,
                        "value_l2_warm_points_per_s": pts_v / (t_w * 1e-3), "ms_p50_l2_warm": float(np.median(ms_w)),
                        "host_ms_p50": float(np.median(host_v)),
                        "host_stage_ms_mean": dict(zip(["deskew_enqueue", "voxelgrid", "iterations", "insert_and_eigen", "delete", "total"],
-                                                      (1e3 * np.mean([o[7:13] for o in outs_v], axis=0)).round(4).tolist()))},
+                                                      (1e3 * np.mean([o[7:13] for o in outs_v], axis=0)).round(4).tolist())),
+                       "git": git_head()},
             "e2e": {"value": pts_e / (t_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": t_e / K, "ms_p50": float(np.median(ms_e)),
                     "api": "dlt_lio_prefetch_scan(scan k+1) + dlt_lio_process_scan(scan k), pinned host buffers: every scan's 48-byte records cross "
@@ -549,24 +707,31 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "parity": parity,
+            "replay": replay_rec,
+            "c4": c4,
         }
         emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity.get("ok", False):
+        print("bench.py: PARITY FAILED against the oracle: " + json.dumps(parity), file=sys.stderr)
+        return 3
     return 0
 
 
-def main_c4(args, K, W, rank, local_rank, world, dist):
+def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
     """BASELINE config C4: a ~50 M-point map (tiles x tiles shifted copies of the C2 map) spatially sharded over the
     ranks; every rank evaluates the query points it owns and the 158-double normal equations are summed with one
     NCCL all-reduce per IEKF iteration (dlt_lio_set_reduce).  Poses hop from tile to tile, so consecutive scans
-    touch different parts of the map.  Strong scaling: the work per scan is fixed."""
+    touch different parts of the map.  Strong scaling: the work per scan is fixed.  Returns the JSON line on rank 0 (None elsewhere)."""
     import torch
 
     from daliti_b200.lio import LaserMapping
 
-    work = build_workload(0, K + W, "c2")  # every rank sees the same scans: they cooperate on each one
+    if work is None:
+        work = build_workload(0, K + W, "c2")  # every rank sees the same scans: they cooperate on each one
     seq, scans = work["seq"], work["scans"]
     base = work["map_pts"]
     pitch = 270.0
@@ -602,8 +767,15 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
             exchange = "peer" if attach_peers(lm) else "nccl (peer mailboxes could not be mapped)"
         if exchange != "peer":
             exchange = exchange if exchange != "none" else "nccl"
-            with torch.cuda.stream(stream):
-                lm.set_allreduce(f"cuda:{local_rank}")
+            try:  # the library's own transport: ncclAllReduce issued from C on the handle's stream (include/daliti_b200_nccl.h)
+                from daliti_b200.sharded import attach_native_nccl
+
+                attach_native_nccl(lm, local_rank)
+                exchange += " (native: dlt_nccl_allreduce)"
+            except Exception:
+                with torch.cuda.stream(stream):
+                    lm.set_allreduce(f"cuda:{local_rank}")
+                exchange += " (torch.distributed callback)"
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
     dev_scans = [torch.from_numpy(np.ascontiguousarray(p)).to(f"cuda:{local_rank}") for p, _, _ in scans]
     pin_scans = [torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p, _, _ in scans]
@@ -661,21 +833,24 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
         t_v, t_e, launches, live_sum = float(mx[0]), float(mx[1]), int(sm[2]), int(sm[3])
     else:
         live_sum = live
+    line = None
     if rank == 0:
         pts_total = float(sum(o[0] for o in outs_v))
+        loop_txt = {-1: "library default (host loop over dlt_measure; with peers the sum over the ranks happens inside k_residual)",
+                    0: "host loop over dlt_measure", 1: "device-resident loop + blend + insert", 2: "device-resident loop, blend / insert host-driven"}[args.device_loop]
         line = {
             "metric": METRIC, "value": pts_total / (t_v * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_v / K, "ms_p50": float(np.median(ms_v)), "ms_p99": float(np.percentile(ms_v, 99)), "scans_per_s": K / (t_v * 1e-3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
             "config": {"workload": f"C4: {n_map / 1e6:.1f}M-pt voxel-hash map ({T}x{T} tiles of the C2 map) spatially sharded over {world} GPU(s), "
-                                   "C2 scans at poses hopping between tiles, all-reduce of H^T H / H^T r per iteration inside the device-resident loop, map_incremental with the owners' decisions exchanged",
+                                   "C2 scans at poses hopping between tiles, H^T H / H^T r summed over the ranks per iteration, map_incremental with the owners' decisions exchanged",
                        "iterations": 4, "n_raw_mean": float(np.mean([o[0] for o in outs_v])), "n_down_mean": float(np.mean([o[1] for o in outs_v])),
-                       "map_points": n_map, "live_points_incl_halos": live_sum, "map_build_s": t_build,
+                       "map_points": n_map, "live_points_incl_halos": live_sum, "map_build_s": t_build, "loop": loop_txt,
                        "effct_feat_mean": float(np.mean([o[3] for o in outs_v])),
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
                        "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                        "parallelism": (f"map sharded {world}-way by 32-cell tiles + halo; 158 doubles summed over the ranks per iteration "
-                                       + ("inside k_residual through NVLink peer mailboxes (CUDA IPC), solve step fused behind it: no collective launch"
+                                       + ("inside k_residual through NVLink peer mailboxes (CUDA IPC): no collective launch"
                                           if exchange == "peer" else "by an NCCL all-reduce between k_residual and k_iekf_step")) if world > 1 else "single GPU, unsharded",
                        "shard_exchange": exchange},
             "e2e": {"value": float(sum(o[0] for o in outs_e)) / (t_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(np.mean([o[0] for o in outs_e]) * 48 + 22 * 8 * 22),
@@ -685,12 +860,10 @@ def main_c4(args, K, W, rank, local_rank, world, dist):
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": None, "cpu_baseline": None,
         }
-        emit(line)
     lm.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    del dev_scans, pin_scans, flush_buf
+    torch.cuda.empty_cache()
+    return line
 
 
 def main_c5(args, K, W, rank, local_rank, world, dist):

@@ -126,7 +126,7 @@ struct dlt_handle_s {
     int far_hint = 1;                  // unresolved queries of the previous scan: queue the exact-neighbour fallback behind the loop?
     // fused loop kernels (dlt_loop_kernels.cuh): one launch per iteration, or -- cooperative launch -- one per scan
     int loop_fused = 1;                // DLT_LOOP_FUSED=0: the classic three kernels per iteration
-    int loop_coop = 1;                 // DLT_LOOP_COOP=0: k_iekf_iter launches instead of the persistent k_iekf_loop
+    int loop_coop = 0;                 // DLT_LOOP_COOP=1: the persistent cooperative k_iekf_loop instead of k_iekf_iter launches (measured slower on B200)
     int loop_blocks = 0;               // grid of the loop kernels (0 = not sized yet); DLT_LOOP_BLOCKS caps it (several sequences per GPU)
     GridBar *d_bar = nullptr;
     // front end (dlt_frontend_sample): sensor cloud staging, grown on demand
@@ -558,6 +558,7 @@ int dlt_set_stream(dlt_handle h, void *s) {
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     return DLT_OK;
 }
+void *dlt_stream(dlt_handle h) { return h ? (void *)h->stream : nullptr; }
 int dlt_sync(dlt_handle h) {
     if (!h) return DLT_E_INVALID;
     DLT_RT(h, rt::sync(h->stream));

@@ -73,6 +73,18 @@ DLT_D int loop_chunk_size(int n, int n_blocks) {  // smallest multiple of 32 wit
     return c > kLoopChunkMax ? kLoopChunkMax : c;
 }
 
+// instrumentation: the solver's thread 0 leaves globaltimer stamps (ns) of the iteration's stages in dev->clocks[it][9..14]
+#if defined(DLT_EMU)
+#define DLT_GSTAMP(dev, it, slot)
+DLT_D void spin_pause() {}
+#else
+#define DLT_GSTAMP(dev, it, slot)                                              \
+    do {                                                                       \
+        if (threadIdx.x == 0) (dev)->clocks[it][slot] = (long long)peer_now_ns(); \
+    } while (0)
+DLT_D void spin_pause() { __nanosleep(40); }
+#endif
+
 // grid-wide barrier over co-resident blocks (cooperative launch): sense by generation count
 DLT_D void grid_barrier(GridBar *b, unsigned n_blocks) {
     __syncthreads();
@@ -85,8 +97,7 @@ DLT_D void grid_barrier(GridBar *b, unsigned n_blocks) {
             __threadfence();
             *gen = g + 1u;
         } else {
-            while (*gen == g) {
-            }
+            while (*gen == g) spin_pause();
         }
         __threadfence();
     }
@@ -214,19 +225,22 @@ __global__ void __launch_bounds__(kLoopBlock, DLT_LOOP_MINBLOCKS) k_iekf_loop(Lo
         const int do_match = (it == 0 || *(volatile const int *)&a.dev->b.rematch_en) ? 1 : 0;
         if (threadIdx.x < 24) reinterpret_cast<double *>(&sm.P)[threadIdx.x] = __ldcg(&a.dev->b.state[threadIdx.x]);
         __syncthreads();
+        if (solver) DLT_GSTAMP(a.dev, it, 9);
         loop_iter_chunks<EXT>(a, sm, n, do_match);
         if (solver) {
+            DLT_GSTAMP(a.dev, it, 10);
             if (threadIdx.x == 0) {
-                while (*(volatile unsigned *)a.mb.ticket != G) {  // every block's partial is in place
-                }
+                while (*(volatile unsigned *)a.mb.ticket != G) spin_pause();  // every block's partial is in place
                 __threadfence();
             }
             __syncthreads();
+            DLT_GSTAMP(a.dev, it, 11);
             const bool ok = loop_iter_finish_reduce<EXT>(a, n, la);
             if (threadIdx.x == 0) {
                 __threadfence();
                 *(volatile unsigned *)&a.bar->r_seq = (unsigned)it + 1u;  // the normal equations are in a.mb.result
             }
+            DLT_GSTAMP(a.dev, it, 12);
             if (ok) {
                 iekf_step_block(a.dev, a.mb.result, a.n_ptr, a.vox_ptr, NormalEq<EXT>::D);
                 if (threadIdx.x == 0 && !a.dev->b.done && a.dev->b.rematch_en) {  // the next iteration matches again: re-arm its counters
@@ -235,17 +249,18 @@ __global__ void __launch_bounds__(kLoopBlock, DLT_LOOP_MINBLOCKS) k_iekf_loop(Lo
                     a.knn.nn_count[1] = 0;
                 }
             }
+            DLT_GSTAMP(a.dev, it, 13);
         }
         if (eig_block) {  // eigen-decomposition of this iteration's pose block while the solver solves (behind it when they coincide)
             if (threadIdx.x == 0) {
-                while (*(volatile unsigned *)&a.bar->r_seq != (unsigned)it + 1u) {
-                }
+                while (*(volatile unsigned *)&a.bar->r_seq != (unsigned)it + 1u) spin_pause();
                 __threadfence();
             }
             __syncthreads();
             if (threadIdx.x < 32) eigen6_warp(a.mb.result, a.eig_out, threadIdx.x);
         }
         grid_barrier(a.bar, G);
+        if (solver) DLT_GSTAMP(a.dev, it, 14);
     }
     if (solver && threadIdx.x == 0) a.bar->r_seq = 0u;  // (nobody reads it past the last barrier)
 }

@@ -104,6 +104,10 @@ class LaserMapping:
 
     def close(self):
         if getattr(self, "h", None):
+            if getattr(self, "_nccl", None):
+                self.lib.dlt_sync(self.device.h)
+                self.lib.dlt_nccl_destroy(self._nccl)
+                self._nccl = None
             self.lib.dlt_lio_destroy(self.h)
             self.h = None
             self.device.h = None
@@ -231,6 +235,26 @@ class LaserMapping:
 
         self._red_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)(_cb)
         self._ck(self.lib.dlt_lio_set_reduce(self.h, self._red_cb, None, None))
+
+    def attach_native_nccl(self, unique_id: bytes, rank: int, world: int, device: int):
+        """Sharded map with the library's own NCCL transport (include/daliti_b200_nccl.h): ncclAllReduce(sum, double) enqueued on
+        the handle's stream from C, no Python on the data path.  unique_id: native_nccl_unique_id() of rank 0, handed to
+        every rank by the caller."""
+        comm = C.c_void_p()
+        idb = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self.lib.dlt_nccl_last_error.restype = C.c_char_p
+        if self.lib.dlt_nccl_create(idb, C.c_int(rank), C.c_int(world), C.c_int(device), C.byref(comm)) != 0:
+            raise DltError("dlt_nccl_create: " + (self.lib.dlt_nccl_last_error() or b"").decode())
+        if self.lib.dlt_nccl_attach(comm, self.h) != 0:
+            raise DltError("dlt_nccl_attach failed")
+        self._nccl = comm
+
+    def native_nccl_unique_id(self) -> bytes:
+        idb = (C.c_ubyte * 128)()
+        self.lib.dlt_nccl_last_error.restype = C.c_char_p
+        if self.lib.dlt_nccl_unique_id(idb) != 0:
+            raise DltError("dlt_nccl_unique_id: " + (self.lib.dlt_nccl_last_error() or b"").decode())
+        return bytes(idb)
 
     def peer_export(self) -> bytes:
         from .binding import PEER_BLOB_BYTES

@@ -72,3 +72,14 @@ def attach_peers(obj):
     if ok:
         obj.peer_detach()
     return False
+
+
+def attach_native_nccl(lm, device: int):
+    """Collective: rank 0 draws an NCCL unique id, torch.distributed carries its 128 bytes to the other ranks (once; any
+    backend), every rank creates the library's own communicator and binds it to `lm` (dlt_nccl_attach).  From then on the
+    sums over the ranks are plain ncclAllReduce calls issued from C on the handle's stream."""
+    import torch.distributed as dist
+
+    box = [lm.native_nccl_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    lm.attach_native_nccl(box[0], dist.get_rank(), dist.get_world_size(), device)

@@ -71,6 +71,8 @@ const char *dlt_last_error(dlt_handle h);
 /* Adopt an external CUDA stream (cudaStream_t) for all work of this handle, or NULL to go
  * back to the handle's own stream.  Used to order work with torch / NCCL.                       */
 int dlt_set_stream(dlt_handle h, void *cuda_stream);
+/* The stream (cudaStream_t) the handle currently launches on: what a reduce callback has to enqueue its collective on.     */
+void *dlt_stream(dlt_handle h);
 int dlt_sync(dlt_handle h);
 
 /* ---- map: replaces the global `KD_TREE<PointType> ikdtree` (laserMapping.cpp:164) ---------- */

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for h in ("daliti_b200.h", "daliti_b200_lio.h"):
+    for h in ("daliti_b200.h", "daliti_b200_lio.h", "daliti_b200_nccl.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         for m in re.finditer(r"\b(dlt_[a-z0-9_]+)\s*\(", src):
@@ -77,7 +77,7 @@ def test_headers_are_plain_c():
     """the drop-in boundary is a C ABI: both headers must compile as C99 and as C++14 on their own"""
     import subprocess
 
-    for h in ("daliti_b200.h", "daliti_b200_lio.h"):
+    for h in ("daliti_b200.h", "daliti_b200_lio.h", "daliti_b200_nccl.h"):
         src = f'#include "{os.path.join(ROOT, "include", h)}"\n'
         for args in (["gcc", "-x", "c", "-std=c99", "-pedantic"], ["g++", "-x", "c++", "-std=c++14"]):
             r = subprocess.run(args + ["-fsyntax-only", "-Wall", "-Werror", "-"], input=src, text=True, capture_output=True)

@@ -153,7 +153,7 @@ def _tile_owner(xyz, shards, ds=0.5, cell_shift=1, tile_shift=3):
     return ((k & np.uint64(0xFFFFFFFF)) % np.uint64(shards)).astype(np.int64)
 
 
-def _run_lio(lib, rank, world, n_scans=3, peers=False, device_loop=-1, device=0):
+def _run_lio(lib, rank, world, n_scans=3, peers=False, device_loop=-1, device=0, native_nccl=False):
     from daliti_b200.lio import LaserMapping
 
     seq = helpers.small_sequence(seed=22, half=30.0, beams=16, azimuths=240, n_boxes=8)
@@ -167,6 +167,10 @@ def _run_lio(lib, rank, world, n_scans=3, peers=False, device_loop=-1, device=0)
         from daliti_b200.sharded import attach_peers
 
         assert attach_peers(lm)
+    elif world > 1 and native_nccl:  # include/daliti_b200_nccl.h: ncclAllReduce issued from C on the handle's stream
+        from daliti_b200.sharded import attach_native_nccl
+
+        attach_native_nccl(lm, device)
     elif world > 1:
         lm.set_allreduce("cpu")
     states = []
@@ -182,7 +186,7 @@ def _run_lio(lib, rank, world, n_scans=3, peers=False, device_loop=-1, device=0)
     return states
 
 
-def _lio_worker_all(rank, world, port, q, peers=False, device_loop=-1, gpu=False):
+def _lio_worker_all(rank, world, port, q, peers=False, device_loop=-1, gpu=False, native_nccl=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -193,7 +197,7 @@ def _lio_worker_all(rank, world, port, q, peers=False, device_loop=-1, gpu=False
     # (gloo only carries the 128-byte mailbox blobs, once; on GPUs the data path is NVLink peer memory)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = load_library() if gpu else load_library(os.path.join(ROOT, "tests", "emu", "libdaliti_emu.so"))
-    states = _run_lio(lib, rank, world, peers=peers, device_loop=device_loop, device=rank if gpu else 0)
+    states = _run_lio(lib, rank, world, peers=peers, device_loop=device_loop, device=rank if gpu else 0, native_nccl=native_nccl)
     q.put((rank, states))
     dist.destroy_process_group()
 
@@ -265,6 +269,47 @@ def _check_sharded_against_unsharded(got, ref, bitwise_ranks):
         assert d.max() < 1e-5, (k, d.max())
         assert len(np.unique(idx)) == len(pts)  # a bijection: no tile is held twice, none is missing
         np.testing.assert_allclose(owned[:, 3], pts[idx, 3], rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_loop", [0, 2])
+def test_sharded_per_scan_update_two_gpus_native_nccl(gpu_lib, device_loop):
+    """two B200s, one process per GPU, the library's own NCCL transport (daliti_b200_nccl.h): ncclAllReduce of the 158 doubles
+    issued from C between the residual pass and the solve (and of the per-point map_incremental decisions); torch.distributed
+    only carries the 128-byte unique id once."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    if not gpu_lib.dlt_nccl_available():
+        pytest.skip("libnccl.so.2 not loadable")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 36500 + (os.getpid() % 2000) + device_loop
+    procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, False, device_loop, True, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = _run_lio(gpu_lib, 0, 1)
+    _check_sharded_against_unsharded(got, ref, bitwise_ranks=False)
+
+
+def test_native_nccl_api_without_nccl_or_gpu(dev):
+    """the transport is optional: argument errors come back as codes, and a missing libnccl is reported, not fatal"""
+    import ctypes as C
+
+    lib, is_gpu = dev
+    lib.dlt_nccl_last_error.restype = C.c_char_p
+    assert lib.dlt_nccl_unique_id(None) != 0
+    comm = C.c_void_p()
+    assert lib.dlt_nccl_create(None, 0, 1, 0, C.byref(comm)) != 0
+    assert lib.dlt_nccl_allreduce(None, None, 4) != 0
+    assert lib.dlt_nccl_available() in (0, 1)
 
 
 @pytest.mark.gpu

@@ -24,13 +24,17 @@ def main():
     devs = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p, _, _ in scans]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
     stream = torch.cuda.Stream()
-    # "1g" / "2g": device loop as a CUDA graph with conditional nodes; "0z": host loop with the zero-copy result block (DLT_ZEROCOPY)
-    modes = [a for a in sys.argv[1:]] or ["0", "0z", "2", "1", "1g"]
+    # first character: device_loop; then flags: g = CUDA graph with conditional nodes, n = NO zero-copy result block (host loop),
+    # c = classic three kernels per iteration (DLT_LOOP_FUSED=0), p = the persistent cooperative loop kernel (DLT_LOOP_COOP=1);
+    # default for 1 / 2: one fused launch per iteration
+    modes = [a for a in sys.argv[1:]] or ["0", "0n", "1", "1p", "1c", "2"]
     for rep in range(2):
         for mtag in modes:
             mode = int(mtag[0])
-            os.environ["DLT_LOOP_GRAPH"] = "1" if mtag.endswith("g") else "0"
-            os.environ["DLT_ZEROCOPY"] = "1" if mtag.endswith("z") else "0"
+            os.environ["DLT_LOOP_GRAPH"] = "1" if "g" in mtag[1:] else "0"
+            os.environ["DLT_ZEROCOPY"] = "0" if "n" in mtag[1:] else "1"
+            os.environ["DLT_LOOP_FUSED"] = "0" if "c" in mtag[1:] else "1"
+            os.environ["DLT_LOOP_COOP"] = "1" if "p" in mtag[1:] else "0"
             lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30,
                               device_loop=mode)
             lm.device.set_stream(stream.cuda_stream)
@@ -39,6 +43,7 @@ def main():
             lm.set_state(s0)
             lm.device.map_build(work["map_pts"])
             ev, host = [], []
+            l0 = lm.device.launch_count()
             with torch.cuda.stream(stream):
                 for k in range(n):
                     pts, t_beg, imu = scans[k]
@@ -53,7 +58,9 @@ def main():
                     ev.append((a, b))
                 torch.cuda.synchronize()
             ms = np.array([a.elapsed_time(b) for a, b in ev])[warm:]
-            print(f"device_loop={mtag}: p50 {np.median(ms):.4f} ms  mean {ms.mean():.4f}  host p50 {np.median(host[warm:]):.4f} ms", flush=True)
+            st = lm.get_state()
+            print(f"device_loop={mtag}: p50 {np.median(ms):.4f} ms  mean {ms.mean():.4f}  host p50 {np.median(host[warm:]):.4f} ms   launches/scan "
+                  f"{(lm.device.launch_count() - l0) / n:.1f}  final pos {st[9]:.6f} {st[10]:.6f} {st[11]:.6f}", flush=True)
             lm.close()
 
 

@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scans", type=int, default=100)
     ap.add_argument("--emu", action="store_true")
-    ap.add_argument("--workload", default="mid", choices=["small", "mid", "c2"])
+    ap.add_argument("--workload", default="mid", choices=["small", "mid", "c2", "firstscan"])
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
 
@@ -47,13 +47,16 @@ def main():
 
         work = bench.build_workload(0, args.scans, "c2")
         seq, map_pts, scans, name, thr = work["seq"], work["map_pts"], work["scans"], work["name"], 30
+    elif args.workload == "firstscan":  # no prebuilt map: the first scan builds it (laserMapping.cpp:780-793), the chains start on a sparse map
+        seq = helpers.small_sequence(seed=11, half=50.0, beams=32, azimuths=1024, n_boxes=20, speed=2.0, yaw_rate=0.2)
+        map_pts, name, thr = None, "32x1024 scans, 100 m box world, map built from the first scan", 5
     elif args.workload == "mid":
         seq = helpers.small_sequence(seed=71, half=60.0, beams=32, azimuths=1024, n_boxes=30, speed=2.0, yaw_rate=0.2)
         map_pts, name, thr = synth.sample_map(seq.scene, seed=71), "32x1024 scans, 120 m box world", 5
     else:
         seq = helpers.small_sequence(seed=71, half=25.0, beams=16, azimuths=240, n_boxes=8, speed=2.0, yaw_rate=0.2)
         map_pts, name, thr = synth.sample_map(seq.scene, seed=71), "16x240 scans, 50 m box world", 5
-    out = {"workload": name, "map_points": int(len(map_pts)), "scans": args.scans, "backend": "emulator" if args.emu else "B200"}
+    out = {"workload": name, "map_points": int(len(map_pts)) if map_pts is not None else 0, "scans": args.scans, "backend": "emulator" if args.emu else "B200"}
     for mode in ("chained", "resynced"):
         run = ParityRun(lib, orc, seq, map_pts, threads=min(8, os.cpu_count() or 1), chained=(mode == "chained"), identical=(mode != "chained"),
                         featptsThreshold=thr, max_scan_points=1 << 18 if args.workload == "c2" else 1 << 16)
