@@ -833,6 +833,29 @@ def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
         t_v, t_e, launches, live_sum = float(mx[0]), float(mx[1]), int(sm[2]), int(sm[3])
     else:
         live_sum = live
+    if os.environ.get("BENCH_C4_TIMELINE"):  # development aid: device timeline of two more scans (CUDA events around every kernel group)
+        lm.device.set_profiling(True)
+        with torch.cuda.stream(stream):
+            for k in range(3):
+                pts, t_beg, imu = scans[W + k]
+                lm.on_lidar_msg()
+                lm.device.get_profile(reset=True)
+                barrier()
+                t0 = time.perf_counter()
+                o = lm.process_scan_dev(dev_scans[W + k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
+                host_ms = 1e3 * (time.perf_counter() - t0)
+                tl = lm.device.get_timeline()
+                if k == 2:
+                    txt = [f"rank {rank}: host {host_ms:.3f} ms  stages deskew {1e3*o.t_deskew:.3f} voxel {1e3*o.t_voxel:.3f} iterate {1e3*o.t_iterate:.3f} insert {1e3*o.t_insert:.3f}"]
+                    prev = 0.0
+                    for name, a, b in tl:
+                        if name == "knn8":
+                            continue
+                        txt.append(f"  rank {rank} {name:10s} start {1e3*a:7.1f} dur {1e3*(b-a):6.1f} gap {1e3*(a-prev):6.1f}")
+                        if name != "eigen6":
+                            prev = b
+                    print("\n".join(txt), file=sys.stderr, flush=True)
+        lm.device.set_profiling(False)
     line = None
     if rank == 0:
         pts_total = float(sum(o[0] for o in outs_v))

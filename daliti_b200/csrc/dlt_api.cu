@@ -22,6 +22,9 @@
 using namespace dlt;
 
 std::atomic<unsigned long long> dlt::rt::g_launches{0};
+#if !defined(DLT_EMU)
+int dlt::rt::g_pdl = 1;
+#endif
 
 namespace {
 constexpr int kMaxImuPoses = 512;
@@ -472,6 +475,9 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->have_copy = rt::stream_create(&h->copy_stream) == 0 && rt::event_create_untimed(&h->ev_copy) == 0;
     if (const char *e = std::getenv("DLT_LOOP_GRAPH")) h->use_graph = (e[0] == '1') ? 1 : 0;  // A/B switch for measurements
     if (const char *e = std::getenv("DLT_ZEROCOPY")) h->zerocopy = (e[0] == '1');            // A/B switch for measurements
+#if !defined(DLT_EMU)
+    if (const char *e = std::getenv("DLT_PDL")) rt::g_pdl = (e[0] == '1') ? 1 : 0;  // process-wide A/B switch for measurements
+#endif
     if (const char *e = std::getenv("DLT_LOOP_FUSED")) h->loop_fused = (e[0] == '1');
     if (const char *e = std::getenv("DLT_LOOP_COOP")) h->loop_coop = (e[0] == '1');
     h->have_aux = rt::stream_create(&h->aux_stream) == 0 && rt::event_create_untimed(&h->ev_fork) == 0 && rt::event_create_untimed(&h->ev_join) == 0;
@@ -1376,9 +1382,10 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
         // unsharded: the classification kernel also claims cells and places the voxel bids.  Sharded: the owners' decisions are
         // exchanged first (k_incr_push / k_incr_pull through the peer mailboxes, gated like everything here), then every rank
         // inserts what falls into its tiles + halo
-        FuseInsert fi = {sharded_finish ? 0 : 1, h->scratch, h->d_cellslot, h->d_vslot};
-        if (!sharded_finish)
-            if (int rs = prepare_scratch(h, n_upper, true, &fi.sc)) return rs;
+        FuseInsert fi = {1, h->scratch, h->d_cellslot, h->d_vslot};  // (sharded: the cells are claimed and the bids placed by k_incr_pull)
+        if (int rs = prepare_scratch(h, n_upper, true, &fi.sc)) return rs;
+        const FuseInsert fi_pull = fi;
+        if (sharded_finish) fi.on = 0;
         DLT_LAUNCH(k_incr_classify, div_up(n_upper, 256), 256, h->stream, (const float4 *)h->d_down, 0, P, (const float4 *)h->knn.nbr,
                    (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6, la, h->map,
                    (const int *)h->map.n_live, (const unsigned char *)h->knn.flags, (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key, fi);
@@ -1388,9 +1395,10 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
             DLT_LAUNCH(k_incr_push, Gx, 256, h->stream, h->d_peer, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
                        (const unsigned char *)h->knn.flags, 0, (unsigned char)kFlagForeign, (const int *)gate.go, (const int *)gate.n_ptr);
             DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
-            DLT_LAUNCH(k_incr_pull, Gx, 256, h->stream, h->d_peer, 0, h->d_dsflag, h->d_addflag, h->d_counters + 6, (const int *)gate.go, (const int *)gate.n_ptr);
+            DLT_LAUNCH(k_incr_pull, Gx, 256, h->stream, h->d_peer, 0, h->d_dsflag, h->d_addflag, h->d_counters + 6, (const int *)gate.go, (const int *)gate.n_ptr,
+                       h->map, (const float4 *)h->d_pw, fi_pull);
         }
-        int ri = insert_points(h, h->d_pw, n_upper, true, gate, sharded_finish ? nullptr : &fi.sc);
+        int ri = insert_points(h, h->d_pw, n_upper, true, gate, &fi_pull.sc);
         if (ri) return ri;
         DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     }
@@ -1448,7 +1456,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
 
 int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_out *out) {
     if (!h || !out) return DLT_E_INVALID;
-    const bool zc = h->zerocopy && !h->peer_on && !h->prof_on;
+    const bool zc = h->zerocopy && !h->prof_on;  // (with peers the block that is published is the sum over the ranks)
     bool launched = false;
     int rc = measure_dev_impl(h, pose24, do_match, h->d_result, zc, &launched);
     if (rc) return rc;
@@ -1462,7 +1470,14 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
             if ((spins & 0xFFFu) == 0u) {  // a kernel that died never raises the flag: ask the stream now and then
                 const int q = rt::stream_query(h->stream);
                 if (q == 2) DLT_FAIL(h, DLT_E_CUDA, std::string("stream error while waiting for the result block: ") + rt::last_error());
-                if (q == 0 && *flag != want) DLT_FAIL(h, DLT_E_CUDA, "the stream drained without the result flag");
+                if (q == 0 && *flag != want) {  // the kernel returned without publishing: with peers that is an exchange that timed out
+                    if (h->peer_on) {
+                        DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
+                        DLT_RT(h, rt::sync(h->stream));
+                        if (*h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in this evaluation)");
+                    }
+                    DLT_FAIL(h, DLT_E_CUDA, "the stream drained without the result flag");
+                }
             }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
@@ -1639,10 +1654,13 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     Pose P = pose_from(pose24);
     DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
     FuseInsert fi = {0, h->scratch, h->d_cellslot, h->d_vslot};
-    if (!sharded) {  // unsharded: the classification kernel also claims cells and places the voxel bids
-        if (int rs = prepare_scratch(h, n, false, &fi.sc)) return rs;
+    const bool peer_pull = sharded && h->have_match && h->peer_on;
+    if (!sharded || peer_pull) {  // unsharded: the classification kernel also claims cells and places the voxel bids; with peer
+        if (int rs = prepare_scratch(h, n, false, &fi.sc)) return rs;  // mailboxes k_incr_pull does, once it knows every decision
         fi.on = 1;
     }
+    const FuseInsert fi_pull = fi;
+    if (peer_pull) fi.on = 0;
     DLT_LAUNCH(k_incr_classify, div_up(n, 256), 256, h->stream, (const float4 *)h->d_down, n, P, (const float4 *)h->knn.nbr,
                (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
                LoopArgs{nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull, nullptr}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
@@ -1652,7 +1670,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
                    (const unsigned char *)h->knn.flags, n, (unsigned char)kFlagForeign, (const int *)nullptr, (const int *)nullptr);
         DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
         DLT_LAUNCH(k_incr_pull, div_up(n, 256), 256, h->stream, h->d_peer, n, h->d_dsflag, h->d_addflag, h->d_counters + 6, (const int *)nullptr,
-                   (const int *)nullptr);
+                   (const int *)nullptr, h->map, (const float4 *)h->d_pw, fi_pull);
     } else if (sharded && h->have_match) {  // owners decide, everybody learns every decision, every rank inserts into its tiles + halo
                                      // (without a match pass every rank already agrees: all points are PointToAdd)
         DLT_LAUNCH(k_incr_pack, div_up(n, 256), 256, h->stream, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag, n, h->d_flagbuf);
@@ -1661,7 +1679,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
         DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
         DLT_LAUNCH(k_incr_unpack, div_up(n, 256), 256, h->stream, (const double *)h->d_flagbuf, n, h->d_dsflag, h->d_addflag, h->d_counters + 6);
     }
-    int rc = insert_points(h, h->d_pw, n, true, InsertGate{nullptr, nullptr}, fi.on ? &fi.sc : nullptr);
+    int rc = insert_points(h, h->d_pw, n, true, InsertGate{nullptr, nullptr}, fi_pull.on ? &fi_pull.sc : nullptr);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
     if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));

@@ -22,6 +22,16 @@
 #define DLT_HD __host__ __device__ __forceinline__
 #define DLT_D __device__ __forceinline__
 
+// Programmatic dependent launch: every kernel of this library is launched with the programmatic-stream-serialization
+// attribute (dlt_rt.h), so its launch overlaps the tail of the kernel in front of it in the stream; in return the FIRST
+// statement of every kernel waits here until that kernel has completed and its writes are visible.  (Without the
+// attribute -- graph capture, cooperative launch -- the instruction returns at once.)
+#if defined(DLT_EMU)
+#define DLT_PDL_WAIT()
+#else
+#define DLT_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
+
 namespace dlt {
 
 constexpr int kK = 5;               // NUM_MATCH_POINTS, laserMapping.cpp:77

@@ -73,6 +73,7 @@ DLT_D bool fe_convert(const FeParams &P, const unsigned char *rec, float &x, flo
 __global__ void __launch_bounds__(kFeBlock)
     k_fe_convert(FeParams P, const unsigned char *__restrict__ cloud, const int *__restrict__ rs_index, float4 *__restrict__ tmp /* [n_cand][3] */,
                  unsigned char *__restrict__ keep, unsigned *__restrict__ local_pos, unsigned *__restrict__ blk_total) {
+    DLT_PDL_WAIT();
     __shared__ unsigned warp_tot[kFeBlock / 32];
     const int j = blockIdx.x * kFeBlock + threadIdx.x;
     int k = 0;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kFeBlock)
 }
 
 __global__ void __launch_bounds__(1024) k_fe_offsets(const unsigned *__restrict__ blk_total, int n_blk, unsigned *__restrict__ blk_off, int *__restrict__ n_out) {
+    DLT_PDL_WAIT();
     __shared__ unsigned warp_tot[32];
     __shared__ unsigned carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(1024) k_fe_offsets(const unsigned *__restrict_
 __global__ void __launch_bounds__(kFeBlock)
     k_fe_scatter(int n_cand, const float4 *__restrict__ tmp, const unsigned char *__restrict__ keep, const unsigned *__restrict__ local_pos,
                  const unsigned *__restrict__ blk_off, float4 *__restrict__ out /* 48-byte records */, int cap) {
+    DLT_PDL_WAIT();
     const int j = blockIdx.x * kFeBlock + threadIdx.x;
     if (j >= n_cand || !keep[j]) return;
     const unsigned o = blk_off[blockIdx.x] + local_pos[j];

@@ -187,6 +187,7 @@ DLT_D void loop_load_pose(const LoopK &a, LoopSmem &sm) {
 // ------------------------------------------------------------------ one launch = one iteration
 template <bool EXT>
 __global__ void __launch_bounds__(kLoopBlock, DLT_LOOP_MINBLOCKS) k_iekf_iter(LoopK a) {
+    DLT_PDL_WAIT();
     __shared__ LoopSmem sm;
     const dlt_iekf_block &c = a.dev->b;
     if (c.done) return;  // block-uniform: the loop ended in an earlier launch of this scan
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(kLoopBlock, DLT_LOOP_MINBLOCKS) k_iekf_iter(Lo
 // written by one SM only, and the eigen-decomposition runs next to it on the second to last block.
 template <bool EXT>
 __global__ void __launch_bounds__(kLoopBlock, DLT_LOOP_MINBLOCKS) k_iekf_loop(LoopK a) {
+    DLT_PDL_WAIT();
     __shared__ LoopSmem sm;
     const unsigned G = gridDim.x;
     const int n = *a.n_ptr;

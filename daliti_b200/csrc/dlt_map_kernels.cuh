@@ -141,6 +141,7 @@ DLT_D bool gate_open(const InsertGate &g, int &n) {
 // cell_slot[i] <- table slot of the point's cell (-1: not taking part / not kept by this shard).
 __global__ void k_map_claim(MapView m, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
                             const unsigned char *__restrict__ add_flag, int *__restrict__ cell_slot, int apply_shard_filter, InsertGate gate) {
+    DLT_PDL_WAIT();
     if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -161,6 +162,7 @@ __global__ void k_map_claim(MapView m, const float4 *__restrict__ pts, int n, co
 // ------------------------------------------------------------------ phase 3: append
 __global__ void k_map_append(MapView m, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ add_flag,
                              const int *__restrict__ cell_slot, InsertGate gate) {
+    DLT_PDL_WAIT();
     if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -197,6 +199,7 @@ DLT_D int ds_bid_point(const MapView &m, const DsScratch &sc, float4 p, int i);
 
 __global__ void k_ds_bid(MapView m, DsScratch sc, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
                          int *__restrict__ vslot, InsertGate gate) {
+    DLT_PDL_WAIT();
     if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -234,6 +237,7 @@ struct FuseInsert {
 // Clears the live bits of the points it removes; sets add_flag[i] when it must be added.
 __global__ void k_ds_resolve(MapView m, DsScratch sc, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
                              const int *__restrict__ vslot, const int *__restrict__ cell_slot, unsigned char *__restrict__ add_flag, InsertGate gate) {
+    DLT_PDL_WAIT();
     if (!gate_open(gate, n)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -307,6 +311,7 @@ struct BoxSet {
 };
 
 __global__ void k_map_delete_boxes(MapView m, BoxSet boxes, int n_buckets, int *__restrict__ deleted) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int b = i >> 3, s = (i & 7) - 1;
     int hit = 0;
@@ -333,6 +338,7 @@ __global__ void k_map_delete_boxes(MapView m, BoxSet boxes, int n_buckets, int *
 }
 
 __global__ void k_map_export(MapView m, int n_buckets, float4 *__restrict__ out, int cap, int *__restrict__ counter) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int b = i >> 3, s = (i & 7) - 1;
     if (b >= n_buckets || s < 0) return;

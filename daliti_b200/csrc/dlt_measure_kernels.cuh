@@ -449,6 +449,7 @@ DLT_D void knn_warp_query(const MapView &m, const float4 *__restrict__ q_pts, in
 __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
     k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, const int *__restrict__ list,
           const int *__restrict__ count, LoopArgs la) {
+    DLT_PDL_WAIT();
     __shared__ float4 s_cand[kKnnWarps][kCandSlots];
     __shared__ int s_cid[kKnnWarps][kCandSlots];
     __shared__ int s_wl[kKnnWarps][kWlMax];
@@ -681,6 +682,7 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
 __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
     k_knn8(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
            int *__restrict__ unres_count, LoopArgs la) {
+    DLT_PDL_WAIT();
     __shared__ Pose sP;
     int is_match = -1;
     if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
@@ -707,6 +709,7 @@ constexpr int kFarTile = 128;  // buckets per shared-memory tile
 __global__ void __launch_bounds__(kFarWarps * 32)
     k_far_scan(MapView m, int n_buckets, const float4 *__restrict__ qw, const int *__restrict__ far_list, int far_off, int nfar,
                int n_slices, Cand *__restrict__ partial /* [far][slice][5] */) {
+    DLT_PDL_WAIT();
     __shared__ float4 tile[kFarTile * 8];
     const int groups = (nfar + kFarWarps * 32 - 1) / (kFarWarps * 32);
     const int slice = blockIdx.y;
@@ -757,6 +760,7 @@ __global__ void __launch_bounds__(kFarWarps * 32)
 
 __global__ void k_far_merge(const int *__restrict__ far_list, int far_off, int nfar, int n_slices, const Cand *__restrict__ partial,
                             float max_sq_dist, KnnOut out) {
+    DLT_PDL_WAIT();
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfar; f += gridDim.x * blockDim.x) {
         Cand best[kK];
 #pragma unroll
@@ -792,6 +796,7 @@ constexpr int kNn1Tile = 64;  // buckets per shared-memory tile
 __global__ void __launch_bounds__(kNn1Block)
     k_nn1(MapView m, const int *__restrict__ n_buckets_ptr, const float4 *__restrict__ qw, const int *__restrict__ nn_list,
           const int *__restrict__ nn_count, unsigned long long *__restrict__ nn_key, int *gate) {
+    DLT_PDL_WAIT();
     __shared__ float4 tile[kNn1Tile * 8];
     if (gate && *gate != 1) return;
     if (gate && nn_count[1] > 0) {  // a bucket chain overflowed the ring search: the host runs the full exact fallback instead
@@ -1311,6 +1316,7 @@ DLT_D void iekf_step_block(IekfDev *dev, const double *__restrict__ result, cons
 
 __global__ void __launch_bounds__(kIekfBlock) k_iekf_step(IekfDev *dev, const double *__restrict__ result, const int *__restrict__ n_down_ptr,
                                                            const int *__restrict__ vox_status_ptr, int D /* 6 or 12 */) {
+    DLT_PDL_WAIT();
     if (dev->b.done) return;  // block-uniform
     iekf_step_block(dev, result, n_down_ptr, vox_status_ptr, D);
 }
@@ -1532,6 +1538,7 @@ DLT_D void residual_final_reduce(const MeasureBufs &mb, unsigned n_parts, int n,
 template <bool EXT>
 __global__ void __launch_bounds__(kResidBlock)
     k_residual(MeasureBufs mb, int n, int do_match, Pose P_param, float plane_thr, LoopArgs la) {
+    DLT_PDL_WAIT();
     using NE = NormalEq<EXT>;
     constexpr int D = NE::D, NR = NE::NR;
     __shared__ double s_part[kResidBlock / 32][NR];
@@ -1696,7 +1703,8 @@ DLT_D void eigen6_warp(const double *__restrict__ result, double *__restrict__ e
         }
     }
 }
-__global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result, double *__restrict__ eig_out) { eigen6_warp(result, eig_out, threadIdx.x); }
+__global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result, double *__restrict__ eig_out) {
+    DLT_PDL_WAIT(); eigen6_warp(result, eig_out, threadIdx.x); }
 
 // ------------------------------------------------------------------ map_incremental classification
 // laserMapping.cpp:582-630: decide per downsampled point whether it is added raw
@@ -1706,6 +1714,7 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_p
                                 unsigned char *__restrict__ add_flag, int *__restrict__ class_counts /* [0] downsample adds, [1] raw adds */,
                                 LoopArgs la, MapView m, const int *__restrict__ live_ptr, const unsigned char *__restrict__ flags,
                                 const int *__restrict__ nn_pos, const unsigned long long *__restrict__ nn_key, FuseInsert fi) {
+    DLT_PDL_WAIT();
     __shared__ Pose sP;
     if (!insert_gate(la, n)) return;  // block-uniform
     if (la.ctl) {  // pose after the zeta blend, flg_EKF_inited after the loop
@@ -1793,11 +1802,13 @@ __global__ void k_incr_classify(const float4 *__restrict__ down, int n, Pose P_p
 // exchanged as doubles so that the same sum all-reduce that carries the normal equations can carry them (one owner per
 // query, so the sum IS the decision); afterwards every rank knows every decision and inserts what falls into its tiles + halo.
 __global__ void k_incr_pack(const unsigned char *__restrict__ ds_flag, const unsigned char *__restrict__ add_flag, int n, double *__restrict__ buf) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) buf[i] = ds_flag[i] ? 1.0 : (add_flag[i] ? 2.0 : 0.0);
 }
 __global__ void k_incr_unpack(const double *__restrict__ buf, int n, unsigned char *__restrict__ ds_flag, unsigned char *__restrict__ add_flag,
                               int *__restrict__ class_counts) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int code = 0;
     if (i < n) {
@@ -1815,6 +1826,7 @@ __global__ void k_incr_unpack(const double *__restrict__ buf, int n, unsigned ch
 // pointBodyToWorld over the downsampled scan (laserMapping.cpp:786-789), every point flagged for a raw add
 __global__ void k_scan_to_world(const float4 *__restrict__ down, int n, Pose P, float4 *__restrict__ pw, unsigned char *__restrict__ ds_flag,
                                 unsigned char *__restrict__ add_flag) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 pb = down[i];

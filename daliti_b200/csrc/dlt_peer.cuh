@@ -17,6 +17,7 @@
 #pragma once
 #include "../../include/daliti_b200.h"
 #include "dlt_common.cuh"
+#include "dlt_map_kernels.cuh"
 #if defined(DLT_EMU)
 #include <chrono>
 #endif
@@ -114,6 +115,7 @@ DLT_D bool peer_allreduce_block(PeerComm *pc, double *R, int n) {
 // (*gate_go == 1, the same on every rank), with feats_down_size read from the device.
 __global__ void k_incr_push(PeerComm *pc, const unsigned char *__restrict__ ds_flag, const unsigned char *__restrict__ add_flag,
                             const unsigned char *__restrict__ flags, int n, unsigned char foreign_bit, const int *gate_go, const int *gate_n) {
+    DLT_PDL_WAIT();
     __shared__ int s_last;
     if (gate_go && *gate_go != 1) return;  // block-uniform
     if (gate_n) n = *gate_n;
@@ -134,8 +136,12 @@ __global__ void k_incr_push(PeerComm *pc, const unsigned char *__restrict__ ds_f
     if (threadIdx.x == 0) pc->dec_ticket = 0u;
 }
 // ... and every rank, once all owners have published, reads all n decisions from its own mailbox.
+// fi.on: the first two insert phases ride along (k_map_claim with the shard filter + k_ds_bid for the point just decided: neither
+// needs another thread's result), which saves two launches per scan.
 __global__ void k_incr_pull(PeerComm *pc, int n, unsigned char *__restrict__ ds_flag, unsigned char *__restrict__ add_flag,
-                            int *__restrict__ class_counts, const int *gate_go, const int *gate_n) {
+                            int *__restrict__ class_counts, const int *gate_go, const int *gate_n, MapView m, const float4 *__restrict__ pts,
+                            FuseInsert fi) {
+    DLT_PDL_WAIT();
     __shared__ int s_timeout;
     if (gate_go && *gate_go != 1) return;  // block-uniform
     if (gate_n) n = *gate_n;
@@ -153,6 +159,18 @@ __global__ void k_incr_pull(PeerComm *pc, int n, unsigned char *__restrict__ ds_
         code = *(const volatile unsigned char *)&peer_dec(pc->box[me], par, pc->dec_cap)[i];
         ds_flag[i] = code == 1 ? 1 : 0;
         add_flag[i] = code == 2 ? 1 : 0;
+        if (fi.on) {
+            int cs = -1, vs = -1;
+            const float4 p = pts[i];
+            if (code != 0) {
+                int cx, cy, cz;
+                cell_of_point(m, p.x, p.y, p.z, cx, cy, cz);
+                if (shard_keeps_cell(m, cx, cy, cz, kShardHalo)) cs = map_claim(m, pack_key(cx, cy, cz));
+            }
+            if (code == 1) vs = ds_bid_point(m, fi.sc, p, i);
+            fi.cell_slot[i] = cs;
+            fi.vslot[i] = vs;
+        }
     }
     unsigned bd = __ballot_sync(0xffffffffu, code == 1), ba = __ballot_sync(0xffffffffu, code == 2);
     if ((threadIdx.x & 31) == 0) {

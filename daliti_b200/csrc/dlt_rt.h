@@ -132,11 +132,26 @@ inline void shared_close(void *p, size_t bytes) {
 
 #else  // ------------------------------------------------------------------ CUDA
 
-namespace dlt { namespace rt { extern std::atomic<unsigned long long> g_launches; } }
-#define DLT_LAUNCH(kernel, grid, block, stream, ...)                      \
-    do {                                                                  \
-        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);            \
-        ++dlt::rt::g_launches;                                            \
+namespace dlt { namespace rt {
+extern std::atomic<unsigned long long> g_launches;
+extern int g_pdl;  // 1: launch with the programmatic-stream-serialization attribute (DLT_PDL=0 switches it off)
+} }
+// Every kernel starts with DLT_PDL_WAIT() (dlt_common.cuh), so it may be launched as a programmatic dependent of the
+// kernel in front of it: the launch latency then overlaps that kernel's tail instead of following its completion.
+#define DLT_LAUNCH(kernel, grid, block, stream_, ...)                                                   \
+    do {                                                                                                \
+        cudaLaunchConfig_t cfg__ = {};                                                                  \
+        cfg__.gridDim = dim3(grid);                                                                     \
+        cfg__.blockDim = dim3(block);                                                                   \
+        cfg__.dynamicSmemBytes = 0;                                                                     \
+        cfg__.stream = (stream_);                                                                       \
+        cudaLaunchAttribute attr__[1];                                                                  \
+        attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+        attr__[0].val.programmaticStreamSerializationAllowed = 1;                                       \
+        cfg__.attrs = attr__;                                                                           \
+        cfg__.numAttrs = dlt::rt::g_pdl ? 1 : 0;                                                        \
+        cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                                                \
+        ++dlt::rt::g_launches;                                                                          \
     } while (0)
 
 namespace dlt {

@@ -58,6 +58,7 @@ DLT_HD float ordered_to_float(unsigned u) {
 }
 
 __global__ void k_scan_reset(ScanScalars *sc) {
+    DLT_PDL_WAIT();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         for (int a = 0; a < 3; a++) {
             sc->bbox_min[a] = 0xFFFFFFFFu;
@@ -74,6 +75,7 @@ __global__ void k_scan_reset(ScanScalars *sc) {
 // which raw point has the smallest normal_x (ties: lowest index) -- the point the
 // reference's std::sort by normal_x (IMU_Processing.hpp:216) leaves at begin()
 __global__ void k_scan_first(const float4 *__restrict__ raw, int n, ScanScalars *sc) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long key = 0xFFFFFFFFFFFFFFFFull;
     if (i < n) {
@@ -127,6 +129,7 @@ constexpr int kDeskewBlock = 128;
 __global__ void __launch_bounds__(kDeskewBlock)
     k_scan_deskew(const float4 *__restrict__ raw, int n, const ImuPoseDev *__restrict__ poses, int n_pose, Pose st, int do_deskew,
                   float4 *__restrict__ undist, ScanScalars *sc) {
+    DLT_PDL_WAIT();
     __shared__ float4 stage[kDeskewBlock * kRawStride4];
     __shared__ unsigned s_mn[3], s_mx[3];
     const int base = blockIdx.x * kDeskewBlock;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(kDeskewBlock)
 
 // bounding box only (input already float4, e.g. dlt_scan_set_points)
 __global__ void k_scan_bbox(const float4 *__restrict__ pts, int n, ScanScalars *sc) {
+    DLT_PDL_WAIT();
     __shared__ unsigned s_mn[3], s_mx[3];
     if (threadIdx.x < 3) {
         s_mn[threadIdx.x] = 0xFFFFFFFFu;
@@ -247,6 +251,7 @@ DLT_D unsigned vox_idx_of(const VoxGrid &g, float x, float y, float z) {
 // mark occupied voxels in the bitmap; remember every point's idx
 __global__ void k_vox_mark(const float4 *__restrict__ pts, int n, float leaf, ScanScalars *sc, unsigned *__restrict__ bitmap,
                            long long bitmap_bits, unsigned *__restrict__ vidx) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     VoxGrid g = vox_grid_of(sc, leaf);
     int status = g.status;
@@ -306,6 +311,7 @@ DLT_D void vox_scan_block_totals(ScanScalars *sc, const unsigned *__restrict__ b
 __global__ void __launch_bounds__(kScanBlock)
     k_vox_scan1(const unsigned *__restrict__ bitmap, ScanScalars *sc, unsigned *__restrict__ wprefix, unsigned *__restrict__ blksum,
                 unsigned *__restrict__ blkoff, unsigned *__restrict__ ticket) {
+    DLT_PDL_WAIT();
     __shared__ unsigned warp_tot[kScanBlock / 32];
     __shared__ int s_last;
     const int n_words = sc->n_words;
@@ -366,6 +372,7 @@ constexpr double kFix = 16777216.0;  // 2^24
 __global__ void k_vox_accum(const float4 *__restrict__ pts, int n, const ScanScalars *sc, const unsigned *__restrict__ bitmap,
                             const unsigned *__restrict__ wprefix, const unsigned *__restrict__ blkoff, const unsigned *__restrict__ vidx,
                             VoxAcc acc, int *__restrict__ voxel_of_point) {
+    DLT_PDL_WAIT();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || sc->vox_status) return;
     unsigned idx = vidx[i];
@@ -386,6 +393,7 @@ __global__ void k_vox_accum(const float4 *__restrict__ pts, int n, const ScanSca
 // vox_status == 1 (PCL: leaf too small for the data): output = input.
 __global__ void k_vox_final(ScanScalars *sc, VoxAcc acc, unsigned *__restrict__ bitmap, const float4 *__restrict__ pts, float4 *__restrict__ down,
                             int n) {
+    DLT_PDL_WAIT();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int status = sc->vox_status;
     const int n_down = sc->n_down;

@@ -35,6 +35,7 @@ def main():
             os.environ["DLT_ZEROCOPY"] = "0" if "n" in mtag[1:] else "1"
             os.environ["DLT_LOOP_FUSED"] = "0" if "c" in mtag[1:] else "1"
             os.environ["DLT_LOOP_COOP"] = "1" if "p" in mtag[1:] else "0"
+            os.environ["DLT_PDL"] = "0" if "s" in mtag[1:] else "1"  # s = plain stream serialisation (no programmatic dependent launch)
             lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30,
                               device_loop=mode)
             lm.device.set_stream(stream.cuda_stream)
