@@ -223,6 +223,8 @@ static int launch_knn(dlt_handle h, const float4 *d_q, int n, int n_grid, int bo
     {
         ProfScope prof8(h, 7);  // the dominant kernel on its own (group 0 spans the whole match pass)
         int g8 = div_up(n_grid, kKnn8Block / 8);
+        const int wave8 = h->n_sm * DLT_KNN8_MINBLOCKS;  // what is resident at once: the kernel strides, so a partial second wave never forms
+        if (g8 > wave8) g8 = wave8;
         if (g8 < 1) g8 = 1;
         DLT_LAUNCH(k_knn8, g8, kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la);
     }

@@ -62,6 +62,7 @@ struct LoopSmem {
     Cand bestw[kKnnWarps][kK];
     int nb[kKnnWarps];
     int unres[kLoopChunkMax];
+    int wl8[kLoopBlock / 32][kKnn8WlInts];  // knn8_group: bucket index of every visit
     int n_unres;
     int last;
     double part[kLoopBlock / 32][NormalEq<true>::NR];
@@ -123,7 +124,7 @@ DLT_D bool loop_iter_chunks(const LoopK &a, LoopSmem &sm, int n, int do_match) {
             if (tid == 0) sm.n_unres = 0;
             __syncthreads();
             for (int q0 = c0 + warp * 4; q0 < c1; q0 += (kLoopBlock / 32) * 4)  // warp-uniform
-                knn8_group(a.m, a.down, c1, 1, sm.P, a.max_sq_dist, a.knn, sm.unres, &sm.n_unres, q0, lane, kLoopChunkMax);
+                knn8_group(a.m, a.down, c1, 1, sm.P, a.max_sq_dist, a.knn, sm.unres, &sm.n_unres, q0, lane, sm.wl8[warp], kLoopChunkMax);
             __syncthreads();
             const int nu = min(sm.n_unres, kLoopChunkMax);
             if (warp < kKnnWarps)

@@ -469,15 +469,22 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
 }
 
 // ------------------------------------------------------------------ first pass: 8 lanes per query over the 3x3x3 block
-// Four queries per warp.  The 8 lanes of a group probe the 27 cells in 4 rounds and fetch two 128-byte
-// buckets per step (lane 0 the header, lanes 1-7 one point each; both loads in flight before the first
-// is consumed).  Every lane keeps the 5 best of the points it saw as 64-bit keys (d2 bits << 32 | id;
-// d2 >= 0, so the bit pattern orders like the float) plus the smallest d2 it ever dropped; the 8 sorted
-// lists are merged with five 8-lane mins and the winners' coordinates are re-read from their (L1-hot)
-// buckets.  Keys order by (d2, id), the stated order is (d2, x, y, z, id): whenever two of the six best
-// share a d2 -- inside the winners or at the k-th boundary -- the query is left to the warp-per-query
-// kernel above, which applies the stated order exactly.  A query is finished here when the 3^3 block
-// proves its 5 best exact (the common case on a mapped surface); the rest go to `unres_list`.
+// Four queries per warp.  The 8 lanes of a group probe the 27 cells in 4 rounds (the table slot of the NEXT round is
+// requested before the buckets of the current one are consumed) and fetch two 128-byte buckets per step (lane 0 the
+// header, lanes 1-7 one point each; both loads in flight before the first is consumed).
+//
+// Selection works on 32-bit keys.  d2 >= 0, so its bit pattern orders like the float; the low 9 bits of the pattern are
+// replaced by a tag that names the candidate inside the group: (visit << 3) | lane-in-group, `visit` = which of the
+// group's (at most 64) bucket fetches brought it in.  Keys are unique, a key identifies its point (the bucket index of
+// every visit is kept in shared memory) and sorting keys sorts by d2 truncated to 14 mantissa bits.  Every lane keeps the
+// five smallest keys it saw with a branch-free min / max insertion plus the smallest key it ever dropped; the 8 sorted
+// lists merge with five 8-lane mins.  Whenever the SIX best keys have pairwise different truncated distances the five
+// winners are exactly the five smallest d2 in exact order (anything else has a truncated distance >= the sixth's, hence
+// a larger d2 than the fifth); their coordinates are re-read from the (L1-hot) buckets and d2 is recomputed -- the same
+// expression on the same inputs, so the same bits.  Otherwise (two of the six agree to 14 bits: about one query in a
+// thousand; this includes every exact d2 tie, which the stated order (d2, x, y, z, id) has to break), or when the 3^3
+// block cannot prove the result exact, or after more than 64 bucket fetches, the query goes to `unres_list` for the
+// warp-per-query kernel above, which searches from scratch with exact comparisons.
 #ifndef DLT_KNN8_BLOCK
 #define DLT_KNN8_BLOCK 256
 #endif
@@ -485,65 +492,73 @@ constexpr int kKnn8Block = DLT_KNN8_BLOCK;
 #ifndef DLT_KNN8_MINBLOCKS
 #define DLT_KNN8_MINBLOCKS 6
 #endif
-constexpr unsigned long long kKeyInf = (0x7F800000ull << 32) | 0x7FFFFFFFull;
-// Opt-in variant (default off: the committed profiles and bench lines are of the build without it; A/B with
-// tools/knn_variants.py).  A query is only finished here when d2[4] < thr = (cov - slack)^2 * 0.99999, cov = distance to the
-// faces of the 3^3 block.  So a candidate with d2 >= thr can never be one of the five winners of a FINISHED query, nor tie
-// with its fifth: it need not be kept, and a cell whose box distance is >= thr need not be probed at all.  Queries this
-// leaves without five candidates go to k_knn exactly as before (k_knn searches from scratch).  Result-identical by
-// construction; the emulator suite passes with it on.  On a surface it drops about half of the sorted inserts (the sphere
-// of radius cov against the 3 m block) and the corner / edge cells of queries that sit off-centre in their cell.
-#ifndef DLT_KNN8_PRUNE
-#define DLT_KNN8_PRUNE 0
-#endif
+constexpr unsigned kKey32Inf = 0xFFFFFFFFu;
+constexpr int kKnn8TagBits = 9;                       // 6 bits visit + 3 bits lane-in-group
+constexpr int kKnn8Visits = 64;                       // bucket fetches per group that a tag can name
+constexpr unsigned kKey32Finite = 0x7F800000u >> kKnn8TagBits;  // truncated pattern of +inf
+constexpr int kKnn8WlInts = 4 * kKnn8Visits;          // shared-memory ints per warp (bucket index of every visit)
 
-DLT_D unsigned long long group8_min_u64(unsigned long long k) {
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
-        k = t < k ? t : k;
-    }
-    return k;
-}
 DLT_D unsigned group8_min_u32(unsigned k) {
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) k = min(k, __shfl_xor_sync(0xffffffffu, k, o));
     return k;
 }
-// keep the kK smallest keys, ascending; `dropped` <- smallest d2 bits that ever fell off the list
-DLT_D void topk_insert_key(unsigned long long (&b)[kK], unsigned long long k, unsigned &dropped) {
-    if (k < b[kK - 1]) {
-        dropped = min(dropped, (unsigned)(b[kK - 1] >> 32));
-        b[kK - 1] = k;
+// keep the kK smallest keys, ascending (branch-free; k = kKey32Inf is a no-op); `dropped` <- smallest key that fell off the list
+DLT_D void topk_insert_k32(unsigned (&b)[kK], unsigned k, unsigned &dropped) {
+    dropped = min(dropped, max(k, b[kK - 1]));
+    b[kK - 1] = min(b[kK - 1], k);
 #pragma unroll
-        for (int t = kK - 1; t > 0; t--) {
-            const unsigned long long lo = b[t] < b[t - 1] ? b[t] : b[t - 1];
-            const unsigned long long hi = b[t] < b[t - 1] ? b[t - 1] : b[t];
-            b[t - 1] = lo;
-            b[t] = hi;
-        }
-    } else {
-        dropped = min(dropped, (unsigned)(k >> 32));
+    for (int t = kK - 1; t > 0; t--) {
+        const unsigned lo = min(b[t], b[t - 1]), hi = max(b[t], b[t - 1]);
+        b[t - 1] = lo;
+        b[t] = hi;
     }
 }
-// one staged bucket line: lane `sub` of the group holds 16 bytes of bucket bb (sub 0 = header)
-DLT_D void knn8_consume(const float4 v, int &bb, int lane, int sub, float qx, float qy, float qz, unsigned long long (&best)[kK],
-                        unsigned &dropped, float thr) {
+// one staged bucket line: lane `sub` of the group holds 16 bytes of bucket bb (sub 0 = header); tag = (visit << 3) | sub
+DLT_D void knn8_consume(const float4 v, int &bb, int lane, int sub, float qx, float qy, float qz, unsigned (&best)[kK], unsigned &dropped,
+                        unsigned tag, bool tag_ok) {
     const int hdr_next = __shfl_sync(0xffffffffu, __float_as_int(v.z), lane & ~7);
     const unsigned hdr_mask = __shfl_sync(0xffffffffu, __float_as_uint(v.w), lane & ~7);
-    if (bb >= 0 && sub >= 1 && ((hdr_mask >> (sub - 1)) & 1u)) {
-        const float d2 = calc_dist(qx, qy, qz, v.x, v.y, v.z);
-#if DLT_KNN8_PRUNE
-        if (d2 < thr)
-#endif
-        topk_insert_key(best, ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(unsigned)(bb * 8 + sub), dropped);
-    }
+    const float d2 = calc_dist(qx, qy, qz, v.x, v.y, v.z);
+    const bool has = bb >= 0 && tag_ok && (((hdr_mask << 1) >> sub) & 1u);  // (bit 0 of the shifted mask = the header lane: never set)
+    const unsigned key = has ? ((__float_as_uint(d2) & ~((1u << kKnn8TagBits) - 1u)) | tag) : kKey32Inf;
+    topk_insert_k32(best, key, dropped);
     bb = (bb >= 0) ? hdr_next : -1;
 }
+// first table slot of a cell's probe sequence, requested early; knn8_find_finish completes the lookup
+struct Probe {
+    unsigned long long key;
+    unsigned h;
+    Slot s;
+    bool on;
+};
+DLT_D Probe knn8_find_begin(const MapView &m, bool on, int cx, int cy, int cz) {
+    Probe p;
+    p.on = on;
+    p.key = pack_key(cx, cy, cz);
+    p.h = hash_key(p.key) & m.table_mask;
+    p.s.key = kEmptyKey;
+    p.s.bucket = -1;
+    p.s.pad = 0;
+    if (on) p.s = load_slot(&m.table[p.h]);
+    return p;
+}
+DLT_D int knn8_find_finish(const MapView &m, const Probe &p) {
+    if (!p.on) return -1;
+    Slot s = p.s;
+    unsigned h = p.h;
+    for (unsigned probe = 0; probe <= m.table_mask; probe++) {
+        if (s.key == p.key) return s.bucket;
+        if (s.key == kEmptyKey) return -1;
+        h = (h + 1) & m.table_mask;
+        s = load_slot(&m.table[h]);
+    }
+    return -1;
+}
 
-// the four queries q0 .. q0+3 of one warp
+// the four queries q0 .. q0+3 of one warp; wl = this warp's kKnn8WlInts ints of shared memory
 DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n, int body_frame, const Pose &P, float max_sq_dist, const KnnOut &out,
-                      int *unres_list, int *unres_count, int q0, int lane, int unres_cap = 0x7FFFFFFF) {
+                      int *unres_list, int *unres_count, int q0, int lane, int *wl, int unres_cap = 0x7FFFFFFF) {
     const unsigned FULL = 0xffffffffu;
     const int grp = lane >> 3, sub = lane & 7;
     const int qi = q0 + grp;
@@ -569,40 +584,21 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
             }
         }
     }
-    unsigned long long best[kK];
+    unsigned best[kK];
 #pragma unroll
-    for (int t = 0; t < kK; t++) best[t] = kKeyInf;
-    unsigned dropped = 0x7F800000u;
-    float thr = INFINITY;
-#if DLT_KNN8_PRUNE
-    const float slack_p = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
-    {  // the same expressions as the `resolved` test below
-        float cov = INFINITY;
-        cov = fminf(cov, qx - (float)(cx - 1) * cell_edge);
-        cov = fminf(cov, (float)(cx + 2) * cell_edge - qx);
-        cov = fminf(cov, qy - (float)(cy - 1) * cell_edge);
-        cov = fminf(cov, (float)(cy + 2) * cell_edge - qy);
-        cov = fminf(cov, qz - (float)(cz - 1) * cell_edge);
-        cov = fminf(cov, (float)(cz + 2) * cell_edge - qz);
-        cov -= slack_p;
-        thr = (cov > 0.f) ? cov * cov * 0.99999f : 0.f;
-    }
-#endif
+    for (int t = 0; t < kK; t++) best[t] = kKey32Inf;
+    unsigned dropped = kKey32Inf;
+    int *gwl = wl + grp * kKnn8Visits;
+    int visit = 0;        // warp-uniform: bucket fetches so far (two per step)
+    bool ovf = false;     // this group needed a fetch beyond what a tag can name
 
+    // cell ci = r * 8 + sub of the 3^3 block, in the order (x fastest)
+    Probe pr = knn8_find_begin(m, work, cx + (sub % 3) - 1, cy + ((sub / 3) % 3) - 1, cz + (sub / 9) - 1);
     for (int r = 0; r < 4; r++) {
-        const int ci = r * 8 + sub;
-        int b = -1;
-#if DLT_KNN8_PRUNE
-        if (work && ci < 27) {
-            const int ox = (ci % 3) - 1, oy = ((ci / 3) % 3) - 1, oz = (ci / 9) - 1;
-            const float gx = axis_gap(qx, cx + ox, cell_edge, slack_p), gy = axis_gap(qy, cy + oy, cell_edge, slack_p),
-                        gz = axis_gap(qz, cz + oz, cell_edge, slack_p);
-            const float bd = gx * gx + gy * gy + gz * gz;  // every point of the cell is at least this far (conservatively)
-            if (!(bd * 0.99999f >= thr)) b = map_find(m, pack_key(cx + ox, cy + oy, cz + oz));
-        }
-#else
-        if (work && ci < 27) b = map_find(m, pack_key(cx + (ci % 3) - 1, cy + ((ci / 3) % 3) - 1, cz + (ci / 9) - 1));
-#endif
+        const int cn = (r + 1) * 8 + sub;  // next round's cell: its slot is in flight while this round's buckets are consumed
+        Probe nx = knn8_find_begin(m, work && r < 3 && cn < 27, cx + (cn % 3) - 1, cy + ((cn / 3) % 3) - 1, cz + (cn / 9) - 1);
+        const int b = knn8_find_finish(m, pr);
+        pr = nx;
         unsigned gb = (__ballot_sync(FULL, b >= 0) >> (grp * 8)) & 0xFFu;  // this group's found cells
         while (__any_sync(FULL, gb != 0u)) {                                // warp-uniform
             const int s0 = gb ? (__ffs((int)gb) - 1) : -1;
@@ -617,36 +613,57 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (bb0 >= 0) v0 = reinterpret_cast<const float4 *>(&m.buckets[bb0])[sub];  // 8 lanes x 16 B = one line
                 if (bb1 >= 0) v1 = reinterpret_cast<const float4 *>(&m.buckets[bb1])[sub];
-                knn8_consume(v0, bb0, lane, sub, qx, qy, qz, best, dropped, thr);
-                knn8_consume(v1, bb1, lane, sub, qx, qy, qz, best, dropped, thr);
+                const bool tag_ok = visit < kKnn8Visits;  // warp-uniform
+                if (!tag_ok && (bb0 >= 0 || bb1 >= 0)) ovf = true;
+                if (tag_ok && sub == 0) {
+                    gwl[visit] = bb0;
+                    gwl[visit + 1] = bb1;
+                }
+                const unsigned tag = ((unsigned)visit << 3) | (unsigned)sub;
+                knn8_consume(v0, bb0, lane, sub, qx, qy, qz, best, dropped, tag, tag_ok);
+                knn8_consume(v1, bb1, lane, sub, qx, qy, qz, best, dropped, tag + 8u, tag_ok);
+                visit += 2;
             }
         }
     }
-    // ---- merge the group's 8 sorted lists: five rounds of 8-lane min, the owner pops its head
+    // ---- merge the group's 8 sorted lists: five rounds of 8-lane min, the owner (named by the tag) pops its head
     int nb = 0;
-    unsigned prevd = 0xFFFFFFFFu;
+    unsigned prevt = 0xFFFFFFFFu;  // truncated distance of the previous winner
     bool tie = false;
-    unsigned long long mine = kKeyInf;
+    unsigned mine = kKey32Inf;
 #pragma unroll
     for (int t = 0; t < kK; t++) {
-        const unsigned long long w = group8_min_u64(best[0]);
-        const bool valid = (unsigned)(w >> 32) < 0x7F800000u;
-        if (valid && best[0] == w) {  // ids are unique: exactly one owner
+        const unsigned w = group8_min_u32(best[0]);
+        const unsigned wt = w >> kKnn8TagBits;
+        const bool valid = wt < kKey32Finite;
+        if (valid && (int)(w & 7u) == sub) {
 #pragma unroll
             for (int u = 0; u < kK - 1; u++) best[u] = best[u + 1];
-            best[kK - 1] = kKeyInf;
+            best[kK - 1] = kKey32Inf;
         }
         nb += valid ? 1 : 0;
-        const unsigned wd = (unsigned)(w >> 32);
-        if (valid && wd == prevd) tie = true;
-        prevd = wd;
+        if (valid && wt == prevt) tie = true;
+        prevt = wt;
         if (sub == t) mine = w;
     }
-    // the group's 6th-smallest d2: a remaining list head or something a lane dropped earlier
-    const unsigned sixth = group8_min_u32(min((unsigned)(best[0] >> 32), dropped));
+    // the group's 6th-smallest key: a remaining list head or something a lane dropped earlier
+    const unsigned sixth = group8_min_u32(min(best[0], dropped));
+    if (nb == kK && (sixth >> kKnn8TagBits) == prevt) tie = true;
+    __syncwarp();  // the visit list (written by lane 0 of the group) is read by lanes 0-4
+    // exact distances of the winners, from their coordinates
+    const bool cand_ok = work && nb == kK && !tie && !ovf;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float myd2 = INFINITY;
+    int id = -1;
+    if (cand_ok && sub < kK) {
+        const int osub = (int)(mine & 7u);
+        id = gwl[(mine >> 3) & (unsigned)(kKnn8Visits - 1)] * 8 + osub;
+        p = m.buckets[id >> 3].pts[osub - 1];
+        myd2 = calc_dist(qx, qy, qz, p.x, p.y, p.z);
+    }
+    const float d5 = __shfl_sync(FULL, myd2, (grp << 3) + (kK - 1));
+    __syncwarp();  // (the next group of this warp reuses the visit list)
     if (!work) return;
-    const float d5 = (nb == kK) ? __uint_as_float(prevd) : INFINITY;
-    if (nb == kK && sixth == prevd) tie = true;
     const float slack = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
     float cov = INFINITY;
     cov = fminf(cov, qx - (float)(cx - 1) * cell_edge);
@@ -656,7 +673,7 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
     cov = fminf(cov, qz - (float)(cz - 1) * cell_edge);
     cov = fminf(cov, (float)(cz + 2) * cell_edge - qz);
     cov -= slack;
-    const bool resolved = (nb == kK) && !tie && cov > 0.f && d5 < cov * cov * 0.99999f;
+    const bool resolved = cand_ok && cov > 0.f && d5 < cov * cov * 0.99999f;
     if (!resolved) {
         if (sub == 0) {
             const int pos = atomicAdd(unres_count, 1);
@@ -665,9 +682,7 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
         return;
     }
     if (sub < kK) {
-        const int id = (int)(unsigned)(mine & 0xFFFFFFFFull);
-        const float4 p = m.buckets[id >> 3].pts[(id & 7) - 1];
-        out.nbr[(size_t)qi * kK + sub] = make_float4(p.x, p.y, p.z, __uint_as_float((unsigned)(mine >> 32)));
+        out.nbr[(size_t)qi * kK + sub] = make_float4(p.x, p.y, p.z, myd2);
         out.nbr_id[(size_t)qi * kK + sub] = id;
     }
     if (sub == 0) {
@@ -677,13 +692,14 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
 }
 
 // Warp-stride over groups of four queries, so the grid may be sized from an estimate of n (the
-// device-resident loop launches before the host knows feats_down_size).  Also zeroes far_count for
-// the warp-per-query pass that follows in stream order.
+// device-resident loop launches before the host knows feats_down_size) and capped at what is resident in one wave.
+// Also zeroes far_count for the warp-per-query pass that follows in stream order.
 __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
     k_knn8(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
            int *__restrict__ unres_count, LoopArgs la) {
     DLT_PDL_WAIT();
     __shared__ Pose sP;
+    __shared__ int s_wl[kKnn8Block / 32][kKnn8WlInts];
     int is_match = -1;
     if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -694,7 +710,7 @@ __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x * (kKnn8Block / 32) * 4;
     for (int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4; q0 < n; q0 += stride)  // warp-uniform
-        knn8_group(m, q_pts, n, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane);
+        knn8_group(m, q_pts, n, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane, s_wl[warp]);
 }
 
 // ------------------------------------------------------------------ exact fallback for unresolved queries
