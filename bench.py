@@ -471,6 +471,7 @@ def main():
         s0, mean_acc, last_imu = initial_state(seq)
         lm2 = LaserMapping(dev=dict(device=local_rank, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * n_map)), featptsThreshold=30,
                            device_loop=device_loop, **work["lm_kwargs"])
+        lm2.collect_after_scan = False  # the call as the library delivers it: map_incremental keeps running on its own stream (async_insert)
         lm2.device.set_stream(stream.cuda_stream)
         lm2.force_imu_ready(mean_acc, last_imu)
         lm2.set_state(s0)
@@ -690,6 +691,7 @@ def main():
                        "n_raw_mean": n_raw_mean, "n_down_mean": n_down_mean, "effct_feat_mean": float(np.mean([o[6] for o in outs_v])),
                        "ekf_stops": int(sum(o[3] for o in outs_v)), "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
                        "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
+                       "insert": "async_insert (library default): map_incremental of scan k runs on the handle's insert stream; the step's end event marks the final pose, the insert overlaps the next scan's deskew / VoxelGrid and its first match pass waits for it on the device",
                        "parallelism": "1 sequence per GPU, no data-path collective" if world > 1 else "single GPU",
                        "host_cores_of_this_rank": pinned_cores,
                        "value_l2_warm_points_per_s": pts_v / (t_w * 1e-3), "ms_p50_l2_warm": float(np.median(ms_w)),
@@ -872,6 +874,7 @@ def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
                        "effct_feat_mean": float(np.mean([o[3] for o in outs_v])),
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
                        "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
+                       "insert": "async_insert (library default): map_incremental of scan k runs on the handle's insert stream; the step's end event marks the final pose, the insert overlaps the next scan's deskew / VoxelGrid and its first match pass waits for it on the device",
                        "parallelism": (f"map sharded {world}-way by 32-cell tiles + halo; 158 doubles summed over the ranks per iteration "
                                        + ("inside k_residual through NVLink peer mailboxes (CUDA IPC): no collective launch"
                                           if exchange == "peer" else "by an NCCL all-reduce between k_residual and k_iekf_step")) if world > 1 else "single GPU, unsharded",
@@ -912,6 +915,7 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
         for w, st in zip(works, streams):
             lm = LaserMapping(dev=dict(device=local_rank, max_scan_points=1 << 16, max_map_points=max(1 << 20, 2 * len(w["map_pts"])),
                                        voxel_bitmap_bits=1 << 25), featptsThreshold=30, device_loop=args.device_loop)
+            lm.collect_after_scan = False
             lm.device.set_stream(st.cuda_stream)
             s0, mean_acc, last_imu = initial_state(w["seq"])
             lm.force_imu_ready(mean_acc, last_imu)

@@ -73,7 +73,7 @@ _SYMBOLS = [
     "dlt_scan_get_voxel_of_point", "dlt_measure", "dlt_measure_dev", "dlt_effective_points", "dlt_get_nearest",
     "dlt_fetch_result", "dlt_degeneracy", "dlt_degeneracy_begin", "dlt_map_incremental", "dlt_set_profiling", "dlt_get_profile", "dlt_launch_count",
     "dlt_scan_downsample_async", "dlt_iekf_update", "dlt_get_timeline", "dlt_get_iekf_clocks", "dlt_set_shard_reduce", "dlt_result_dev", "dlt_frontend_sample", "dlt_frontend_read", "dlt_scan_prefetch",
-    "dlt_peer_export", "dlt_peer_attach", "dlt_peer_detach",
+    "dlt_peer_export", "dlt_peer_attach", "dlt_peer_detach", "dlt_map_incremental_async", "dlt_map_incremental_collect", "dlt_debug_counters",
 ]
 
 
@@ -275,6 +275,11 @@ class ScanToMap:
         vec = np.zeros(36, np.float64)
         self._ck(self.lib.dlt_degeneracy(self.h, _p(ev), _p(vec)))
         return ev, vec.reshape(6, 6)
+
+    def debug_counters(self) -> np.ndarray:
+        out = np.zeros(16, np.int32)
+        self._ck(self.lib.dlt_debug_counters(self.h, _p(out)))
+        return out
 
     def map_incremental(self, pose24, flg_EKF_inited: bool = True):
         ps = _f64(pose24).reshape(24)

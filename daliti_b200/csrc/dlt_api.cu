@@ -46,6 +46,17 @@ struct dlt_handle_s {
     cudaStream_t aux_stream = nullptr;
     rt::Event ev_fork, ev_join;
     bool have_aux = false, eig_pending = false;
+    // map_incremental off the critical path (dlt_map_incremental_async): its kernels run on their own stream behind the last
+    // evaluation of the measurement model; the main stream only waits for them where the next scan first touches what they
+    // touch (ev_classified: the downsampled scan may be overwritten; ev_inserted: the map and the neighbour buffers)
+    cudaStream_t ins_stream = nullptr;
+    rt::Event ev_loop_done, ev_classified, ev_inserted;
+    bool have_ins = false;
+    bool cls_pending = false;       // the main stream has not been ordered behind ev_classified yet
+    bool ins_pending = false;       // ... behind ev_inserted
+    bool ins_uncollected = false;   // the counters of that insert have not been adopted on the host
+    int *h_ins_ints = nullptr;      // pinned: d_counters[0..8) as the insert left them
+    int last_ins_ds = 0, last_ins_raw = 0;
     std::string err;
     int cap = 0;  // per-point array capacity (max_scan_points)
     int n_sm = 148;
@@ -113,6 +124,7 @@ struct dlt_handle_s {
     size_t peer_map_bytes[DLT_MAX_PEERS] = {};
     // (DLT_ZEROCOPY=0 opts out): dlt_measure's result block is stored by k_residual straight into pinned host memory and the
     // host spins on a flag there instead of issuing a device->host copy and synchronising the stream
+    bool knn_reuse = true;  // rematch passes prove neighbour sets unchanged where they can (DLT_KNN_REUSE=0: always search; A/B switch)
     bool zerocopy = true;  // measured on B200 (round 2): -22 us per C2 scan against the copy + stream synchronisation; DLT_ZEROCOPY=0 switches it off
     unsigned long long zc_seq = 0;
     bool peer_on = false;
@@ -219,14 +231,16 @@ static int map_reset(dlt_handle h) {
 // n_grid sizes the k_knn8 grid (an estimate of n is fine: the kernel strides); with la.ctl the kernels take n, the pose
 // and the do_match decision from device memory.  far_count is zeroed by k_knn8, the hand-over counter by k_residual
 // (the classic callers without a residual pass clear it themselves).
-static int launch_knn(dlt_handle h, const float4 *d_q, int n, int n_grid, int body_frame, const Pose &P, LoopArgs la) {
+static int launch_knn(dlt_handle h, const float4 *d_q, int n, int n_grid, int body_frame, const Pose &P, LoopArgs la, bool reuse = false) {
     {
         ProfScope prof8(h, 7);  // the dominant kernel on its own (group 0 spans the whole match pass)
-        int g8 = div_up(n_grid, kKnn8Block / 8);
+        // reuse: one query per thread first (most neighbour sets of a rematch pass are proven unchanged), the rest in groups of 8 lanes
+        int g8 = reuse ? div_up(n_grid, kKnn8Block) : div_up(n_grid, kKnn8Block / 8);
         const int wave8 = h->n_sm * DLT_KNN8_MINBLOCKS;  // what is resident at once: the kernel strides, so a partial second wave never forms
         if (g8 > wave8) g8 = wave8;
         if (g8 < 1) g8 = 1;
-        DLT_LAUNCH(k_knn8, g8, kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la);
+        DLT_LAUNCH(k_knn8, g8, kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la,
+                   reuse ? 1 : 0, h->d_counters + 12);
     }
     int grid = div_up(n_grid, kKnnWarps);
     const int cap_grid = h->n_sm * 8;
@@ -291,6 +305,34 @@ static int map_check_error(dlt_handle h) {
     if (h->h_ints[2] != 0) h->map_dead = true;
     if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
     if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
+    return DLT_OK;
+}
+
+// ---- asynchronous map_incremental: ordering of the main stream behind the insert stream, adoption of its counters
+static inline int ins_wait_classified(dlt_handle h) {  // before anything overwrites the downsampled scan
+    if (h->cls_pending) {
+        DLT_RT(h, rt::stream_wait(h->stream, h->ev_classified));
+        h->cls_pending = false;
+    }
+    return DLT_OK;
+}
+static int ins_finish(dlt_handle h) {  // before anything reads or changes the map, the neighbour buffers or the counters
+    if (h->ins_pending) {
+        DLT_RT(h, rt::stream_wait(h->stream, h->ev_inserted));
+        h->ins_pending = false;
+        h->cls_pending = false;
+    }
+    if (h->ins_uncollected) {
+        DLT_RT(h, rt::event_sync(h->ev_inserted));
+        h->ins_uncollected = false;
+        std::memcpy(h->h_ints, h->h_ins_ints, 8 * sizeof(int));
+        h->counters_fresh = true;
+        h->last_ins_ds = h->h_ints[6];
+        h->last_ins_raw = h->h_ints[7];
+        if (h->h_ints[2] != 0) h->map_dead = true;
+        if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
+        if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
+    }
     return DLT_OK;
 }
 
@@ -425,6 +467,8 @@ int dlt_destroy(dlt_handle h) {
     if (!h) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
     if (h->own_stream) rt::sync(h->own_stream);
+    if (h->ins_stream) rt::sync(h->ins_stream);
+    h->cls_pending = h->ins_pending = h->ins_uncollected = false;
     for (void *p : h->allocs) rt::release(p);
     for (void *p : {(void *)h->d_sensor, (void *)h->d_fe_tmp, (void *)h->d_fe_keep, (void *)h->d_fe_pos, (void *)h->d_fe_blk, (void *)h->d_fe_blkoff,
                     (void *)h->d_fe_index})
@@ -433,6 +477,13 @@ int dlt_destroy(dlt_handle h) {
     rt::pinned_release(h->h_ints);
     rt::pinned_release(h->h_sc);
     rt::pinned_release(h->h_iekf);
+    rt::pinned_release(h->h_ins_ints);
+    if (h->have_ins) {
+        rt::event_destroy(h->ev_loop_done);
+        rt::event_destroy(h->ev_classified);
+        rt::event_destroy(h->ev_inserted);
+    }
+    rt::stream_destroy(h->ins_stream);
     dlt_peer_detach(h);
     if (h->peer_box) rt::shared_release(h->peer_box, h->peer_bytes, &h->peer_blob);
     rt::release(h->d_peer);
@@ -477,12 +528,15 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->have_copy = rt::stream_create(&h->copy_stream) == 0 && rt::event_create_untimed(&h->ev_copy) == 0;
     if (const char *e = std::getenv("DLT_LOOP_GRAPH")) h->use_graph = (e[0] == '1') ? 1 : 0;  // A/B switch for measurements
     if (const char *e = std::getenv("DLT_ZEROCOPY")) h->zerocopy = (e[0] == '1');            // A/B switch for measurements
+    if (const char *e = std::getenv("DLT_KNN_REUSE")) h->knn_reuse = (e[0] == '1');
 #if !defined(DLT_EMU)
     if (const char *e = std::getenv("DLT_PDL")) rt::g_pdl = (e[0] == '1') ? 1 : 0;  // process-wide A/B switch for measurements
 #endif
     if (const char *e = std::getenv("DLT_LOOP_FUSED")) h->loop_fused = (e[0] == '1');
     if (const char *e = std::getenv("DLT_LOOP_COOP")) h->loop_coop = (e[0] == '1');
     h->have_aux = rt::stream_create(&h->aux_stream) == 0 && rt::event_create_untimed(&h->ev_fork) == 0 && rt::event_create_untimed(&h->ev_join) == 0;
+    h->have_ins = rt::stream_create(&h->ins_stream) == 0 && rt::event_create_untimed(&h->ev_loop_done) == 0 &&
+                  rt::event_create_untimed(&h->ev_classified) == 0 && rt::event_create_untimed(&h->ev_inserted) == 0;
 
     // search cell edge = ds_map * 2^shift with 3 edges covering sqrt(max_sq_dist)
     int shift = 1;
@@ -517,7 +571,7 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
          !dalloc(h, &h->d_blkoff, (size_t)h->n_scan_blocks) && !dalloc(h, &h->d_vidx, cap) && !dalloc(h, &h->acc.sx, cap) &&
          !dalloc(h, &h->acc.sy, cap) && !dalloc(h, &h->acc.sz, cap) && !dalloc(h, &h->acc.si, cap) && !dalloc(h, &h->acc.cnt, cap) &&
          !dalloc(h, &h->acc.idx, cap) && !dalloc(h, &h->d_vop, cap) && !dalloc(h, &h->knn.qw, cap) && !dalloc(h, &h->knn.nbr, cap * kK) &&
-         !dalloc(h, &h->knn.nbr_id, cap * kK) && !dalloc(h, &h->knn.nbr_cnt, cap) && !dalloc(h, &h->knn.flags, cap) &&
+         !dalloc(h, &h->knn.nbr_id, cap * kK) && !dalloc(h, &h->knn.nbr_cnt, cap) && !dalloc(h, &h->knn.flags, cap) && !dalloc(h, &h->knn.d6lb, cap) &&
          !dalloc(h, &h->knn.far_list, cap) && !dalloc(h, &h->knn.nn_list, cap) && !dalloc(h, &h->knn.nn_pos, cap) && !dalloc(h, &h->knn.nn_key, cap) && !dalloc(h, &h->d_plane, cap) && !dalloc(h, &h->d_coeff, cap) && !dalloc(h, &h->d_sel, cap) &&
          !dalloc(h, &h->d_eff, cap) && !dalloc(h, &h->d_partials, (size_t)blocks_max * NormalEq<true>::NR) &&
          !dalloc(h, &h->d_result, (size_t)kResultDoubles) && !dalloc(h, &h->d_ticket, 4) &&
@@ -534,6 +588,8 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->h_ints = (int *)p;
     ok = ok && rt::pinned_alloc(&p, sizeof(ScanScalars)) == 0;
     h->h_sc = (ScanScalars *)p;
+    ok = ok && rt::pinned_alloc(&p, 16 * sizeof(int)) == 0;
+    h->h_ins_ints = (int *)p;
     if (!ok) {
         dlt_destroy(h);
         return DLT_E_CUDA;
@@ -562,6 +618,7 @@ const char *dlt_last_error(dlt_handle h) { return h ? h->err.c_str() : "null han
 
 int dlt_set_stream(dlt_handle h, void *s) {
     if (!h) return DLT_E_INVALID;
+    if (int ri = ins_finish(h)) return ri;
     rt::sync(h->stream);
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     return DLT_OK;
@@ -569,6 +626,7 @@ int dlt_set_stream(dlt_handle h, void *s) {
 void *dlt_stream(dlt_handle h) { return h ? (void *)h->stream : nullptr; }
 int dlt_sync(dlt_handle h) {
     if (!h) return DLT_E_INVALID;
+    if (int ri = ins_finish(h)) return ri;
     DLT_RT(h, rt::sync(h->stream));
     return DLT_OK;
 }
@@ -577,6 +635,7 @@ int dlt_sync(dlt_handle h) {
 int dlt_map_build(dlt_handle h, const float *xyzi, int n) {
     if (!h || (n > 0 && !xyzi) || n < 0) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     int rc = map_reset(h);
     if (rc) return rc;
     h->have_match = false;
@@ -587,6 +646,7 @@ int dlt_map_build_from_scan(dlt_handle h, const double *pose24) {
     if (!h || !pose24) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_build_from_scan before a downsampled scan is set");
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     if (int rn = resolve_n_down(h)) return rn;
     int rc = map_reset(h);
     if (rc) return rc;
@@ -603,6 +663,7 @@ int dlt_map_build_from_scan(dlt_handle h, const double *pose24) {
 int dlt_map_add(dlt_handle h, const float *xyzi, int n, int downsample_on) {
     if (!h || (n > 0 && !xyzi) || n < 0) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     if (int rd = map_refuse_if_dead(h)) return rd;
     h->have_match = false;
     return add_host_points(h, xyzi, n, downsample_on);
@@ -612,6 +673,7 @@ int dlt_map_delete_boxes(dlt_handle h, const float *boxes6, int nb, int *deleted
     if (!h || nb < 0 || (nb > 0 && !boxes6)) return DLT_E_INVALID;
     if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     h->counters_fresh = false;
     DLT_RT(h, rt::fill(h->d_counters + 3, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
@@ -639,6 +701,7 @@ int dlt_map_delete_boxes(dlt_handle h, const float *boxes6, int nb, int *deleted
 int dlt_map_valid_count(dlt_handle h, int *n) {
     if (!h || !n) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     if (!h->counters_fresh) {
         DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
         DLT_RT(h, rt::sync(h->stream));
@@ -651,6 +714,7 @@ int dlt_map_valid_count(dlt_handle h, int *n) {
 int dlt_map_export(dlt_handle h, float *xyzi, int cap, int *n) {
     if (!h || !n || cap < 0 || (cap > 0 && !xyzi)) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     DLT_RT(h, rt::fill(h->d_counters + 4, 0, sizeof(int), h->stream));
     DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
@@ -674,6 +738,7 @@ int dlt_map_export(dlt_handle h, float *xyzi, int cap, int *n) {
 int dlt_map_knn(dlt_handle h, const float *q, int nq, float *out_xyzi, float *out_d2, int *out_cnt) {
     if (!h || nq < 0 || (nq > 0 && (!q || !out_xyzi || !out_d2 || !out_cnt))) return DLT_E_INVALID;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     h->have_match = false;  // the neighbour buffers of the current scan are reused
     Pose P = {};
     std::vector<float> stage;
@@ -857,6 +922,7 @@ int dlt_scan_downsample(dlt_handle h, int *n_down) {
     if (!h || !n_down) return DLT_E_INVALID;
     if (!h->have_raw) DLT_FAIL(h, DLT_E_STATE, "dlt_scan_downsample before dlt_scan_deskew");
     rt::set_device(h->cfg.device);
+    if (int ri = ins_wait_classified(h)) return ri;
     const int n = h->n_raw;
     h->n_down = 0;
     *n_down = 0;
@@ -886,6 +952,7 @@ int dlt_scan_downsample_async(dlt_handle h) {
     if (!h) return DLT_E_INVALID;
     if (!h->have_raw) DLT_FAIL(h, DLT_E_STATE, "dlt_scan_downsample_async before dlt_scan_deskew");
     rt::set_device(h->cfg.device);
+    if (int ri = ins_wait_classified(h)) return ri;
     h->have_match = false;
     h->have_down = true;
     if (h->n_raw == 0) {
@@ -927,6 +994,7 @@ int dlt_scan_set_down(dlt_handle h, const float *xyzi, int n) {
     if (!h || n < 0 || (n > 0 && !xyzi)) return DLT_E_INVALID;
     if (n > h->cap) DLT_FAIL(h, DLT_E_CAPACITY, "scan larger than max_scan_points");
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     if (n > 0) DLT_RT(h, rt::h2d(h->d_down, xyzi, (size_t)n * sizeof(float4), h->stream));
     h->n_down = n;
     h->have_down = true;
@@ -1079,6 +1147,7 @@ static int measure_dev_impl(dlt_handle h, const double *pose24, int do_match, do
     if (!do_match && !h->have_match) DLT_FAIL(h, DLT_E_STATE, "dlt_measure(do_match=0) before any match pass");
     if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     // right behind dlt_scan_downsample_async feats_down_size is still on the device: the kernels read it there (grids from
     // an estimate / an upper bound) and it comes back with the result block, so no synchronisation is spent on it
     if (int rp = issue_prefetch(h)) return rp;  // (this scan's uploads are queued by now)
@@ -1103,7 +1172,9 @@ static int measure_dev_impl(dlt_handle h, const double *pose24, int do_match, do
     if (do_match) {
         h->nfar_known = false;
         ProfScope prof(h, 0);
-        int rk = launch_knn(h, (const float4 *)h->d_down, n, n_grid, 1, P, la);
+        // a rematch pass of the same scan against the same map: neighbour sets that can be proven unchanged are not searched again
+        const bool reuse = h->have_match && h->knn_reuse && h->map.shard_count <= 1;
+        int rk = launch_knn(h, (const float4 *)h->d_down, n, n_grid, 1, P, la, reuse);
         if (rk) return rk;
         h->have_match = true;
     }
@@ -1189,7 +1260,7 @@ static bool build_loop_graph(dlt_handle h, const MeasureBufs &mb) {
     const int g8 = 24 * h->n_sm, gk = 8 * h->n_sm, gr = div_up(h->cap, kResidBlock);
     if (cudaStreamBeginCaptureToGraph(cs, ibody, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail();
     capturing = true;
-    k_knn8<<<g8, kKnn8Block, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la);
+    k_knn8<<<g8, kKnn8Block, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la, 0, (int *)nullptr);
     k_knn<<<gk, kKnnWarps * 32, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, (const int *)h->d_unres,
                                            (const int *)(h->d_counters + 8), la);
     cudaGraph_t out = nullptr;
@@ -1224,6 +1295,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
     if (blk->max_iteration < 1 || blk->max_iteration > DLT_IEKF_MAX_ITER) DLT_FAIL(h, DLT_E_INVALID, "max_iteration out of range");
     if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     if (h->peer_on) reduce = nullptr;  // the sum over ranks happens inside k_residual (peer mailboxes), the solve step stays fused
     const int n_iter = blk->max_iteration;
     // host -> device: everything up to (not including) the out fields
@@ -1625,7 +1697,21 @@ int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
 }
 
 // ------------------------------------------------------------------ map_incremental
-int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_ds, int *n_raw) {
+namespace {
+struct StreamSwap {  // enqueue on another stream for the lifetime of the scope
+    dlt_handle h;
+    cudaStream_t saved;
+    bool on;
+    StreamSwap(dlt_handle h_, cudaStream_t s, bool on_) : h(h_), saved(h_->stream), on(on_) {
+        if (on) h->stream = s;
+    }
+    ~StreamSwap() {
+        if (on) h->stream = saved;
+    }
+};
+}  // namespace
+
+static int map_incremental_impl(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_ds, int *n_raw, bool want_async) {
     if (!h || !pose24) return DLT_E_INVALID;
     if (!h->have_down) DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental before a scan");
     const bool sharded = h->map.shard_count > 1;
@@ -1633,8 +1719,10 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
         DLT_FAIL(h, DLT_E_STATE, "dlt_map_incremental on a sharded map needs dlt_peer_attach or dlt_set_shard_reduce");
     if (int rd = map_refuse_if_dead(h)) return rd;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     if (int rn = resolve_n_down(h)) return rn;
     const int n = h->n_down;
+    h->last_ins_ds = h->last_ins_raw = 0;
     if (n_ds) *n_ds = 0;
     if (n_raw) *n_raw = 0;
     if (n == 0) return DLT_OK;
@@ -1654,6 +1742,14 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
         }
     }
     Pose P = pose_from(pose24);
+    // Asynchronous form (unsharded map, every query resolved, so no host decision is pending): the insert kernels go to their own
+    // stream behind what the main stream holds now; nothing here waits for them.
+    const bool async = want_async && !sharded && h->have_ins && !h->prof_on && !(h->have_match && !(h->nfar_known && h->h_last_nfar == 0));
+    if (async) {
+        DLT_RT(h, rt::event_record(h->ev_loop_done, h->stream));
+        DLT_RT(h, rt::stream_wait(h->ins_stream, h->ev_loop_done));
+    }
+    StreamSwap swap(h, h->ins_stream, async);
     DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));
     FuseInsert fi = {0, h->scratch, h->d_cellslot, h->d_vslot};
     const bool peer_pull = sharded && h->have_match && h->peer_on;
@@ -1667,6 +1763,7 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
                (const int *)h->knn.nbr_cnt, (double)h->cfg.ds_map, flg_EKF_inited ? 1 : 0, h->d_pw, h->d_dsflag, h->d_addflag, h->d_counters + 6,
                LoopArgs{nullptr, nullptr, nullptr, 0, 0, 0ull, 0ull, nullptr}, h->map, (const int *)h->map.n_live, h->have_match ? (const unsigned char *)h->knn.flags : (const unsigned char *)nullptr,
                (const int *)h->knn.nn_pos, (const unsigned long long *)h->knn.nn_key, fi);
+    if (async) DLT_RT(h, rt::event_record(h->ev_classified, h->stream));  // the downsampled scan has been read
     if (sharded && h->have_match && h->peer_on) {  // owners store their decisions straight into every rank's mailbox
         DLT_LAUNCH(k_incr_push, div_up(n, 256), 256, h->stream, h->d_peer, (const unsigned char *)h->d_dsflag, (const unsigned char *)h->d_addflag,
                    (const unsigned char *)h->knn.flags, n, (unsigned char)kFlagForeign, (const int *)nullptr, (const int *)nullptr);
@@ -1684,15 +1781,49 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
     int rc = insert_points(h, h->d_pw, n, true, InsertGate{nullptr, nullptr}, fi_pull.on ? &fi_pull.sc : nullptr);
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
+    if (async) {
+        DLT_RT(h, rt::d2h(h->h_ins_ints, h->d_counters, 8 * sizeof(int), h->stream));
+        DLT_RT(h, rt::event_record(h->ev_inserted, h->stream));
+        h->cls_pending = h->ins_pending = h->ins_uncollected = true;
+        h->counters_fresh = false;
+        return DLT_OK;  // counts: dlt_map_incremental_collect
+    }
     if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
     rc = map_check_error(h);  // reads the 8 counters back
     if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in map_incremental)");
+    h->last_ins_ds = h->h_ints[6];
+    h->last_ins_raw = h->h_ints[7];
     if (n_ds) *n_ds = h->h_ints[6];
     if (n_raw) *n_raw = h->h_ints[7];
     return rc;
 }
 
+int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_ds, int *n_raw) {
+    return map_incremental_impl(h, pose24, flg_EKF_inited, n_ds, n_raw, false);
+}
+int dlt_map_incremental_async(dlt_handle h, const double *pose24, int flg_EKF_inited) {
+    return map_incremental_impl(h, pose24, flg_EKF_inited, nullptr, nullptr, true);
+}
+int dlt_map_incremental_collect(dlt_handle h, int *n_ds, int *n_raw) {
+    if (!h) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    const int rc = ins_finish(h);
+    if (n_ds) *n_ds = h->last_ins_ds;
+    if (n_raw) *n_raw = h->last_ins_raw;
+    return rc;
+}
+
 double *dlt_result_dev(dlt_handle h) { return h ? h->d_result : nullptr; }
+
+int dlt_debug_counters(dlt_handle h, int *out16) {
+    if (!h || !out16) return DLT_E_INVALID;
+    rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
+    DLT_RT(h, rt::d2h(h->h_ints + 40, h->d_counters, 16 * sizeof(int), h->stream));
+    DLT_RT(h, rt::sync(h->stream));
+    std::memcpy(out16, h->h_ints + 40, 16 * sizeof(int));
+    return DLT_OK;
+}
 
 int dlt_set_shard_reduce(dlt_handle h, dlt_reduce_fn reduce, void *ctx) {
     if (!h) return DLT_E_INVALID;
@@ -1706,6 +1837,7 @@ int dlt_peer_export(dlt_handle h, unsigned char *blob) {
     if (!h || !blob) return DLT_E_INVALID;
     if (h->cfg.shard_count < 2 || h->cfg.shard_count > DLT_MAX_PEERS) DLT_FAIL(h, DLT_E_STATE, "dlt_peer_export needs 2 <= shard_count <= DLT_MAX_PEERS");
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     if (!h->peer_box) {
         const size_t dec_cap = ((size_t)h->cfg.max_scan_points + 127) & ~(size_t)127;
         h->peer_bytes = sizeof(PeerBox) + 2 * dec_cap;
@@ -1722,6 +1854,7 @@ int dlt_peer_detach(dlt_handle h) {
     if (!h) return DLT_E_INVALID;
     if (!h->peer_on) return DLT_OK;
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     rt::sync(h->stream);
     for (int r = 0; r < DLT_MAX_PEERS; r++) {
         if (h->peer_maps[r]) rt::shared_close(h->peer_maps[r], h->peer_map_bytes[r]);
@@ -1737,6 +1870,7 @@ int dlt_peer_attach(dlt_handle h, const unsigned char *blobs) {
     if (!h->peer_box) DLT_FAIL(h, DLT_E_STATE, "dlt_peer_attach before dlt_peer_export");
     if (h->peer_on || h->peer_detached) DLT_FAIL(h, DLT_E_STATE, "peers are already attached or were detached (attach once per handle)");
     rt::set_device(h->cfg.device);
+    if (int ri = ins_finish(h)) return ri;
     h->err.clear();
     const int W = h->cfg.shard_count, me = h->cfg.shard_rank;
     PeerComm pc;

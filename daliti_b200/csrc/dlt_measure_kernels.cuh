@@ -134,6 +134,8 @@ struct KnnOut {
     int *nbr_id;           // [n][5] bucket*8+slot
     int *nbr_cnt;          // [n]
     unsigned char *flags;  // [n]
+    float *d6lb;           // [n] lower bound of the squared distance from the query to every map point that is NOT one of its five
+                           //     neighbours (0 = none known): lets a later match pass of the same scan prove the set unchanged
     int *far_list;         // indices of unresolved queries
     int *far_count;
     // The subset of them that map_incremental cannot classify from what the rings saw (see k_nn1): their single
@@ -558,11 +560,11 @@ DLT_D int knn8_find_finish(const MapView &m, const Probe &p) {
 
 // the four queries q0 .. q0+3 of one warp; wl = this warp's kKnn8WlInts ints of shared memory
 DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n, int body_frame, const Pose &P, float max_sq_dist, const KnnOut &out,
-                      int *unres_list, int *unres_count, int q0, int lane, int *wl, int unres_cap = 0x7FFFFFFF) {
+                      int *unres_list, int *unres_count, int q0, int lane, int *wl, int unres_cap = 0x7FFFFFFF, const int *qlist = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int grp = lane >> 3, sub = lane & 7;
-    const int qi = q0 + grp;
-    const bool live = qi < n;
+    const bool live = q0 + grp < n;  // (with a list: n = its length)
+    const int qi = qlist ? (live ? qlist[q0 + grp] : 0) : q0 + grp;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     int cx = 0, cy = 0, cz = 0;
     bool work = false;
@@ -676,6 +678,7 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
     const bool resolved = cand_ok && cov > 0.f && d5 < cov * cov * 0.99999f;
     if (!resolved) {
         if (sub == 0) {
+            out.d6lb[qi] = 0.f;
             const int pos = atomicAdd(unres_count, 1);
             if (pos < unres_cap) unres_list[pos] = qi;  // (the fused loop kernels size their block-local list to the chunk: never full)
         }
@@ -688,7 +691,59 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
     if (sub == 0) {
         out.nbr_cnt[qi] = kK;
         out.flags[qi] = (d5 <= max_sq_dist) ? kFlagMatched : (unsigned char)0;
+        // every other point of the block is at least as far as the sixth key says (its distance bits were truncated downwards),
+        // every point outside the block farther than the block's faces
+        out.d6lb[qi] = fminf(__uint_as_float(sixth & ~((1u << kKnn8TagBits) - 1u)), cov * cov * 0.99999f);
     }
+}
+
+// ---- a later match pass of the same scan (rematch, laserMapping.cpp:847 with rematch_en): most neighbour sets can be PROVEN
+// unchanged.  The query moved by delta since the pass that found its five neighbours (largest distance d5) and every other map
+// point was then at least sqrt(d6lb) away: if d5 + delta < sqrt(d6lb) - delta the same five are still strictly nearer than
+// everything else, so only their distances are recomputed (the same fp32 expression a search evaluates) and re-ordered in the
+// stated order.  Anything else is searched again.  Returns true when the set was reused.
+DLT_D bool knn_try_reuse(const float4 *__restrict__ down, int i, const Pose &P, float max_sq_dist, const KnnOut &out) {
+    const float4 qb = down[i];
+    float qx, qy, qz;
+    body_to_world(P, qb.x, qb.y, qb.z, qx, qy, qz);
+    const float4 old = out.qw[i];
+    out.qw[i] = make_float4(qx, qy, qz, qb.w);
+    const float d6 = out.d6lb[i];
+    if (!(d6 > 0.f) || out.nbr_cnt[i] != kK || (out.flags[i] & ~kFlagMatched)) return false;
+    Cand c[kK];
+#pragma unroll
+    for (int j = 0; j < kK; j++) {
+        const float4 e = out.nbr[(size_t)i * kK + j];
+        c[j].x = e.x;
+        c[j].y = e.y;
+        c[j].z = e.z;
+        c[j].d2 = e.w;
+        c[j].id = out.nbr_id[(size_t)i * kK + j];
+    }
+    const float delta = sqrtf(calc_dist(qx, qy, qz, old.x, old.y, old.z)) * 1.00001f + 1e-12f;
+    const float reach = sqrtf(c[kK - 1].d2) * 1.00001f + 2.f * delta;  // no neighbour is farther than this from the new position
+    const float wall = sqrtf(d6) * 0.99999f;                            // no other point was nearer than this to the old one
+    if (!(delta < 0.25f) || !(reach < wall)) return false;
+#pragma unroll
+    for (int j = 0; j < kK; j++) c[j].d2 = calc_dist(qx, qy, qz, c[j].x, c[j].y, c[j].z);
+#pragma unroll
+    for (int a = 1; a < kK; a++)  // insertion sort in the stated order (d2, x, y, z, id)
+#pragma unroll
+        for (int b = a; b > 0; b--)
+            if (cand_less(c[b], c[b - 1])) {
+                const Cand t = c[b];
+                c[b] = c[b - 1];
+                c[b - 1] = t;
+            }
+#pragma unroll
+    for (int j = 0; j < kK; j++) {
+        out.nbr[(size_t)i * kK + j] = make_float4(c[j].x, c[j].y, c[j].z, c[j].d2);
+        out.nbr_id[(size_t)i * kK + j] = c[j].id;
+    }
+    out.flags[i] = (c[kK - 1].d2 <= max_sq_dist) ? kFlagMatched : (unsigned char)0;
+    const float w2 = wall - delta;  // the bound seen from the new position (for a third pass)
+    out.d6lb[i] = w2 > 0.f ? w2 * w2 * 0.99999f : 0.f;
+    return true;
 }
 
 // Warp-stride over groups of four queries, so the grid may be sized from an estimate of n (the
@@ -696,7 +751,7 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
 // Also zeroes far_count for the warp-per-query pass that follows in stream order.
 __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
     k_knn8(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
-           int *__restrict__ unres_count, LoopArgs la) {
+           int *__restrict__ unres_count, LoopArgs la, int reuse, int *__restrict__ reuse_stats) {
     DLT_PDL_WAIT();
     __shared__ Pose sP;
     __shared__ int s_wl[kKnn8Block / 32][kKnn8WlInts];
@@ -708,6 +763,26 @@ __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
         out.nn_count[1] = 0;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (reuse) {  // block-uniform.  Chunks of one query per thread: prove the old set still right, search the rest again
+        __shared__ int s_redo[kKnn8Block];
+        __shared__ int s_nredo;
+        for (int c0 = blockIdx.x * kKnn8Block; c0 < n; c0 += gridDim.x * kKnn8Block) {  // block-uniform
+            if (threadIdx.x == 0) s_nredo = 0;
+            __syncthreads();
+            const int i = c0 + threadIdx.x;
+            if (i < n && !knn_try_reuse(q_pts, i, sP, max_sq_dist, out)) s_redo[atomicAdd(&s_nredo, 1)] = i;
+            __syncthreads();
+            const int nr = s_nredo;
+            if (threadIdx.x == 0 && reuse_stats) {  // instrumentation: queries seen / searched again by the reuse passes
+                atomicAdd(reuse_stats, min(kKnn8Block, n - c0));
+                atomicAdd(reuse_stats + 1, nr);
+            }
+            for (int q0 = warp * 4; q0 < nr; q0 += (kKnn8Block / 32) * 4)  // warp-uniform
+                knn8_group(m, q_pts, nr, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane, s_wl[warp], 0x7FFFFFFF, s_redo);
+            __syncthreads();
+        }
+        return;
+    }
     const int stride = gridDim.x * (kKnn8Block / 32) * 4;
     for (int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4; q0 < n; q0 += stride)  // warp-uniform
         knn8_group(m, q_pts, n, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane, s_wl[warp]);

@@ -27,6 +27,7 @@ inline int event_record(Event, cudaStream_t) { return 0; }
 inline float event_elapsed_ms(Event, Event) { return 0.f; }
 inline int event_create_untimed(Event *) { return 0; }
 inline int stream_wait(cudaStream_t, Event) { return 0; }
+inline int event_sync(Event) { return 0; }
 inline int alloc(void **p, size_t bytes) {
     size_t n = (bytes + 255) & ~(size_t)255;
     if (n == 0) n = 256;
@@ -167,6 +168,7 @@ inline float event_elapsed_ms(Event a, Event b) {
 }
 inline int event_create_untimed(Event *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess ? 0 : 1; }
 inline int stream_wait(cudaStream_t s, Event e) { return cudaStreamWaitEvent(s, e, 0) == cudaSuccess ? 0 : 1; }
+inline int event_sync(Event e) { return cudaEventSynchronize(e) == cudaSuccess ? 0 : 1; }
 inline int alloc(void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 256) == cudaSuccess ? 0 : 1; }
 inline void release(void *p) {
     if (p) cudaFree(p);

@@ -640,6 +640,19 @@ int LaserMapping::reduce_trampoline(void *self, double *result_dev, int n) {
         }                                         \
     } while (0)
 
+int LaserMapping::collect_insert(int *n_ds, int *n_raw) {
+    int a = last_added_ds, b = last_added_raw;
+    if (insert_pending) {
+        insert_pending = false;
+        LM_CK(dlt_map_incremental_collect(dev_, &a, &b));
+        last_added_ds = a;
+        last_added_raw = b;
+    }
+    if (n_ds) *n_ds = a;
+    if (n_raw) *n_raw = b;
+    return 0;
+}
+
 int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, const ImuSample *imu, int n_imu, const dlt_lio_thermal *th,
                                dlt_lio_scan_out *out, bool pts_on_device, double observation_end_time_in) {
     const double LASER_POINT_COV = 0.0015;  // laserMapping.cpp:76
@@ -649,6 +662,10 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
                                                {0, 0, 0}, {1, 0, 0, 0}, {0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
     if (!th) th = &no_thermal;
     std::memset(out, 0, sizeof(*out));
+    if (insert_pending) {  // adopt the previous scan's map_incremental (errors of that insert surface here)
+        int a = 0, b = 0;
+        if (int rc = collect_insert(&a, &b)) return rc;
+    }
     iters.clear();
     const double t_begin = wall();
     if (flg_first_scan) {  // :736-740
@@ -1002,8 +1019,16 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         if (!EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn || peers)) {
             double pose[24];
             state.pose24(pose);
-            LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
-            out->added = out->n_added_ds + out->n_added_raw;
+            if (cfg.async_insert && cfg.dev.shard_count <= 1) {
+                // off the critical path: the insert kernels run on their own stream while this call returns and the next
+                // scan's deskew / VoxelGrid are enqueued; the counts are adopted by dlt_lio_collect_insert or the next scan
+                LM_CK(dlt_map_incremental_async(dev_, pose, flg_EKF_inited ? 1 : 0));
+                out->n_added_ds = out->n_added_raw = out->added = -1;
+                insert_pending = true;
+            } else {
+                LM_CK(dlt_map_incremental(dev_, pose, flg_EKF_inited ? 1 : 0, &out->n_added_ds, &out->n_added_raw));
+                out->added = out->n_added_ds + out->n_added_raw;
+            }
         }
         out->t_insert = wall() - t0;
         if (want_eig) {
@@ -1036,7 +1061,7 @@ void dlt_lio_default_config(dlt_lio_config *c) {
     for (int i = 0; i < 9; i++) c->extrinR[i] = (i % 4 == 0) ? 1.0 : 0.0;
     c->degeneracy_eig_threshold = 100.0;
     c->device_loop = -1;  // by measurement: host loop on one GPU, device-resident loop on a sharded map
-    c->reserved = 0;
+    c->async_insert = 1;  // map_incremental off the critical path (its counts arrive with dlt_lio_collect_insert / the next scan)
 }
 
 int dlt_lio_create(const dlt_lio_config *cfg, dlt_lio *out) {
@@ -1175,6 +1200,10 @@ int dlt_lio_peer_detach(dlt_lio h) {
     if (!h) return DLT_E_INVALID;
     h->lm->peers = false;
     return dlt_peer_detach(h->lm->dev_);
+}
+int dlt_lio_collect_insert(dlt_lio h, int *n_added_ds, int *n_added_raw) {
+    if (!h) return DLT_E_INVALID;
+    return h->lm->collect_insert(n_added_ds, n_added_raw);
 }
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap) {
     if (!h) return DLT_E_INVALID;

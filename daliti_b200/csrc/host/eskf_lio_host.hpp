@@ -185,6 +185,9 @@ class LaserMapping {
     dlt_lio_reduce_fn reduce_fn = nullptr;  // sharded map: sums the partial normal equations over the ranks
     void *reduce_ctx = nullptr;
     double *reduce_buf_dev = nullptr;
+    bool insert_pending = false;  // dlt_map_incremental_async is in flight: its counts have not been adopted yet
+    int last_added_ds = 0, last_added_raw = 0;
+    int collect_insert(int *n_ds, int *n_raw);
     bool peers = false;  // dlt_lio_peer_attach: the sums over the ranks happen inside the kernels (peer mailboxes), no callback
     ImuProcess imu_;
     StatesGroup state, last_nodegared_state, last_state;

@@ -21,7 +21,7 @@ class LioConfig(C.Structure):
         ("extrinR", C.c_double * 9),
         ("degeneracy_eig_threshold", C.c_double),
         ("device_loop", C.c_int),
-        ("reserved", C.c_int),
+        ("async_insert", C.c_int),
     ]
 
 
@@ -59,7 +59,7 @@ _LIO_SYMBOLS = [
     "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
     "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
     "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_process_cloud", "dlt_lio_prefetch_scan", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
-    "dlt_lio_peer_export", "dlt_lio_peer_attach", "dlt_lio_peer_detach",
+    "dlt_lio_peer_export", "dlt_lio_peer_attach", "dlt_lio_peer_detach", "dlt_lio_collect_insert",
 ]
 
 
@@ -96,6 +96,7 @@ class LaserMapping:
             self.h = None
             raise DltError(f"dlt_lio_create failed: {_ERR.get(rc, rc)}")
         self.out = LioScanOut()
+        self.collect_after_scan = True
         # a non-owning view of the device handle (map export, neighbour read-back, ...)
         self.device = ScanToMap.__new__(ScanToMap)
         self.device.lib = self.lib
@@ -167,6 +168,21 @@ class LaserMapping:
         th = C.byref(thermal) if thermal is not None else None
         self._ck(self.lib.dlt_lio_process_scan(self.h, pp, C.c_int(n), C.c_double(lidar_beg_time), _p(im), C.c_int(im.shape[0]), th,
                                                C.byref(self.out)))
+        return self._collect()
+
+    def collect_insert(self):
+        """async_insert: wait for the last scan's map_incremental, return its (downsample adds, raw adds)"""
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.dlt_lio_collect_insert(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def _collect(self):
+        # The library's default leaves map_incremental running when process_scan returns (added = -1).  This wrapper waits for
+        # it by default so that callers read the counts of THIS scan (tests); collect_after_scan = False keeps the call as the
+        # library delivers it (bench.py).
+        if self.out.added < 0 and self.collect_after_scan:
+            self.out.n_added_ds, self.out.n_added_raw = self.collect_insert()
+            self.out.added = self.out.n_added_ds + self.out.n_added_raw
         return self.out
 
     def prefetch_scan(self, pts48):
@@ -185,7 +201,7 @@ class LaserMapping:
         th = C.byref(thermal) if thermal is not None else None
         self._ck(self.lib.dlt_lio_process_scan_dev(self.h, C.c_void_p(pts48_dev_ptr), C.c_int(n), C.c_double(lidar_beg_time),
                                                    C.c_double(observation_end_time), _p(im), C.c_int(im.shape[0]), th, C.byref(self.out)))
-        return self.out
+        return self._collect()
 
     def process_cloud(self, cloud, layout, sensor, header_stamp, imu7, point_filter_num=5, min_range=0.5, max_range=1000.0, thermal=None):
         """sensor PointCloud2 payload (uint8) -> front end on the device -> the per-scan update (dlt_lio_process_cloud)"""
@@ -198,7 +214,7 @@ class LaserMapping:
         self._ck(self.lib.dlt_lio_process_cloud(self.h, _p(buf), C.c_int(buf.size // int(layout[0])), lay, C.c_int(code), C.c_int(point_filter_num),
                                                 C.c_float(min_range), C.c_float(max_range), C.c_double(header_stamp), _p(im), C.c_int(im.shape[0]), th,
                                                 C.byref(self.out), C.byref(ns)))
-        return self.out, ns.value
+        return self._collect(), ns.value
 
     def set_allreduce(self, device: str = "cuda"):
         """Sharded map: sum over torch.distributed ranks whatever the library hands to the callback (the partial normal

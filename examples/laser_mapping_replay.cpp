@@ -124,6 +124,10 @@ int main(int argc, char **argv) {
             return 1;
         }
         if (!out.had_points) continue;  // "No point, not ready for odometry, skip this scan" (:755-759)
+        if (out.added < 0) {  // async_insert (default): map_incremental is still running; a logger that wants its counts waits here
+            dlt_lio_collect_insert(g_lio, &out.n_added_ds, &out.n_added_raw);
+            out.added = out.n_added_ds + out.n_added_raw;
+        }
         dlt_lio_get_state(g_lio, s.data());
         double truth[3];
         sensor_at((k + 1) * kSweep, truth);

@@ -236,6 +236,13 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
 
 /* ---- map_incremental()                                       laserMapping.cpp:582-630, 1167 - */
 int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, int *n_add_downsample, int *n_add_raw);
+/* The same, off the critical path: the kernels are queued on the handle's insert stream behind what the main stream holds
+ * now and the call returns at once.  Every later call that reads or changes the map (the next match pass included) is
+ * ordered behind them on the device; the next VoxelGrid only behind the classification pass that still reads the
+ * downsampled scan.  dlt_map_incremental_collect waits on the host and reports the add counts and a map overflow.
+ * Falls back to the synchronous form on a sharded map or when unresolved queries need the exact-neighbour fallback. */
+int dlt_map_incremental_async(dlt_handle h, const double *pose24, int flg_EKF_inited);
+int dlt_map_incremental_collect(dlt_handle h, int *n_add_downsample, int *n_add_raw);
 /* Sharded map (shard_count > 1): the rank that owns a query point decides whether it is added (it holds the
  * point's neighbours); `reduce` sums the n per-point decision codes (doubles in DEVICE memory) over the ranks in
  * place on the handle's stream, after which every rank inserts the accepted points that fall into its tiles + halo.
@@ -262,6 +269,10 @@ int dlt_peer_detach(dlt_handle h);
 /* ---- instrumentation (no reference counterpart) ---------------------------------------------- */
 /* Per-kernel-group device time from CUDA events on the launching stream.  Groups: 0 k_knn,
  * 1 k_residual, 2 deskew, 3 VoxelGrid, 4 map insert, 5 exact-neighbour fallback, 6 k_iekf_step, 7 k_knn8 alone (inside group 0).      */
+/* Instrumentation: the handle's 16 device counters ([0] buckets allocated, [1] live points, [2] sticky map error, [5] unresolved
+ * queries of the last match pass, [6] / [7] adds of the last map_incremental, [12] / [13] queries seen / searched again by the
+ * rematch passes that reuse proven neighbour sets -- cumulative).  Synchronises the handle.                               */
+int dlt_debug_counters(dlt_handle h, int *out16);
 int dlt_set_profiling(dlt_handle h, int on);
 int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset);
 /* Spans recorded since the last dlt_get_profile(reset): (group, start ms, end ms) triples relative to the

@@ -40,7 +40,11 @@ typedef struct dlt_lio_config {
                                 1: blend and insert also queued on the device behind the loop: one synchronisation
                                    (on a sharded map this needs attached peers, dlt_lio_peer_attach; otherwise it acts as 2);
                                -1 (default): 0 on a single-GPU map, 2 on a sharded map (measured)      */
-    int reserved;
+    int async_insert;        /* 1 (default): map_incremental (:582-630, 1164-1168) runs off the critical path, on its own
+                                stream behind the last evaluation of the measurement model: dlt_lio_process_scan returns
+                                once the pose is final, with added / n_added_* = -1; the counts (and an overflow of the
+                                map) are reported by dlt_lio_collect_insert or picked up by the next scan.  Unsharded maps
+                                only; 0 = wait for the insert inside the call, as the reference does.                  */
 } dlt_lio_config;
 
 /* State left behind by tis_cbk / tn_cbk (laserMapping.cpp:471-498): g_tis_odom_delta and
@@ -123,6 +127,9 @@ int dlt_lio_set_reduce(dlt_lio h, dlt_lio_reduce_fn reduce, void *ctx, double *r
 int dlt_lio_peer_export(dlt_lio h, unsigned char *blob);
 int dlt_lio_peer_attach(dlt_lio h, const unsigned char *blobs);
 int dlt_lio_peer_detach(dlt_lio h); /* back to the callback; a handle attaches at most once */
+/* async_insert: wait for the map_incremental of the last scan and report its add counts (the reference logs them as
+ * kdtree_incremental add_point_size, laserMapping.cpp:626-629).  Without a pending insert: the last counts again.  */
+int dlt_lio_collect_insert(dlt_lio h, int *n_added_ds, int *n_added_raw);
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap);
 /* IMUpose list of the last scan's forward propagation (22 doubles each)                          */
 int dlt_lio_get_imu_poses(dlt_lio h, double *pose22, int cap);

@@ -1,9 +1,9 @@
-"""Opt-in kernel variants (daliti_b200/csrc/Makefile `variants`) must be result-identical to the default build: the same
-kernel sources compiled with the variant's macro under the kernel-logic emulator, compared bit for bit."""
+"""Switchable paths of the library must be result-identical to each other: the zero-copy result block against the copy +
+synchronise path, map_incremental off the critical path (async_insert) against the synchronous call."""
 import os
-import subprocess
 
 import numpy as np
+import pytest
 
 import helpers
 from daliti_b200 import synth
@@ -12,60 +12,13 @@ from daliti_b200.binding import ScanToMap, load_library
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build_emu_variant(tmp_path, *defines):
-    emu = os.path.join(ROOT, "tests", "emu")
-    csrc = os.path.join(ROOT, "daliti_b200", "csrc")
-    out = str(tmp_path / "libdaliti_emu_variant.so")
-    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-DDLT_EMU", *["-D" + d for d in defines], "-I" + emu, "-I" + csrc, "-w", "-shared",
-           "-x", "c++", os.path.join(csrc, "dlt_api.cu"), os.path.join(csrc, "host", "eskf_lio_host.cpp"), "-x", "c++", os.path.join(emu, "cuda_emu.cpp"), "-o", out]
-    subprocess.run(cmd, check=True)
-    return load_library(out)
-
-
-def _match_pass(lib, map_pts, down, pose):
-    dm = ScanToMap(lib, max_scan_points=8192, max_map_points=1 << 17)
-    dm.map_build(map_pts)
-    dm.scan_set_down(down)
-    m = dm.measure(pose, True)
-    first = (m.effct_feat_num, m.n_unresolved, m.HtH.copy(), m.Htr.copy())
-    nbr, cnt, sel = dm.get_nearest(len(down))
-    n_ds, n_raw = dm.map_incremental(pose, True)
-    out = (first, nbr.copy(), cnt.copy(), sel.copy(), (n_ds, n_raw), dm.map_export())
-    dm.close()
-    return out
-
-
-def test_knn8_prune_variant_is_result_identical(emu_lib, tmp_path):
-    """DLT_KNN8_PRUNE: candidates / cells beyond the radius that can finish a query in the first pass are skipped"""
-    var = _build_emu_variant(tmp_path, "DLT_KNN8_PRUNE=1")
-    for seed, sparse in ((31, False), (32, True)):
-        seq = helpers.small_sequence(seed=seed, half=30.0, beams=16, azimuths=240, n_boxes=8)
-        map_pts = synth.sample_map(seq.scene, seed=seed)
-        if sparse:  # a map that covers part of the scene: many unresolved / far queries
-            map_pts = map_pts[map_pts[:, 0] < 0.0]
-        pts, t_beg, imu = seq.scan(0)
-        dm = ScanToMap(emu_lib, max_scan_points=8192, max_map_points=4096)
-        dm.scan_deskew(pts)
-        down = dm.scan_get_down(dm.scan_downsample())
-        dm.close()
-        pose = seq.traj.pose24(0.1)
-        a = _match_pass(emu_lib, map_pts, down, pose)
-        b = _match_pass(var, map_pts, down, pose)
-        assert a[0][0] == b[0][0] and a[0][1] == b[0][1]
-        np.testing.assert_array_equal(a[0][2], b[0][2])  # H^T H: same points, same order of summation
-        np.testing.assert_array_equal(a[0][3], b[0][3])
-        for x, y in zip(a[1:4], b[1:4]):
-            np.testing.assert_array_equal(x, y)  # neighbours (coordinates, d2), counts, point_selected_surf
-        assert a[4] == b[4]
-        assert set(map(tuple, a[5].tolist())) == set(map(tuple, b[5].tolist()))
-
-
-def _replay(lib, n_scans=3):
+def _replay(lib, n_scans=3, collect=True, **cfg):
     from daliti_b200.lio import LaserMapping
 
     seq = helpers.small_sequence(seed=41, half=30.0, beams=16, azimuths=240, n_boxes=8)
     map_pts = synth.sample_map(seq.scene, seed=41)
-    lm = LaserMapping(lib, dev=dict(max_scan_points=8192, max_map_points=1 << 17), featptsThreshold=5, device_loop=0)
+    lm = LaserMapping(lib, dev=dict(max_scan_points=8192, max_map_points=1 << 17), featptsThreshold=5, device_loop=0, **cfg)
+    lm.collect_after_scan = collect
     lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
     lm.set_state(helpers.state612(seq.traj, seq.t_start))
     lm.device.map_build(map_pts)
@@ -75,6 +28,9 @@ def _replay(lib, n_scans=3):
         lm.on_lidar_msg()
         o = lm.process_scan(pts, t_beg, imu)
         out.append((lm.get_state().copy(), o.n_iters, o.added, [np.array(it.HtH) for it in lm.iters()]))
+    if not collect:
+        out.append(lm.collect_insert())
+    out.append(set(map(tuple, lm.device.map_export().tolist())))
     lm.close()
     return out
 
@@ -85,7 +41,8 @@ def test_zerocopy_result_path_is_result_identical(emu_lib, monkeypatch):
     a = _replay(emu_lib)
     monkeypatch.setenv("DLT_ZEROCOPY", "1")
     b = _replay(emu_lib)
-    for (sa, ia, aa, ha), (sb, ib, ab, hb) in zip(a, b):
+    assert a[-1] == b[-1]  # map contents
+    for (sa, ia, aa, ha), (sb, ib, ab, hb) in zip(a[:-1], b[:-1]):
         assert (ia, aa) == (ib, ab)
         np.testing.assert_array_equal(sa, sb)
         for x, y in zip(ha, hb):
@@ -100,3 +57,56 @@ def test_zerocopy_result_path_is_result_identical(emu_lib, monkeypatch):
     m = dm.measure(pose, True)
     assert m.effct_feat_num == 0 and not m.HtH.any()
     dm.close()
+
+
+def _check_async_insert(lib, n_scans):
+    """async_insert = 1 (library default): map_incremental runs on its own stream and process_scan returns with added = -1;
+    the next scan's deskew / VoxelGrid overlap it and its first match pass waits for it on the device.  Against
+    async_insert = 0: the same states, iterations, normal equations, add counts and map contents, bit for bit."""
+    sync = _replay(lib, n_scans, async_insert=0)
+    waited = _replay(lib, n_scans, async_insert=1)            # the wrapper collects after every scan
+    free = _replay(lib, n_scans, collect=False, async_insert=1)  # nothing waits on the host until the end
+    assert sync[-1] == waited[-1] == free[-1]
+    for k in range(n_scans):
+        (s0, i0, a0, h0), (s1, i1, a1, h1), (s2, i2, a2, h2) = sync[k], waited[k], free[k]
+        assert (i0, a0) == (i1, a1) and i0 == i2 and a2 == -1
+        np.testing.assert_array_equal(s0, s1)
+        np.testing.assert_array_equal(s0, s2)
+        for x, y, z in zip(h0, h1, h2):
+            np.testing.assert_array_equal(x, y)
+            np.testing.assert_array_equal(x, z)
+    n_ds, n_raw = free[-2]
+    assert n_ds + n_raw == sync[n_scans - 1][2]
+
+
+def test_async_insert_is_result_identical(emu_lib):
+    _check_async_insert(emu_lib, 3)
+
+
+@pytest.mark.gpu
+def test_async_insert_is_result_identical_gpu(gpu_lib):
+    _check_async_insert(gpu_lib, 8)
+
+
+def _check_knn_reuse(lib, monkeypatch, n_scans):
+    """Rematch passes prove most neighbour sets unchanged instead of searching again (knn_try_reuse); with DLT_KNN_REUSE=0 every
+    match pass searches.  Same states, iterations, normal equations, add counts and map contents, bit for bit."""
+    a = _replay(lib, n_scans)
+    assert any(len(h) >= 3 for _, _, _, h in a[:n_scans])  # scans with a rematch pass behind the first one
+    monkeypatch.setenv("DLT_KNN_REUSE", "0")
+    b = _replay(lib, n_scans)
+    assert a[-1] == b[-1]
+    for (sa, ia, aa, ha), (sb, ib, ab, hb) in zip(a[:n_scans], b[:n_scans]):
+        assert (ia, aa) == (ib, ab)
+        np.testing.assert_array_equal(sa, sb)
+        for x, y in zip(ha, hb):
+            np.testing.assert_array_equal(x, y)
+
+
+def test_knn_reuse_is_result_identical(emu_lib, monkeypatch):
+    _check_knn_reuse(emu_lib, monkeypatch, 3)
+
+
+@pytest.mark.gpu
+def test_knn_reuse_is_result_identical_gpu(gpu_lib, monkeypatch):
+    _check_knn_reuse(gpu_lib, monkeypatch, 8)

@@ -36,8 +36,11 @@ def main():
             os.environ["DLT_LOOP_FUSED"] = "0" if "c" in mtag[1:] else "1"
             os.environ["DLT_LOOP_COOP"] = "1" if "p" in mtag[1:] else "0"
             os.environ["DLT_PDL"] = "0" if "s" in mtag[1:] else "1"  # s = plain stream serialisation (no programmatic dependent launch)
+            os.environ["DLT_KNN_REUSE"] = "0" if "r" in mtag[1:] else "1"  # r = every match pass searches (no reuse of proven neighbour sets)
+            async_insert = 0 if "i" in mtag[1:] else 1                     # i = map_incremental inside the call (synchronous)
             lm = LaserMapping(dev=dict(device=0, max_scan_points=1 << 18, max_map_points=max(1 << 22, 2 * len(work["map_pts"]))), featptsThreshold=30,
-                              device_loop=mode)
+                              device_loop=mode, async_insert=async_insert)
+            lm.collect_after_scan = False
             lm.device.set_stream(stream.cuda_stream)
             s0, mean_acc, last_imu = bench.initial_state(seq)
             lm.force_imu_ready(mean_acc, last_imu)
