@@ -375,6 +375,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--seqs-per-gpu", type=int, default=8, help="c5: independent sequences driven concurrently on every GPU (one stream + host thread each)")
+    ap.add_argument("--c5-threads", type=int, default=0, help="c5: native worker threads of dlt_lio_replay_sequences per GPU (0 = min(sequences, host cores of the rank))")
     ap.add_argument("--device-loop", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="-1: the library's default (host loop); 1: iteration loop, zeta blend and map insert resident on the device (one sync "
                          "per scan); 2: loop on the device, blend/insert host-driven; 0: one host round trip per iteration")
@@ -893,10 +894,9 @@ def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
 
 
 def main_c5(args, K, W, rank, local_rank, world, dist):
-    """BASELINE config C5: independent 32-beam sequences, S per GPU driven concurrently (one handle + stream + host thread
-    each), no data-path collective.  A step = one scan of every sequence; value = aggregate raw points / s."""
-    import threading
-
+    """BASELINE config C5: independent 32-beam sequences, S per GPU replayed concurrently by the library's native multi-sequence
+    driver (dlt_lio_replay_sequences: one handle + CUDA streams per sequence, worker threads that multiplex sequences as
+    coroutines), no data-path collective.  A step = one scan of every sequence; value = aggregate raw points / s."""
     import torch
 
     from daliti_b200.lio import LaserMapping
@@ -910,7 +910,13 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
         dev_scans.append([torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p, _, _ in w["scans"]])
         pin_scans.append([torch.from_numpy(np.ascontiguousarray(p)).pin_memory() for p, _, _ in w["scans"]])
 
+    from daliti_b200.lio import replay_sequences
+
+    n_thr = args.c5_threads if args.c5_threads > 0 else max(1, min(S, len(os.sched_getaffinity(0))))
+
     def run(mode, K=K):
+        """every sequence replays W warm-up scans, then K timed scans, through dlt_lio_replay_sequences: native worker threads,
+        several sequences per thread as coroutines that switch wherever the library waits for the device"""
         lms = []
         for w, st in zip(works, streams):
             lm = LaserMapping(dev=dict(device=local_rank, max_scan_points=1 << 16, max_map_points=max(1 << 20, 2 * len(w["map_pts"])),
@@ -922,60 +928,34 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
             lm.set_state(s0)
             lm.device.map_build(w["map_pts"])
             lms.append(lm)
-        torch.cuda.synchronize()
-        gate = threading.Barrier(S + 1)
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
-        stats = [None] * S
-        errs = []
 
-        def worker(i):
-            try:
-                lm, st, w = lms[i], streams[i], works[i]
-                pts_total, nd, eff = 0, 0, 0
-                with torch.cuda.stream(st):
-                    for k in range(W + K):
-                        pts, t_beg, imu = w["scans"][k]
-                        if k == W:
-                            gate.wait()   # warm-up done everywhere
-                            gate.wait()   # start event recorded
-                        lm.on_lidar_msg()
-                        if mode == "dev":
-                            o = lm.process_scan_dev(dev_scans[i][k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
-                        else:
-                            if k + 1 < W + K:
-                                lm.prefetch_scan(pin_scans[i][k + 1])  # double-buffered upload
-                            o = lm.process_scan(pin_scans[i][k], t_beg, imu)
-                        if k >= W:
-                            pts_total += o.n_raw
-                            nd += o.n_down
-                            eff += lm.iters()[-1].effct_feat_num if o.n_iters else 0
-                    ends[i].record(st)
-                stats[i] = (pts_total, nd, eff)
-            except Exception as e:  # surface worker failures in the main thread
-                errs.append(repr(e))
-                try:
-                    gate.abort()
-                except Exception:
-                    pass
+        def lists(lo, hi):
+            out = []
+            for i, w in enumerate(works):
+                if mode == "dev":
+                    out.append([(dev_scans[i][k], w["scans"][k][1], w["scans"][k][2], w["scans"][k][1] + float(w["scans"][k][0][-1, 6])) for k in range(lo, hi)])
+                else:
+                    out.append([(pin_scans[i][k], w["scans"][k][1], w["scans"][k][2]) for k in range(lo, hi)])
+            return out
 
-        ths = [threading.Thread(target=worker, args=(i,)) for i in range(S)]
-        for t in ths:
-            t.start()
-        gate.wait()
+        replay_sequences(lms, lists(0, W), n_threads=n_thr, prefetch=(mode != "dev"), want_outs=False)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         start = torch.cuda.Event(enable_timing=True)
-        start.record(torch.cuda.current_stream())
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(S)]
         l0 = lms[0].device.launch_count()
-        gate.wait()
-        for t in ths:
-            t.join()
+        start.record(torch.cuda.current_stream())
+        outs = replay_sequences(lms, lists(W, W + K), n_threads=n_thr, prefetch=(mode != "dev"))
+        for e, st in zip(ends, streams):
+            e.record(st)
         torch.cuda.synchronize()
-        if errs:
-            raise RuntimeError("; ".join(errs))
         ms = max(start.elapsed_time(e) for e in ends)
         n_launch = lms[0].device.launch_count() - l0
+        stats = []
+        for lm, o in zip(lms, outs):
+            eff = lm.iters()[-1].effct_feat_num if o and o[-1].n_iters else 0
+            stats.append((sum(x.n_raw for x in o), sum(x.n_down for x in o), eff * len(o)))
         for lm in lms:
             lm.close()
         return ms, stats, n_launch
@@ -1002,16 +982,16 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
             "metric": METRIC, "value": pts_v / (ms_v * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_v / K,
             "scans_per_s": n_seq * K / (ms_v * 1e-3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 geometry / f64 normal equations", "data": "synthetic",
-            "config": {"workload": f"{works[0]['name']}: {n_seq} sequences, {S} per GPU driven concurrently (one handle + CUDA stream + host thread each), "
+            "config": {"workload": f"{works[0]['name']}: {n_seq} sequences, {S} per GPU replayed concurrently by dlt_lio_replay_sequences (one handle + CUDA streams each; {n_thr} native worker threads per GPU, sequences multiplexed as coroutines), "
                                    f"{K} scans per sequence timed (BASELINE names 1000: bounded here by scan synthesis time)",
                        "iterations": 4, "sequences": n_seq, "seqs_per_gpu": S, "n_raw_mean": pts_v / (n_seq * K),
                        "n_down_mean": float(sum(s[1] for s in st_v)) / (S * K), "effct_feat_mean": float(sum(s[2] for s in st_v)) / (S * K),
                        "map_points_per_sequence": int(np.mean([len(w["map_pts"]) for w in works])),
                        "l2": "not flushed: the concurrent sequences' maps (S x ~70 MB of buckets + tables) exceed the 126 MB L2 for S >= 2",
-                       "timing": "one CUDA event before the workers are released to the last worker's end event (max over sequences and ranks)",
+                       "timing": "one CUDA event before dlt_lio_replay_sequences to the last sequence's end event (max over sequences and ranks)", "worker_threads_per_gpu": n_thr,
                        "parallelism": "independent sequences, no data-path collective"},
             "e2e": {"value": pts_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(pts_e / (world * K) * 48), "d2h_bytes_per_step": int(S * 18064),
-                    "ms_per_step": ms_e / K, "api": "dlt_lio_prefetch_scan(next) + dlt_lio_process_scan (pinned host buffers), one host thread per sequence"},
+                    "ms_per_step": ms_e / K, "api": "dlt_lio_replay_sequences with pinned host buffers: dlt_lio_prefetch_scan(next) + dlt_lio_process_scan per scan"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
         }
         emit(line)

@@ -22,6 +22,8 @@
 using namespace dlt;
 
 std::atomic<unsigned long long> dlt::rt::g_launches{0};
+thread_local void (*dlt::rt::t_wait_hook)(void *) = nullptr;
+thread_local void *dlt::rt::t_wait_ctx = nullptr;
 #if !defined(DLT_EMU)
 int dlt::rt::g_pdl = 1;
 #endif
@@ -124,6 +126,7 @@ struct dlt_handle_s {
     size_t peer_map_bytes[DLT_MAX_PEERS] = {};
     // (DLT_ZEROCOPY=0 opts out): dlt_measure's result block is stored by k_residual straight into pinned host memory and the
     // host spins on a flag there instead of issuing a device->host copy and synchronising the stream
+    int reuse_seen_last = 0, reuse_redo_last = 0, reuse_holdoff = 0;  // reuse_feedback
     bool knn_reuse = true;  // rematch passes prove neighbour sets unchanged where they can (DLT_KNN_REUSE=0: always search; A/B switch)
     bool zerocopy = true;  // measured on B200 (round 2): -22 us per C2 scan against the copy + stream synchronisation; DLT_ZEROCOPY=0 switches it off
     unsigned long long zc_seq = 0;
@@ -224,6 +227,7 @@ static int map_reset(dlt_handle h) {
     h->map_dead = false;
     DLT_RT(h, rt::fill(h->map.table, 0xFF, h->table_cap * sizeof(Slot), h->stream));
     DLT_RT(h, rt::fill(h->d_counters, 0, 16 * sizeof(int), h->stream));
+    h->reuse_seen_last = h->reuse_redo_last = 0;
     return DLT_OK;
 }
 
@@ -298,10 +302,22 @@ static int map_refuse_if_dead(dlt_handle h) {
     return DLT_OK;
 }
 
+// The reuse statistics ride back with the map counters once per scan: when more than a quarter of a rematch pass had to be
+// searched again (large corrections between the passes) the warp-per-query kernel is the wrong tool for that many queries, so
+// the next scans search every pass in full and the reuse is tried again a little later.
+static void reuse_feedback(dlt_handle h, const int *c16) {
+    const int seen = c16[12] - h->reuse_seen_last, redo = c16[13] - h->reuse_redo_last;
+    h->reuse_seen_last = c16[12];
+    h->reuse_redo_last = c16[13];
+    if (h->reuse_holdoff > 0) h->reuse_holdoff--;
+    if (seen > 0 && 4 * (long long)redo > (long long)seen) h->reuse_holdoff = 8;
+}
+
 static int map_check_error(dlt_handle h) {
-    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 8 * sizeof(int), h->stream));
+    DLT_RT(h, rt::d2h(h->h_ints, h->d_counters, 16 * sizeof(int), h->stream));
     DLT_RT(h, rt::sync(h->stream));
     h->counters_fresh = true;
+    reuse_feedback(h, h->h_ints);
     if (h->h_ints[2] != 0) h->map_dead = true;
     if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
     if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
@@ -325,8 +341,9 @@ static int ins_finish(dlt_handle h) {  // before anything reads or changes the m
     if (h->ins_uncollected) {
         DLT_RT(h, rt::event_sync(h->ev_inserted));
         h->ins_uncollected = false;
-        std::memcpy(h->h_ints, h->h_ins_ints, 8 * sizeof(int));
+        std::memcpy(h->h_ints, h->h_ins_ints, 16 * sizeof(int));
         h->counters_fresh = true;
+        reuse_feedback(h, h->h_ints);
         h->last_ins_ds = h->h_ints[6];
         h->last_ins_raw = h->h_ints[7];
         if (h->h_ints[2] != 0) h->map_dead = true;
@@ -1173,7 +1190,7 @@ static int measure_dev_impl(dlt_handle h, const double *pose24, int do_match, do
         h->nfar_known = false;
         ProfScope prof(h, 0);
         // a rematch pass of the same scan against the same map: neighbour sets that can be proven unchanged are not searched again
-        const bool reuse = h->have_match && h->knn_reuse && h->map.shard_count <= 1;
+        const bool reuse = h->have_match && h->knn_reuse && h->reuse_holdoff == 0 && h->map.shard_count <= 1;
         int rk = launch_knn(h, (const float4 *)h->d_down, n, n_grid, 1, P, la, reuse);
         if (rk) return rk;
         h->have_match = true;
@@ -1538,6 +1555,7 @@ int dlt_measure(dlt_handle h, const double *pose24, int do_match, dlt_measure_ou
         const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(h->h_ints + 32);
         const unsigned long long want = h->zc_seq;
         for (unsigned spins = 1; *flag != want; spins++) {
+            if (rt::t_wait_hook) rt::t_wait_hook(rt::t_wait_ctx);  // (the multi-sequence driver runs another sequence meanwhile)
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
@@ -1782,7 +1800,7 @@ static int map_incremental_impl(dlt_handle h, const double *pose24, int flg_EKF_
     if (rc) return rc;
     h->have_match = false;  // the map changed: neighbour sets are stale
     if (async) {
-        DLT_RT(h, rt::d2h(h->h_ins_ints, h->d_counters, 8 * sizeof(int), h->stream));
+        DLT_RT(h, rt::d2h(h->h_ins_ints, h->d_counters, 16 * sizeof(int), h->stream));
         DLT_RT(h, rt::event_record(h->ev_inserted, h->stream));
         h->cls_pending = h->ins_pending = h->ins_uncollected = true;
         h->counters_fresh = false;
@@ -1814,6 +1832,12 @@ int dlt_map_incremental_collect(dlt_handle h, int *n_ds, int *n_raw) {
 }
 
 double *dlt_result_dev(dlt_handle h) { return h ? h->d_result : nullptr; }
+
+int dlt_set_thread_wait_hook(void (*fn)(void *), void *ctx) {
+    rt::t_wait_hook = fn;
+    rt::t_wait_ctx = ctx;
+    return DLT_OK;
+}
 
 int dlt_debug_counters(dlt_handle h, int *out16) {
     if (!h || !out16) return DLT_E_INVALID;

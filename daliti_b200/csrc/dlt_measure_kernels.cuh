@@ -560,11 +560,11 @@ DLT_D int knn8_find_finish(const MapView &m, const Probe &p) {
 
 // the four queries q0 .. q0+3 of one warp; wl = this warp's kKnn8WlInts ints of shared memory
 DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n, int body_frame, const Pose &P, float max_sq_dist, const KnnOut &out,
-                      int *unres_list, int *unres_count, int q0, int lane, int *wl, int unres_cap = 0x7FFFFFFF, const int *qlist = nullptr) {
+                      int *unres_list, int *unres_count, int q0, int lane, int *wl, int unres_cap = 0x7FFFFFFF) {
     const unsigned FULL = 0xffffffffu;
     const int grp = lane >> 3, sub = lane & 7;
-    const bool live = q0 + grp < n;  // (with a list: n = its length)
-    const int qi = qlist ? (live ? qlist[q0 + grp] : 0) : q0 + grp;
+    const int qi = q0 + grp;
+    const bool live = qi < n;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     int cx = 0, cy = 0, cz = 0;
     bool work = false;
@@ -591,7 +591,7 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
     for (int t = 0; t < kK; t++) best[t] = kKey32Inf;
     unsigned dropped = kKey32Inf;
     int *gwl = wl + grp * kKnn8Visits;
-    int visit = 0;        // warp-uniform: bucket fetches so far (two per step)
+    int visit = 0;        // group-uniform: buckets this group fetched so far
     bool ovf = false;     // this group needed a fetch beyond what a tag can name
 
     // cell ci = r * 8 + sub of the 3^3 block, in the order (x fastest)
@@ -615,16 +615,15 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (bb0 >= 0) v0 = reinterpret_cast<const float4 *>(&m.buckets[bb0])[sub];  // 8 lanes x 16 B = one line
                 if (bb1 >= 0) v1 = reinterpret_cast<const float4 *>(&m.buckets[bb1])[sub];
-                const bool tag_ok = visit < kKnn8Visits;  // warp-uniform
-                if (!tag_ok && (bb0 >= 0 || bb1 >= 0)) ovf = true;
-                if (tag_ok && sub == 0) {
-                    gwl[visit] = bb0;
-                    gwl[visit + 1] = bb1;
+                const int t0 = visit, t1 = visit + (bb0 >= 0 ? 1 : 0);
+                visit = t1 + (bb1 >= 0 ? 1 : 0);
+                if (visit > kKnn8Visits) ovf = true;
+                if (sub == 0) {
+                    if (bb0 >= 0 && t0 < kKnn8Visits) gwl[t0] = bb0;
+                    if (bb1 >= 0 && t1 < kKnn8Visits) gwl[t1] = bb1;
                 }
-                const unsigned tag = ((unsigned)visit << 3) | (unsigned)sub;
-                knn8_consume(v0, bb0, lane, sub, qx, qy, qz, best, dropped, tag, tag_ok);
-                knn8_consume(v1, bb1, lane, sub, qx, qy, qz, best, dropped, tag + 8u, tag_ok);
-                visit += 2;
+                knn8_consume(v0, bb0, lane, sub, qx, qy, qz, best, dropped, ((unsigned)t0 << 3) | (unsigned)sub, t0 < kKnn8Visits);
+                knn8_consume(v1, bb1, lane, sub, qx, qy, qz, best, dropped, ((unsigned)t1 << 3) | (unsigned)sub, t1 < kKnn8Visits);
             }
         }
     }
@@ -676,6 +675,16 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
     cov = fminf(cov, (float)(cz + 2) * cell_edge - qz);
     cov -= slack;
     const bool resolved = cand_ok && cov > 0.f && d5 < cov * cov * 0.99999f;
+#if defined(DLT_EMU) && defined(DLT_KNN8_STATS)
+    if (sub == 0) {
+        extern long long g_knn8_stats[8];
+        g_knn8_stats[0]++;
+        if (nb < kK) g_knn8_stats[1]++;
+        else if (tie) g_knn8_stats[2]++;
+        else if (ovf) g_knn8_stats[3]++;
+        else if (!resolved) g_knn8_stats[4]++;
+    }
+#endif
     if (!resolved) {
         if (sub == 0) {
             out.d6lb[qi] = 0.f;
@@ -763,23 +772,27 @@ __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
         out.nn_count[1] = 0;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (reuse) {  // block-uniform.  Chunks of one query per thread: prove the old set still right, search the rest again
-        __shared__ int s_redo[kKnn8Block];
-        __shared__ int s_nredo;
-        for (int c0 = blockIdx.x * kKnn8Block; c0 < n; c0 += gridDim.x * kKnn8Block) {  // block-uniform
-            if (threadIdx.x == 0) s_nredo = 0;
-            __syncthreads();
-            const int i = c0 + threadIdx.x;
-            if (i < n && !knn_try_reuse(q_pts, i, sP, max_sq_dist, out)) s_redo[atomicAdd(&s_nredo, 1)] = i;
-            __syncthreads();
-            const int nr = s_nredo;
-            if (threadIdx.x == 0 && reuse_stats) {  // instrumentation: queries seen / searched again by the reuse passes
-                atomicAdd(reuse_stats, min(kKnn8Block, n - c0));
-                atomicAdd(reuse_stats + 1, nr);
+    if (reuse) {  // block-uniform.  One query per thread: prove the old set still right; what cannot be proven is handed to the
+                  // warp-per-query kernel, which searches it again from scratch (typically one query in ten)
+        int seen = 0, redo = 0;
+        for (int i = blockIdx.x * kKnn8Block + threadIdx.x; i < n; i += gridDim.x * kKnn8Block) {
+            seen++;
+            if (!knn_try_reuse(q_pts, i, sP, max_sq_dist, out)) {
+                redo++;
+                out.d6lb[i] = 0.f;
+                unres_list[atomicAdd(unres_count, 1)] = i;
             }
-            for (int q0 = warp * 4; q0 < nr; q0 += (kKnn8Block / 32) * 4)  // warp-uniform
-                knn8_group(m, q_pts, nr, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane, s_wl[warp], 0x7FFFFFFF, s_redo);
-            __syncthreads();
+        }
+        if (reuse_stats) {  // instrumentation: queries seen / searched again by the reuse passes
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                seen += __shfl_xor_sync(0xffffffffu, seen, o);
+                redo += __shfl_xor_sync(0xffffffffu, redo, o);
+            }
+            if (lane == 0) {
+                atomicAdd(reuse_stats, seen);
+                atomicAdd(reuse_stats + 1, redo);
+            }
         }
         return;
     }

@@ -20,6 +20,9 @@
 namespace dlt {
 namespace rt {
 extern std::atomic<unsigned long long> g_launches;
+// dlt_set_thread_wait_hook: called instead of blocking / spinning while this thread waits for the device
+extern thread_local void (*t_wait_hook)(void *);
+extern thread_local void *t_wait_ctx;
 struct Event {};
 inline int event_create(Event *) { return 0; }
 inline void event_destroy(Event) {}
@@ -27,7 +30,10 @@ inline int event_record(Event, cudaStream_t) { return 0; }
 inline float event_elapsed_ms(Event, Event) { return 0.f; }
 inline int event_create_untimed(Event *) { return 0; }
 inline int stream_wait(cudaStream_t, Event) { return 0; }
-inline int event_sync(Event) { return 0; }
+inline int event_sync(Event) {
+    if (t_wait_hook) t_wait_hook(t_wait_ctx);  // (exercises the multi-sequence driver's switching under the emulator)
+    return 0;
+}
 inline int alloc(void **p, size_t bytes) {
     size_t n = (bytes + 255) & ~(size_t)255;
     if (n == 0) n = 256;
@@ -53,7 +59,10 @@ inline int fill(void *d, int byte, size_t n, cudaStream_t) {
     std::memset(d, byte, n);
     return 0;
 }
-inline int sync(cudaStream_t) { return 0; }
+inline int sync(cudaStream_t) {
+    if (t_wait_hook) t_wait_hook(t_wait_ctx);
+    return 0;
+}
 inline int stream_query(cudaStream_t) { return 0; }  // 0 idle, 1 still busy, 2 error
 inline int stream_create(cudaStream_t *s) {
     *s = nullptr;
@@ -157,6 +166,10 @@ extern int g_pdl;  // 1: launch with the programmatic-stream-serialization attri
 
 namespace dlt {
 namespace rt {
+// dlt_set_thread_wait_hook: called instead of blocking / spinning while this thread waits for the device (the multi-sequence
+// driver switches to another sequence's update there)
+extern thread_local void (*t_wait_hook)(void *);
+extern thread_local void *t_wait_ctx;
 typedef cudaEvent_t Event;
 inline int event_create(Event *e) { return cudaEventCreate(e) == cudaSuccess ? 0 : 1; }
 inline void event_destroy(Event e) { cudaEventDestroy(e); }
@@ -168,7 +181,14 @@ inline float event_elapsed_ms(Event a, Event b) {
 }
 inline int event_create_untimed(Event *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess ? 0 : 1; }
 inline int stream_wait(cudaStream_t s, Event e) { return cudaStreamWaitEvent(s, e, 0) == cudaSuccess ? 0 : 1; }
-inline int event_sync(Event e) { return cudaEventSynchronize(e) == cudaSuccess ? 0 : 1; }
+inline int event_sync(Event e) {
+    if (t_wait_hook) {
+        cudaError_t r;
+        while ((r = cudaEventQuery(e)) == cudaErrorNotReady) t_wait_hook(t_wait_ctx);
+        return r == cudaSuccess ? 0 : 1;
+    }
+    return cudaEventSynchronize(e) == cudaSuccess ? 0 : 1;
+}
 inline int alloc(void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 256) == cudaSuccess ? 0 : 1; }
 inline void release(void *p) {
     if (p) cudaFree(p);
@@ -187,7 +207,14 @@ inline int d2d(void *d, const void *s, size_t n, cudaStream_t st) {
     return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : 1;
 }
 inline int fill(void *d, int byte, size_t n, cudaStream_t st) { return cudaMemsetAsync(d, byte, n, st) == cudaSuccess ? 0 : 1; }
-inline int sync(cudaStream_t st) { return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1; }
+inline int sync(cudaStream_t st) {
+    if (t_wait_hook) {
+        cudaError_t r;
+        while ((r = cudaStreamQuery(st)) == cudaErrorNotReady) t_wait_hook(t_wait_ctx);
+        return r == cudaSuccess ? 0 : 1;
+    }
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : 1;
+}
 inline int stream_query(cudaStream_t st) {  // 0 idle, 1 still busy, 2 error
     cudaError_t e = cudaStreamQuery(st);
     return e == cudaSuccess ? 0 : (e == cudaErrorNotReady ? 1 : 2);

@@ -59,8 +59,55 @@ _LIO_SYMBOLS = [
     "dlt_lio_default_config", "dlt_lio_create", "dlt_lio_destroy", "dlt_lio_last_error", "dlt_lio_device", "dlt_lio_on_lidar_msg",
     "dlt_lio_on_edge_count", "dlt_lio_force_imu_ready", "dlt_lio_get_state", "dlt_lio_set_state", "dlt_lio_get_flags",
     "dlt_lio_get_localmap", "dlt_lio_set_reduce", "dlt_lio_process_scan", "dlt_lio_process_scan_dev", "dlt_lio_process_cloud", "dlt_lio_prefetch_scan", "dlt_lio_get_iters", "dlt_lio_get_imu_poses",
-    "dlt_lio_peer_export", "dlt_lio_peer_attach", "dlt_lio_peer_detach", "dlt_lio_collect_insert",
+    "dlt_lio_peer_export", "dlt_lio_peer_attach", "dlt_lio_peer_detach", "dlt_lio_collect_insert", "dlt_lio_replay_sequences",
 ]
+
+
+class LioSeqScan(C.Structure):
+    _fields_ = [("pts48", C.c_void_p), ("n", C.c_int), ("pts_on_device", C.c_int), ("lidar_beg_time", C.c_double),
+                ("observation_end_time", C.c_double), ("imu7", C.c_void_p), ("n_imu", C.c_int), ("lidar_msgs", C.c_int)]
+
+
+class LioSeq(C.Structure):
+    _fields_ = [("h", C.c_void_p), ("scans", C.POINTER(LioSeqScan)), ("n_scans", C.c_int), ("prefetch", C.c_int),
+                ("thermal", C.c_void_p), ("outs", C.POINTER(LioScanOut)), ("rc", C.c_int), ("n_done", C.c_int)]
+
+
+def replay_sequences(lms, scan_lists, n_threads=0, prefetch=False, want_outs=True):
+    """dlt_lio_replay_sequences: lms[i] replays scan_lists[i] = [(pts48, t_beg, imu7[, observation_end_time]), ...] natively, all
+    sequences concurrently (pts48: numpy / pinned torch CPU tensor, or a CUDA tensor).  Returns per-sequence lists of LioScanOut."""
+    lib = lms[0].lib
+    keep, seqs = [], (LioSeq * len(lms))()
+    outs_all = []
+    for i, (lm, scans) in enumerate(zip(lms, scan_lists)):
+        arr = (LioSeqScan * max(1, len(scans)))()
+        for k, sc in enumerate(scans):
+            pts, t_beg, imu = sc[0], sc[1], sc[2]
+            on_dev = bool(getattr(pts, "is_cuda", False))
+            if hasattr(pts, "data_ptr"):
+                n, ptr = int(pts.shape[0]), pts.data_ptr()
+            else:
+                a = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 12)
+                keep.append(a)
+                n, ptr = a.shape[0], a.ctypes.data
+            im = _f64(imu).reshape(-1, 7)
+            keep.append(im)
+            arr[k].pts48, arr[k].n, arr[k].pts_on_device = ptr, n, 1 if on_dev else 0
+            arr[k].lidar_beg_time = float(t_beg)
+            arr[k].observation_end_time = float(sc[3]) if len(sc) > 3 else float(t_beg)
+            arr[k].imu7, arr[k].n_imu, arr[k].lidar_msgs = im.ctypes.data, im.shape[0], 1
+        outs = (LioScanOut * max(1, len(scans)))()
+        keep += [arr, outs]
+        outs_all.append(outs)
+        seqs[i].h, seqs[i].scans, seqs[i].n_scans = lm.h, arr, len(scans)
+        seqs[i].prefetch, seqs[i].thermal = 1 if prefetch else 0, None
+        seqs[i].outs = outs if want_outs else None
+    rc = lib.dlt_lio_replay_sequences(seqs, C.c_int(len(lms)), C.c_int(n_threads))
+    if rc != 0:
+        bad = [i for i in range(len(lms)) if seqs[i].rc != 0]
+        msg = lib.dlt_lio_last_error(lms[bad[0]].h) if bad else b""
+        raise DltError(f"dlt_lio_replay_sequences: {_ERR.get(rc, rc)} (sequences {bad}): {msg.decode() if msg else ''}")
+    return [[o[k] for k in range(len(sl))] for o, sl in zip(outs_all, scan_lists)]
 
 
 class LaserMapping:

@@ -273,6 +273,10 @@ int dlt_peer_detach(dlt_handle h);
  * queries of the last match pass, [6] / [7] adds of the last map_incremental, [12] / [13] queries seen / searched again by the
  * rematch passes that reuse proven neighbour sets -- cumulative).  Synchronises the handle.                               */
 int dlt_debug_counters(dlt_handle h, int *out16);
+/* While THIS thread waits for the device inside any dlt_* call (result block of dlt_measure, stream / event waits) the library
+ * calls fn(ctx) in a loop instead of spinning or blocking; NULL restores the default.  The multi-sequence driver
+ * (dlt_lio_replay_sequences) uses it to run another sequence's update on the same thread meanwhile.                       */
+int dlt_set_thread_wait_hook(void (*fn)(void *), void *ctx);
 int dlt_set_profiling(dlt_handle h, int on);
 int dlt_get_profile(dlt_handle h, double *ms8, long long *count8, int reset);
 /* Spans recorded since the last dlt_get_profile(reset): (group, start ms, end ms) triples relative to the

@@ -131,6 +131,32 @@ int dlt_lio_peer_detach(dlt_lio h); /* back to the callback; a handle attaches a
  * kdtree_incremental add_point_size, laserMapping.cpp:626-629).  Without a pending insert: the last counts again.  */
 int dlt_lio_collect_insert(dlt_lio h, int *n_added_ds, int *n_added_raw);
 int dlt_lio_get_iters(dlt_lio h, dlt_lio_iter *iters, int cap);
+
+/* ---- many independent sequences on one GPU, driven natively (BASELINE config: a batch of independent sequences; the reference
+ * runs one sequence per process and has no counterpart).  Every sequence has its own dlt_lio handle (own map, state, CUDA
+ * streams).  n_threads worker threads (0 = one per host core, at most n_seqs) each replay several sequences as coroutines:
+ * wherever one sequence's update waits for the device the thread goes on with the next sequence's.  Per scan the call is
+ * exactly on_lidar_msg x lidar_msgs, [dlt_lio_prefetch_scan of scan k+1], dlt_lio_process_scan(_dev) of scan k; results are
+ * those of the same calls made one by one.  Returns the first non-zero rc of any sequence (each is reported in seqs[i].rc).  */
+typedef struct dlt_lio_seq_scan {
+    const void *pts48;            /* n PointXYZINormal records, host (pinned for prefetch) or device memory              */
+    int n, pts_on_device;
+    double lidar_beg_time;
+    double observation_end_time;  /* device input only (laserMapping.cpp:546)                                             */
+    const double *imu7;           /* n_imu rows of t, acc[3], gyr[3]                                                      */
+    int n_imu;
+    int lidar_msgs;               /* dlt_lio_on_lidar_msg calls in front of this scan (feat_points_cbk, :424-446)         */
+} dlt_lio_seq_scan;
+typedef struct dlt_lio_seq {
+    dlt_lio h;
+    const dlt_lio_seq_scan *scans;
+    int n_scans;
+    int prefetch;                 /* host buffers: upload scan k+1 while scan k is processed                              */
+    const dlt_lio_thermal *thermal; /* optional, applied to every scan                                                    */
+    dlt_lio_scan_out *outs;       /* optional, n_scans entries                                                            */
+    int rc, n_done;               /* out: status of this sequence, scans completed                                        */
+} dlt_lio_seq;
+int dlt_lio_replay_sequences(dlt_lio_seq *seqs, int n_seqs, int n_threads);
 /* IMUpose list of the last scan's forward propagation (22 doubles each)                          */
 int dlt_lio_get_imu_poses(dlt_lio h, double *pose22, int cap);
 
