@@ -954,7 +954,9 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
         n_launch = lms[0].device.launch_count() - l0
         stats = []
         for lm, o in zip(lms, outs):
-            eff = lm.iters()[-1].effct_feat_num if o and o[-1].n_iters else 0
+            lm.out.n_iters = o[-1].n_iters if o else 0  # (the wrapper's own record was not filled by the native driver)
+            its = lm.iters()
+            eff = its[-1].effct_feat_num if its else 0
             stats.append((sum(x.n_raw for x in o), sum(x.n_down for x in o), eff * len(o)))
         for lm in lms:
             lm.close()
@@ -994,6 +996,20 @@ def main_c5(args, K, W, rank, local_rank, world, dist):
                     "ms_per_step": ms_e / K, "api": "dlt_lio_replay_sequences with pinned host buffers: dlt_lio_prefetch_scan(next) + dlt_lio_process_scan per scan"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
         }
+        # whole-job HBM figure (SURVEY.md 8d formula for the algorithmic bytes of one scan, 2 match passes / 3 iterations as measured
+        # on these scans) -- the configuration whose working set (S maps of ~70 MB) exceeds the 126 MB L2
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            nraw, ndn = line["config"]["n_raw_mean"], line["config"]["n_down_mean"]
+            b_scan = nraw * 48 + nraw * 16 + ndn * 16 + 2 * ndn * 116 + 3 * ndn * 32 + 3 * 92 * 8
+            ach = b_scan * line["scans_per_s"] / world / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": "whole job, per GPU", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                "algorithmic_bytes_per_scan": b_scan, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                                "note": "many concurrent sequences: the maps no longer fit the L2, yet the job moves only this fraction of what HBM could deliver -- the update is a chain "
+                                        "of dependent gathers with a host decision per iteration, bounded by instruction issue and launch rate, not by bytes (DESIGN.md section 5)"}
+        except Exception as e:
+            line["roofline"] = {"error": repr(e)}
         emit(line)
     if dist is not None:
         dist.barrier()

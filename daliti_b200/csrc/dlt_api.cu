@@ -127,6 +127,7 @@ struct dlt_handle_s {
     // (DLT_ZEROCOPY=0 opts out): dlt_measure's result block is stored by k_residual straight into pinned host memory and the
     // host spins on a flag there instead of issuing a device->host copy and synchronising the stream
     int reuse_seen_last = 0, reuse_redo_last = 0, reuse_holdoff = 0;  // reuse_feedback
+    double match_pose[24] = {0};  // pose of the last match pass (dlt_measure)
     bool knn_reuse = true;  // rematch passes prove neighbour sets unchanged where they can (DLT_KNN_REUSE=0: always search; A/B switch)
     bool zerocopy = true;  // measured on B200 (round 2): -22 us per C2 scan against the copy + stream synchronisation; DLT_ZEROCOPY=0 switches it off
     unsigned long long zc_seq = 0;
@@ -251,7 +252,7 @@ static int launch_knn(dlt_handle h, const float4 *d_q, int n, int n_grid, int bo
     if (grid > cap_grid) grid = cap_grid;
     if (grid < 1) grid = 1;
     DLT_LAUNCH(k_knn, grid, kKnnWarps * 32, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, (const int *)h->d_unres,
-               (const int *)(h->d_counters + 8), la);
+               (const int *)(h->d_counters + 8), la, reuse ? 1 : 0);
     return DLT_OK;
 }
 
@@ -349,6 +350,7 @@ static int ins_finish(dlt_handle h) {  // before anything reads or changes the m
         if (h->h_ints[2] != 0) h->map_dead = true;
         if (h->h_ints[2] == 1) DLT_FAIL(h, DLT_E_CAPACITY, "map bucket pool exhausted (raise max_map_points)");
         if (h->h_ints[2] == 2) DLT_FAIL(h, DLT_E_CAPACITY, "map hash table full (raise max_map_points)");
+        if (h->peer_on && *h->h_peer_status != 0) DLT_FAIL(h, DLT_E_STATE, "peer exchange timed out (a rank did not take part in map_incremental)");
     }
     return DLT_OK;
 }
@@ -1190,7 +1192,21 @@ static int measure_dev_impl(dlt_handle h, const double *pose24, int do_match, do
         h->nfar_known = false;
         ProfScope prof(h, 0);
         // a rematch pass of the same scan against the same map: neighbour sets that can be proven unchanged are not searched again
-        const bool reuse = h->have_match && h->knn_reuse && h->reuse_holdoff == 0 && h->map.shard_count <= 1;
+        // ... unless the pose moved so far since the pass that found them that few proofs can succeed (the proof needs twice the
+        // displacement to fit between the 5th and the 6th neighbour distance, a few centimetres on a 0.5 m map): then search
+        bool reuse = h->have_match && h->knn_reuse && h->reuse_holdoff == 0;
+        if (reuse) {
+            double tr = 0.0, dt2 = 0.0;
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++) tr += h->match_pose[3 * i + j] * pose24[3 * i + j];  // trace(R1^T R2)
+                const double d = pose24[9 + i] - h->match_pose[9 + i];
+                dt2 += d * d;
+            }
+            const double c = 0.5 * (tr - 1.0);
+            const double ang = c >= 1.0 ? 0.0 : std::acos(c < -1.0 ? -1.0 : c);
+            if (std::sqrt(dt2) + ang * 30.0 > 0.06 * h->cfg.ds_map) reuse = false;  // displacement of a point 30 m out: 3 cm on a 0.5 m map
+        }
+        std::memcpy(h->match_pose, pose24, sizeof(h->match_pose));
         int rk = launch_knn(h, (const float4 *)h->d_down, n, n_grid, 1, P, la, reuse);
         if (rk) return rk;
         h->have_match = true;
@@ -1279,7 +1295,7 @@ static bool build_loop_graph(dlt_handle h, const MeasureBufs &mb) {
     capturing = true;
     k_knn8<<<g8, kKnn8Block, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la, 0, (int *)nullptr);
     k_knn<<<gk, kKnnWarps * 32, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, (const int *)h->d_unres,
-                                           (const int *)(h->d_counters + 8), la);
+                                           (const int *)(h->d_counters + 8), la, 0);
     cudaGraph_t out = nullptr;
     if (cudaStreamEndCapture(cs, &out) != cudaSuccess) {
         capturing = false;
@@ -1762,7 +1778,10 @@ static int map_incremental_impl(dlt_handle h, const double *pose24, int flg_EKF_
     Pose P = pose_from(pose24);
     // Asynchronous form (unsharded map, every query resolved, so no host decision is pending): the insert kernels go to their own
     // stream behind what the main stream holds now; nothing here waits for them.
-    const bool async = want_async && !sharded && h->have_ins && !h->prof_on && !(h->have_match && !(h->nfar_known && h->h_last_nfar == 0));
+    // (a sharded map with attached peers exchanges the owners' decisions through the mailboxes from inside the kernels, so its
+    // insert can go the same way; with a reduce CALLBACK the library collective stays on the caller's stream: synchronous)
+    const bool async = want_async && (!sharded || (h->have_match && h->peer_on)) && h->have_ins && !h->prof_on &&
+                       !(h->have_match && !(h->nfar_known && h->h_last_nfar == 0));
     if (async) {
         DLT_RT(h, rt::event_record(h->ev_loop_done, h->stream));
         DLT_RT(h, rt::stream_wait(h->ins_stream, h->ev_loop_done));
@@ -1801,6 +1820,7 @@ static int map_incremental_impl(dlt_handle h, const double *pose24, int flg_EKF_
     h->have_match = false;  // the map changed: neighbour sets are stale
     if (async) {
         DLT_RT(h, rt::d2h(h->h_ins_ints, h->d_counters, 16 * sizeof(int), h->stream));
+        if (h->peer_on) DLT_RT(h, rt::d2h(h->h_peer_status, &h->d_peer->status, sizeof(int), h->stream));
         DLT_RT(h, rt::event_record(h->ev_inserted, h->stream));
         h->cls_pending = h->ins_pending = h->ins_uncollected = true;
         h->counters_fresh = false;

@@ -446,30 +446,6 @@ DLT_D void knn_warp_query(const MapView &m, const float4 *__restrict__ q_pts, in
     }
 }
 
-// Warp-per-query kernel.  list == nullptr: queries 0..n-1, one per warp.  Otherwise the queries list[0..*count)
-// (the ones k_knn_ring1 could not resolve) with a warp-stride loop.
-__global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
-    k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, const int *__restrict__ list,
-          const int *__restrict__ count, LoopArgs la) {
-    DLT_PDL_WAIT();
-    __shared__ float4 s_cand[kKnnWarps][kCandSlots];
-    __shared__ int s_cid[kKnnWarps][kCandSlots];
-    __shared__ int s_wl[kKnnWarps][kWlMax];
-    __shared__ Cand s_bestw[kKnnWarps][kK];
-    __shared__ int s_nb[kKnnWarps];
-    __shared__ Pose sP;
-    int is_match = -1;
-    if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_warps = gridDim.x * kKnnWarps;
-    const int limit = list ? *count : n;
-    for (int w = blockIdx.x * kKnnWarps + warp; w < limit; w += total_warps) {  // warp-uniform; no block-level barrier
-        const int qi = list ? list[w] : w;
-        knn_warp_query(m, q_pts, qi, body_frame, sP, max_sq_dist, out, s_cand[warp], s_cid[warp], s_wl[warp], s_bestw[warp], &s_nb[warp], lane);
-        __syncwarp();
-    }
-}
-
 // ------------------------------------------------------------------ first pass: 8 lanes per query over the 3x3x3 block
 // Four queries per warp.  The 8 lanes of a group probe the 27 cells in 4 rounds (the table slot of the NEXT round is
 // requested before the buckets of the current one are consumed) and fetch two 128-byte buckets per step (lane 0 the
@@ -560,11 +536,11 @@ DLT_D int knn8_find_finish(const MapView &m, const Probe &p) {
 
 // the four queries q0 .. q0+3 of one warp; wl = this warp's kKnn8WlInts ints of shared memory
 DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n, int body_frame, const Pose &P, float max_sq_dist, const KnnOut &out,
-                      int *unres_list, int *unres_count, int q0, int lane, int *wl, int unres_cap = 0x7FFFFFFF) {
+                      int *unres_list, int *unres_count, int q0, int lane, int *wl, int unres_cap = 0x7FFFFFFF, const int *qlist = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int grp = lane >> 3, sub = lane & 7;
-    const int qi = q0 + grp;
-    const bool live = qi < n;
+    const bool live = q0 + grp < n;  // (with a list: n = its length)
+    const int qi = qlist ? (live ? qlist[q0 + grp] : 0) : q0 + grp;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     int cx = 0, cy = 0, cz = 0;
     bool work = false;
@@ -711,12 +687,23 @@ DLT_D void knn8_group(const MapView &m, const float4 *__restrict__ q_pts, int n,
 // point was then at least sqrt(d6lb) away: if d5 + delta < sqrt(d6lb) - delta the same five are still strictly nearer than
 // everything else, so only their distances are recomputed (the same fp32 expression a search evaluates) and re-ordered in the
 // stated order.  Anything else is searched again.  Returns true when the set was reused.
-DLT_D bool knn_try_reuse(const float4 *__restrict__ down, int i, const Pose &P, float max_sq_dist, const KnnOut &out) {
+DLT_D bool knn_try_reuse(const MapView &m, const float4 *__restrict__ down, int i, const Pose &P, float max_sq_dist, const KnnOut &out) {
     const float4 qb = down[i];
     float qx, qy, qz;
     body_to_world(P, qb.x, qb.y, qb.z, qx, qy, qz);
     const float4 old = out.qw[i];
     out.qw[i] = make_float4(qx, qy, qz, qb.w);
+    if (m.shard_count > 1) {  // sharded map: the owner of the cell the query is in NOW evaluates it
+        int cx, cy, cz;
+        cell_of_point(m, qx, qy, qz, cx, cy, cz);
+        if (tile_owner(cx, cy, cz, m.tile_shift, m.shard_count) != m.shard_rank) {
+            out.nbr_cnt[i] = 0;
+            out.flags[i] = kFlagForeign;
+            out.d6lb[i] = 0.f;
+            return true;  // nothing to search here
+        }
+        // (a query this rank did not own in the earlier pass carries kFlagForeign and no bound: searched below)
+    }
     const float d6 = out.d6lb[i];
     if (!(d6 > 0.f) || out.nbr_cnt[i] != kK || (out.flags[i] & ~kFlagMatched)) return false;
     Cand c[kK];
@@ -777,7 +764,7 @@ __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
         int seen = 0, redo = 0;
         for (int i = blockIdx.x * kKnn8Block + threadIdx.x; i < n; i += gridDim.x * kKnn8Block) {
             seen++;
-            if (!knn_try_reuse(q_pts, i, sP, max_sq_dist, out)) {
+            if (!knn_try_reuse(m, q_pts, i, sP, max_sq_dist, out)) {
                 redo++;
                 out.d6lb[i] = 0.f;
                 unres_list[atomicAdd(unres_count, 1)] = i;
@@ -799,6 +786,49 @@ __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
     const int stride = gridDim.x * (kKnn8Block / 32) * 4;
     for (int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4; q0 < n; q0 += stride)  // warp-uniform
         knn8_group(m, q_pts, n, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane, s_wl[warp]);
+}
+
+// Warp-per-query kernel.  list == nullptr: queries 0..n-1, one per warp.  Otherwise the queries list[0..*count)
+// (the ones k_knn_ring1 could not resolve) with a warp-stride loop.
+__global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
+    k_knn(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, const int *__restrict__ list,
+          const int *__restrict__ count, LoopArgs la, int bulk) {
+    DLT_PDL_WAIT();
+    __shared__ float4 s_cand[kKnnWarps][kCandSlots];
+    __shared__ int s_cid[kKnnWarps][kCandSlots];
+    __shared__ int s_wl[kKnnWarps][kWlMax];
+    __shared__ Cand s_bestw[kKnnWarps][kK];
+    __shared__ int s_nb[kKnnWarps];
+    __shared__ Pose sP;
+    int is_match = -1;
+    if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_warps = gridDim.x * kKnnWarps;
+    const int limit = list ? *count : n;
+    if (bulk && list) {  // block-uniform.  The list holds ordinary queries (a rematch pass could not prove their old neighbour
+                         // sets): 8 lanes per query first, a warp per query only for what that leaves -- efficient however long
+                         // the list is
+        __shared__ int s_left[kKnnWarps][4];
+        __shared__ int s_nleft[kKnnWarps];
+        __shared__ int s_wl8[kKnnWarps][kKnn8WlInts];
+        for (int g = (blockIdx.x * kKnnWarps + warp) * 4; g < limit; g += total_warps * 4) {  // warp-uniform
+            if (lane == 0) s_nleft[warp] = 0;
+            __syncwarp();
+            knn8_group(m, q_pts, limit, body_frame, sP, max_sq_dist, out, s_left[warp], &s_nleft[warp], g, lane, s_wl8[warp], 4, list);
+            __syncwarp();
+            const int nl = min(s_nleft[warp], 4);
+            for (int u = 0; u < nl; u++) {
+                knn_warp_query(m, q_pts, s_left[warp][u], body_frame, sP, max_sq_dist, out, s_cand[warp], s_cid[warp], s_wl[warp], s_bestw[warp], &s_nb[warp], lane);
+                __syncwarp();
+            }
+        }
+        return;
+    }
+    for (int w = blockIdx.x * kKnnWarps + warp; w < limit; w += total_warps) {  // warp-uniform; no block-level barrier
+        const int qi = list ? list[w] : w;
+        knn_warp_query(m, q_pts, qi, body_frame, sP, max_sq_dist, out, s_cand[warp], s_cid[warp], s_wl[warp], s_bestw[warp], &s_nb[warp], lane);
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------ exact fallback for unresolved queries

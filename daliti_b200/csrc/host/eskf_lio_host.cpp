@@ -1019,7 +1019,7 @@ int LaserMapping::process_scan(const void *pts48, int n, double lidar_beg_time, 
         if (!EKF_stop_flg && (cfg.dev.shard_count <= 1 || reduce_fn || peers)) {
             double pose[24];
             state.pose24(pose);
-            if (cfg.async_insert && cfg.dev.shard_count <= 1) {
+            if (cfg.async_insert && (cfg.dev.shard_count <= 1 || peers)) {
                 // off the critical path: the insert kernels run on their own stream while this call returns and the next
                 // scan's deskew / VoxelGrid are enqueued; the counts are adopted by dlt_lio_collect_insert or the next scan
                 LM_CK(dlt_map_incremental_async(dev_, pose, flg_EKF_inited ? 1 : 0));

@@ -240,7 +240,8 @@ int dlt_map_incremental(dlt_handle h, const double *pose24, int flg_EKF_inited, 
  * now and the call returns at once.  Every later call that reads or changes the map (the next match pass included) is
  * ordered behind them on the device; the next VoxelGrid only behind the classification pass that still reads the
  * downsampled scan.  dlt_map_incremental_collect waits on the host and reports the add counts and a map overflow.
- * Falls back to the synchronous form on a sharded map or when unresolved queries need the exact-neighbour fallback. */
+ * Falls back to the synchronous form on a sharded map WITHOUT attached peers (the reduce callback runs on the caller's
+ * stream) or when unresolved queries need the exact-neighbour fallback.                                             */
 int dlt_map_incremental_async(dlt_handle h, const double *pose24, int flg_EKF_inited);
 int dlt_map_incremental_collect(dlt_handle h, int *n_add_downsample, int *n_add_raw);
 /* Sharded map (shard_count > 1): the rank that owns a query point decides whether it is added (it holds the

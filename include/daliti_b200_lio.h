@@ -43,8 +43,9 @@ typedef struct dlt_lio_config {
     int async_insert;        /* 1 (default): map_incremental (:582-630, 1164-1168) runs off the critical path, on its own
                                 stream behind the last evaluation of the measurement model: dlt_lio_process_scan returns
                                 once the pose is final, with added / n_added_* = -1; the counts (and an overflow of the
-                                map) are reported by dlt_lio_collect_insert or picked up by the next scan.  Unsharded maps
-                                only; 0 = wait for the insert inside the call, as the reference does.                  */
+                                map) are reported by dlt_lio_collect_insert or picked up by the next scan.  Unsharded maps and
+                                sharded maps with attached peers; 0 = wait for the insert inside the call, as the
+                                reference does.                                                                        */
 } dlt_lio_config;
 
 /* State left behind by tis_cbk / tn_cbk (laserMapping.cpp:471-498): g_tis_odom_delta and

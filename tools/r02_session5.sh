@@ -1,0 +1,35 @@
+#!/usr/bin/env bash
+# Round-2 single-GPU session 4: reuse pass handing failures to k_knn, per-group visit tags, native multi-sequence driver (C5).
+set -u
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+T=${TAG:-s5}
+echo "== 1. GPU test-suite"
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest_gpu.log
+tail -4 gpurun_out/${T}_pytest_gpu.log
+echo "== 2. A/B: default | r = no reuse"
+timeout 400 python tools/ab_latency.py ${AB_MODES:-0 0r} 2>&1 | tee gpurun_out/${T}_ab_latency.log | tail -6
+echo "== 3. headline bench"
+timeout 500 python bench.py > gpurun_out/${T}_bench_c2.json 2> gpurun_out/${T}_bench_c2.err; echo "bench rc=$?"
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_c2.json"))
+    print("C2 p50", d.get("ms_p50"), "mean", d.get("ms_per_step"), "e2e p50", d["e2e"].get("ms_p50"), "serial p50", d["e2e"]["serial"].get("ms_p50"), "kernels", d["roofline"].get("kernel_ms_per_scan"), "parity ok", d.get("parity", {}).get("ok"))
+except Exception as e:
+    print("bench line unreadable:", e)
+PY
+echo "== 4. C5 through dlt_lio_replay_sequences"
+nproc
+for cfg in "16 0" "32 0" "64 0" "64 8" "128 0"; do
+  set -- $cfg
+  timeout 400 python bench.py --workload c5 --seqs-per-gpu $1 --c5-threads $2 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_c5_s$1_t$2.json 2> gpurun_out/${T}_bench_c5_s$1_t$2.err; echo "c5 s=$1 t=$2 rc=$?"
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_c5_s$1_t$2.json"))
+    print("  scans/s", round(d["scans_per_s"]), "points/s", round(d["value"] / 1e6), "M  e2e", round(d["e2e"]["value"] / 1e6), "M  threads", d["config"].get("worker_threads_per_gpu"), "launches", d["gpu_launches"])
+except Exception as e:
+    print("  unreadable:", e); print(open("gpurun_out/${T}_bench_c5_s$1_t$2.err").read()[-600:])
+PY
+done
