@@ -697,6 +697,10 @@ def main():
                        "host_cores_of_this_rank": pinned_cores,
                        "value_l2_warm_points_per_s": pts_v / (t_w * 1e-3), "ms_p50_l2_warm": float(np.median(ms_w)),
                        "host_ms_p50": float(np.median(host_v)),
+                       "ms_p90": float(np.percentile(ms_v, 90)), "ms_max": float(ms_v.max()),
+                       "slow_steps": [{"step": int(i), "ms": round(float(ms_v[i]), 4), "iters": int(outs_v[i][2]), "n_down": int(outs_v[i][1]),
+                                       "host_stage_ms": [round(1e3 * float(x), 4) for x in outs_v[i][7:13]]}
+                                      for i in np.argsort(-ms_v)[:5] if ms_v[i] > 1.5 * np.median(ms_v)],
                        "host_stage_ms_mean": dict(zip(["deskew_enqueue", "voxelgrid", "iterations", "insert_and_eigen", "delete", "total"],
                                                       (1e3 * np.mean([o[7:13] for o in outs_v], axis=0)).round(4).tolist())),
                        "git": git_head()},

@@ -928,8 +928,10 @@ static int enqueue_downsample(dlt_handle h) {
     // k_vox_final of an earlier downsample of this very scan reset the bounding box: recompute it from the undistorted points
     if (h->sc_clean) DLT_LAUNCH(k_scan_bbox, G, B, h->stream, (const float4 *)h->d_undist, n, h->d_sc);
     DLT_LAUNCH(k_vox_mark, G, B, h->stream, (const float4 *)h->d_undist, n, h->cfg.ds_scan, h->d_sc, h->d_bitmap, h->bitmap_bits, h->d_vidx);
-    DLT_LAUNCH(k_vox_scan1, h->n_scan_blocks, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, h->d_sc, h->d_wprefix, h->d_blksum, h->d_blkoff,
-               h->d_ticket + 1);
+    {
+        const int gs = h->n_scan_blocks < 2 * h->n_sm ? h->n_scan_blocks : 2 * h->n_sm;  // the kernel strides over the chunks in use
+        DLT_LAUNCH(k_vox_scan1, gs, kScanBlock, h->stream, (const unsigned *)h->d_bitmap, h->d_sc, h->d_wprefix, h->d_blksum, h->d_blkoff, h->d_ticket + 1);
+    }
     DLT_LAUNCH(k_vox_accum, G, B, h->stream, (const float4 *)h->d_undist, n, (const ScanScalars *)h->d_sc, (const unsigned *)h->d_bitmap,
                (const unsigned *)h->d_wprefix, (const unsigned *)h->d_blkoff, (const unsigned *)h->d_vidx, h->acc, h->d_vop);
     DLT_LAUNCH(k_vox_final, G, B, h->stream, h->d_sc, h->acc, h->d_bitmap, (const float4 *)h->d_undist, h->d_down, n);

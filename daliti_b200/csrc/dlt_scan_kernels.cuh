@@ -315,45 +315,49 @@ __global__ void __launch_bounds__(kScanBlock)
     __shared__ unsigned warp_tot[kScanBlock / 32];
     __shared__ int s_last;
     const int n_words = sc->n_words;
-    const int w0 = blockIdx.x * kScanWordsPerBlock + threadIdx.x * 4;
     const int n_blk = (n_words + kScanWordsPerBlock - 1) / kScanWordsPerBlock;
     if (n_blk == 0) {  // nothing marked (status != 0): n_down = 0 / pass-through is decided downstream
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->n_down = 0;
         return;
     }
-    if (blockIdx.x >= n_blk) return;  // block-uniform
-    unsigned c[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) c[k] = (w0 + k < n_words) ? (unsigned)__popc(bitmap[w0 + k]) : 0u;
-    unsigned mine = c[0] + c[1] + c[2] + c[3];
-    unsigned incl = mine;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the grid is a fixed two blocks per SM (the bitmap's size is only known on the device): every block strides over the
+    // 1024-word chunks of the part of the bitmap that this scan's bounding box covers
+    for (int chunk = blockIdx.x; chunk < n_blk; chunk += gridDim.x) {  // block-uniform
+        const int w0 = chunk * kScanWordsPerBlock + threadIdx.x * 4;
+        unsigned c[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    unsigned woff = 0, total = 0;
+        for (int k = 0; k < 4; k++) c[k] = (w0 + k < n_words) ? (unsigned)__popc(bitmap[w0 + k]) : 0u;
+        unsigned mine = c[0] + c[1] + c[2] + c[3];
+        unsigned incl = mine;
 #pragma unroll
-    for (int k = 0; k < kScanBlock / 32; k++) {
-        unsigned t = warp_tot[k];
-        if (k < warp) woff += t;
-        total += t;
-    }
-    unsigned excl = woff + incl - mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();  // (warp_tot of the previous chunk has been read)
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned woff = 0, total = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (w0 + k < n_words) wprefix[w0 + k] = excl;
-        excl += c[k];
+        for (int k = 0; k < kScanBlock / 32; k++) {
+            unsigned t = warp_tot[k];
+            if (k < warp) woff += t;
+            total += t;
+        }
+        unsigned excl = woff + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (w0 + k < n_words) wprefix[w0 + k] = excl;
+            excl += c[k];
+        }
+        if (threadIdx.x == 0) blksum[chunk] = total;
     }
-    if (threadIdx.x == 0) blksum[blockIdx.x] = total;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(ticket, 1u);
-        s_last = (t == (unsigned)n_blk - 1u) ? 1 : 0;
+        s_last = (t == gridDim.x - 1u) ? 1 : 0;
     }
     __syncthreads();
     if (!s_last) return;
