@@ -750,6 +750,7 @@ def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
                                shard_tile_shift=5), featptsThreshold=30, device_loop=args.device_loop,
                       cube_len=1.0e6)  # the local-map cube must cover the whole tiled area: no lasermap_fov_segment deletes
     stream = torch.cuda.Stream(device=local_rank)
+    lm.collect_after_scan = False  # the call as the library delivers it (async_insert)
     lm.device.set_stream(stream.cuda_stream)
     s0, mean_acc, last_imu = initial_state(seq)
     lm.force_imu_ready(mean_acc, last_imu)

@@ -18,7 +18,7 @@ def main():
     import bench
     from daliti_b200.lio import LaserMapping
 
-    n, warm = 45, 5
+    n, warm = int(os.environ.get("AB_SCANS", "45")), 5
     work = bench.build_workload(0, n, "c2")
     seq, scans = work["seq"], work["scans"]
     devs = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p, _, _ in scans]
@@ -46,7 +46,7 @@ def main():
             lm.force_imu_ready(mean_acc, last_imu)
             lm.set_state(s0)
             lm.device.map_build(work["map_pts"])
-            ev, host = [], []
+            ev, host, stages = [], [], []
             l0 = lm.device.launch_count()
             with torch.cuda.stream(stream):
                 for k in range(n):
@@ -56,8 +56,9 @@ def main():
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record(stream)
                     t0 = time.perf_counter()
-                    lm.process_scan_dev(devs[k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
+                    o = lm.process_scan_dev(devs[k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
                     host.append(1e3 * (time.perf_counter() - t0))
+                    stages.append((o.n_iters, o.n_down, [round(1e3 * x, 3) for x in (o.t_deskew, o.t_voxel, o.t_iterate, o.t_insert, o.t_delete, o.t_total)]))
                     b.record(stream)
                     ev.append((a, b))
                 torch.cuda.synchronize()
@@ -65,6 +66,9 @@ def main():
             st = lm.get_state()
             print(f"device_loop={mtag}: p50 {np.median(ms):.4f} ms  mean {ms.mean():.4f}  host p50 {np.median(host[warm:]):.4f} ms   launches/scan "
                   f"{(lm.device.launch_count() - l0) / n:.1f}  final pos {st[9]:.6f} {st[10]:.6f} {st[11]:.6f}", flush=True)
+            slow = [int(i) + warm for i in np.argsort(-ms)[:3] if ms[i] > 1.3 * np.median(ms)]
+            for i in slow:
+                print(f"    slow scan {i}: {ms[i - warm]:.4f} ms  host {host[i]:.4f} ms  iters/n_down/host stages {stages[i]}", flush=True)
             lm.close()
 
 
