@@ -239,13 +239,19 @@ static int map_reset(dlt_handle h) {
 static int launch_knn(dlt_handle h, const float4 *d_q, int n, int n_grid, int body_frame, const Pose &P, LoopArgs la, bool reuse = false) {
     {
         ProfScope prof8(h, 7);  // the dominant kernel on its own (group 0 spans the whole match pass)
-        // reuse: one query per thread first (most neighbour sets of a rematch pass are proven unchanged), the rest in groups of 8 lanes
-        int g8 = reuse ? div_up(n_grid, kKnn8Block) : div_up(n_grid, kKnn8Block / 8);
         const int wave8 = h->n_sm * DLT_KNN8_MINBLOCKS;  // what is resident at once: the kernel strides, so a partial second wave never forms
-        if (g8 > wave8) g8 = wave8;
-        if (g8 < 1) g8 = 1;
-        DLT_LAUNCH(k_knn8, g8, kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la,
-                   reuse ? 1 : 0, h->d_counters + 12);
+        if (reuse) {  // one query per thread: most neighbour sets of a rematch pass are proven unchanged, the rest goes to k_knn
+            int gr = div_up(n_grid, kReuseBlock);
+            if (gr > 8 * h->n_sm) gr = 8 * h->n_sm;
+            if (gr < 1) gr = 1;
+            DLT_LAUNCH(k_knn_reuse, gr, kReuseBlock, h->stream, h->map, d_q, n, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la,
+                       h->d_counters + 12);
+        } else {
+            int g8 = div_up(n_grid, kKnn8Block / 8);
+            if (g8 > wave8) g8 = wave8;
+            if (g8 < 1) g8 = 1;
+            DLT_LAUNCH(k_knn8, g8, kKnn8Block, h->stream, h->map, d_q, n, body_frame, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la);
+        }
     }
     int grid = div_up(n_grid, kKnnWarps);
     const int cap_grid = h->n_sm * 8;
@@ -1295,7 +1301,7 @@ static bool build_loop_graph(dlt_handle h, const MeasureBufs &mb) {
     const int g8 = 24 * h->n_sm, gk = 8 * h->n_sm, gr = div_up(h->cap, kResidBlock);
     if (cudaStreamBeginCaptureToGraph(cs, ibody, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail();
     capturing = true;
-    k_knn8<<<g8, kKnn8Block, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la, 0, (int *)nullptr);
+    k_knn8<<<g8, kKnn8Block, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, h->d_unres, h->d_counters + 8, la);
     k_knn<<<gk, kKnnWarps * 32, 0, cs>>>(h->map, (const float4 *)h->d_down, 0, 1, P, h->cfg.max_sq_dist, h->knn, (const int *)h->d_unres,
                                            (const int *)(h->d_counters + 8), la, 0);
     cudaGraph_t out = nullptr;

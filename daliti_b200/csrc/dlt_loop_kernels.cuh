@@ -56,13 +56,18 @@ struct LoopK {  // everything a loop kernel needs, by value
 
 struct LoopSmem {
     Pose P;
-    float4 cand[kKnnWarps][kCandSlots];
-    int cid[kKnnWarps][kCandSlots];
-    int wl[kKnnWarps][kWlMax];
-    Cand bestw[kKnnWarps][kK];
-    int nb[kKnnWarps];
+    // the two halves of a match pass run one after the other (a block barrier in between): their scratch shares the space
+    union {
+        struct {  // knn_warp_query
+            float4 cand[kKnnWarps][kCandSlots];
+            int cid[kKnnWarps][kCandSlots];
+            int wl[kKnnWarps][kWlMax];
+            Cand bestw[kKnnWarps][kK];
+            int nb[kKnnWarps];
+        };
+        int wl8[kLoopBlock / 32][kKnn8WlInts];  // knn8_group: bucket index of every visit
+    };
     int unres[kLoopChunkMax];
-    int wl8[kLoopBlock / 32][kKnn8WlInts];  // knn8_group: bucket index of every visit
     int n_unres;
     int last;
     double part[kLoopBlock / 32][NormalEq<true>::NR];

@@ -91,7 +91,7 @@ constexpr unsigned char kFlagNeedNN = 8;      // unresolved AND nothing at all w
 #endif
 constexpr int kKnnWarps = 4;
 constexpr int kCandMax = 128;
-constexpr int kWlMax = 96;
+constexpr int kWlMax = 256;  // buckets of one ring batch (dense, raw-built maps: ten and more buckets per cell)
 
 DLT_D Cand cand_inf() {
     Cand c;
@@ -453,15 +453,15 @@ DLT_D void knn_warp_query(const MapView &m, const float4 *__restrict__ q_pts, in
 //
 // Selection works on 32-bit keys.  d2 >= 0, so its bit pattern orders like the float; the low 9 bits of the pattern are
 // replaced by a tag that names the candidate inside the group: (visit << 3) | lane-in-group, `visit` = which of the
-// group's (at most 64) bucket fetches brought it in.  Keys are unique, a key identifies its point (the bucket index of
-// every visit is kept in shared memory) and sorting keys sorts by d2 truncated to 14 mantissa bits.  Every lane keeps the
+// group's (at most 128) bucket fetches brought it in.  Keys are unique, a key identifies its point (the bucket index of
+// every visit is kept in shared memory) and sorting keys sorts by d2 truncated to 13 mantissa bits.  Every lane keeps the
 // five smallest keys it saw with a branch-free min / max insertion plus the smallest key it ever dropped; the 8 sorted
 // lists merge with five 8-lane mins.  Whenever the SIX best keys have pairwise different truncated distances the five
 // winners are exactly the five smallest d2 in exact order (anything else has a truncated distance >= the sixth's, hence
 // a larger d2 than the fifth); their coordinates are re-read from the (L1-hot) buckets and d2 is recomputed -- the same
-// expression on the same inputs, so the same bits.  Otherwise (two of the six agree to 14 bits: about one query in a
+// expression on the same inputs, so the same bits.  Otherwise (two of the six agree to 13 bits: a few queries in a
 // thousand; this includes every exact d2 tie, which the stated order (d2, x, y, z, id) has to break), or when the 3^3
-// block cannot prove the result exact, or after more than 64 bucket fetches, the query goes to `unres_list` for the
+// block cannot prove the result exact, or after more than 128 bucket fetches, the query goes to `unres_list` for the
 // warp-per-query kernel above, which searches from scratch with exact comparisons.
 #ifndef DLT_KNN8_BLOCK
 #define DLT_KNN8_BLOCK 256
@@ -471,8 +471,8 @@ constexpr int kKnn8Block = DLT_KNN8_BLOCK;
 #define DLT_KNN8_MINBLOCKS 6
 #endif
 constexpr unsigned kKey32Inf = 0xFFFFFFFFu;
-constexpr int kKnn8TagBits = 9;                       // 6 bits visit + 3 bits lane-in-group
-constexpr int kKnn8Visits = 64;                       // bucket fetches per group that a tag can name
+constexpr int kKnn8TagBits = 10;                      // 7 bits visit + 3 bits lane-in-group
+constexpr int kKnn8Visits = 128;                      // bucket fetches per group that a tag can name (896 map points in the 3^3 block)
 constexpr unsigned kKey32Finite = 0x7F800000u >> kKnn8TagBits;  // truncated pattern of +inf
 constexpr int kKnn8WlInts = 4 * kKnn8Visits;          // shared-memory ints per warp (bucket index of every visit)
 
@@ -747,7 +747,7 @@ DLT_D bool knn_try_reuse(const MapView &m, const float4 *__restrict__ down, int 
 // Also zeroes far_count for the warp-per-query pass that follows in stream order.
 __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
     k_knn8(MapView m, const float4 *__restrict__ q_pts, int n, int body_frame, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
-           int *__restrict__ unres_count, LoopArgs la, int reuse, int *__restrict__ reuse_stats) {
+           int *__restrict__ unres_count, LoopArgs la) {
     DLT_PDL_WAIT();
     __shared__ Pose sP;
     __shared__ int s_wl[kKnn8Block / 32][kKnn8WlInts];
@@ -759,33 +759,47 @@ __global__ void __launch_bounds__(kKnn8Block, DLT_KNN8_MINBLOCKS)
         out.nn_count[1] = 0;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (reuse) {  // block-uniform.  One query per thread: prove the old set still right; what cannot be proven is handed to the
-                  // warp-per-query kernel, which searches it again from scratch (typically one query in ten)
-        int seen = 0, redo = 0;
-        for (int i = blockIdx.x * kKnn8Block + threadIdx.x; i < n; i += gridDim.x * kKnn8Block) {
-            seen++;
-            if (!knn_try_reuse(m, q_pts, i, sP, max_sq_dist, out)) {
-                redo++;
-                out.d6lb[i] = 0.f;
-                unres_list[atomicAdd(unres_count, 1)] = i;
-            }
-        }
-        if (reuse_stats) {  // instrumentation: queries seen / searched again by the reuse passes
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                seen += __shfl_xor_sync(0xffffffffu, seen, o);
-                redo += __shfl_xor_sync(0xffffffffu, redo, o);
-            }
-            if (lane == 0) {
-                atomicAdd(reuse_stats, seen);
-                atomicAdd(reuse_stats + 1, redo);
-            }
-        }
-        return;
-    }
     const int stride = gridDim.x * (kKnn8Block / 32) * 4;
     for (int q0 = (blockIdx.x * (kKnn8Block / 32) + warp) * 4; q0 < n; q0 += stride)  // warp-uniform
         knn8_group(m, q_pts, n, body_frame, sP, max_sq_dist, out, unres_list, unres_count, q0, lane, s_wl[warp]);
+}
+
+// First kernel of a LATER match pass of the same scan (knn_try_reuse): one query per thread; what cannot be proven unchanged is
+// handed to the warp-per-query kernel (bulk mode), which searches it again from scratch -- typically one query in ten.
+// Also zeroes far_count for that kernel, as k_knn8 does.
+constexpr int kReuseBlock = 128;
+__global__ void __launch_bounds__(kReuseBlock)
+    k_knn_reuse(MapView m, const float4 *__restrict__ q_pts, int n, Pose P, float max_sq_dist, KnnOut out, int *__restrict__ unres_list,
+                int *__restrict__ unres_count, LoopArgs la, int *__restrict__ reuse_stats) {
+    DLT_PDL_WAIT();
+    __shared__ Pose sP;
+    int is_match = -1;
+    if (!loop_resolve(la, P, &sP, n, &is_match)) return;  // block-uniform
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *out.far_count = 0;
+        out.nn_count[0] = 0;
+        out.nn_count[1] = 0;
+    }
+    int seen = 0, redo = 0;
+    for (int i = blockIdx.x * kReuseBlock + threadIdx.x; i < n; i += gridDim.x * kReuseBlock) {
+        seen++;
+        if (!knn_try_reuse(m, q_pts, i, sP, max_sq_dist, out)) {
+            redo++;
+            out.d6lb[i] = 0.f;
+            unres_list[atomicAdd(unres_count, 1)] = i;
+        }
+    }
+    if (reuse_stats) {  // instrumentation: queries seen / searched again by the reuse passes
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            seen += __shfl_xor_sync(0xffffffffu, seen, o);
+            redo += __shfl_xor_sync(0xffffffffu, redo, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(reuse_stats, seen);
+            atomicAdd(reuse_stats + 1, redo);
+        }
+    }
 }
 
 // Warp-per-query kernel.  list == nullptr: queries 0..n-1, one per warp.  Otherwise the queries list[0..*count)
