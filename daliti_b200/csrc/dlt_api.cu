@@ -48,6 +48,9 @@ struct dlt_handle_s {
     cudaStream_t aux_stream = nullptr;
     rt::Event ev_fork, ev_join;
     bool have_aux = false, eig_pending = false;
+    bool eig_zc = false;                 // the last k_eigen6 publishes into pinned host memory (flag at h_ints + 34)
+    unsigned long long eig_seq = 0;
+    cudaStream_t eig_stream = nullptr;
     // map_incremental off the critical path (dlt_map_incremental_async): its kernels run on their own stream behind the last
     // evaluation of the measurement model; the main stream only waits for them where the next scan first touches what they
     // touch (ev_classified: the downsampled scan may be overwritten; ev_inserted: the map and the neighbour buffers)
@@ -1150,9 +1153,9 @@ int dlt_frontend_sample(dlt_handle h, const void *cloud_data, int n_points, cons
     DLT_LAUNCH(k_fe_scatter, G, kFeBlock, h->stream, n_cand, (const float4 *)h->d_fe_tmp, (const unsigned char *)h->d_fe_keep,
                (const unsigned *)h->d_fe_pos, (const unsigned *)h->d_fe_blkoff, h->d_raw, h->cap);
     DLT_RT(h, rt::check_launch());
-    DLT_RT(h, rt::d2h(h->h_ints + 32, h->d_counters + 11, sizeof(int), h->stream));
+    DLT_RT(h, rt::d2h(h->h_ints + 56, h->d_counters + 11, sizeof(int), h->stream));  // (a slot of its own: [32..35] hold the zero-copy flags)
     DLT_RT(h, rt::sync(h->stream));
-    *n_out = h->h_ints[32];
+    *n_out = h->h_ints[56];
     return DLT_OK;
 }
 
@@ -1483,6 +1486,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
         DLT_RT(h, rt::d2h(h->h_result + kEigOffset, h->d_result + kEigOffset, 42 * sizeof(double), h->stream));
         h->eig_valid = true;
         h->eig_pending = false;
+        h->eig_zc = false;
     } else if (int re = dlt_degeneracy_begin(h)) {
         return re;
     }
@@ -1708,12 +1712,19 @@ int dlt_degeneracy_begin(dlt_handle h) {
             DLT_RT(h, rt::stream_wait(h->aux_stream, h->ev_fork));
             s = h->aux_stream;
         }
+        // zero-copy (as for the result block of dlt_measure): the kernel stores the 42 doubles straight into pinned host memory and
+        // then this launch's number into a host flag dlt_degeneracy spins on -- no device->host copy, no stream synchronisation
+        const bool zc = h->zerocopy && !h->prof_on;
+        if (zc) ++h->eig_seq;
         {
             ProfScope profe(h, 8, s);
-            DLT_LAUNCH(k_eigen6, 1, 32, s, (const double *)h->d_result, h->d_result + kEigOffset);
+            DLT_LAUNCH(k_eigen6, 1, 32, s, (const double *)h->d_result, h->d_result + kEigOffset, zc ? h->h_result + kEigOffset : (double *)nullptr,
+                       zc ? reinterpret_cast<unsigned long long *>(h->h_ints + 34) : (unsigned long long *)nullptr, zc ? h->eig_seq : 0ull);
         }
         DLT_RT(h, rt::check_launch());
-        DLT_RT(h, rt::d2h(h->h_result + kEigOffset, h->d_result + kEigOffset, 42 * sizeof(double), s));
+        if (!zc) DLT_RT(h, rt::d2h(h->h_result + kEigOffset, h->d_result + kEigOffset, 42 * sizeof(double), s));
+        h->eig_zc = zc;
+        h->eig_stream = s;
         if (h->have_aux) {
             DLT_RT(h, rt::event_record(h->ev_join, h->aux_stream));
             h->eig_pending = true;
@@ -1727,7 +1738,22 @@ int dlt_degeneracy(dlt_handle h, double *eigvals6, double *eigvecs36) {
     if (!h || !eigvals6 || !eigvecs36) return DLT_E_INVALID;
     int rc = dlt_degeneracy_begin(h);
     if (rc) return rc;
-    if (h->eig_pending) {
+    if (h->eig_zc) {
+        const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(h->h_ints + 34);
+        for (unsigned spins = 1; *flag != h->eig_seq; spins++) {
+            if (rt::t_wait_hook) rt::t_wait_hook(rt::t_wait_ctx);
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0xFFFu) == 0u) {  // a kernel that died never raises the flag
+                const int q = rt::stream_query(h->eig_stream);
+                if (q == 2) DLT_FAIL(h, DLT_E_CUDA, std::string("stream error while waiting for the eigen block: ") + rt::last_error());
+                if (q == 0 && *flag != h->eig_seq) DLT_FAIL(h, DLT_E_CUDA, "the stream drained without the eigen flag");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        // (ev_join stays pending: the main stream still orders its next write of d_result behind the kernel, eig_join)
+    } else if (h->eig_pending) {
         DLT_RT(h, rt::sync(h->aux_stream));
         h->eig_pending = false;
     } else {

@@ -819,9 +819,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32, DLT_KNN_MINBLOCKS)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_warps = gridDim.x * kKnnWarps;
     const int limit = list ? *count : n;
-    if (bulk && list) {  // block-uniform.  The list holds ordinary queries (a rematch pass could not prove their old neighbour
-                         // sets): 8 lanes per query first, a warp per query only for what that leaves -- efficient however long
-                         // the list is
+    if (bulk && list && limit > total_warps) {  // block-uniform.  The list holds ordinary queries (a rematch pass could not prove
+                         // their old neighbour sets) and is longer than one round of a warp per query: 8 lanes per query first, a
+                         // warp per query only for what that leaves -- efficient however long the list is.  (A list that fits one
+                         // round is finished sooner by the plain loop below: one search latency instead of two.)
         __shared__ int s_left[kKnnWarps][4];
         __shared__ int s_nleft[kKnnWarps];
         __shared__ int s_wl8[kKnnWarps][kKnn8WlInts];
@@ -1851,8 +1852,18 @@ DLT_D void eigen6_warp(const double *__restrict__ result, double *__restrict__ e
         }
     }
 }
-__global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result, double *__restrict__ eig_out) {
-    DLT_PDL_WAIT(); eigen6_warp(result, eig_out, threadIdx.x); }
+__global__ void __launch_bounds__(32) k_eigen6(const double *__restrict__ result, double *__restrict__ eig_out, double *zc_out, unsigned long long *zc_flag,
+                                               unsigned long long zc_seq) {
+    DLT_PDL_WAIT();
+    eigen6_warp(result, eig_out, threadIdx.x);
+    if (zc_out) {  // publish into pinned host memory, then raise the flag dlt_degeneracy spins on
+        __syncwarp();
+        for (int k = threadIdx.x; k < 42; k += 32) zc_out[k] = eig_out[k];
+        __threadfence_system();
+        __syncwarp();
+        if (threadIdx.x == 0) *(volatile unsigned long long *)zc_flag = zc_seq;
+    }
+}
 
 // ------------------------------------------------------------------ map_incremental classification
 // laserMapping.cpp:582-630: decide per downsampled point whether it is added raw

@@ -12,8 +12,10 @@ if [ "$N" = "2" ]; then
 fi
 echo "== default bench at N=$N"
 timeout 600 $TR --master-port 29701 bench.py --gpus $N --steps 40 --warmup 5 > gpurun_out/g${N}_bench_default.json 2> gpurun_out/g${N}_bench_default.err; echo "rc=$?"
+if [ "${SKIP_C4_ALONE:-0}" != "1" ]; then
 echo "== c4 alone, peer exchange, host loop"
 timeout 400 $TR --master-port 29711 bench.py --gpus $N --workload c4 --steps 60 --warmup 5 > gpurun_out/g${N}_c4_peer.json 2> gpurun_out/g${N}_c4_peer.err; echo "rc=$?"
+fi
 echo "== c5, 64 sequences over $N GPUs"
 timeout 500 $TR --master-port 29721 bench.py --gpus $N --workload c5 --seqs-per-gpu $((64 / N)) --steps 30 --warmup 3 > gpurun_out/g${N}_c5.json 2> gpurun_out/g${N}_c5.err; echo "rc=$?"
 python - <<PY
