@@ -96,6 +96,7 @@ struct dlt_handle_s {
     unsigned *d_bitmap = nullptr, *d_wprefix = nullptr, *d_blksum = nullptr, *d_blkoff = nullptr, *d_vidx = nullptr;
     long long bitmap_bits = 0;
     int n_scan_blocks = 0;
+    size_t n_pool_runs = 0;  // runs of kPoolRun buckets (MapView::pool_box_*)
     VoxAcc acc;
     int *d_vop = nullptr;
     // measure
@@ -231,6 +232,8 @@ static int map_reset(dlt_handle h) {
     h->map_dead = false;
     DLT_RT(h, rt::fill(h->map.table, 0xFF, h->table_cap * sizeof(Slot), h->stream));
     DLT_RT(h, rt::fill(h->d_counters, 0, 16 * sizeof(int), h->stream));
+    DLT_RT(h, rt::fill(h->map.pool_box_min, 0x7F, 3 * h->n_pool_runs * sizeof(int), h->stream));  // min > max: unused run
+    DLT_RT(h, rt::fill(h->map.pool_box_max, 0x80, 3 * h->n_pool_runs * sizeof(int), h->stream));
     h->reuse_seen_last = h->reuse_redo_last = 0;
     return DLT_OK;
 }
@@ -592,6 +595,8 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
     h->scratch.mask = (unsigned)(sc_cap - 1);
     h->scratch_cap = sc_cap;
 
+    h->n_pool_runs = bucket_cap / kPoolRun + 1;
+    ok = ok && !dalloc(h, &h->map.pool_box_min, 3 * h->n_pool_runs) && !dalloc(h, &h->map.pool_box_max, 3 * h->n_pool_runs);
     ok = ok && !dalloc(h, &h->map.table, tcap) && !dalloc(h, &h->map.buckets, bucket_cap) && !dalloc(h, &h->d_counters, 16) && !dalloc(h, &h->d_unres, cap) &&
          !dalloc(h, &h->d_raw, cap * kRawStride4) && !dalloc(h, &h->d_undist, cap) && !dalloc(h, &h->d_down, cap) &&
          !dalloc(h, &h->d_poses, kMaxImuPoses) && !dalloc(h, &h->d_sc, 1) && !dalloc(h, &h->d_bitmap, words) &&
@@ -1494,6 +1499,8 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
         IekfDev *ctl = h->d_iekf;
         if (far_q) {
             ProfScope prof(h, 5);
+            DLT_LAUNCH(k_nn1_seed, h->n_sm, kSeedBlock, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
+                       (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
             DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 2 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
         }
@@ -1805,6 +1812,8 @@ static int map_incremental_impl(dlt_handle h, const double *pose24, int flg_EKF_
             if (rc) return rc;
         } else if (h->h_ints[9] > 0) {
             ProfScope prof(h, 5);
+            DLT_LAUNCH(k_nn1_seed, h->n_sm, kSeedBlock, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
+                       (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, (int *)nullptr);
             DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 2 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, (int *)nullptr);
         }

@@ -65,6 +65,10 @@ struct MapView {
     int *n_buckets;  // device counter: buckets allocated so far
     int *n_live;     // device counter: live points
     int *error;      // device sticky error flag (1 = bucket pool exhausted, 2 = table full)
+    // per run of 64 consecutive buckets of the pool: the box of the search cells those buckets belong to (cell coordinates,
+    // min[3] and max[3] arrays; an unused run has min > max).  Buckets are allocated in the order cells are first touched, so the
+    // runs are spatially compact; the nearest-point search of far queries (k_nn1) skips runs whose box is too far away.
+    int *pool_box_min, *pool_box_max;
     float ds;        // downsample voxel edge (filter_size_map)
     int cell_shift;  // cell edge = ds * 2^cell_shift
     // spatial sharding across GPUs (shard_count == 1: off)
@@ -82,6 +86,12 @@ DLT_HD unsigned long long pack_key(int cx, int cy, int cz) {
     return ((unsigned long long)((unsigned)cx & 0x1FFFFFu) << 42) | ((unsigned long long)((unsigned)cy & 0x1FFFFFu) << 21) |
            (unsigned long long)((unsigned)cz & 0x1FFFFFu);
 }
+DLT_HD void unpack_key(unsigned long long k, int &cx, int &cy, int &cz) {  // inverse of pack_key (21-bit two's complement fields)
+    cx = ((int)((unsigned)(k >> 42) << 11)) >> 11;
+    cy = ((int)((unsigned)(k >> 21) << 11)) >> 11;
+    cz = ((int)((unsigned)k << 11)) >> 11;
+}
+constexpr int kPoolRun = 64;  // buckets per pool run (k_nn1 streams the pool in tiles of this size)
 DLT_HD unsigned hash_key(unsigned long long k) {  // murmur3 finaliser
     k ^= k >> 33;
     k *= 0xff51afd7ed558ccdull;

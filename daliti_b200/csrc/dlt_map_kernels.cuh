@@ -47,6 +47,17 @@ DLT_D void bucket_init(Bucket *B, unsigned long long key) {
     B->next = -1;
     B->mask = 0u;
 }
+// a bucket of cell `key` was allocated at pool index b: widen the box of its pool run
+DLT_D void pool_box_touch(const MapView &m, int b, unsigned long long key) {
+    int c[3];
+    unpack_key(key, c[0], c[1], c[2]);
+    const int r = b / kPoolRun;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        atomicMin(&m.pool_box_min[3 * r + a], c[a]);
+        atomicMax(&m.pool_box_max[3 * r + a], c[a]);
+    }
+}
 
 // Find-or-create the table slot of a cell; returns the slot index (-1: table full).
 // The head bucket index written by the creator is only read by LATER kernels.
@@ -61,6 +72,7 @@ DLT_D int map_claim(const MapView &m, unsigned long long key) {
                 b = -1;
             } else {
                 bucket_init(&m.buckets[b], key);
+                pool_box_touch(m, b, key);
             }
             m.table[h].bucket = b;
             return (int)h;
@@ -95,6 +107,7 @@ DLT_D bool map_append(const MapView &m, int b, float4 p) {
                 return false;
             }
             bucket_init(&m.buckets[fresh], B->key);
+            pool_box_touch(m, fresh, B->key);
             __threadfence();
             int prev = atomicCAS(&B->next, -1, fresh);
             nb = (prev == -1) ? fresh : prev;  // a lost race leaves `fresh` empty and unlinked

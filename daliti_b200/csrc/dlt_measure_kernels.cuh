@@ -936,46 +936,149 @@ __global__ void k_far_merge(const int *__restrict__ far_list, int far_off, int n
 }
 
 // ------------------------------------------------------------------ nearest map point of the kFlagNeedNN queries
-// Brute force, k = 1: lane = query, the bucket pool is split into gridDim.y slices that are streamed through shared
-// memory, slices combine with a 64-bit atomicMin on (d2 bits << 32 | id).  Sized to fill the machine (the full exact
-// fallback above keeps five candidates with coordinates per lane and runs at a fraction of this rate).
+// Exact, k = 1, over the whole bucket pool -- but not all of it is looked at.  The pool is cut into runs of kPoolRun
+// consecutive buckets whose cell boxes are kept up to date where buckets are allocated (pool_box_touch; allocation order is
+// first-touch order, so a run is spatially compact).
+//   k_nn1_seed  one live sample point per run against every query: the smallest of those distances is a TRUE upper bound
+//               of each query's nearest distance (combined with a 64-bit atomicMin on (d2 bits << 32 | id), like everything here)
+//   k_nn1       lane = query, the pool in gridDim.y slices of whole runs streamed through shared memory; a run is only staged
+//               when some query of the block could still find something nearer (or equally near, for the id tie-break) inside
+//               its box than what it already holds
+// On a map that covers the scene the far queries' nearest points lie in a handful of runs; the pass that took 0.8 ms of brute
+// force on the 2.2 M-point C2 map reads a few percent of the pool.  Same keys as the brute force by construction.
 constexpr int kNn1Block = 128;
-constexpr int kNn1Tile = 64;  // buckets per shared-memory tile
+constexpr int kNn1Tile = kPoolRun;  // buckets per shared-memory tile = one pool run
+
+DLT_D bool nn1_gate(const int *nn_count, int *gate) {
+    if (gate && *gate != 1) return false;
+    if (gate && nn_count[1] > 0) {  // a bucket chain overflowed the ring search: the host runs the full exact fallback instead
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *gate = 2;
+        return false;
+    }
+    return nn_count[0] > 0;
+}
+
+constexpr int kSeedBlock = 256;
+constexpr int kSeedBatch = 8;  // queries per block barrier
+__global__ void __launch_bounds__(kSeedBlock)
+    k_nn1_seed(MapView m, const int *__restrict__ n_buckets_ptr, const float4 *__restrict__ qw, const int *__restrict__ nn_list,
+               const int *__restrict__ nn_count, unsigned long long *__restrict__ nn_key, int *gate) {
+    DLT_PDL_WAIT();
+    __shared__ unsigned long long s_min[kSeedBatch][kSeedBlock / 32];
+    if (!nn1_gate(nn_count, gate)) return;  // block-uniform
+    const int nn = nn_count[0];
+    const int n_buckets = min(*n_buckets_ptr, m.bucket_cap);
+    const int n_runs = (n_buckets + kPoolRun - 1) / kPoolRun;
+    // the work is queries x sampled runs: with many queries every `step`-th run is sampled (any subset gives a valid bound)
+    const int step = 1 + nn / 512;
+    const int n_samp = (n_runs + step - 1) / step;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s0 = blockIdx.x * kSeedBlock; s0 < n_samp; s0 += gridDim.x * kSeedBlock) {  // block-uniform
+        // this thread's sample: the first live point of the first bucket of its run that has one (of the first four)
+        const int r = (s0 + threadIdx.x) * step;
+        float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        int sid = -1;
+        if (r < n_runs) {
+            for (int k = 0; k < 4 && sid < 0; k++) {
+                const int b = r * kPoolRun + k;
+                if (b >= n_buckets) break;
+                const unsigned msk = m.buckets[b].mask & 0x7Fu;
+                if (msk) {
+                    const int sl = __ffs((int)msk) - 1;
+                    sp = m.buckets[b].pts[sl];
+                    sid = b * 8 + 1 + sl;
+                }
+            }
+        }
+        for (int f0 = 0; f0 < nn; f0 += kSeedBatch) {  // block-uniform: every query against the block's samples, one atomic per query and block
+            unsigned long long key[kSeedBatch];
+#pragma unroll
+            for (int u = 0; u < kSeedBatch; u++) {
+                key[u] = 0xFFFFFFFFFFFFFFFFull;
+                if (f0 + u < nn && sid >= 0) {
+                    const float4 q = qw[nn_list[f0 + u]];
+                    key[u] = ((unsigned long long)__float_as_uint(calc_dist(q.x, q.y, q.z, sp.x, sp.y, sp.z)) << 32) | (unsigned)sid;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long t = __shfl_xor_sync(0xffffffffu, key[u], o);
+                    key[u] = t < key[u] ? t : key[u];
+                }
+            }
+            __syncthreads();  // (s_min of the previous batch has been read)
+            if (lane == 0) {
+#pragma unroll
+                for (int u = 0; u < kSeedBatch; u++) s_min[u][warp] = key[u];
+            }
+            __syncthreads();
+            if (threadIdx.x < kSeedBatch && f0 + (int)threadIdx.x < nn) {
+                unsigned long long best = s_min[threadIdx.x][0];
+#pragma unroll
+                for (int w = 1; w < kSeedBlock / 32; w++) best = s_min[threadIdx.x][w] < best ? s_min[threadIdx.x][w] : best;
+                if (best != 0xFFFFFFFFFFFFFFFFull) atomicMin(&nn_key[f0 + threadIdx.x], best);
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kNn1Block)
     k_nn1(MapView m, const int *__restrict__ n_buckets_ptr, const float4 *__restrict__ qw, const int *__restrict__ nn_list,
           const int *__restrict__ nn_count, unsigned long long *__restrict__ nn_key, int *gate) {
     DLT_PDL_WAIT();
     __shared__ float4 tile[kNn1Tile * 8];
-    if (gate && *gate != 1) return;
-    if (gate && nn_count[1] > 0) {  // a bucket chain overflowed the ring search: the host runs the full exact fallback instead
-        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *gate = 2;
-        return;
-    }
+    __shared__ int s_need;
+    if (!nn1_gate(nn_count, gate)) return;  // block-uniform
     const int nn = nn_count[0];
-    if (nn == 0) return;
     const int n_buckets = min(*n_buckets_ptr, m.bucket_cap);
+    const int n_runs = (n_buckets + kPoolRun - 1) / kPoolRun;
     const int n_slices = gridDim.y;
-    const int per = (n_buckets + n_slices - 1) / n_slices;
-    const int b0 = blockIdx.y * per, b1 = min(n_buckets, b0 + per);
+    const int per = (n_runs + n_slices - 1) / n_slices;  // whole runs per slice
+    const int r_lo = blockIdx.y * per, r_hi = min(n_runs, r_lo + per);
     const int groups = (nn + kNn1Block - 1) / kNn1Block;
+    const float cell_edge = m.ds * (float)(1 << m.cell_shift);
     for (int g = blockIdx.x; g < groups; g += gridDim.x) {  // block-uniform
         const int f = g * kNn1Block + threadIdx.x;
         const bool live = f < nn;
-        float qx = 0.f, qy = 0.f, qz = 0.f;
+        float qx = 0.f, qy = 0.f, qz = 0.f, slack = 0.f;
+        unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
         if (live) {
             const float4 q = qw[nn_list[f]];
             qx = q.x;
             qy = q.y;
             qz = q.z;
+            slack = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
+            best = nn_key[f];  // the seed pass's upper bound (other blocks may lower it meanwhile: any value read is valid)
         }
-        unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
-        for (int tb = b0; tb < b1; tb += kNn1Tile) {
-            const int nb = min(kNn1Tile, b1 - tb);
+        const unsigned long long best0 = best;
+        for (int r = r_lo; r < r_hi; r++) {  // block-uniform
+            // can this run hold anything at most as far as what the lane has?  (box of the cells its buckets belong to)
+            bool need = false;
+            if (live) {
+                float bd = 0.f;
+                bool empty = false;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const int cmin = m.pool_box_min[3 * r + a], cmax = m.pool_box_max[3 * r + a];
+                    if (cmin > cmax) empty = true;
+                    const float q = (a == 0) ? qx : (a == 1) ? qy : qz;
+                    const float lo = (float)cmin * cell_edge, hi = (float)(cmax + 1) * cell_edge;
+                    float gap = fmaxf(fmaxf(lo - q, q - hi), 0.f) - slack;
+                    gap = gap > 0.f ? gap : 0.f;
+                    bd = bd + gap * gap;
+                }
+                const float bestd = __uint_as_float((unsigned)(best >> 32));  // (+inf pattern or NaN pattern of all-ones: the test below then passes)
+                need = !empty && !(bd * 0.99999f > bestd);
+            }
+            __syncthreads();  // (the tile of the previous run has been consumed; s_need is free)
+            if (threadIdx.x == 0) s_need = 0;
             __syncthreads();
+            if (need) s_need = 1;
+            __syncthreads();
+            if (!s_need) continue;  // block-uniform
+            const int tb = r * kPoolRun, nb = min(kPoolRun, n_buckets - tb);
             for (int k = threadIdx.x; k < nb * 8; k += kNn1Block) tile[k] = reinterpret_cast<const float4 *>(&m.buckets[tb])[k];
             __syncthreads();
-            if (live) {
+            if (need) {
                 for (int k = 0; k < nb; k++) {
                     unsigned msk = __float_as_uint(tile[k * 8].w) & 0x7Fu;
                     while (msk) {
@@ -989,7 +1092,7 @@ __global__ void __launch_bounds__(kNn1Block)
                 }
             }
         }
-        if (live && best != 0xFFFFFFFFFFFFFFFFull) atomicMin(&nn_key[f], best);
+        if (live && best < best0) atomicMin(&nn_key[f], best);
     }
 }
 

@@ -22,11 +22,14 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
-def run_sequence(lib, oracle, seq, map_pts, n_scans, ext=False, max_pts=4096, check_map=True, read_nearest=True, **cfg_kw):
+def run_sequence(lib, oracle, seq, map_pts, n_scans, ext=False, max_pts=4096, check_map=True, read_nearest=True, pre_delete=None, **cfg_kw):
     kind = MAP_REF if oracle.ref_ok else MAP_PORT
     lio = helpers.start_oracle_lio(oracle, seq, map_pts, kind, extrinsic_est_en=1 if ext else 0, **cfg_kw)
     dm = ScanToMap(lib, max_scan_points=max_pts, max_map_points=max(4 * len(map_pts), 16384), extrinsic_est_en=1 if ext else 0)
     dm.map_build(map_pts)
+    if pre_delete is not None:  # boxes removed from both maps before the first scan (Delete_Point_Boxes, ikd_Tree.cpp:631-658)
+        boxes = np.asarray(pre_delete, np.float32).reshape(-1, 6)
+        assert dm.map_delete_boxes(boxes) == lio.map().delete_boxes(boxes) > 0
     total_eff = 0
     for k in range(n_scans):
         pts, t_beg, imu = seq.scan(k)
@@ -118,3 +121,15 @@ def test_map_incremental_far_points_nearest_only(dev, oracle):
     run_sequence(lib, oracle, seq, map_pts, 3, max_pts=32768 if is_gpu else 8192, read_nearest=False, featptsThreshold=5)
 
 
+
+
+def test_map_incremental_far_points_after_box_delete(dev, oracle):
+    """the nearest-point pass for far queries (k_nn1_seed / k_nn1) works from one LIVE sample per pool run and skips runs whose
+    cell box is too far: with part of the map box-deleted the runs there hold dead points only (and boxes that are still
+    set), so a bound taken from a dead point, or a run skipped although it holds the nearest live one, would change the add
+    lists or the map contents against the reference tree"""
+    lib, is_gpu = dev
+    seq = helpers.small_sequence(seed=3, half=25.0, beams=16, azimuths=240 if not is_gpu else 900, n_boxes=6)
+    map_pts = synth.sample_map(seq.scene, seed=3, region=(-8.0, 8.0, -8.0, 8.0))
+    boxes = [[-8.5, -8.5, -5.0, -2.0, 8.5, 50.0], [3.0, 2.0, -5.0, 8.5, 8.5, 50.0]]  # two sides of the mapped patch
+    run_sequence(lib, oracle, seq, map_pts, 3, max_pts=32768 if is_gpu else 8192, read_nearest=False, pre_delete=boxes, featptsThreshold=5)
