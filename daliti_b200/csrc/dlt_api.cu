@@ -1501,7 +1501,7 @@ int dlt_iekf_update(dlt_handle h, dlt_iekf_block *blk, dlt_reduce_fn reduce, voi
             ProfScope prof(h, 5);
             DLT_LAUNCH(k_nn1_seed, h->n_sm, kSeedBlock, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
-            DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 2 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
+            DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 8 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, &ctl->b.insert_status);
         }
         if (!fused_run) DLT_RT(h, rt::fill(h->d_counters + 6, 0, 2 * sizeof(int), h->stream));  // downsample adds, raw adds (far_count is re-armed by the next k_knn8)
@@ -1814,7 +1814,7 @@ static int map_incremental_impl(dlt_handle h, const double *pose24, int flg_EKF_
             ProfScope prof(h, 5);
             DLT_LAUNCH(k_nn1_seed, h->n_sm, kSeedBlock, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, (int *)nullptr);
-            DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 2 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
+            DLT_LAUNCH(k_nn1, dim3(kNn1GroupsX, 8 * h->n_sm), kNn1Block, h->stream, h->map, (const int *)h->map.n_buckets, (const float4 *)h->knn.qw,
                        (const int *)h->knn.nn_list, (const int *)h->knn.nn_count, h->knn.nn_key, (int *)nullptr);
         }
     }

@@ -61,11 +61,17 @@ DLT_D void pool_box_touch(const MapView &m, int b, unsigned long long key) {
 
 // Find-or-create the table slot of a cell; returns the slot index (-1: table full).
 // The head bucket index written by the creator is only read by LATER kernels.
-DLT_D int map_claim(const MapView &m, unsigned long long key) {
+// created (optional): the caller allocates the head bucket itself (k_map_claim reserves one contiguous range per block, which
+// keeps the pool runs of a bulk insert spatially compact); *created <- 1 when this call made the cell.
+DLT_D int map_claim(const MapView &m, unsigned long long key, int *created = nullptr) {
     unsigned h = hash_key(key) & m.table_mask;
     for (unsigned probe = 0; probe <= m.table_mask; probe++) {
         unsigned long long old = atomicCAS(&m.table[h].key, kEmptyKey, key);
         if (old == kEmptyKey) {
+            if (created) {
+                *created = 1;
+                return (int)h;
+            }
             int b = atomicAdd(m.n_buckets, 1);
             if (b >= m.bucket_cap) {
                 atomicExch(m.error, 1);
@@ -155,21 +161,49 @@ DLT_D bool gate_open(const InsertGate &g, int &n) {
 __global__ void k_map_claim(MapView m, const float4 *__restrict__ pts, int n, const unsigned char *__restrict__ ds_flag,
                             const unsigned char *__restrict__ add_flag, int *__restrict__ cell_slot, int apply_shard_filter, InsertGate gate) {
     DLT_PDL_WAIT();
-    if (!gate_open(gate, n)) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (!ds_flag[i] && !add_flag[i]) {
-        cell_slot[i] = -1;
-        return;
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (!gate_open(gate, n)) return;  // block-uniform
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int slot = -1, created = 0;
+    unsigned long long key = 0ull;
+    if (i < n && (ds_flag[i] || add_flag[i])) {
+        float4 p = pts[i];
+        int cx, cy, cz;
+        cell_of_point(m, p.x, p.y, p.z, cx, cy, cz);
+        if (!(apply_shard_filter && !shard_keeps_cell(m, cx, cy, cz, kShardHalo))) {
+            key = pack_key(cx, cy, cz);
+            slot = map_claim(m, key, &created);
+        }
     }
-    float4 p = pts[i];
-    int cx, cy, cz;
-    cell_of_point(m, p.x, p.y, p.z, cx, cy, cz);
-    if (apply_shard_filter && !shard_keeps_cell(m, cx, cy, cz, kShardHalo)) {
-        cell_slot[i] = -1;
-        return;
+    if (i < n) cell_slot[i] = slot;
+    // the cells this block created get consecutive head buckets: one reservation per block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, created != 0);
+    const int rank_in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int w = 0; w < n_warps; w++) {
+            const int c = s_warp[w];
+            s_warp[w] = total;
+            total += c;
+        }
+        s_base = total > 0 ? atomicAdd(m.n_buckets, total) : 0;
     }
-    cell_slot[i] = map_claim(m, pack_key(cx, cy, cz));
+    __syncthreads();
+    if (created) {
+        int b = s_base + s_warp[warp] + rank_in_warp;
+        if (b >= m.bucket_cap) {
+            atomicExch(m.error, 1);
+            b = -1;
+        } else {
+            bucket_init(&m.buckets[b], key);
+            pool_box_touch(m, b, key);
+        }
+        m.table[slot].bucket = b;
+    }
 }
 
 // ------------------------------------------------------------------ phase 3: append

@@ -949,6 +949,12 @@ __global__ void k_far_merge(const int *__restrict__ far_list, int far_off, int n
 constexpr int kNn1Block = 128;
 constexpr int kNn1Tile = kPoolRun;  // buckets per shared-memory tile = one pool run
 
+// A point at squared distance d2 from the query lies in a cell at most this many cells away (Chebyshev distance between the cell
+// indices, which come from floor(x / ds) >> shift): a point of a cell k cells away is at least (k - 1) cell edges away.
+DLT_D int nn1_reach(float d2, float cell_edge) {
+    const float r = sqrtf(d2) * 1.00001f / cell_edge;
+    return r < 1.0e9f ? (int)r + 2 : 0x3FFFFFFF;
+}
 DLT_D bool nn1_gate(const int *nn_count, int *gate) {
     if (gate && *gate != 1) return false;
     if (gate && nn_count[1] > 0) {  // a bucket chain overflowed the ring search: the host runs the full exact fallback instead
@@ -1040,6 +1046,7 @@ __global__ void __launch_bounds__(kNn1Block)
         const int f = g * kNn1Block + threadIdx.x;
         const bool live = f < nn;
         float qx = 0.f, qy = 0.f, qz = 0.f, slack = 0.f;
+        int qcx = 0, qcy = 0, qcz = 0, reach = 0x3FFFFFFF;  // cells farther than `reach` (Chebyshev) cannot hold anything as near as `best`
         unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
         if (live) {
             const float4 q = qw[nn_list[f]];
@@ -1048,6 +1055,8 @@ __global__ void __launch_bounds__(kNn1Block)
             qz = q.z;
             slack = 4e-7f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 16.f * cell_edge);
             best = nn_key[f];  // the seed pass's upper bound (other blocks may lower it meanwhile: any value read is valid)
+            cell_of_point(m, qx, qy, qz, qcx, qcy, qcz);
+            if (best != 0xFFFFFFFFFFFFFFFFull) reach = nn1_reach(__uint_as_float((unsigned)(best >> 32)), cell_edge);
         }
         const unsigned long long best0 = best;
         for (int r = r_lo; r < r_hi; r++) {  // block-uniform
@@ -1080,14 +1089,23 @@ __global__ void __launch_bounds__(kNn1Block)
             __syncthreads();
             if (need) {
                 for (int k = 0; k < nb; k++) {
-                    unsigned msk = __float_as_uint(tile[k * 8].w) & 0x7Fu;
+                    const float4 hd = tile[k * 8];
+                    unsigned msk = __float_as_uint(hd.w) & 0x7Fu;
+                    // the bucket's own cell: every point of it is at least (Chebyshev cell distance - 1) cell edges away
+                    int cx, cy, cz;
+                    unpack_key(((unsigned long long)__float_as_uint(hd.y) << 32) | (unsigned long long)__float_as_uint(hd.x), cx, cy, cz);
+                    const int dcell = max(max(abs(cx - qcx), abs(cy - qcy)), abs(cz - qcz));
+                    if (dcell > reach) continue;
                     while (msk) {
                         const int sl = __ffs((int)msk) - 1;
                         msk &= msk - 1u;
                         const float4 e = tile[k * 8 + 1 + sl];
                         const float d2 = calc_dist(qx, qy, qz, e.x, e.y, e.z);
                         const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)((tb + k) * 8 + 1 + sl);
-                        best = key < best ? key : best;
+                        if (key < best) {
+                            best = key;
+                            reach = nn1_reach(d2, cell_edge);
+                        }
                     }
                 }
             }

@@ -17,7 +17,8 @@ def main():
     import bench
     from daliti_b200.lio import LaserMapping
 
-    n = 8
+    n = int(os.environ.get("TL_SCANS", "8"))
+    show = [int(x) for x in os.environ.get("TL_PRINT", f"{n - 2},{n - 1}").split(",")]
     wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
     work = bench.build_workload(0, n, wl)
     seq, scans = work["seq"], work["scans"]
@@ -26,18 +27,18 @@ def main():
     lm.force_imu_ready(mean_acc, last_imu)
     lm.set_state(s0)
     lm.device.map_build(work["map_pts"])
-    lm.device.set_profiling(True)
     devs = [torch.from_numpy(np.ascontiguousarray(p)).cuda() for p, _, _ in scans]
     for k in range(n):
         pts, t_beg, imu = scans[k]
         lm.on_lidar_msg()
+        lm.device.set_profiling(k in show)  # (event pairs around every kernel group: only where the timeline is printed)
         lm.device.get_profile(reset=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         o = lm.process_scan_dev(devs[k].data_ptr(), len(pts), t_beg, t_beg + float(pts[-1, 6]), imu)
         host_ms = 1e3 * (time.perf_counter() - t0)
         tl = lm.device.get_timeline()
-        if k >= n - 2:
+        if k in show:
             print(f"--- scan {k}: n_raw {o.n_raw} n_down {o.n_down} iters {o.n_iters} added {o.added} deleted {o.deleted} unresolved {[it.effct_feat_num for it in lm.iters()]}")
             print(f"--- scan {k}: host {host_ms:.3f} ms; stages deskew {1e3*o.t_deskew:.3f} voxel {1e3*o.t_voxel:.3f} iterate {1e3*o.t_iterate:.3f} insert {1e3*o.t_insert:.3f}")
             prev_end = 0.0
