@@ -462,7 +462,16 @@ def main():
     work_c4 = None
     if world > 1 and not args.no_c4:  # the sharded-map leg: every rank cooperates on the SAME scans (rank 0's)
         work_c4 = work if (rank == 0 and args.workload == "c2" and len(work["scans"]) >= k4 + W) else build_workload(0, k4 + W, "c2")
-    all_cores = sorted(os.sched_getaffinity(0))
+    # ---- N > 1: the sharded-map configuration (C4) rides along, so that the scaling record holds a partitioned curve too.  It runs
+    # FIRST, in the state a sharded job has: every rendezvous of the sharded ranks waits for the slowest host thread, and behind
+    # the replica legs (per-rank core blocks, their threads and allocations) the same configuration measured 0.38-0.39 ms at 8 GPUs
+    # against 0.243 ms in a process of its own (profiles/r02_g8_bench_default.json, r02_g8_default_b.json, r02_g8_c4_host.json).
+    c4_line, c4_err = None, None
+    if world > 1 and not args.no_c4:
+        try:
+            c4_line = measure_c4(args, k4, W, rank, local_rank, world, dist, work=work_c4)
+        except Exception as e:
+            c4_err = repr(e)
     pinned_cores = None if os.environ.get("BENCH_NO_PIN") else pin_rank(local_rank, world)
     seq, scans = work["seq"], work["scans"]
     n_map = len(work["map_pts"])
@@ -650,30 +659,19 @@ def main():
         except Exception as e:
             parity = {"ok": False, "error": repr(e)}
 
-    # ---- N > 1: the sharded-map configuration (C4) rides along, so that the scaling record holds a partitioned curve too
     c4 = None
     if world > 1 and not args.no_c4:
-        try:
-            # the sharded ranks meet once per iteration: a rank whose host thread waits for a core stalls all of them, so this leg
-            # runs on the process's full core set again (the per-rank blocks are for replicas that must not disturb each other);
-            # measured at 8 GPUs with 4 cores per rank: 0.376 ms pinned against 0.243 ms for the same configuration unpinned
-            if pinned_cores is not None and not os.environ.get("BENCH_C4_PINNED"):
-                try:
-                    os.sched_setaffinity(0, all_cores)
-                except Exception:
-                    pass
-            c4_line = measure_c4(args, k4, W, rank, local_rank, world, dist, work=work_c4)
-            if rank == 0:
-                c4 = {"ms_p50": c4_line["ms_p50"], "ms_per_step": c4_line["ms_per_step"], "ms_p99": c4_line["ms_p99"], "points_per_s": c4_line["value"],
-                      "scans_per_s": c4_line["scans_per_s"], "steps": c4_line["steps"], "nranks": world, "scaling": "strong",
-                      "exchange": c4_line["config"]["shard_exchange"], "loop": c4_line["config"]["loop"], "map_points": c4_line["config"]["map_points"],
-                      "live_points_incl_halos": c4_line["config"]["live_points_incl_halos"], "map_build_s": c4_line["config"]["map_build_s"],
-                      "e2e": c4_line["e2e"], "gpu_launches": c4_line["gpu_launches"], "workload": c4_line["config"]["workload"],
-                      "unsharded_replica_ms_p50_same_run": float(np.median(ms_v)),
-                      "host_cores": "the process's full core set (not the per-rank block of the replica legs)" if not os.environ.get("BENCH_C4_PINNED") else "per-rank block",
-                      "sharded_over_unsharded_p50": c4_line["ms_p50"] / float(np.median(ms_v))}
-        except Exception as e:
-            c4 = {"error": repr(e)}
+        if c4_err is not None:
+            c4 = {"error": c4_err}
+        elif rank == 0 and c4_line is not None:
+            c4 = {"ms_p50": c4_line["ms_p50"], "ms_per_step": c4_line["ms_per_step"], "ms_p99": c4_line["ms_p99"], "points_per_s": c4_line["value"],
+                  "scans_per_s": c4_line["scans_per_s"], "steps": c4_line["steps"], "nranks": world, "scaling": "strong",
+                  "exchange": c4_line["config"]["shard_exchange"], "loop": c4_line["config"]["loop"], "map_points": c4_line["config"]["map_points"],
+                  "live_points_incl_halos": c4_line["config"]["live_points_incl_halos"], "map_build_s": c4_line["config"]["map_build_s"],
+                  "e2e": c4_line["e2e"], "gpu_launches": c4_line["gpu_launches"], "workload": c4_line["config"]["workload"],
+                  "unsharded_replica_ms_p50_same_run": float(np.median(ms_v)),
+                  "order": "measured before the replica legs, on the process's full core set",
+                  "sharded_over_unsharded_p50": c4_line["ms_p50"] / float(np.median(ms_v))}
 
     if rank == 0:
         n_raw_mean = float(np.mean([o[0] for o in outs_v]))
