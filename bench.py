@@ -18,6 +18,7 @@ normal equations inside the timed region).  One JSON line on stdout (rank 0).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -508,6 +509,11 @@ def main():
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         outs, host_ms = [], []
         launches0 = None
+        # no collector pauses between a step's start event and its first launch: a generation-2 collection of this script's own
+        # objects landed inside the same step of every run (1-4 ms of idle GPU inside one event pair; the host clock around the
+        # call itself showed nothing)
+        gc.collect()
+        gc.disable()
         with torch.cuda.stream(stream):
             for k in range(W + K):
                 pts, t_beg, imu = scans[k]
@@ -533,6 +539,7 @@ def main():
                                  o.t_deskew, o.t_voxel, o.t_iterate, o.t_insert, o.t_delete, o.t_total, o.deleted, o.degenerate))
             barrier()
             launches = lmx.device.launch_count() - launches0
+        gc.enable()
         ms = np.array([a.elapsed_time(b) for a, b in ev])
         return lmx, ms, np.array(host_ms), outs, launches
 
@@ -699,7 +706,7 @@ def main():
                        "deleted_total": int(sum(o[13] for o in outs_v)), "degenerate_scans": int(sum(o[14] for o in outs_v)),
                        "n_raw_mean": n_raw_mean, "n_down_mean": n_down_mean, "effct_feat_mean": float(np.mean([o[6] for o in outs_v])),
                        "ekf_stops": int(sum(o[3] for o in outs_v)), "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
-                       "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
+                       "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks; Python's cyclic collector is off inside the timed loop (gc.collect() before it)",
                        "insert": "async_insert (library default): map_incremental of scan k runs on the handle's insert stream; the step's end event marks the final pose, the insert overlaps the next scan's deskew / VoxelGrid and its first match pass waits for it on the device",
                        "parallelism": "1 sequence per GPU, no data-path collective" if world > 1 else "single GPU",
                        "host_cores_of_this_rank": pinned_cores,
@@ -807,6 +814,8 @@ def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         outs = []
         launches0 = 0
+        gc.collect()
+        gc.disable()
         with torch.cuda.stream(stream):
             for k in range(W + K):
                 pts, t_beg, imu = scans[k]
@@ -832,6 +841,7 @@ def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
                     ev[k - W][1].record(stream)
                     outs.append((o.n_raw, o.n_down, o.n_iters, lm.iters()[-1].effct_feat_num if o.n_iters else 0))
             barrier()
+        gc.enable()
         return np.array([a.elapsed_time(b) for a, b in ev]), outs, lm.device.launch_count() - launches0
 
     sampler = ClockSampler(local_rank)
@@ -887,7 +897,7 @@ def measure_c4(args, K, W, rank, local_rank, world, dist, work=None):
                        "map_points": n_map, "live_points_incl_halos": live_sum, "map_build_s": t_build, "loop": loop_txt,
                        "effct_feat_mean": float(np.mean([o[3] for o in outs_v])),
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA-event pair)",
-                       "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
+                       "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks; Python's cyclic collector is off inside the timed loop (gc.collect() before it)",
                        "insert": "async_insert (library default): map_incremental of scan k runs on the handle's insert stream; the step's end event marks the final pose, the insert overlaps the next scan's deskew / VoxelGrid and its first match pass waits for it on the device",
                        "parallelism": (f"map sharded {world}-way by 32-cell tiles + halo; 158 doubles summed over the ranks per iteration "
                                        + ("inside k_residual through NVLink peer mailboxes (CUDA IPC): no collective launch"

@@ -234,7 +234,7 @@ def test_sharded_per_scan_update_two_processes(emu_lib, mode):
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000) + {"callback": 0, "peers": 1, "peers_host_loop": 2, "peers_device_finish": 3}[mode]
+    port = 31500 + (os.getpid() % 500) * 4 + {"callback": 0, "peers": 1, "peers_host_loop": 2, "peers_device_finish": 3}[mode]  # (x4: parallel workers have consecutive pids)
     peers = mode != "callback"
     loop = {"peers_host_loop": 0, "peers_device_finish": 1}.get(mode, -1)
     procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, peers, loop)) for r in range(2)]
@@ -287,7 +287,7 @@ def test_sharded_per_scan_update_two_gpus_native_nccl(gpu_lib, device_loop):
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 36500 + (os.getpid() % 2000) + device_loop
+    port = 36500 + (os.getpid() % 500) * 4 + device_loop
     procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, False, device_loop, True, True)) for r in range(2)]
     for p in procs:
         p.start()
@@ -325,7 +325,7 @@ def test_sharded_per_scan_update_two_gpus_peer_memory(gpu_lib, mode):
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 33500 + (os.getpid() % 2000) + (1 if mode == "peers" else 2)
+    port = 33500 + (os.getpid() % 500) * 4 + (1 if mode == "peers" else 2)
     procs = [ctx.Process(target=_lio_worker_all, args=(r, 2, port, q, True, 0 if mode == "peers_host_loop" else -1, True)) for r in range(2)]
     for p in procs:
         p.start()
