@@ -110,3 +110,27 @@ def test_knn_reuse_is_result_identical(emu_lib, monkeypatch):
 @pytest.mark.gpu
 def test_knn_reuse_is_result_identical_gpu(gpu_lib, monkeypatch):
     _check_knn_reuse(gpu_lib, monkeypatch, 8)
+
+
+def test_reuse_statistics_and_debug_counters(emu_lib):
+    """dlt_debug_counters: the rematch passes of a replay report how many queries they saw and how many of those had to be searched
+    again; on a map that covers the scene most neighbour sets are proven unchanged"""
+    from daliti_b200.lio import LaserMapping
+
+    seq = helpers.small_sequence(seed=41, half=30.0, beams=16, azimuths=240, n_boxes=8)
+    map_pts = synth.sample_map(seq.scene, seed=41)
+    lm = LaserMapping(emu_lib, dev=dict(max_scan_points=8192, max_map_points=1 << 17), featptsThreshold=5, device_loop=0)
+    lm.force_imu_ready([0.0, 0.0, synth.G], np.concatenate([[seq.t_start - 0.005], [0, 0, synth.G], [0, 0, seq.traj.yaw_rate]]))
+    lm.set_state(helpers.state612(seq.traj, seq.t_start))
+    lm.device.map_build(map_pts)
+    n_rematch = 0
+    for k in range(3):
+        pts, t_beg, imu = seq.scan(k)
+        lm.on_lidar_msg()
+        o = lm.process_scan(pts, t_beg, imu)
+        n_rematch += sum(1 for it in lm.iters()[1:] if it.did_match) * o.n_down
+    c = lm.device.debug_counters()
+    assert c[1] == lm.device.map_valid_count() and c[2] == 0
+    assert n_rematch > 0 and c[12] == n_rematch  # every query of every rematch pass went through the reuse kernel
+    assert 0 <= c[13] < 0.5 * c[12]               # ... and most were not searched again
+    lm.close()

@@ -3,7 +3,7 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 BENCH_C4_TIMELINE=1 timeout 400 $TR --master-port 29731 bench.py --gpus $N --workload c4 --steps 60 --warmup 5 > gpurun_out/g${N}_c4_peer_b.json 2> gpurun_out/g${N}_c4_peer_b.err; echo "rc=$?"
 grep -E "rank [0-9]" gpurun_out/g${N}_c4_peer_b.err | head -80

@@ -2,7 +2,7 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 500 $TR --master-port 29771 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/g${N}_default_c.json 2> gpurun_out/g${N}_default_c.err; echo "rc=$?"
 timeout 300 $TR --master-port 29772 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/g${N}_ref.json 2> gpurun_out/g${N}_ref.err; echo "ref rc=$?"

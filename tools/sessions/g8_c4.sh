@@ -4,7 +4,7 @@
 set -u
 N=${1:-8}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 BENCH_C4_TIMELINE=1 timeout 400 $TR --master-port 29741 bench.py --gpus $N --workload c4 --steps 40 --warmup 5 > gpurun_out/g${N}_c4_host.json 2> gpurun_out/g${N}_c4_host.err; echo "rc=$?"
 grep -E "rank [0-9]" gpurun_out/g${N}_c4_host.err | sort -s -k2,2n | head -120 > gpurun_out/g${N}_c4_timeline.txt

@@ -3,7 +3,7 @@
 set -u
 N=${1:-8}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29761 bench.py --gpus $N --steps 40 --warmup 5 > gpurun_out/g${N}_default_b.json 2> gpurun_out/g${N}_default_b.err; echo "rc=$?"
 python - <<PY

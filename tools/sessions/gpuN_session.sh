@@ -4,7 +4,7 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 if [ "$N" = "2" ]; then
   echo "== sharded GPU tests"

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 400 python bench.py > gpurun_out/fin2_bench_c2.json 2> gpurun_out/fin2_bench_c2.err; echo "bench rc=$?"
 python - <<PY
 import json

@@ -2,7 +2,7 @@
 # Round-2 final single-GPU validation: GPU suite, smoke(), headline bench (both arms), ncu --set full of one scan.
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-fin}
 echo "== 1. GPU test-suite"
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest_gpu.log

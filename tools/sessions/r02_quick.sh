@@ -2,7 +2,7 @@
 # quick single-GPU check: GPU suite + a short headline bench
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-q}
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest_gpu.log
 tail -4 gpurun_out/${T}_pytest_gpu.log

@@ -3,7 +3,7 @@
 # one --set full capture of the hot kernels.  Every step is bounded by its own timeout; results land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-s1}
 
 echo "== 1. GPU test-suite"

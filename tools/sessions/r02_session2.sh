@@ -3,7 +3,7 @@
 # headline bench, C5 with 16 / 64 sequences, C4 unsharded, and an ncu --set full capture of EVERY kernel of one scan.
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-s2}
 echo "== 1. k_knn8 A/B against the previous build"
 timeout 300 python tools/knn_variants.py 2>&1 | tee gpurun_out/${T}_knn_variants.log | tail -6

@@ -2,7 +2,7 @@
 # Round-2 single-GPU session 3: reuse of proven neighbour sets on rematch passes + map_incremental off the critical path.
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-s3}
 echo "== 1. GPU test-suite"
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest_gpu.log

@@ -2,7 +2,7 @@
 # Round-2 single-GPU session 4: reuse pass handing failures to k_knn, per-group visit tags, native multi-sequence driver (C5).
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-s4}
 echo "== 1. GPU test-suite"
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest_gpu.log

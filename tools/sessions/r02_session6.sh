@@ -3,7 +3,7 @@
 # single-GPU workloads on the final code (C1, C3, C4 unsharded).
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-s6}
 echo "== 1. A/B over 105 scans: default | r = no reuse | i = synchronous insert"
 AB_SCANS=105 timeout 500 python tools/ab_latency.py 0 0r 0i 2>&1 | tee gpurun_out/${T}_ab_latency.log | tail -24

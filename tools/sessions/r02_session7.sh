@@ -3,7 +3,7 @@
 # reuse pass as its own kernel.
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-s7}
 echo "== 1. GPU test-suite"
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${T}_pytest_gpu.log

@@ -2,7 +2,7 @@
 # Round-2 single-GPU session 9: the far-query scan (scan 86 of the C2 replay) under the device timeline, then the 105-scan A/B.
 set -u
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 T=${TAG:-s9}
 echo "== 1. timeline of scans 85-87"
 TL_SCANS=88 TL_PRINT=85,86 timeout 400 python tools/timeline.py c2 2>&1 | grep -v "k_iekf_step\|gj_warp" | tee gpurun_out/${T}_timeline.log | tail -50
