@@ -342,7 +342,8 @@ REPLAY_SCANS = 100  # BASELINE.json configs[1] is a 100-scan replay: latency per
 
 def base_config(work):
     """the `config` object: the same keys and values in both arms (everything run-specific goes to `detail`)"""
-    return {"workload": work["name"], "iterations": 4, "map_points": int(len(work["map_pts"]))}
+    return {"workload": work["name"], "iterations": 4, "map_points": int(len(work["map_pts"])),
+            "l2": "GPU arm: L2 flushed between timed steps (256 MiB memset outside the per-step CUDA-event pair)"}
 
 
 def pin_rank(local_rank, world):
