@@ -627,6 +627,13 @@ int dlt_create(const dlt_config *cfg, dlt_handle *out) {
         dlt_destroy(h);
         return DLT_E_CUDA;
     }
+    // pinned staging starts from zero: the zero-copy flags in h_ints are compared with sequence numbers that start at 1, and a
+    // recycled allocation may still hold an earlier handle's flag (seen as a result block that was never written)
+    std::memset(h->h_iekf, 0, sizeof(dlt_iekf_block));
+    std::memset(h->h_result, 0, kResultDoubles * sizeof(double));
+    std::memset(h->h_ints, 0, 64 * sizeof(int));
+    std::memset(h->h_sc, 0, sizeof(ScanScalars));
+    std::memset(h->h_ins_ints, 0, 16 * sizeof(int));
     h->map.n_buckets = h->d_counters + 0;
     h->map.n_live = h->d_counters + 1;
     h->map.error = h->d_counters + 2;
